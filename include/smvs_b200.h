@@ -1,0 +1,227 @@
+/*
+ * smvs_b200.h -- C ABI of libsmvs_b200.so: the SMVS per-view depth-refinement
+ * hot path (Gauss-Newton construct -> block-Jacobi PCG -> node update /
+ * active set, lighting fit, SGM cost volume + 8-path aggregation) as
+ * hand-written sm_100a CUDA kernels.
+ *
+ * The reference (flanggut/smvs) has no FFI layer; the seams this ABI replaces
+ * are C++ member calls inside DepthOptimizer and SGMStereo. Each entry point
+ * names the reference code it stands in for (paths relative to the reference
+ * root). INTEGRATION.md shows the patched bodies of those reference functions.
+ *
+ * Conventions
+ *  - every call returns 0 on success, a negative smvsb_status on error; the
+ *    message is available from smvsb_last_error(). No C++ exception crosses.
+ *  - the caller owns every host buffer; the library copies in / out. Host
+ *    buffers may be pageable or pinned.
+ *  - a smvsb_ctx owns its device memory and one CUDA stream on the device it
+ *    was created for. Contexts are independent: one per host thread / per
+ *    reference view, as the reference runs one DepthOptimizer per pool thread
+ *    (app/smvsrecon.cc:658-733). No global mutable state.
+ *  - images are interleaved row-major exactly like mve::Image<T>:
+ *    data[(y * w + x) * channels + c].
+ *  - there is NO CPU fallback: without a CUDA device every call fails with
+ *    SMVSB_ERR_CUDA.
+ */
+#ifndef SMVS_B200_H
+#define SMVS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smvsb_ctx smvsb_ctx;
+
+typedef enum smvsb_status
+{
+    SMVSB_OK = 0,
+    SMVSB_ERR_INVALID = -1,   /* bad argument / call order (std::invalid_argument in the reference) */
+    SMVSB_ERR_CUDA = -2,      /* CUDA runtime error or no device */
+    SMVSB_ERR_ALLOC = -3,     /* device allocation failed */
+    SMVSB_ERR_STATE = -4      /* required state (views / surface / system) not set */
+} smvsb_status;
+
+/* ConjugateGradient::ReturnInfo, lib/conjugate_gradient.h:22-27 */
+typedef enum smvsb_cg_info
+{
+    SMVSB_CG_CONVERGENCE = 0,
+    SMVSB_CG_MAX_ITERATIONS = 1,
+    SMVSB_CG_INVALID_INPUT = 2
+} smvsb_cg_info;
+
+/* Result of one fused inner Newton loop (smvsb_newton_loop). */
+typedef struct smvsb_newton_stats
+{
+    int32_t newton_steps;        /* lib/depth_optimizer.cc:214,228 */
+    int32_t cg_iterations;       /* sum of Status::num_iterations, :257 */
+    int32_t nan_break;           /* 1 if the loop left through :267 */
+    int32_t reserved;
+    uint64_t n_active;           /* active nodes after the last step, :300-303 */
+    double pixel_iterations;     /* sum over steps of samples of processed patches */
+    double ms_construct;         /* device time, CUDA events */
+    double ms_solve;
+    double ms_update;
+} smvsb_newton_stats;
+
+/* ---- lifetime ------------------------------------------------------- */
+
+int smvsb_create (int device, smvsb_ctx** out);
+void smvsb_destroy (smvsb_ctx* ctx);
+/* Message of the last failed call on ctx (or, with ctx == NULL, of the last
+ * failed smvsb_create / context-free call on this thread). Never NULL. */
+const char* smvsb_last_error (const smvsb_ctx* ctx);
+/* Library identification ("smvs_b200 <version> sm_100a"). */
+const char* smvsb_version (void);
+/* Number of kernel launches issued on this context since creation. */
+uint64_t smvsb_launch_count (const smvsb_ctx* ctx);
+
+/* ---- inputs --------------------------------------------------------- */
+
+/*
+ * Per-scale image data, once per StereoView::set_scale
+ * (lib/stereo_view.cc:24-46; consumed at lib/gauss_newton_step.cc:168-198,
+ * 435-440).
+ *   main_grad          w*h*2   StereoView::get_image_gradients() of the main view
+ *   main_shading       w*h     get_shading_image()      or NULL (no -S)
+ *   main_shading_grad  w*h*2   get_shading_gradients()  or NULL
+ *   flen_px            StereoView::get_flen()          (lib/stereo_view.h:132-139)
+ *   inv_flen           StereoView::get_inverse_flen()  (lib/stereo_view.h:141-148)
+ *   sub_grad[k]        sub_w[k]*sub_h[k]*2  gradients of neighbour k
+ *   sub_hess[k]        sub_w[k]*sub_h[k]*3  Hessian (xx, xy, yy) of neighbour k
+ *   Mi                 n_sub*9 row-major, ti n_sub*3: DepthOptimizer::Mi/ti
+ *                      (lib/depth_optimizer.cc:679-699)
+ */
+int smvsb_set_views (smvsb_ctx* ctx, int w, int h, double flen_px,
+    double inv_flen, const float* main_grad, const float* main_shading,
+    const float* main_shading_grad, int n_sub, const int* sub_w,
+    const int* sub_h, const float* const* sub_grad,
+    const float* const* sub_hess, const double* Mi, const double* ti);
+
+/*
+ * The Surface and the per-patch visibility lists (DepthOptimizer::subsurfaces).
+ *   scale, npx, npy, start_x, start_y   grid of lib/surface.cc:28-37: patch
+ *       (idx, idy) has id idy*npx+idx, covers pixels start + id*2^scale;
+ *       node (idx, idy) has id idy*(npx+1)+idx (lib/surface.h:199-203)
+ *   nodes        (npx+1)*(npy+1)*4   f, dx, dy, dxy per node (lib/bicubic_patch.h:29-36)
+ *   node_valid   (npx+1)*(npy+1)     0 where Surface::nodes[i] == nullptr
+ *   patch_valid  npx*npy             0 where Surface::patches[i] == nullptr
+ *   vis_off      npx*npy+1, vis_ids  CSR of subsurfaces[patch] (neighbour ids,
+ *                                    in the reference's order)
+ */
+int smvsb_set_surface (smvsb_ctx* ctx, int scale, int npx, int npy,
+    int start_x, int start_y, const double* nodes, const uint8_t* node_valid,
+    const uint8_t* patch_valid, const uint32_t* vis_off,
+    const uint8_t* vis_ids);
+
+/* Replace node values only (same grid / validity / visibility). */
+int smvsb_set_nodes (smvsb_ctx* ctx, const double* nodes);
+
+/* ---- the Gauss-Newton step ----------------------------------------- */
+
+/*
+ * GaussNewtonStep::construct (lib/gauss_newton_step.cc:33-143): gradient,
+ * block-sparse Hessian and inverted block-diagonal preconditioner for the
+ * current surface; they stay on the device.
+ *   active_nodes  (npx+1)*(npy+1) bytes, or NULL = every valid node active
+ *                 (lib/depth_optimizer.cc:204-212)
+ *   light16       GlobalLighting parameters or NULL (lighting == nullptr)
+ */
+int smvsb_gn_construct (smvsb_ctx* ctx, const uint8_t* active_nodes,
+    const double* light16, double regularization,
+    double light_surf_regularization);
+
+/*
+ * ConjugateGradient::solve(H, -g, &x, &P) (lib/conjugate_gradient.h:72-202)
+ * on the system of the last smvsb_gn_construct. err_tol < 0 selects the
+ * caller's rule of lib/depth_optimizer.cc:247 (0.01 * ||g||). x stays on the
+ * device (smvsb_get_delta reads it).
+ */
+int smvsb_cg_solve (smvsb_ctx* ctx, int max_iter, double err_tol,
+    double q_tol, int* iters, int* info);
+
+/* delta = CG solution, (npx+1)*(npy+1)*4 doubles. */
+int smvsb_get_delta (smvsb_ctx* ctx, double* delta);
+/* Overwrite the CG solution (parity tests of the update step). */
+int smvsb_set_delta (smvsb_ctx* ctx, const double* delta);
+
+/*
+ * lib/depth_optimizer.cc:271-303: reprojections of every pixel of every
+ * processed patch before/after Surface::update_nodes(delta)
+ * (lib/surface.cc:957-981), then the new active set (or, with full_opt, only
+ * the mean shift, :275-289). The active set used is the one given to the last
+ * smvsb_gn_construct; the new one replaces it on the device and is copied to
+ * active_out (may be NULL).
+ */
+int smvsb_update_nodes (smvsb_ctx* ctx, double reproj_thresh, int full_opt,
+    uint8_t* active_out, uint64_t* n_active, double* mean_shift);
+
+/*
+ * The whole inner loop of DepthOptimizer::run_newton_iterations
+ * (lib/depth_optimizer.cc:204-304): all valid nodes active, then
+ * construct -> CG (max 200 iterations, tolerance 0.01 * ||g||) -> NaN check
+ * -> update -> active set, while active > initial/20 and steps < max_steps.
+ */
+int smvsb_newton_loop (smvsb_ctx* ctx, const double* light16,
+    double regularization, double light_surf_regularization, int max_steps,
+    int full_opt, smvsb_newton_stats* stats);
+
+/* ---- outputs -------------------------------------------------------- */
+
+int smvsb_get_nodes (smvsb_ctx* ctx, double* nodes_out);
+/* Surface::get_depth_map (lib/surface.cc:155-168): w*h floats, 0 outside. */
+int smvsb_get_depth (smvsb_ctx* ctx, float* depth_wh);
+/* Surface::get_normal_map(inv_flen) (lib/surface.cc:170-183): w*h*3. */
+int smvsb_get_normals (smvsb_ctx* ctx, float* normals_wh3);
+
+/*
+ * Parity-test access to the linear system in the reference's layout
+ * (lib/block_sparse_matrix.h:95-97): blocks sorted by block column then block
+ * row, each 4x4 row-major, inner = 4 * block row, outer = num_nodes+1 prefix.
+ * Pass NULL for anything not wanted; *nnzb_h / *nnzb_p receive block counts
+ * (call once with NULL arrays to size the buffers).
+ */
+int smvsb_debug_get_system (smvsb_ctx* ctx, double* g, double* Hvals,
+    uint64_t* Houter, uint64_t* Hinner, uint64_t* nnzb_h, double* Pvals,
+    uint64_t* Pouter, uint64_t* Pinner, uint64_t* nnzb_p);
+/* y = H x with the device SpMV kernel (parity of lib/block_sparse_matrix.h:276-298). */
+int smvsb_debug_spmv (smvsb_ctx* ctx, const double* x, double* y);
+
+/*
+ * LightOptimizer::fit_lighting_to_image (lib/light_optimizer.cc:22-55) on the
+ * current surface and the main view's shading image: 16 SH coefficients.
+ * nccl_comm: NULL for the reference's per-view behaviour; otherwise an
+ * ncclComm_t -- the 16x16+16 normal equations are summed over the
+ * communicator before the pseudo inverse (opt-in global lighting, changes
+ * results w.r.t. the reference).
+ */
+int smvsb_fit_lighting (smvsb_ctx* ctx, double* params16_out,
+    void* nccl_comm);
+
+/* ---- SGM ------------------------------------------------------------ */
+
+/*
+ * SGMStereo::run_sgm (lib/sgm_stereo.cc:98-124) = create_cost_volume
+ * (:192-244) + aggregate_sgm_costs (:429-667, SSE branch: constant P2) +
+ * depth_from_sgm_volume (:274-306), for one main / neighbour luminance pair
+ * that is already at SGM working resolution.
+ *   M, t       fp32 reprojection main -> neighbour at these sizes
+ *              (mve::CameraInfo::fill_reprojection, lib/sgm_stereo.cc:158-160)
+ *   depth_out  w*h floats
+ *   cost_out / sgm_out  optional w*h*num_steps uint16 dumps (NULL to skip)
+ *   ms_out     optional double[3]: device ms of cost volume, aggregation, WTA
+ * num_steps must be a multiple of 32 and <= 256.
+ */
+int smvsb_sgm (int device, int w, int h, const uint8_t* main_lum,
+    int nw, int nh, const uint8_t* neigh_lum, const float* M, const float* t,
+    float min_depth, float max_depth, int num_steps, uint16_t penalty1,
+    uint16_t penalty2, float* depth_out, uint16_t* cost_out,
+    uint16_t* sgm_out, double* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SMVS_B200_H */

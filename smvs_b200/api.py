@@ -1,0 +1,266 @@
+"""ctypes host-side mirror of include/smvs_b200.h.
+
+Python plumbing for the tests and the benchmark: it calls the C ABI of
+smvs_b200/libsmvs_b200.so (hand-written sm_100a kernels) with numpy host
+buffers, exactly as the patched reference C++ would.
+There is no fallback: a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsmvs_b200.so")
+
+EXPORTS = [
+    "smvsb_create", "smvsb_destroy", "smvsb_last_error", "smvsb_version",
+    "smvsb_launch_count", "smvsb_set_views", "smvsb_set_surface",
+    "smvsb_set_nodes", "smvsb_gn_construct", "smvsb_cg_solve",
+    "smvsb_get_delta", "smvsb_set_delta", "smvsb_update_nodes",
+    "smvsb_newton_loop", "smvsb_get_nodes", "smvsb_get_depth",
+    "smvsb_get_normals", "smvsb_debug_get_system", "smvsb_debug_spmv",
+    "smvsb_fit_lighting", "smvsb_sgm",
+]
+
+
+class SmvsbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"smvs_b200 error {code}: {msg}")
+        self.code = code
+
+
+class NewtonStats(C.Structure):
+    _fields_ = [("newton_steps", C.c_int32), ("cg_iterations", C.c_int32),
+                ("nan_break", C.c_int32), ("reserved", C.c_int32),
+                ("n_active", C.c_uint64), ("pixel_iterations", C.c_double),
+                ("ms_construct", C.c_double), ("ms_solve", C.c_double),
+                ("ms_update", C.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libsmvs_b200.so; raises if it was not built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SmvsbError(-100, f"{LIB_PATH} missing: run "
+                             "`python -m smvs_b200.build` (or __graft_entry__.build())")
+        L = C.CDLL(LIB_PATH)
+        L.smvsb_last_error.restype = C.c_char_p
+        L.smvsb_last_error.argtypes = [C.c_void_p]
+        L.smvsb_version.restype = C.c_char_p
+        L.smvsb_launch_count.restype = C.c_uint64
+        L.smvsb_launch_count.argtypes = [C.c_void_p]
+        L.smvsb_destroy.argtypes = [C.c_void_p]
+        L.smvsb_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _u8(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.uint8)
+
+
+class Context:
+    """One smvsb_ctx: device memory + stream of one reference view."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().smvsb_create(int(device), C.byref(self._h))
+        if rc != 0:
+            raise SmvsbError(rc, lib().smvsb_last_error(None).decode())
+        self.device = device
+        self.n_nodes = 0
+        self.n_patches = 0
+        self.w = self.h = 0
+
+    def close(self):
+        if self._h:
+            lib().smvsb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SmvsbError(rc, lib().smvsb_last_error(self._h).decode())
+
+    @property
+    def launches(self):
+        return int(lib().smvsb_launch_count(self._h))
+
+    # -- inputs ----------------------------------------------------------
+    def set_views(self, main_grad, sub_grads, sub_hess, Mi, ti, flen_px,
+                  inv_flen, main_shading=None, main_shading_grad=None):
+        main_grad = _f32(main_grad)
+        h, w = main_grad.shape[:2]
+        n = len(sub_grads)
+        sg = [_f32(a) for a in sub_grads]
+        sh = [_f32(a) for a in sub_hess]
+        sw = (C.c_int * max(n, 1))(*[a.shape[1] for a in sg])
+        shh = (C.c_int * max(n, 1))(*[a.shape[0] for a in sg])
+        gp = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in sg])
+        hp = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in sh])
+        Mi = _f64(Mi)
+        ti = _f64(ti)
+        ms, msg = _f32(main_shading), _f32(main_shading_grad)
+        self._check(lib().smvsb_set_views(
+            self._h, w, h, C.c_double(flen_px), C.c_double(inv_flen), _p(main_grad),
+            _p(ms), _p(msg), n, sw, shh, gp, hp, _p(Mi), _p(ti)))
+        self.w, self.h = w, h
+
+    def set_surface(self, scale, npx, npy, start_x, start_y, nodes, node_valid,
+                    patch_valid, vis_off, vis_ids):
+        nodes = _f64(nodes)
+        nv, pv = _u8(node_valid), _u8(patch_valid)
+        vo = np.ascontiguousarray(vis_off, dtype=np.uint32)
+        vi = _u8(vis_ids)
+        if vi.size == 0:
+            vi = np.zeros(1, dtype=np.uint8)
+        self._check(lib().smvsb_set_surface(
+            self._h, int(scale), int(npx), int(npy), int(start_x), int(start_y),
+            _p(nodes), _p(nv), _p(pv), _p(vo), _p(vi)))
+        self.n_nodes = (npx + 1) * (npy + 1)
+        self.n_patches = npx * npy
+
+    def set_nodes(self, nodes):
+        nodes = _f64(nodes)
+        self._check(lib().smvsb_set_nodes(self._h, _p(nodes)))
+
+    # -- Gauss-Newton ----------------------------------------------------
+    def gn_construct(self, active=None, light16=None, regularization=0.01,
+                     light_surf_regularization=0.0):
+        a, l = _u8(active), _f64(light16)
+        self._check(lib().smvsb_gn_construct(
+            self._h, _p(a), _p(l), C.c_double(regularization),
+            C.c_double(light_surf_regularization)))
+
+    def cg_solve(self, max_iter=200, err_tol=-1.0, q_tol=1e-3):
+        it, info = C.c_int(0), C.c_int(0)
+        self._check(lib().smvsb_cg_solve(self._h, int(max_iter), C.c_double(err_tol),
+                                         C.c_double(q_tol), C.byref(it), C.byref(info)))
+        return it.value, info.value
+
+    def get_delta(self):
+        x = np.empty(self.n_nodes * 4, dtype=np.float64)
+        self._check(lib().smvsb_get_delta(self._h, _p(x)))
+        return x
+
+    def set_delta(self, delta):
+        d = _f64(delta)
+        self._check(lib().smvsb_set_delta(self._h, _p(d)))
+
+    def update_nodes(self, reproj_thresh=0.15, full_opt=False):
+        act = np.empty(self.n_nodes, dtype=np.uint8)
+        n_active, shift = C.c_uint64(0), C.c_double(0)
+        self._check(lib().smvsb_update_nodes(
+            self._h, C.c_double(reproj_thresh), int(full_opt), _p(act),
+            C.byref(n_active), C.byref(shift)))
+        return act, int(n_active.value), float(shift.value)
+
+    def newton_loop(self, light16=None, regularization=0.01,
+                    light_surf_regularization=0.0, max_steps=200, full_opt=False):
+        l = _f64(light16)
+        st = NewtonStats()
+        self._check(lib().smvsb_newton_loop(
+            self._h, _p(l), C.c_double(regularization),
+            C.c_double(light_surf_regularization), int(max_steps), int(full_opt),
+            C.byref(st)))
+        return dict(newton_steps=st.newton_steps, cg_iterations=st.cg_iterations,
+                    nan=bool(st.nan_break), n_active=int(st.n_active),
+                    pixel_iterations=float(st.pixel_iterations),
+                    ms_construct=st.ms_construct, ms_solve=st.ms_solve,
+                    ms_update=st.ms_update)
+
+    # -- outputs ---------------------------------------------------------
+    def get_nodes(self):
+        out = np.empty((self.n_nodes, 4), dtype=np.float64)
+        self._check(lib().smvsb_get_nodes(self._h, _p(out)))
+        return out
+
+    def get_depth(self):
+        out = np.empty((self.h, self.w), dtype=np.float32)
+        self._check(lib().smvsb_get_depth(self._h, _p(out)))
+        return out
+
+    def get_normals(self):
+        out = np.empty((self.h, self.w, 3), dtype=np.float32)
+        self._check(lib().smvsb_get_normals(self._h, _p(out)))
+        return out
+
+    def debug_get_system(self):
+        nh, npc = C.c_uint64(0), C.c_uint64(0)
+        self._check(lib().smvsb_debug_get_system(
+            self._h, None, None, None, None, C.byref(nh), None, None, None,
+            C.byref(npc)))
+        n = self.n_nodes
+        g = np.empty(n * 4, dtype=np.float64)
+        Hv = np.empty((int(nh.value), 16), dtype=np.float64)
+        Ho = np.empty(n + 1, dtype=np.uint64)
+        Hi = np.empty(int(nh.value), dtype=np.uint64)
+        Pv = np.empty((int(npc.value), 16), dtype=np.float64)
+        Po = np.empty(n + 1, dtype=np.uint64)
+        Pi = np.empty(int(npc.value), dtype=np.uint64)
+        self._check(lib().smvsb_debug_get_system(
+            self._h, _p(g), _p(Hv), _p(Ho), _p(Hi), C.byref(nh), _p(Pv), _p(Po),
+            _p(Pi), C.byref(npc)))
+        return dict(g=g, Hvals=Hv, Houter=Ho, Hinner=Hi, Pvals=Pv, Pouter=Po, Pinner=Pi)
+
+    def debug_spmv(self, x):
+        x = _f64(x)
+        y = np.empty_like(x)
+        self._check(lib().smvsb_debug_spmv(self._h, _p(x), _p(y)))
+        return y
+
+    def fit_lighting(self, nccl_comm=None):
+        out = np.zeros(16, dtype=np.float64)
+        comm = C.c_void_p(nccl_comm) if nccl_comm else None
+        self._check(lib().smvsb_fit_lighting(self._h, _p(out), comm))
+        return out
+
+
+def sgm(main_lum, neigh_lum, M, t, min_depth, max_depth, num_steps=128,
+        penalty1=6, penalty2=96, device=0, volumes=False):
+    """SGMStereo::run_sgm for one luminance pair (smvsb_sgm)."""
+    main_lum, neigh_lum = _u8(main_lum), _u8(neigh_lum)
+    h, w = main_lum.shape
+    nh, nw = neigh_lum.shape
+    M, t = _f32(M), _f32(t)
+    depth = np.empty((h, w), dtype=np.float32)
+    cost = np.empty((h, w, num_steps), dtype=np.uint16) if volumes else None
+    S = np.empty((h, w, num_steps), dtype=np.uint16) if volumes else None
+    ms = np.zeros(3, dtype=np.float64)
+    rc = lib().smvsb_sgm(int(device), w, h, _p(main_lum), nw, nh, _p(neigh_lum),
+                         _p(M), _p(t), C.c_float(min_depth), C.c_float(max_depth),
+                         int(num_steps), C.c_uint16(penalty1), C.c_uint16(penalty2),
+                         _p(depth), _p(cost), _p(S), _p(ms))
+    if rc != 0:
+        raise SmvsbError(rc, lib().smvsb_last_error(None).decode())
+    return dict(depth=depth, cost=cost, sgm=S, ms=ms)

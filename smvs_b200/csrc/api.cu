@@ -1,0 +1,735 @@
+/*
+ * api.cu -- the C ABI of include/smvs_b200.h over the kernels.
+ * Host code here is plumbing: argument checks, uploads, launch order of the
+ * Newton loop (lib/depth_optimizer.cc:204-304). No numeric step of the hot
+ * path runs on the host; the one exception is the 16x16 pseudo inverse that
+ * closes the lighting fit (lib/light_optimizer.cc:50-52), a 16x16 SVD.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <dlfcn.h>
+
+#include "common.cuh"
+
+namespace smvsb {
+void fill_basis_table (std::vector<double>& tab, int ps, int step);
+std::string const& sgm_last_error (void);
+int sgm_run (int device, int w, int h, uint8_t const* main_lum, int nw, int nh,
+    uint8_t const* neigh_lum, float const* M, float const* t,
+    float min_depth, float max_depth, int num_steps, uint16_t penalty1,
+    uint16_t penalty2, float* depth_out, uint16_t* cost_out,
+    uint16_t* sgm_out, double* ms_out);
+}
+
+namespace {
+
+thread_local std::string g_last_error = "";
+
+template <typename F>
+int
+guarded (smvsb_ctx* ctx, F&& fn)
+{
+    try
+    {
+        if (ctx != nullptr)
+        {
+            cudaError_t e = cudaSetDevice(ctx->device);
+            if (e != cudaSuccess)
+                throw smvsb::Error(SMVSB_ERR_CUDA,
+                    std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+        }
+        fn();
+        return SMVSB_OK;
+    }
+    catch (smvsb::Error const& e)
+    {
+        if (ctx) ctx->last_error = e.msg; else g_last_error = e.msg;
+        return e.code;
+    }
+    catch (std::exception const& e)
+    {
+        if (ctx) ctx->last_error = e.what(); else g_last_error = e.what();
+        return SMVSB_ERR_INVALID;
+    }
+}
+
+void
+require (bool cond, int code, char const* msg)
+{
+    if (!cond)
+        throw smvsb::Error(code, msg);
+}
+
+template <typename T>
+void
+upload (smvsb_ctx* c, smvsb::DevBuf<T>& buf, T const* host, size_t n)
+{
+    buf.reserve(std::max<size_t>(n, 1));
+    if (n > 0)
+        CUDA_CHECK(cudaMemcpyAsync(buf.p, host, n * sizeof(T),
+            cudaMemcpyHostToDevice, c->stream));
+}
+
+template <typename T>
+void
+download (smvsb_ctx* c, T* host, T const* dev, size_t n)
+{
+    CUDA_CHECK(cudaMemcpyAsync(host, dev, n * sizeof(T),
+        cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+int
+sampling_for_scale (int scale)
+{
+    /* lib/gauss_newton_step.cc:157-161 */
+    int sampling = 4;
+    if (scale < 5) sampling = 2;
+    if (scale < 3) sampling = 1;
+    return sampling;
+}
+
+/* One-sided Jacobi SVD based pseudo inverse of a symmetric 16x16 matrix,
+ * singular values within 1e-12 of zero dropped
+ * (math::matrix_pseudo_inverse as called at lib/light_optimizer.cc:51). */
+void
+pseudo_inverse_16 (double const* A, double* Ainv)
+{
+    int const N = 16;
+    double U[256], V[256];
+    std::copy(A, A + 256, U);
+    std::fill(V, V + 256, 0.0);
+    for (int i = 0; i < N; ++i) V[i * N + i] = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep)
+    {
+        double off = 0.0;
+        for (int p = 0; p < N - 1; ++p)
+            for (int q = p + 1; q < N; ++q)
+            {
+                double alpha = 0, beta = 0, gamma = 0;
+                for (int i = 0; i < N; ++i)
+                {
+                    alpha += U[i * N + p] * U[i * N + p];
+                    beta += U[i * N + q] * U[i * N + q];
+                    gamma += U[i * N + p] * U[i * N + q];
+                }
+                double const lim = std::sqrt(alpha * beta);
+                if (gamma == 0.0 || std::abs(gamma) <= 1e-16 * lim)
+                    continue;
+                off = std::max(off, std::abs(gamma) / (lim > 0 ? lim : 1.0));
+                double const zeta = (beta - alpha) / (2.0 * gamma);
+                double const t = (zeta >= 0 ? 1.0 : -1.0)
+                    / (std::abs(zeta) + std::sqrt(1.0 + zeta * zeta));
+                double const cs = 1.0 / std::sqrt(1.0 + t * t);
+                double const sn = cs * t;
+                for (int i = 0; i < N; ++i)
+                {
+                    double const up = U[i * N + p], uq = U[i * N + q];
+                    U[i * N + p] = cs * up - sn * uq;
+                    U[i * N + q] = sn * up + cs * uq;
+                    double const vp = V[i * N + p], vq = V[i * N + q];
+                    V[i * N + p] = cs * vp - sn * vq;
+                    V[i * N + q] = sn * vp + cs * vq;
+                }
+            }
+        if (off < 1e-15)
+            break;
+    }
+    double sinv[16];
+    for (int j = 0; j < N; ++j)
+    {
+        double n = 0.0;
+        for (int i = 0; i < N; ++i) n += U[i * N + j] * U[i * N + j];
+        n = std::sqrt(n);
+        for (int i = 0; i < N; ++i)
+            U[i * N + j] = (n > 0.0 ? U[i * N + j] / n : 0.0);
+        sinv[j] = (n >= -1e-12 && n <= 1e-12) ? 0.0 : 1.0 / n;
+    }
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j)
+        {
+            double s = 0.0;
+            for (int k = 0; k < N; ++k)
+                s += V[i * N + k] * sinv[k] * U[j * N + k];
+            Ainv[i * N + j] = s;
+        }
+}
+
+void
+ensure_system_buffers (smvsb_ctx* c)
+{
+    size_t const np = c->n_patches, nn = c->n_nodes;
+    c->patch_H.reserve(np * 256);
+    c->patch_g.reserve(np * 16);
+    c->patch_proc.reserve(np);
+    c->H.reserve(nn * 144);
+    c->P.reserve(nn * 16);
+    c->g.reserve(nn * 4);
+    c->x.reserve(nn * 4);
+    c->light.reserve(16);
+}
+
+void
+set_active (smvsb_ctx* c, uint8_t const* active_nodes)
+{
+    if (active_nodes != nullptr)
+        upload(c, c->active, active_nodes, c->n_nodes);
+    else
+    {
+        /* every valid node active, lib/depth_optimizer.cc:204-212 */
+        c->active.reserve(c->n_nodes);
+        CUDA_CHECK(cudaMemcpyAsync(c->active.p, c->node_valid.p, c->n_nodes,
+            cudaMemcpyDeviceToDevice, c->stream));
+    }
+}
+
+void
+construct (smvsb_ctx* c, double const* light16, double reg, double light_reg)
+{
+    require(c->have_views && c->have_surface, SMVSB_ERR_STATE,
+        "smvsb_set_views and smvsb_set_surface must precede construct");
+    if (light16 != nullptr)
+    {
+        require(c->have_shading, SMVSB_ERR_STATE,
+            "lighting given but the main view has no shading image");
+        upload(c, c->light, light16, 16);
+    }
+    ensure_system_buffers(c);
+    smvsb::launch_construct(c, light16 != nullptr, reg, light_reg);
+    c->have_system = true;
+}
+
+} /* namespace */
+
+extern "C" {
+
+const char*
+smvsb_version (void)
+{
+    return "smvs_b200 0.1.0 sm_100a";
+}
+
+const char*
+smvsb_last_error (const smvsb_ctx* ctx)
+{
+    return ctx ? ctx->last_error.c_str() : g_last_error.c_str();
+}
+
+uint64_t
+smvsb_launch_count (const smvsb_ctx* ctx)
+{
+    return ctx ? ctx->launches : 0;
+}
+
+int
+smvsb_create (int device, smvsb_ctx** out)
+{
+    return guarded(nullptr, [&]() {
+        require(out != nullptr, SMVSB_ERR_INVALID, "out must not be NULL");
+        *out = nullptr;
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw smvsb::Error(SMVSB_ERR_CUDA, std::string("no CUDA device "
+                "(smvs_b200 has no CPU fallback): ")
+                + cudaGetErrorString(e));
+        require(device >= 0 && device < count, SMVSB_ERR_INVALID,
+            "device index out of range");
+        CUDA_CHECK(cudaSetDevice(device));
+        smvsb_ctx* c = new smvsb_ctx();
+        c->device = device;
+        try
+        {
+            CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream,
+                cudaStreamNonBlocking));
+            for (int i = 0; i < 4; ++i)
+                CUDA_CHECK(cudaEventCreate(&c->ev[i]));
+            CUDA_CHECK(cudaDeviceGetAttribute(&c->num_sms,
+                cudaDevAttrMultiProcessorCount, device));
+        }
+        catch (...)
+        {
+            delete c;
+            throw;
+        }
+        *out = c;
+    });
+}
+
+void
+smvsb_destroy (smvsb_ctx* ctx)
+{
+    if (ctx == nullptr)
+        return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 4; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int
+smvsb_set_views (smvsb_ctx* ctx, int w, int h, double flen_px,
+    double inv_flen, const float* main_grad, const float* main_shading,
+    const float* main_shading_grad, int n_sub, const int* sub_w,
+    const int* sub_h, const float* const* sub_grad,
+    const float* const* sub_hess, const double* Mi, const double* ti)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(w > 0 && h > 0 && main_grad != nullptr, SMVSB_ERR_INVALID,
+            "main view missing");
+        require(n_sub >= 0 && n_sub <= SMVSB_MAX_SUBS, SMVSB_ERR_INVALID,
+            "n_sub out of range (max 32)");
+        require((main_shading == nullptr) == (main_shading_grad == nullptr),
+            SMVSB_ERR_INVALID, "shading image and gradient go together");
+        require(n_sub == 0 || (sub_w && sub_h && sub_grad && sub_hess && Mi
+            && ti), SMVSB_ERR_INVALID, "neighbour arrays missing");
+        smvsb_ctx* c = ctx;
+        c->w = w; c->h = h; c->flen = flen_px; c->inv_flen = inv_flen;
+        size_t const npix = static_cast<size_t>(w) * h;
+        upload(c, c->main_grad, main_grad, npix * 2);
+        c->have_shading = (main_shading != nullptr);
+        if (c->have_shading)
+        {
+            upload(c, c->main_shading, main_shading, npix);
+            upload(c, c->main_shading_grad, main_shading_grad, npix * 2);
+        }
+        c->n_sub = n_sub;
+        std::vector<float const*> ptrs(std::max(n_sub, 1), nullptr);
+        std::vector<int> dims(std::max(2 * n_sub, 2), 0);
+        std::vector<double> mt(std::max(12 * n_sub, 12), 0.0);
+        smvsb::DevBuf<float> stage_g, stage_h;
+        for (int k = 0; k < n_sub; ++k)
+        {
+            require(sub_w[k] > 0 && sub_h[k] > 0 && sub_grad[k]
+                && sub_hess[k], SMVSB_ERR_INVALID, "neighbour image missing");
+            size_t const n = static_cast<size_t>(sub_w[k]) * sub_h[k];
+            smvsb::SubViewDev& sv = c->subs[k];
+            sv.w = sub_w[k]; sv.h = sub_h[k];
+            sv.texels.reserve(n * SMVSB_NB_STRIDE);
+            upload(c, stage_g, sub_grad[k], n * 2);
+            upload(c, stage_h, sub_hess[k], n * 3);
+            smvsb::launch_pack_subview(c, stage_g.p, stage_h.p, sv.texels.p,
+                sv.w, sv.h);
+            ptrs[k] = sv.texels.p;
+            dims[2 * k] = sv.w; dims[2 * k + 1] = sv.h;
+            std::copy(Mi + 9 * k, Mi + 9 * k + 9, mt.begin() + 12 * k);
+            std::copy(ti + 3 * k, ti + 3 * k + 3, mt.begin() + 12 * k + 9);
+        }
+        upload(c, c->sub_ptrs, ptrs.data(), ptrs.size());
+        upload(c, c->sub_dims, dims.data(), dims.size());
+        upload(c, c->Mt, mt.data(), mt.size());
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));   /* staging buffers */
+        c->have_views = true;
+        c->have_system = false;
+    });
+}
+
+int
+smvsb_set_surface (smvsb_ctx* ctx, int scale, int npx, int npy, int start_x,
+    int start_y, const double* nodes, const uint8_t* node_valid,
+    const uint8_t* patch_valid, const uint32_t* vis_off,
+    const uint8_t* vis_ids)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_views, SMVSB_ERR_STATE,
+            "smvsb_set_views must precede smvsb_set_surface");
+        require(scale >= 0 && scale <= 8, SMVSB_ERR_INVALID,
+            "scale out of range");
+        require(npx > 0 && npy > 0, SMVSB_ERR_INVALID, "empty patch grid");
+        require(nodes && node_valid && patch_valid && vis_off && vis_ids,
+            SMVSB_ERR_INVALID, "surface arrays missing");
+        int const ps = 1 << scale;
+        int const sampling = sampling_for_scale(scale);
+        require(ps % sampling == 0, SMVSB_ERR_INVALID,
+            "patch size below sampling");
+        int const npos = ps / sampling;
+        require(npos == 4 || npos == 8, SMVSB_ERR_INVALID,
+            "this build handles scales 2..5 (16 or 64 samples per patch)");
+        require(start_x >= 0 && start_y >= 0
+            && start_x + npx * ps <= ctx->w && start_y + npy * ps <= ctx->h,
+            SMVSB_ERR_INVALID, "patch grid exceeds the main image");
+        smvsb_ctx* c = ctx;
+        c->scale = scale; c->ps = ps; c->sampling = sampling; c->npos = npos;
+        c->npx = npx; c->npy = npy; c->start_x = start_x; c->start_y = start_y;
+        c->n_patches = npx * npy;
+        c->n_nodes = (npx + 1) * (npy + 1);
+        size_t const total_vis = vis_off[c->n_patches];
+        for (size_t i = 0; i < total_vis; ++i)
+            require(vis_ids[i] < c->n_sub, SMVSB_ERR_INVALID,
+                "visibility id out of range");
+        upload(c, c->nodes, nodes, static_cast<size_t>(c->n_nodes) * 4);
+        upload(c, c->node_valid, node_valid, c->n_nodes);
+        upload(c, c->patch_valid, patch_valid, c->n_patches);
+        upload(c, c->vis_off, vis_off, static_cast<size_t>(c->n_patches) + 1);
+        upload(c, c->vis_ids, vis_ids, total_vis);
+        c->h_node_valid.assign(node_valid, node_valid + c->n_nodes);
+        c->h_patch_valid.assign(patch_valid, patch_valid + c->n_patches);
+        std::vector<double> tab;
+        smvsb::fill_basis_table(tab, ps, sampling);
+        upload(c, c->basis_s, tab.data(), tab.size());
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        smvsb::fill_basis_table(tab, ps, 1);
+        upload(c, c->basis_f, tab.data(), tab.size());
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        set_active(c, nullptr);
+        c->have_surface = true;
+        c->have_system = false;
+    });
+}
+
+int
+smvsb_set_nodes (smvsb_ctx* ctx, const double* nodes)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_surface, SMVSB_ERR_STATE, "no surface set");
+        require(nodes != nullptr, SMVSB_ERR_INVALID, "nodes missing");
+        upload(ctx, ctx->nodes, nodes, static_cast<size_t>(ctx->n_nodes) * 4);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        ctx->have_system = false;
+    });
+}
+
+int
+smvsb_gn_construct (smvsb_ctx* ctx, const uint8_t* active_nodes,
+    const double* light16, double regularization,
+    double light_surf_regularization)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_views && ctx->have_surface, SMVSB_ERR_STATE,
+            "views / surface not set");
+        set_active(ctx, active_nodes);
+        construct(ctx, light16, regularization, light_surf_regularization);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int
+smvsb_cg_solve (smvsb_ctx* ctx, int max_iter, double err_tol, double q_tol,
+    int* iters, int* info)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_system, SMVSB_ERR_STATE,
+            "smvsb_gn_construct must precede smvsb_cg_solve");
+        smvsb::run_cg(ctx, max_iter, err_tol, q_tol, iters, info, nullptr);
+    });
+}
+
+int
+smvsb_get_delta (smvsb_ctx* ctx, double* delta)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_system && delta, SMVSB_ERR_STATE, "no solution");
+        download(ctx, delta, ctx->x.p, static_cast<size_t>(ctx->n_nodes) * 4);
+    });
+}
+
+int
+smvsb_set_delta (smvsb_ctx* ctx, const double* delta)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_surface && delta, SMVSB_ERR_STATE, "no surface");
+        upload(ctx, ctx->x, delta, static_cast<size_t>(ctx->n_nodes) * 4);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int
+smvsb_update_nodes (smvsb_ctx* ctx, double reproj_thresh, int full_opt,
+    uint8_t* active_out, uint64_t* n_active, double* mean_shift)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_surface && ctx->x.p != nullptr, SMVSB_ERR_STATE,
+            "no delta to apply");
+        smvsb::launch_update(ctx, reproj_thresh, full_opt != 0, n_active,
+            mean_shift);
+        if (active_out)
+            download(ctx, active_out, ctx->active.p, ctx->n_nodes);
+        ctx->have_system = false;
+    });
+}
+
+int
+smvsb_newton_loop (smvsb_ctx* ctx, const double* light16,
+    double regularization, double light_surf_regularization, int max_steps,
+    int full_opt, smvsb_newton_stats* stats)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        smvsb_ctx* c = ctx;
+        require(c->have_views && c->have_surface, SMVSB_ERR_STATE,
+            "views / surface not set");
+        smvsb_newton_stats st;
+        std::memset(&st, 0, sizeof(st));
+
+        /* lib/depth_optimizer.cc:203-213 */
+        set_active(c, nullptr);
+        uint64_t num_initial = 0;
+        for (uint8_t v : c->h_node_valid) num_initial += (v != 0);
+        uint64_t num_active = num_initial;
+        double const samples = double(c->npos) * c->npos;
+
+        float ms = 0.f;
+        for (; st.newton_steps < max_steps && num_active > num_initial / 20;)
+        {
+            st.newton_steps += 1;
+            unsigned long long n_proc = 0;
+            smvsb::launch_count_processed(c, &n_proc);
+            st.pixel_iterations += samples * double(n_proc);
+
+            CUDA_CHECK(cudaEventRecord(c->ev[0], c->stream));
+            construct(c, light16, regularization, light_surf_regularization);
+            CUDA_CHECK(cudaEventRecord(c->ev[1], c->stream));
+
+            int iters = 0, info = 0;
+            bool x0_nan = false;
+            smvsb::run_cg(c, 200, -1.0, 1e-3, &iters, &info, &x0_nan);
+            CUDA_CHECK(cudaEventRecord(c->ev[2], c->stream));
+            st.cg_iterations += iters;
+            if (x0_nan)     /* lib/depth_optimizer.cc:267 */
+            {
+                st.nan_break = 1;
+                CUDA_CHECK(cudaEventSynchronize(c->ev[2]));
+                CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+                st.ms_construct += ms;
+                CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]));
+                st.ms_solve += ms;
+                break;
+            }
+            double mean_shift = 0.0;
+            smvsb::launch_update(c, 0.15, full_opt != 0, &num_active,
+                &mean_shift);
+            CUDA_CHECK(cudaEventRecord(c->ev[3], c->stream));
+            CUDA_CHECK(cudaEventSynchronize(c->ev[3]));
+            CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+            st.ms_construct += ms;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]));
+            st.ms_solve += ms;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
+            st.ms_update += ms;
+            if (full_opt)
+            {
+                /* lib/depth_optimizer.cc:275-289 */
+                if (mean_shift < 0.01)
+                    break;
+                continue;
+            }
+        }
+        st.n_active = num_active;
+        c->have_system = false;
+        if (stats) *stats = st;
+    });
+}
+
+int
+smvsb_get_nodes (smvsb_ctx* ctx, double* nodes_out)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_surface && nodes_out, SMVSB_ERR_STATE,
+            "no surface set");
+        download(ctx, nodes_out, ctx->nodes.p,
+            static_cast<size_t>(ctx->n_nodes) * 4);
+    });
+}
+
+int
+smvsb_get_depth (smvsb_ctx* ctx, float* depth_wh)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_surface && depth_wh, SMVSB_ERR_STATE,
+            "no surface set");
+        size_t const n = static_cast<size_t>(ctx->w) * ctx->h;
+        ctx->image_out.reserve(n * 3);
+        smvsb::launch_render_depth(ctx, ctx->image_out.p);
+        download(ctx, depth_wh, ctx->image_out.p, n);
+    });
+}
+
+int
+smvsb_get_normals (smvsb_ctx* ctx, float* normals_wh3)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_surface && normals_wh3, SMVSB_ERR_STATE,
+            "no surface set");
+        size_t const n = static_cast<size_t>(ctx->w) * ctx->h * 3;
+        ctx->image_out.reserve(n);
+        smvsb::launch_render_normals(ctx, ctx->image_out.p);
+        download(ctx, normals_wh3, ctx->image_out.p, n);
+    });
+}
+
+int
+smvsb_debug_get_system (smvsb_ctx* ctx, double* g, double* Hvals,
+    uint64_t* Houter, uint64_t* Hinner, uint64_t* nnzb_h, double* Pvals,
+    uint64_t* Pouter, uint64_t* Pinner, uint64_t* nnzb_p)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        smvsb_ctx* c = ctx;
+        require(c->have_system, SMVSB_ERR_STATE, "no system constructed");
+        int const nn = c->n_nodes, ns = c->npx + 1;
+        std::vector<uint8_t> active(nn), proc(c->n_patches);
+        download(c, active.data(), c->active.p, nn);
+        download(c, proc.data(), c->patch_proc.p, c->n_patches);
+        if (g)
+            download(c, g, c->g.p, static_cast<size_t>(nn) * 4);
+        std::vector<double> H, P;
+        if (Hvals)
+        {
+            H.resize(static_cast<size_t>(nn) * 144);
+            download(c, H.data(), c->H.p, H.size());
+        }
+        if (Pvals)
+        {
+            P.resize(static_cast<size_t>(nn) * 16);
+            download(c, P.data(), c->P.p, P.size());
+        }
+        /* A block (row i, col j) exists in the reference iff some processed
+         * patch holds both nodes and both are active
+         * (lib/gauss_newton_step.cc:99-121). Walk columns, then rows. */
+        uint64_t nh = 0, np = 0;
+        for (int j = 0; j < nn; ++j)
+        {
+            if (Houter) Houter[j] = nh;
+            if (Pouter) Pouter[j] = np;
+            int const jx = j % ns, jy = j / ns;
+            if (!c->h_node_valid[j] || !active[j])
+                continue;
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx)
+                {
+                    int const ix = jx + dx, iy = jy + dy;
+                    if (ix < 0 || ix > c->npx || iy < 0 || iy > c->npy)
+                        continue;
+                    int const i = iy * ns + ix;
+                    if (!c->h_node_valid[i] || !active[i])
+                        continue;
+                    bool shared = false;
+                    for (int pb = 0; pb < 2 && !shared; ++pb)
+                        for (int pa = 0; pa < 2 && !shared; ++pa)
+                        {
+                            int const px = jx - 1 + pa, py = jy - 1 + pb;
+                            if (px < 0 || px >= c->npx || py < 0
+                                || py >= c->npy)
+                                continue;
+                            if (!proc[py * c->npx + px])
+                                continue;
+                            if (ix >= px && ix <= px + 1 && iy >= py
+                                && iy <= py + 1)
+                                shared = true;
+                        }
+                    if (!shared)
+                        continue;
+                    /* block (row i, col j) is stencil slot of row i towards
+                     * j: offset (jx-ix, jy-iy) = (-dx, -dy) */
+                    if (Hvals)
+                    {
+                        int const k = (-dy + 1) * 3 + (-dx + 1);
+                        std::copy(H.begin() + (static_cast<size_t>(i) * 9 + k)
+                            * 16, H.begin() + (static_cast<size_t>(i) * 9 + k)
+                            * 16 + 16, Hvals + nh * 16);
+                    }
+                    if (Hinner) Hinner[nh] = static_cast<uint64_t>(i) * 4;
+                    nh += 1;
+                    if (i == j)
+                    {
+                        if (Pvals)
+                            std::copy(P.begin() + static_cast<size_t>(i) * 16,
+                                P.begin() + static_cast<size_t>(i) * 16 + 16,
+                                Pvals + np * 16);
+                        if (Pinner) Pinner[np] = static_cast<uint64_t>(i) * 4;
+                        np += 1;
+                    }
+                }
+        }
+        if (Houter) Houter[nn] = nh;
+        if (Pouter) Pouter[nn] = np;
+        if (nnzb_h) *nnzb_h = nh;
+        if (nnzb_p) *nnzb_p = np;
+    });
+}
+
+int
+smvsb_debug_spmv (smvsb_ctx* ctx, const double* x, double* y)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_system && x && y, SMVSB_ERR_STATE, "no system");
+        size_t const n = static_cast<size_t>(ctx->n_nodes) * 4;
+        ctx->r.reserve(n); ctx->Ad.reserve(n);
+        upload(ctx, ctx->r, x, n);
+        smvsb::launch_spmv(ctx, ctx->r.p, ctx->Ad.p);
+        download(ctx, y, ctx->Ad.p, n);
+    });
+}
+
+int
+smvsb_fit_lighting (smvsb_ctx* ctx, double* params16_out, void* nccl_comm)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        smvsb_ctx* c = ctx;
+        require(c->have_surface && c->have_shading && params16_out,
+            SMVSB_ERR_STATE, "surface and shading image required");
+        double Ab[272];
+        smvsb::run_fit_lighting(c, Ab);
+        if (nccl_comm != nullptr)
+        {
+            /* Opt-in global lighting: sum the normal equations over the
+             * communicator. ncclAllReduce is taken from the NCCL already
+             * loaded in this process (the one that made the communicator). */
+            typedef int (*allreduce_fn)(const void*, void*, size_t, int, int,
+                void*, cudaStream_t);
+            allreduce_fn fn = reinterpret_cast<allreduce_fn>(
+                dlsym(RTLD_DEFAULT, "ncclAllReduce"));
+            require(fn != nullptr, SMVSB_ERR_STATE,
+                "ncclAllReduce not found in this process");
+            c->light_partials.reserve(272);
+            upload(c, c->light_partials, Ab, 272);
+            int const ncclDouble = 8, ncclSum = 0;
+            int const rc = fn(c->light_partials.p, c->light_partials.p, 272,
+                ncclDouble, ncclSum, nccl_comm, c->stream);
+            require(rc == 0, SMVSB_ERR_CUDA, "ncclAllReduce failed");
+            download(c, Ab, c->light_partials.p, 272);
+        }
+        double Ainv[256];
+        pseudo_inverse_16(Ab, Ainv);
+        for (int i = 0; i < 16; ++i)
+        {
+            double s = 0.0;
+            for (int j = 0; j < 16; ++j)
+                s += Ainv[i * 16 + j] * Ab[256 + j];
+            params16_out[i] = s;
+        }
+    });
+}
+
+int
+smvsb_sgm (int device, int w, int h, const uint8_t* main_lum, int nw, int nh,
+    const uint8_t* neigh_lum, const float* M, const float* t,
+    float min_depth, float max_depth, int num_steps, uint16_t penalty1,
+    uint16_t penalty2, float* depth_out, uint16_t* cost_out,
+    uint16_t* sgm_out, double* ms_out)
+{
+    int const rc = smvsb::sgm_run(device, w, h, main_lum, nw, nh, neigh_lum,
+        M, t, min_depth, max_depth, num_steps, penalty1, penalty2, depth_out,
+        cost_out, sgm_out, ms_out);
+    if (rc != SMVSB_OK)
+        g_last_error = smvsb::sgm_last_error();
+    return rc;
+}
+
+} /* extern "C" */

@@ -1,0 +1,204 @@
+/*
+ * common.cuh -- context, device buffers and small helpers shared by the
+ * smvs_b200 kernels. sm_100a only; there is no host fallback anywhere.
+ */
+#ifndef SMVSB_COMMON_CUH
+#define SMVSB_COMMON_CUH
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/smvs_b200.h"
+
+#define SMVSB_MAX_SUBS 32          /* neighbours per reference view */
+#define SMVSB_NB_STRIDE 8          /* floats per packed neighbour texel */
+
+/* Throws smvsb::Error (caught at the ABI boundary). */
+#define CUDA_CHECK(call)                                                     \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess)                                              \
+            throw smvsb::Error(SMVSB_ERR_CUDA, std::string(#call) + ": "     \
+                + cudaGetErrorString(e__));                                  \
+    } while (0)
+
+namespace smvsb {
+
+struct Error
+{
+    int code;
+    std::string msg;
+    Error (int c, std::string const& m) : code(c), msg(m) {}
+};
+
+/* Owning device buffer; grows, never shrinks. */
+template <typename T>
+struct DevBuf
+{
+    T* p = nullptr;
+    size_t cap = 0;      /* elements */
+
+    DevBuf (void) = default;
+    DevBuf (DevBuf const&) = delete;
+    DevBuf& operator= (DevBuf const&) = delete;
+    ~DevBuf (void) { if (p) cudaFree(p); }
+
+    void reserve (size_t n)
+    {
+        if (n <= cap)
+            return;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess)
+        {
+            p = nullptr;
+            throw Error(SMVSB_ERR_ALLOC, std::string("cudaMalloc of ")
+                + std::to_string(n * sizeof(T)) + " bytes: "
+                + cudaGetErrorString(e));
+        }
+        cap = n;
+    }
+};
+
+/* One neighbour view on the device: packed texels
+ * (gx, gy, hxx, hxy, hyy, 0, 0, 0) -- one 32-byte sector per texel. */
+struct SubViewDev
+{
+    int w = 0, h = 0;
+    DevBuf<float> texels;
+};
+
+/* Arguments shared by the Gauss-Newton kernels (passed by value). */
+struct SurfaceDev
+{
+    int scale, ps, sampling, npos;      /* npos = ps / sampling */
+    int npx, npy, start_x, start_y;
+    int n_nodes, n_patches;
+    int w, h;                           /* main view size */
+    double flen, inv_flen;
+    int n_sub;
+    double const* nodes;                /* n_nodes * 4 */
+    uint8_t const* node_valid;
+    uint8_t const* patch_valid;
+    uint32_t const* vis_off;
+    uint8_t const* vis_ids;
+    uint8_t const* active;              /* current active set */
+    float const* main_grad;             /* w*h*2 */
+    float const* main_shading;          /* w*h or null */
+    float const* main_shading_grad;     /* w*h*2 or null */
+    float const* const* sub_texels;     /* device array of n_sub pointers */
+    int const* sub_dims;                /* device array: w0,h0,w1,h1,... */
+    double const* Mt;                   /* device: n_sub * 12 (M 9, t 3) */
+    double const* basis_s;              /* sampled positions: 3 * npos * 4 */
+    double const* basis_f;              /* all pixel positions: 3 * ps * 4 */
+};
+
+} /* namespace smvsb */
+
+struct smvsb_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string last_error;
+    uint64_t launches = 0;
+    int num_sms = 0;
+
+    /* views */
+    bool have_views = false;
+    int w = 0, h = 0, n_sub = 0;
+    double flen = 0, inv_flen = 0;
+    smvsb::DevBuf<float> main_grad, main_shading, main_shading_grad;
+    bool have_shading = false;
+    smvsb::SubViewDev subs[SMVSB_MAX_SUBS];
+    smvsb::DevBuf<float const*> sub_ptrs;
+    smvsb::DevBuf<int> sub_dims;
+    smvsb::DevBuf<double> Mt;
+
+    /* surface */
+    bool have_surface = false;
+    int scale = 0, ps = 0, sampling = 0, npos = 0;
+    int npx = 0, npy = 0, start_x = 0, start_y = 0;
+    int n_nodes = 0, n_patches = 0;
+    smvsb::DevBuf<double> nodes;
+    smvsb::DevBuf<uint8_t> node_valid, patch_valid, vis_ids;
+    smvsb::DevBuf<uint32_t> vis_off;
+    smvsb::DevBuf<uint8_t> active, active_new;
+    smvsb::DevBuf<double> basis_s, basis_f;
+    std::vector<uint8_t> h_node_valid, h_patch_valid;
+
+    /* linear system */
+    bool have_system = false;
+    smvsb::DevBuf<double> patch_H;      /* n_patches * 256 */
+    smvsb::DevBuf<double> patch_g;      /* n_patches * 16 */
+    smvsb::DevBuf<uint8_t> patch_proc;  /* n_patches */
+    smvsb::DevBuf<double> H;            /* n_nodes * 9 * 16 */
+    smvsb::DevBuf<double> P;            /* n_nodes * 16 */
+    smvsb::DevBuf<double> g;            /* n_nodes * 4 */
+    smvsb::DevBuf<double> light;        /* 16 */
+
+    /* CG */
+    smvsb::DevBuf<double> x, r, d, z, Ad;
+    smvsb::DevBuf<double> cg_partials;
+    smvsb::DevBuf<unsigned int> cg_sync;
+    smvsb::DevBuf<double> cg_result;    /* iters, info, ... */
+
+    /* update */
+    smvsb::DevBuf<double> patch_shift;  /* n_patches * 2: sum, count */
+    smvsb::DevBuf<unsigned long long> counters;
+
+    /* lighting */
+    smvsb::DevBuf<double> light_partials;
+
+    /* render */
+    smvsb::DevBuf<float> image_out;
+};
+
+namespace smvsb {
+
+inline SurfaceDev
+surface_args (smvsb_ctx* c)
+{
+    SurfaceDev s;
+    s.scale = c->scale; s.ps = c->ps; s.sampling = c->sampling;
+    s.npos = c->npos;
+    s.npx = c->npx; s.npy = c->npy;
+    s.start_x = c->start_x; s.start_y = c->start_y;
+    s.n_nodes = c->n_nodes; s.n_patches = c->n_patches;
+    s.w = c->w; s.h = c->h; s.flen = c->flen; s.inv_flen = c->inv_flen;
+    s.n_sub = c->n_sub;
+    s.nodes = c->nodes.p; s.node_valid = c->node_valid.p;
+    s.patch_valid = c->patch_valid.p;
+    s.vis_off = c->vis_off.p; s.vis_ids = c->vis_ids.p;
+    s.active = c->active.p;
+    s.main_grad = c->main_grad.p;
+    s.main_shading = c->have_shading ? c->main_shading.p : nullptr;
+    s.main_shading_grad = c->have_shading ? c->main_shading_grad.p : nullptr;
+    s.sub_texels = c->sub_ptrs.p; s.sub_dims = c->sub_dims.p;
+    s.Mt = c->Mt.p;
+    s.basis_s = c->basis_s.p; s.basis_f = c->basis_f.p;
+    return s;
+}
+
+/* kernels / launchers implemented in the .cu files */
+void launch_pack_subview (smvsb_ctx* c, float const* grad, float const* hess,
+    float* texels, int w, int h);
+void launch_construct (smvsb_ctx* c, bool use_light, double reg,
+    double light_reg);
+void launch_spmv (smvsb_ctx* c, double const* x, double* y);
+void run_cg (smvsb_ctx* c, int max_iter, double err_tol, double q_tol,
+    int* iters, int* info, bool* x0_nan);
+void launch_update (smvsb_ctx* c, double thresh, bool full_opt,
+    uint64_t* n_active, double* mean_shift);
+void launch_render_depth (smvsb_ctx* c, float* out_dev);
+void launch_render_normals (smvsb_ctx* c, float* out_dev);
+void run_fit_lighting (smvsb_ctx* c, double* A_b_host /*272*/);
+void launch_count_processed (smvsb_ctx* c, unsigned long long* n_proc_host);
+
+} /* namespace smvsb */
+
+#endif

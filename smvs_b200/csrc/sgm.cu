@@ -1,0 +1,541 @@
+/*
+ * sgm.cu -- SGMStereo::run_sgm on the GPU (reference: lib/sgm_stereo.cc).
+ *
+ *   K6  sgm_cost_kernel     create_cost_volume (:192-244): plane sweep of the
+ *                           neighbour luminance at num_steps inverse-depth
+ *                           planes (warped_neighbors_for_depth :150-190, fp32,
+ *                           byte bilinear with +0.5 rounding), 9x7 census
+ *                           (:126-148) of main image and of every warped
+ *                           slice, Hamming distance; 255 where the warped
+ *                           pixel is 0. The reference materialises the warped
+ *                           volume (uint8) and its census volume (uint64,
+ *                           2.1 GB at 2 MP x 128); here a block keeps one
+ *                           warped tile with halo in shared memory per plane
+ *                           and only the uint8 cost leaves the SM.
+ *   K7  sgm_path_kernel     aggregate_sgm_costs (:429-667), SSE branch
+ *                           (constant P2, uint16 arithmetic): one warp per
+ *                           scan line of a direction, disparities across the
+ *                           lanes, L_r carried in registers, min over
+ *                           disparities by warp shuffles. Diagonals follow the
+ *                           line with wrap-around at the image border, where
+ *                           the reference restarts the path (:515-534).
+ *   K8  sgm_wta_kernel      depth_from_sgm_volume (:274-306).
+ *
+ * Layouts: cost C[pixel][disp] uint8, sum S[pixel][disp] uint16 (pixel-major,
+ * disparity contiguous, like the reference's sse_*_volume), so a warp's
+ * access to one pixel is one coalesced 128 B / 256 B segment.
+ */
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace smvsb {
+
+namespace {
+
+constexpr int CT_X = 32, CT_Y = 8;             /* cost kernel pixel tile */
+constexpr int CH_X = CT_X + 8, CH_Y = CT_Y + 6; /* with census halo */
+
+struct SgmParams
+{
+    int w, h, nw, nh, D;
+    float M[9];
+    float t[3];
+};
+
+/* warped_neighbors_for_depth for one pixel / plane, :150-190 */
+__device__ __forceinline__ uint8_t
+warp_pixel (SgmParams const& p, uint8_t const* __restrict__ neigh, int x,
+    int y, float depth)
+{
+    float const px = 0.5f + static_cast<float>(x);
+    float const py = 0.5f + static_cast<float>(y);
+    float tp[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+    {
+        float s = __fmul_rn(p.M[3 * r], px);
+        s = __fadd_rn(s, __fmul_rn(p.M[3 * r + 1], py));
+        s = __fadd_rn(s, p.M[3 * r + 2]);      /* * 1.f */
+        tp[r] = s;
+    }
+    float q0 = __fadd_rn(__fmul_rn(tp[0], depth), p.t[0]);
+    float q1 = __fadd_rn(__fmul_rn(tp[1], depth), p.t[1]);
+    float const q2 = __fadd_rn(__fmul_rn(tp[2], depth), p.t[2]);
+    if (q2 < 0)
+        return 0;
+    q0 = __fdiv_rn(q0, q2);
+    q1 = __fdiv_rn(q1, q2);
+    q0 = __fsub_rn(q0, 0.5f);
+    q1 = __fsub_rn(q1, 0.5f);
+    if (q0 < 0 || q1 < 0 || q0 > static_cast<float>(p.nw - 1)
+        || q1 > static_cast<float>(p.nh - 1))
+        return 0;
+
+    /* mve::Image<uint8_t>::linear_at */
+    float const xx = fmaxf(0.0f, fminf(static_cast<float>(p.nw - 1), q0));
+    float const yy = fmaxf(0.0f, fminf(static_cast<float>(p.nh - 1), q1));
+    int const fx = static_cast<int>(xx), fy = static_cast<int>(yy);
+    int const fx1 = min(fx + 1, p.nw - 1), fy1 = min(fy + 1, p.nh - 1);
+    float const w1 = __fsub_rn(xx, static_cast<float>(fx));
+    float const w0 = __fsub_rn(1.0f, w1);
+    float const w3 = __fsub_rn(yy, static_cast<float>(fy));
+    float const w2 = __fsub_rn(1.0f, w3);
+    float const v00 = neigh[fy * p.nw + fx], v10 = neigh[fy * p.nw + fx1];
+    float const v01 = neigh[fy1 * p.nw + fx], v11 = neigh[fy1 * p.nw + fx1];
+    float s = __fmul_rn(v00, __fmul_rn(w0, w2));
+    s = __fadd_rn(s, __fmul_rn(v10, __fmul_rn(w1, w2)));
+    s = __fadd_rn(s, __fmul_rn(v01, __fmul_rn(w0, w3)));
+    s = __fadd_rn(s, __fmul_rn(v11, __fmul_rn(w1, w3)));
+    s = __fadd_rn(s, 0.5f);
+    return static_cast<uint8_t>(s);
+}
+
+/* 9x7 census around tile-local (lx, ly) of a CH_X x CH_Y byte tile; bit
+ * order as census_filter builds it (x outer, y inner, MSB first). */
+__device__ __forceinline__ unsigned long long
+census63 (uint8_t const* tile, int lx, int ly)
+{
+    uint8_t const thr = tile[(ly + 3) * CH_X + lx + 4];
+    unsigned long long c = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i)
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+        {
+            c <<= 1;
+            c |= (thr < tile[(ly + j) * CH_X + lx + i]) ? 1ull : 0ull;
+        }
+    return c;
+}
+
+__global__ void __launch_bounds__(CT_X * CT_Y)
+sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
+    uint8_t const* __restrict__ neigh, float const* __restrict__ depths,
+    uint8_t* __restrict__ cost)
+{
+    __shared__ uint8_t s_tile[CH_X * CH_Y];
+    __shared__ float s_depths[256];
+    int const tid = threadIdx.y * CT_X + threadIdx.x;
+    int const x0 = blockIdx.x * CT_X, y0 = blockIdx.y * CT_Y;
+    int const x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    bool const inside = (x < p.w && y < p.h);
+    bool const interior = inside && x >= 4 && x < p.w - 5 && y >= 3
+        && y < p.h - 4;
+
+    for (int i = tid; i < p.D; i += CT_X * CT_Y)
+        s_depths[i] = depths[i];
+
+    /* main census, once */
+    for (int i = tid; i < CH_X * CH_Y; i += CT_X * CT_Y)
+    {
+        int const gx = x0 - 4 + i % CH_X, gy = y0 - 3 + i / CH_X;
+        s_tile[i] = (gx >= 0 && gx < p.w && gy >= 0 && gy < p.h)
+            ? main_img[gy * p.w + gx] : 0;
+    }
+    __syncthreads();
+    unsigned long long main_census = 0;
+    if (interior && s_tile[(threadIdx.y + 3) * CH_X + threadIdx.x + 4] != 0)
+        main_census = census63(s_tile, threadIdx.x, threadIdx.y);
+
+    size_t const pix = static_cast<size_t>(y) * p.w + x;
+    for (int d = 0; d < p.D; ++d)
+    {
+        __syncthreads();
+        float const depth = s_depths[d];
+        for (int i = tid; i < CH_X * CH_Y; i += CT_X * CT_Y)
+        {
+            int const gx = x0 - 4 + i % CH_X, gy = y0 - 3 + i / CH_X;
+            s_tile[i] = (gx >= 0 && gx < p.w && gy >= 0 && gy < p.h)
+                ? warp_pixel(p, neigh, gx, gy, depth) : 0;
+        }
+        __syncthreads();
+        if (!inside)
+            continue;
+        uint8_t const centre =
+            s_tile[(threadIdx.y + 3) * CH_X + threadIdx.x + 4];
+        uint8_t c = 255;
+        if (centre != 0)
+        {
+            unsigned long long wc = 0;
+            if (interior)
+                wc = census63(s_tile, threadIdx.x, threadIdx.y);
+            c = static_cast<uint8_t>(__popcll(main_census ^ wc));
+        }
+        cost[pix * p.D + d] = c;
+    }
+}
+
+/* ------------------------------------------------------------------ */
+
+enum PathKind
+{
+    PATH_L2R = 0, PATH_R2L, PATH_T2B, PATH_T2B_D1, PATH_T2B_D2,
+    PATH_B2T, PATH_B2T_D1, PATH_B2T_D2
+};
+
+/*
+ * One warp per line. DPL = disparities per lane (D = 32 * DPL).
+ * fill_path_cost_sse (:361-406):
+ *   L(p,i) = C(p,i) + min(L(q,i), L(q,i-1)+P1, L(q,i+1)+P1, min_k L(q,k)+P2)
+ *            - min_k L(q,k)            (all uint16, wrap-around)
+ * and copy_cost_and_add_to_sgm (:408-426) where a path starts.
+ * `first` = this pass initialises S (no read of S).
+ */
+template <int DPL>
+__global__ void __launch_bounds__(128)
+sgm_path_kernel (int w, int h, int kind, unsigned P1, unsigned P2,
+    uint8_t const* __restrict__ cost, uint16_t* __restrict__ S, int first)
+{
+    int const D = 32 * DPL;
+    int const line = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int const lane = threadIdx.x & 31;
+    bool const horizontal = (kind == PATH_L2R || kind == PATH_R2L);
+    int const n_lines = horizontal ? h : w;
+    if (line >= n_lines)
+        return;
+    int const steps = horizontal ? w : h;
+    unsigned Lp[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) Lp[i] = 0;
+
+    for (int s = 0; s < steps; ++s)
+    {
+        int x, y;
+        bool start;
+        switch (kind)
+        {
+        case PATH_L2R: x = s; y = line; start = (s == 0); break;
+        case PATH_R2L: x = w - 1 - s; y = line; start = (s == 0); break;
+        case PATH_T2B: x = line; y = s; start = (s == 0); break;
+        case PATH_B2T: x = line; y = h - 1 - s; start = (s == 0); break;
+        case PATH_T2B_D1:   /* predecessor (x-1, y-1) */
+            x = (line + s) % w; y = s; start = (s == 0 || x == 0); break;
+        case PATH_T2B_D2:   /* predecessor (x+1, y-1) */
+            x = ((line - s) % w + w) % w; y = s;
+            start = (s == 0 || x == w - 1); break;
+        case PATH_B2T_D1:   /* predecessor (x-1, y+1) */
+            x = (line + s) % w; y = h - 1 - s;
+            start = (s == 0 || x == 0); break;
+        default:            /* PATH_B2T_D2: predecessor (x+1, y+1) */
+            x = ((line - s) % w + w) % w; y = h - 1 - s;
+            start = (s == 0 || x == w - 1); break;
+        }
+        size_t const base = (static_cast<size_t>(y) * w + x) * D + lane * DPL;
+
+        unsigned C[DPL];
+        if (DPL == 4)
+        {
+            uchar4 const c4 = *reinterpret_cast<uchar4 const*>(cost + base);
+            C[0] = c4.x; C[1] = c4.y; C[2] = c4.z; C[3] = c4.w;
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) C[i] = cost[base + i];
+        }
+
+        unsigned L[DPL];
+        if (start)
+        {
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) L[i] = C[i];
+        }
+        else
+        {
+            unsigned mn = Lp[0];
+#pragma unroll
+            for (int i = 1; i < DPL; ++i) mn = min(mn, Lp[i]);
+            for (int off = 16; off > 0; off >>= 1)
+                mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+            unsigned const below = __shfl_up_sync(0xffffffffu, Lp[DPL - 1], 1);
+            unsigned const above = __shfl_down_sync(0xffffffffu, Lp[0], 1);
+            unsigned const far = (mn + P2) & 0xffffu;
+#pragma unroll
+            for (int i = 0; i < DPL; ++i)
+            {
+                unsigned best = min(Lp[i], far);
+                bool const has_lo = (i > 0) || (lane > 0);
+                bool const has_hi = (i < DPL - 1) || (lane < 31);
+                unsigned const lo = (i > 0) ? Lp[i - 1] : below;
+                unsigned const hi = (i < DPL - 1) ? Lp[i + 1] : above;
+                if (has_lo) best = min(best, (lo + P1) & 0xffffu);
+                if (has_hi) best = min(best, (hi + P1) & 0xffffu);
+                L[i] = (((C[i] + best) & 0xffffu) - mn) & 0xffffu;
+            }
+        }
+
+        /* S += L */
+        if (DPL == 4)
+        {
+            uint2* sp = reinterpret_cast<uint2*>(S + base);
+            uint2 v = make_uint2(0u, 0u);
+            if (!first)
+                v = *sp;
+            unsigned const s0 = ((v.x & 0xffffu) + L[0]) & 0xffffu;
+            unsigned const s1 = ((v.x >> 16) + L[1]) & 0xffffu;
+            unsigned const s2 = ((v.y & 0xffffu) + L[2]) & 0xffffu;
+            unsigned const s3 = ((v.y >> 16) + L[3]) & 0xffffu;
+            *sp = make_uint2(s0 | (s1 << 16), s2 | (s3 << 16));
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < DPL; ++i)
+            {
+                unsigned const old = first ? 0u : S[base + i];
+                S[base + i] = static_cast<uint16_t>((old + L[i]) & 0xffffu);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) Lp[i] = L[i];
+    }
+}
+
+/* The extra copy_cost_and_add_to_sgm calls at the corners: column 0 of the
+ * d1 volume and column w-1 of the d2 volume are (re)initialised for ALL y
+ * after row 0 / row h-1 already were (:521-534, :600-613), so those four
+ * corner pixels receive C once more per vertical sweep. */
+__global__ void
+sgm_corner_kernel (int w, int h, int D, uint8_t const* __restrict__ cost,
+    uint16_t* __restrict__ S)
+{
+    int const i = threadIdx.x;
+    if (i >= D)
+        return;
+    size_t const px[4] = { 0, static_cast<size_t>(w - 1),
+        static_cast<size_t>(h - 1) * w,
+        static_cast<size_t>(h - 1) * w + w - 1 };
+    for (int k = 0; k < 4; ++k)
+    {
+        size_t const o = px[k] * D + i;
+        S[o] = static_cast<uint16_t>((S[o] + cost[o]) & 0xffffu);
+    }
+}
+
+/* depth_from_sgm_volume, :274-306: first minimum over the planes. */
+template <int DPL>
+__global__ void
+sgm_wta_kernel (int npix, uint16_t const* __restrict__ S,
+    uint8_t const* __restrict__ main_img, float const* __restrict__ depths,
+    float* __restrict__ out)
+{
+    int const D = 32 * DPL;
+    int const p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int const lane = threadIdx.x & 31;
+    if (p >= npix)
+        return;
+    unsigned best = 0xffffu;    /* numeric_limits<uint16_t>::max() */
+    int best_i = 0;
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i)
+    {
+        unsigned const v = S[static_cast<size_t>(p) * D + lane * DPL + i];
+        if (v < best)
+        {
+            best = v;
+            best_i = lane * DPL + i;
+            found = true;
+        }
+    }
+    /* key = value << 16 | index: min picks the lowest value, then index;
+     * lanes without a strict improvement over 0xffff report index 0 only
+     * if nobody found anything (min_index stays 0 in the reference). */
+    unsigned key = found ? ((best << 16) | best_i) : 0xffffffffu;
+    for (int off = 16; off > 0; off >>= 1)
+        key = min(key, __shfl_xor_sync(0xffffffffu, key, off));
+    if (lane == 0)
+    {
+        int const idx = (key == 0xffffffffu) ? 0 : static_cast<int>(
+            key & 0xffffu);
+        out[p] = (idx < 2 || main_img[p] < 25) ? 0.0f : depths[idx];
+    }
+}
+
+__global__ void
+u8_to_u16_kernel (size_t n, uint8_t const* __restrict__ in,
+    uint16_t* __restrict__ out)
+{
+    size_t const i = static_cast<size_t>(blockIdx.x) * blockDim.x
+        + threadIdx.x;
+    if (i < n)
+        out[i] = in[i];
+}
+
+template <int DPL>
+void
+run_paths (int w, int h, unsigned P1, unsigned P2, uint8_t const* cost,
+    uint16_t* S, cudaStream_t st)
+{
+    int const order[8] = { PATH_L2R, PATH_R2L, PATH_T2B, PATH_T2B_D1,
+        PATH_T2B_D2, PATH_B2T, PATH_B2T_D1, PATH_B2T_D2 };
+    for (int k = 0; k < 8; ++k)
+    {
+        bool const horizontal = (order[k] == PATH_L2R || order[k] == PATH_R2L);
+        int const lines = horizontal ? h : w;
+        int const blocks = (lines * 32 + 127) / 128;
+        sgm_path_kernel<DPL><<<blocks, 128, 0, st>>>(w, h, order[k], P1, P2,
+            cost, S, k == 0 ? 1 : 0);
+        CUDA_CHECK(cudaGetLastError());
+    }
+    sgm_corner_kernel<<<1, 32 * DPL, 0, st>>>(w, h, 32 * DPL, cost, S);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+template <int DPL>
+void
+run_wta (int npix, uint16_t const* S, uint8_t const* main_img,
+    float const* depths, float* out, cudaStream_t st)
+{
+    int const blocks = (npix * 32 + 255) / 256;
+    sgm_wta_kernel<DPL><<<blocks, 256, 0, st>>>(npix, S, main_img, depths,
+        out);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+thread_local std::string g_sgm_error;
+
+} /* namespace */
+
+std::string const&
+sgm_last_error (void)
+{
+    return g_sgm_error;
+}
+
+int
+sgm_run (int device, int w, int h, uint8_t const* main_lum, int nw, int nh,
+    uint8_t const* neigh_lum, float const* M, float const* t,
+    float min_depth, float max_depth, int num_steps, uint16_t penalty1,
+    uint16_t penalty2, float* depth_out, uint16_t* cost_out,
+    uint16_t* sgm_out, double* ms_out)
+{
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    int rc = SMVSB_OK;
+    try
+    {
+        if (!(w > 9 && h > 7 && nw > 1 && nh > 1 && main_lum && neigh_lum
+            && M && t && depth_out))
+            throw Error(SMVSB_ERR_INVALID, "smvsb_sgm: bad image arguments");
+        if (num_steps < 32 || num_steps > 256 || num_steps % 32 != 0
+            || (num_steps / 32 != 1 && num_steps / 32 != 2
+                && num_steps / 32 != 4 && num_steps / 32 != 8))
+            throw Error(SMVSB_ERR_INVALID,
+                "smvsb_sgm: num_steps must be 32, 64, 128 or 256");
+        /* the O(D) recurrence equals the reference's O(D^2) minimum only
+         * for P1 <= P2 and without uint16 wrap-around */
+        if (penalty1 > penalty2 || penalty2 > 16384)
+            throw Error(SMVSB_ERR_INVALID,
+                "smvsb_sgm: need penalty1 <= penalty2 <= 16384");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+            throw Error(SMVSB_ERR_CUDA, "no CUDA device (no CPU fallback)");
+        if (device < 0 || device >= count)
+            throw Error(SMVSB_ERR_INVALID, "device index out of range");
+        CUDA_CHECK(cudaSetDevice(device));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; ++i)
+            CUDA_CHECK(cudaEventCreate(&ev[i]));
+
+        /* plane depths, lib/sgm_stereo.cc:195-203 (fp32 recurrence) */
+        std::vector<float> depths(num_steps);
+        {
+            float inv_depth = 1.0f / max_depth;
+            float const increment = (1.0f / min_depth - inv_depth)
+                / (num_steps - 1);
+            for (int i = 0; i < num_steps; ++i)
+            {
+                depths[i] = 1.0f / inv_depth;
+                inv_depth += increment;
+            }
+        }
+
+        size_t const npix = static_cast<size_t>(w) * h;
+        size_t const nvox = npix * num_steps;
+        DevBuf<uint8_t> d_main, d_neigh, d_cost;
+        DevBuf<uint16_t> d_S;
+        DevBuf<float> d_depths, d_out;
+        d_main.reserve(npix);
+        d_neigh.reserve(static_cast<size_t>(nw) * nh);
+        d_cost.reserve(nvox);
+        d_S.reserve(nvox);
+        d_depths.reserve(num_steps);
+        d_out.reserve(npix);
+        CUDA_CHECK(cudaMemcpyAsync(d_main.p, main_lum, npix,
+            cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(d_neigh.p, neigh_lum,
+            static_cast<size_t>(nw) * nh, cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(d_depths.p, depths.data(),
+            num_steps * sizeof(float), cudaMemcpyHostToDevice, st));
+
+        SgmParams p;
+        p.w = w; p.h = h; p.nw = nw; p.nh = nh; p.D = num_steps;
+        std::copy(M, M + 9, p.M);
+        std::copy(t, t + 3, p.t);
+
+        CUDA_CHECK(cudaEventRecord(ev[0], st));
+        dim3 const cb(CT_X, CT_Y);
+        dim3 const cg((w + CT_X - 1) / CT_X, (h + CT_Y - 1) / CT_Y);
+        sgm_cost_kernel<<<cg, cb, 0, st>>>(p, d_main.p, d_neigh.p, d_depths.p,
+            d_cost.p);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaEventRecord(ev[1], st));
+
+        int const dpl = num_steps / 32;
+        switch (dpl)
+        {
+        case 1: run_paths<1>(w, h, penalty1, penalty2, d_cost.p, d_S.p, st); break;
+        case 2: run_paths<2>(w, h, penalty1, penalty2, d_cost.p, d_S.p, st); break;
+        case 4: run_paths<4>(w, h, penalty1, penalty2, d_cost.p, d_S.p, st); break;
+        default: run_paths<8>(w, h, penalty1, penalty2, d_cost.p, d_S.p, st); break;
+        }
+        CUDA_CHECK(cudaEventRecord(ev[2], st));
+        switch (dpl)
+        {
+        case 1: run_wta<1>((int)npix, d_S.p, d_main.p, d_depths.p, d_out.p, st); break;
+        case 2: run_wta<2>((int)npix, d_S.p, d_main.p, d_depths.p, d_out.p, st); break;
+        case 4: run_wta<4>((int)npix, d_S.p, d_main.p, d_depths.p, d_out.p, st); break;
+        default: run_wta<8>((int)npix, d_S.p, d_main.p, d_depths.p, d_out.p, st); break;
+        }
+        CUDA_CHECK(cudaEventRecord(ev[3], st));
+
+        CUDA_CHECK(cudaMemcpyAsync(depth_out, d_out.p, npix * sizeof(float),
+            cudaMemcpyDeviceToHost, st));
+        if (sgm_out)
+            CUDA_CHECK(cudaMemcpyAsync(sgm_out, d_S.p,
+                nvox * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (cost_out)
+        {
+            /* widen through the (now free) S buffer */
+            u8_to_u16_kernel<<<static_cast<unsigned>((nvox + 255) / 256), 256,
+                0, st>>>(nvox, d_cost.p, d_S.p);
+            CUDA_CHECK(cudaGetLastError());
+            CUDA_CHECK(cudaMemcpyAsync(cost_out, d_S.p,
+                nvox * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+        }
+        if (ms_out)
+        {
+            float ms;
+            for (int i = 0; i < 3; ++i)
+            {
+                CUDA_CHECK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+                ms_out[i] = ms;
+            }
+        }
+    }
+    catch (Error const& e)
+    {
+        g_sgm_error = e.msg;
+        rc = e.code;
+    }
+    for (int i = 0; i < 4; ++i)
+        if (ev[i]) cudaEventDestroy(ev[i]);
+    if (st) cudaStreamDestroy(st);
+    return rc;
+}
+
+} /* namespace smvsb */
