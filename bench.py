@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- Gauss-Newton Mpix-iters/s of the SMVS depth-refinement hot path.
+
+Workload (BASELINE.json configs[1]): 1 reference view + 6 neighbours,
+1920x1080, finest scale of `-o2` (scale 2: 478x268 patches of 4x4 px, 16
+samples each, every pixel sampled), no shading. One STEP = one inner Newton
+loop of DepthOptimizer::run_newton_iterations (lib/depth_optimizer.cc:204-304:
+construct -> PCG -> node update / active set, repeated until < 5 % of the nodes
+are active) started from the same perturbed surface. A pixel-iteration is one
+sample of one processed patch in one Newton step.
+
+  value  pixel-iterations / device time of the loop (CUDA events on the
+         library's stream, inputs resident in HBM)
+  e2e    the same loop through the C ABI from HOST buffers: smvsb_set_views +
+         smvsb_set_surface (H2D of all images and the surface) +
+         smvsb_newton_loop + smvsb_get_nodes (D2H), wall clock around the
+         calls with a device synchronize on both sides
+
+N > 1 (torchrun, one rank per GPU): reference views are independent units
+(app/smvsrecon.cc:658-733), so every rank refines its own view (seed = rank);
+no data-path collective; weak scaling. `value` = pixel-iterations of all ranks
+/ max-over-ranks time.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref:
+the reference's sources compiled verbatim against the MVE shim; or the
+oracle port when that is absent) on bounded windows of the same workload, one
+window per host thread (the reference's ThreadPool runs one view per thread).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from smvs_b200.workload import build_workload  # noqa: E402,F401  (tests import it from here)
+
+WIDTH, HEIGHT, N_SUB, SCALE = 1920, 1080, 6, 2
+REGULARIZATION = 0.01          # app/smvsrecon.cc:712 with alpha = 1
+METRIC = "Gauss-Newton Mpix-iters/sec"
+UNIT = "Mpix-iters/s"
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arms (oracle used as the thing timed ONLY here, as the task allows)
+# ---------------------------------------------------------------------------
+
+def _ref_scene_for(wl):
+    """A reference DepthOptimizer state fed with exactly the workload's
+    prepared arrays."""
+    from oracle import ref as oref
+    R = oref.RefScene(wl.scene, init_linear=wl.shading is not None)
+    R.set_arrays(0, wl.main_grad, None)
+    for k in range(wl.scene.n_sub):
+        R.set_arrays(k + 1, wl.sub_grads[k], wl.sub_hess[k])
+    if wl.shading is not None:
+        R.set_shading(wl.shading, wl.shading_grad)
+    R.surface_create(wl.scale, np.full((wl.scene.height, wl.scene.width), 5.0, np.float32))
+    info = R.surface_info()
+    assert (info["npx"], info["npy"], info["start_x"], info["start_y"]) == \
+        (wl.npx, wl.npy, wl.start_x, wl.start_y)
+    R.surface_set(wl.nodes, wl.node_valid, wl.patch_valid)
+    R.set_visibility(wl.vis_off, wl.vis_ids)
+    return R
+
+
+def _windows(wl, n, frac_x=4, frac_y=4):
+    nx, ny = max(wl.npx // frac_x, 1), max(wl.npy // frac_y, 1)
+    out = []
+    for i in range(n):
+        gx, gy = i % frac_x, (i // frac_x) % frac_y
+        out.append((gx * nx, gy * ny, nx, ny))
+    return out
+
+
+def cpu_reference_run(wl, threads, repeats=1):
+    """Newton loops of the reference on `threads` bounded windows (1/16 of the
+    patch grid each) run concurrently, one per host thread. Returns
+    (pixel_iterations, seconds, description)."""
+    from oracle import ref as oref
+    if not oref.available():
+        raise RuntimeError("oracle/_ref missing")
+    wins = _windows(wl, threads)
+    scenes = []
+    for (x0, y0, nx, ny) in wins:
+        scenes.append((_ref_scene_for(wl.restrict(x0, y0, nx, ny)),
+                       wl.restrict(x0, y0, nx, ny)))
+    results = [None] * threads
+
+    def work(i):
+        R, sub = scenes[i]
+        tot = 0.0
+        for _ in range(repeats):
+            R.surface_set(sub.nodes, sub.node_valid, sub.patch_valid)
+            st = R.newton_loop(None, REGULARIZATION, 0.0)
+            tot += st["pixel_iterations"]
+        results[i] = tot
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    for R, _ in scenes:
+        R.close()
+    desc = (f"{threads} thread(s) x {repeats} Newton loop(s), each on a "
+            f"{wins[0][2]}x{wins[0][3]}-patch window (1/16 of the {wl.npx}x{wl.npy} grid) "
+            f"of the same 2 MP / 6-neighbour scale-2 workload")
+    return float(sum(results)), dt, desc
+
+
+# ---------------------------------------------------------------------------
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    threads = max(1, min(os.cpu_count() or 1, 16))
+    wl = build_workload(WIDTH, HEIGHT, N_SUB, SCALE, shading=False, seed_index=0)
+    for _ in range(args.warmup):
+        cpu_reference_run(wl, threads)
+    pix, secs = 0.0, 0.0
+    desc = ""
+    for _ in range(args.steps):
+        p, s, desc = cpu_reference_run(wl, threads)
+        pix += p
+        secs += s
+    value = pix / secs / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "1 ref view + 6 neighbours, 1920x1080, scale 2 (-o2), "
+                               "no shading: inner Newton loop",
+                   "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads,
+                         "kind": "reference", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    from smvs_b200 import api
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (smvs_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wl = build_workload(WIDTH, HEIGHT, N_SUB, SCALE, shading=False, seed_index=rank)
+    ctx = api.Context(local)
+    nodes_out = None
+
+    def e2e_step():
+        wl.push_views(ctx)
+        wl.push_surface(ctx)
+        st = ctx.newton_loop(None, REGULARIZATION, 0.0)
+        return st, ctx.get_nodes()
+
+    def resident_step():
+        ctx.set_nodes(wl.nodes)             # reset; not part of the timed loop
+        return ctx.newton_loop(None, REGULARIZATION, 0.0)
+
+    # warm-up (both paths)
+    wl.push(ctx)
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    e2e_step()
+
+    # ---- device-resident arm --------------------------------------------
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = ctx.launches
+    t_dev_ms, pix, newton, cg = 0.0, 0.0, 0, 0
+    t_split = np.zeros(3)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st = resident_step()
+        t_dev_ms += st["ms_total"]
+        pix += st["pixel_iterations"]
+        newton += st["newton_steps"]
+        cg += st["cg_iterations"]
+        t_split += [st["ms_construct"], st["ms_solve"], st["ms_update"]]
+    barrier()
+    wall_resident = time.perf_counter() - t0
+    launches = ctx.launches - launches0
+    clocks = sampler.stop()
+
+    # ---- end-to-end arm ---------------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    pix_e2e = 0.0
+    for _ in range(args.steps):
+        st, nodes_out = e2e_step()
+        pix_e2e += st["pixel_iterations"]
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+
+    # ---- reduce over ranks ---------------------------------------------------
+    vals = torch.tensor([t_dev_ms, wall_e2e, pix, pix_e2e, float(launches)],
+                        dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = vals.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        t_dev_ms, wall_e2e = float(mx[0]), float(mx[1])
+        pix, pix_e2e, launches = float(sm[2]), float(sm[3]), float(sm[4])
+
+    if rank == 0:
+        value = pix / (t_dev_ms * 1e-3) / 1e6
+        e2e_value = pix_e2e / wall_e2e / 1e6
+
+        # roofline of the dominant kernel: the PCG (one persistent launch per
+        # Newton step). Algorithmic bytes per CG iteration per node
+        # (DESIGN.md section 5): H 9*128 + P 128 + vector traffic 12*32.
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        n_nodes = (wl.npx + 1) * (wl.npy + 1)
+        bytes_per_iter = n_nodes * (9 * 128 + 128 + 12 * 32)
+        cg_ms = float(t_split[1])
+        achieved = (bytes_per_iter * cg / max(cg_ms * 1e-3, 1e-12)) / 1e9
+        roofline = {"bound": "hbm", "kernel": "cg_kernel (persistent PCG)",
+                    "achieved": achieved, "peak": hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                    "algorithmic_bytes_per_launch": bytes_per_iter * cg / max(newton, 1),
+                    "launches_timed": newton}
+
+        cpu_base = None
+        if not args.no_cpu_baseline:
+            try:
+                p, s, desc = cpu_reference_run(wl, 1, repeats=2)
+                cpu_base = {"value": p / s / 1e6, "unit": UNIT, "cores": 1,
+                            "kind": "reference", "sample": desc}
+            except Exception as exc:      # noqa: BLE001
+                cpu_base = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                            "sample": f"unavailable: {exc}"}
+
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": t_dev_ms / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "1 ref view + 6 neighbours, 1920x1080, scale 2 (-o2), "
+                                   "no shading: inner Newton loop from a 2% perturbed surface",
+                       "views_per_gpu": 1, "parallelism": f"views sharded, {world} GPU(s)",
+                       "l2": "inputs_exceed_l2 (images 265 MB, H 148 MB, patch blocks 262 MB)",
+                       "newton_steps_per_loop": newton / max(args.steps, 1),
+                       "cg_iterations_per_loop": cg / max(args.steps, 1),
+                       "ms_construct_solve_update": [float(x) / max(args.steps, 1)
+                                                     for x in t_split]},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": wl.h2d_bytes(),
+                    "d2h_bytes_per_step": int(nodes_out.nbytes),
+                    "ms_per_step": 1e3 * wall_e2e / max(args.steps, 1)},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_base,
+            "wall_s_resident": wall_resident,
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="smvs_b200", choices=["smvs_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_product(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

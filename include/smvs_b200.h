@@ -64,6 +64,8 @@ typedef struct smvsb_newton_stats
     double ms_construct;         /* device time, CUDA events */
     double ms_solve;
     double ms_update;
+    double ms_total;             /* first launch to last result, incl. the
+                                    per-step host read-back of the scalars */
 } smvsb_newton_stats;
 
 /* ---- lifetime ------------------------------------------------------- */

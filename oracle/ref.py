@@ -292,3 +292,64 @@ class RefScene:
         t = np.empty(3, dtype=np.float32)
         lib().ref_reprojection(self.h_, a, b, aw, ah, bw, bh, _p(M), _p(t))
         return M, t
+
+
+# ---------------------------------------------------------------------------
+# unit-level entry points (the reference's own known-answer tests run on them)
+# ---------------------------------------------------------------------------
+
+class Units:
+    """Per-function access to the compiled reference (BicubicPatch,
+    Correspondence, surfderiv, sh, ldl_inverse)."""
+
+    name = "reference (oracle/_ref)"
+
+    @staticmethod
+    def bicubic_eval(nodes16, x, y):
+        n = np.ascontiguousarray(nodes16, dtype=np.float64).reshape(16)
+        out = np.empty(6, dtype=np.float64)
+        lib().ref_bicubic_eval(_p(n), C.c_double(x), C.c_double(y), _p(out))
+        return out
+
+    @staticmethod
+    def node_derivatives(x, y, patchsize=0.0):
+        out = np.empty(96, dtype=np.float64)
+        lib().ref_bicubic_node_derivatives(C.c_double(x), C.c_double(y),
+                                           C.c_double(patchsize), _p(out))
+        return out
+
+    @staticmethod
+    def correspondence(M, t, u, v, w, wx=0.0, wy=0.0, grad=(0.0, 0.0), dn=None):
+        M = np.ascontiguousarray(M, dtype=np.float64).reshape(9)
+        t = np.ascontiguousarray(t, dtype=np.float64).reshape(3)
+        g = np.ascontiguousarray(grad, dtype=np.float64).reshape(2)
+        dn = np.zeros(96) if dn is None else np.ascontiguousarray(dn, dtype=np.float64)
+        proj = np.empty(2); jac = np.empty(4); c_dn = np.empty((16, 2)); j_dn = np.empty((16, 2))
+        depth = C.c_double(0)
+        lib().ref_correspondence(_p(M), _p(t), C.c_double(u), C.c_double(v), C.c_double(w),
+                                 C.c_double(wx), C.c_double(wy), _p(g), _p(dn), _p(proj),
+                                 _p(jac), _p(c_dn), _p(j_dn), C.byref(depth))
+        return dict(proj=proj, jac=jac, c_dn=c_dn, jac_dn=j_dn, depth=depth.value)
+
+    @staticmethod
+    def surface_derivatives(dn, x, y, f, w, dx, dy, dxy, dxx, dyy):
+        dn = np.ascontiguousarray(dn, dtype=np.float64)
+        normal = np.empty(3); div = np.empty(6); dd = np.empty(96); nd = np.empty(48)
+        lib().ref_surface_derivatives(_p(dn), *[C.c_double(a) for a in
+                                                (x, y, f, w, dx, dy, dxy, dxx, dyy)],
+                                      _p(normal), _p(div), _p(dd), _p(nd))
+        return dict(normal=normal, div=div, div_deriv=dd, normal_deriv=nd)
+
+    @staticmethod
+    def sh_4band(normal):
+        n = np.ascontiguousarray(normal, dtype=np.float64)
+        sh = np.empty(16); d = np.empty(48)
+        lib().ref_sh_4band(_p(n), _p(sh), _p(d))
+        return sh, d
+
+    @staticmethod
+    def ldl_inverse(A):
+        A = np.array(A, dtype=np.float64, copy=True)
+        n = A.shape[0]
+        lib().ref_ldl_inverse(_p(A), n)
+        return A

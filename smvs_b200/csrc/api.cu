@@ -480,6 +480,10 @@ smvsb_newton_loop (smvsb_ctx* ctx, const double* light16,
         double const samples = double(c->npos) * c->npos;
 
         float ms = 0.f;
+        cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+        CUDA_CHECK(cudaEventCreate(&ev_begin));
+        CUDA_CHECK(cudaEventCreate(&ev_end));
+        CUDA_CHECK(cudaEventRecord(ev_begin, c->stream));
         for (; st.newton_steps < max_steps && num_active > num_initial / 20;)
         {
             st.newton_steps += 1;
@@ -525,6 +529,12 @@ smvsb_newton_loop (smvsb_ctx* ctx, const double* light16,
                 continue;
             }
         }
+        CUDA_CHECK(cudaEventRecord(ev_end, c->stream));
+        CUDA_CHECK(cudaEventSynchronize(ev_end));
+        CUDA_CHECK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+        st.ms_total = ms;
+        cudaEventDestroy(ev_begin);
+        cudaEventDestroy(ev_end);
         st.n_active = num_active;
         c->have_system = false;
         if (stats) *stats = st;

@@ -159,7 +159,7 @@ def _surface_normal(u, v, depth: DepthField, w, h, f_px):
     return n / np.linalg.norm(n, axis=-1, keepdims=True)
 
 
-def _invert_warp(M, t, depth: DepthField, pu, pv, iters=25):
+def _invert_warp(M, t, depth: DepthField, pu, pv, iters=8):
     """Find main-view (u,v) with warp(u,v,depth(u,v)) = (pu,pv)."""
     u = pu.copy()
     v = pv.copy()
@@ -210,13 +210,20 @@ def make_scene(width, height, n_sub, seed_index=0, shading=False,
     ys, xs = np.mgrid[0:height, 0:width]
     pu = xs.astype(np.float64) + 0.5
     pv = ys.astype(np.float64) + 0.5
-    images = [np.clip(np.rint(255.0 * radiance(pu, pv)), 0, 255).astype(np.uint8)]
-    for k in range(1, n_sub + 1):
+    def render(k):
+        if k == 0:
+            return np.clip(np.rint(255.0 * radiance(pu, pv)), 0, 255).astype(np.uint8)
         R = rot[k].astype(np.float64).reshape(3, 3)
         M = K @ R @ Kinv
         t = K @ trans[k].astype(np.float64)
         u, v = _invert_warp(M, t, depth, pu, pv)
-        images.append(np.clip(np.rint(255.0 * radiance(u, v)), 0, 255).astype(np.uint8))
+        return np.clip(np.rint(255.0 * radiance(u, v)), 0, 255).astype(np.uint8)
+
+    # numpy releases the GIL inside its loops: render the views concurrently
+    # (the result does not depend on the scheduling)
+    import concurrent.futures
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, 1 + n_sub)) as ex:
+        images = list(ex.map(render, range(1 + n_sub)))
 
     true_depth = depth(pu, pv).astype(np.float32)
     init_depth = (depth(pu, pv) * pert(pu, pv)).astype(np.float32)

@@ -1,0 +1,272 @@
+"""Parity of the CUDA path (through the C ABI of include/smvs_b200.h) against
+(1) the committed golden fixtures and (2) the compiled-verbatim reference
+run live on the same seeded inputs.
+
+Tolerances. The Gauss-Newton path is fp64 with a different (but fixed)
+summation order and FMA contraction, so values agree to ~1e-13 relative; the
+tests ask for 1e-9 on g / H / P / CG solution and for EQUAL iteration counts
+and active sets. Depth maps (float32 outputs) must agree to 1e-6 relative,
+far inside the 1e-4 of BASELINE.json. SGM is integer work: bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from smvs_b200 import api, synth
+from oracle import ref as oref
+
+from util_scene import Pair, rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-9
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name), allow_pickle=False)
+
+
+def ctx_from_golden(G):
+    ctx = api.Context(0)
+    n = int(G["n_sub"])
+    sh = G["shading"] if "shading" in G else None
+    shg = G["shading_grad"] if "shading_grad" in G else None
+    ctx.set_views(G["main_grad"], [G[f"sub_grad{k}"] for k in range(n)],
+                  [G[f"sub_hess{k}"] for k in range(n)], G["Mi"], G["ti"],
+                  float(G["flen"]), float(G["inv_flen"]), sh, shg)
+    ctx.set_surface(int(G["scale"]), int(G["npx"]), int(G["npy"]), int(G["start_x"]),
+                    int(G["start_y"]), G["nodes"], G["node_valid"], G["patch_valid"],
+                    G["vis_off"], G["vis_ids"])
+    return ctx
+
+
+def assert_system_equal(gs, rs):
+    assert np.array_equal(gs["Houter"], rs["Houter"])
+    assert np.array_equal(gs["Hinner"], rs["Hinner"])
+    assert np.array_equal(gs["Pouter"], rs["Pouter"])
+    assert np.array_equal(gs["Pinner"], rs["Pinner"])
+    assert rel_err(gs["g"], rs["g"]) < TOL
+    assert rel_err(gs["Hvals"], rs["Hvals"]) < TOL
+    assert rel_err(gs["Pvals"], rs["Pvals"]) < TOL
+
+
+@pytest.mark.parametrize("fixture", ["gn_s2.npz", "gn_s4.npz"])
+def test_golden_construct_cg(fixture):
+    G = load(fixture)
+    with ctx_from_golden(G) as ctx:
+        for tag in G["variants"]:
+            light = G["light"] if tag in ("lit", "litR") else None
+            ctx.gn_construct(G[f"{tag}_active"], light, float(G["regularization"]),
+                             float(G[f"{tag}_lreg"]))
+            gs = ctx.debug_get_system()
+            rs = {k: G[f"{tag}_{k}"] for k in
+                  ("g", "Hvals", "Houter", "Hinner", "Pvals", "Pouter", "Pinner")}
+            assert_system_equal(gs, rs)
+            it, info = ctx.cg_solve()
+            assert it == int(G[f"{tag}_cg_iters"]) and info == int(G[f"{tag}_cg_info"])
+            assert rel_err(ctx.get_delta(), G[f"{tag}_x"]) < 1e-8
+
+
+@pytest.mark.parametrize("fixture", ["gn_s2.npz", "gn_s4.npz"])
+def test_golden_update_and_loop(fixture):
+    G = load(fixture)
+    with ctx_from_golden(G) as ctx:
+        ctx.gn_construct(G["full_active"], None, float(G["regularization"]), 0.0)
+        ctx.cg_solve()
+        act, n_act, shift = ctx.update_nodes()
+        assert np.array_equal(act, G["upd_active"])
+        assert n_act == int(G["upd_n_active"])
+        assert abs(shift - float(G["upd_mean_shift"])) < 1e-9 * max(1.0, abs(shift))
+        assert rel_err(ctx.get_nodes(), G["upd_nodes"]) < TOL
+
+        ctx.set_nodes(G["nodes"])
+        light = G["light"] if "light" in G else None
+        st = ctx.newton_loop(light, float(G["regularization"]), 0.0)
+        assert st["newton_steps"] == int(G["loop_newton_steps"])
+        assert st["cg_iterations"] == int(G["loop_cg_iterations"])
+        assert st["pixel_iterations"] == float(G["loop_pixel_iterations"])
+        assert st["n_active"] == int(G["loop_n_active"])
+        assert rel_err(ctx.get_nodes(), G["loop_nodes"]) < 1e-8
+        d, dr = ctx.get_depth(), G["loop_depth"]
+        assert np.array_equal(d > 0, dr > 0)
+        assert rel_err(d, dr) < 1e-6
+        assert np.max(np.abs(ctx.get_normals() - G["loop_normals"])) < 1e-6
+
+
+def test_golden_sgm_bit_exact():
+    G = load("sgm.npz")
+    r = api.sgm(G["main"], G["neigh"], G["M"], G["t"], float(G["min_depth"]),
+                float(G["max_depth"]), int(G["D"]), volumes=True)
+    assert np.array_equal(r["cost"], G["cost"].astype(np.uint16))
+    assert np.array_equal(r["sgm"], G["sgm"])
+    assert np.array_equal(r["depth"], G["depth"])
+
+
+# ---------------------------------------------------------------------------
+# live reference, larger / odd shapes
+# ---------------------------------------------------------------------------
+
+needs_ref = pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h,n_sub,scale", [(640, 480, 2, 2), (640, 480, 3, 3),
+                                             (417, 311, 2, 4), (640, 480, 6, 5)])
+def test_live_construct_parity(w, h, n_sub, scale):
+    P = Pair(w, h, n_sub, scale)
+    try:
+        rng = np.random.default_rng(scale)
+        full = P.node_valid.copy()
+        part = (full & (rng.random(full.shape) < 0.25)).astype(np.uint8)
+        none = np.zeros_like(full)
+        for act, reg in ((full, 0.01), (part, 0.01), (full, 0.0)):
+            P.R.gn_construct(act, None, reg, 0.0)
+            P.ctx.gn_construct(act, None, reg, 0.0)
+            assert_system_equal(P.ctx.debug_get_system(), P.R.get_system())
+            x = rng.standard_normal(P.ctx.n_nodes * 4)
+            assert rel_err(P.ctx.debug_spmv(x), P.R.hessian_multiply(x)) < TOL
+        # empty active set: empty system, lib/gauss_newton_step.cc:73-79
+        P.ctx.gn_construct(none, None, 0.01, 0.0)
+        gs = P.ctx.debug_get_system()
+        assert len(gs["Hvals"]) == 0 and not gs["g"].any()
+    finally:
+        P.close()
+
+
+@needs_ref
+def test_live_ragged_surface_and_neighbour_sizes():
+    """Holes in the surface, patches with 0..n visible neighbours."""
+    P = Pair(400, 300, 3, 2, seed_index=5, gpu=True)
+    try:
+        rng = np.random.default_rng(3)
+        pv = P.patch_valid.copy()
+        pv[rng.random(pv.shape) < 0.2] = 0
+        npx, npy = P.info["npx"], P.info["npy"]
+        nv = np.zeros_like(P.node_valid)
+        pv2 = pv.reshape(npy, npx)
+        nv2 = nv.reshape(npy + 1, npx + 1)
+        for dy in (0, 1):
+            for dx in (0, 1):
+                nv2[dy:dy + npy, dx:dx + npx] |= pv2
+        P.node_valid, P.patch_valid = nv, pv
+        P.R.surface_set(P.nodes, nv, pv)
+        # thin the visibility lists at random
+        off, ids = [0], []
+        for p in range(npx * npy):
+            lst = [i for i in P.vis_ids[P.vis_off[p]:P.vis_off[p + 1]] if rng.random() < 0.7]
+            if pv[p] and not lst:
+                lst = [int(rng.integers(0, 3))]
+            ids += lst
+            off.append(len(ids))
+        P.vis_off, P.vis_ids = np.array(off, np.uint32), np.array(ids, np.uint8)
+        P.R.set_visibility(P.vis_off, P.vis_ids)
+        P.push_surface()
+        P.R.gn_construct(nv, None, 0.01, 0.0)
+        P.ctx.gn_construct(nv, None, 0.01, 0.0)
+        assert_system_equal(P.ctx.debug_get_system(), P.R.get_system())
+        xr, itr, _ = P.R.cg_solve()
+        itg, _ = P.ctx.cg_solve()
+        assert itg == itr and rel_err(P.ctx.get_delta(), xr) < 1e-8
+        ar, nr, _ = P.R.update_nodes(xr, nv)
+        ag, ng, _ = P.ctx.update_nodes()
+        assert ng == nr and np.array_equal(ag, ar)
+    finally:
+        P.close()
+
+
+@needs_ref
+def test_live_shading_newton_loop():
+    P = Pair(640, 480, 3, 2, shading=True)
+    try:
+        lr, lg = P.R.fit_lighting(), P.ctx.fit_lighting()
+        # 16x16 pseudo inverse of an ill-conditioned normal matrix
+        assert rel_err(lg, lr) < 1e-5
+        for lreg in (0.0, 5.0):
+            P.R.gn_construct(P.node_valid, lr, 0.01, lreg)
+            P.ctx.gn_construct(P.node_valid, lr, 0.01, lreg)
+            assert_system_equal(P.ctx.debug_get_system(), P.R.get_system())
+        sr = P.R.newton_loop(lr, 0.01, 0.0)
+        sg = P.ctx.newton_loop(lr, 0.01, 0.0)
+        for k in ("newton_steps", "cg_iterations", "n_active", "pixel_iterations"):
+            assert sg[k] == sr[k], k
+        d, dr = P.ctx.get_depth(), P.R.surface_depth()
+        assert np.array_equal(d > 0, dr > 0) and rel_err(d, dr) < 1e-6
+    finally:
+        P.close()
+
+
+@needs_ref
+def test_live_full_opt_mean_shift():
+    P = Pair(320, 240, 2, 3)
+    try:
+        P.R.gn_construct(P.node_valid, None, 0.01, 0.0)
+        P.ctx.gn_construct(P.node_valid, None, 0.01, 0.0)
+        xr, _, _ = P.R.cg_solve()
+        P.ctx.cg_solve()
+        ar, nr, mr = P.R.update_nodes(xr, P.node_valid, full_opt=True)
+        ag, ng, mg = P.ctx.update_nodes(full_opt=True)
+        assert abs(mg - mr) < 1e-9 * max(abs(mr), 1e-12)
+        assert np.array_equal(ag, ar)     # unchanged in full_opt mode
+    finally:
+        P.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h,D", [(333, 207, 64), (640, 480, 128), (200, 150, 32)])
+def test_live_sgm_bit_exact(w, h, D):
+    sc = synth.make_scene(w, h, 1, seed_index=9)
+    R = oref.RefScene(sc)
+    dmin, dmax = float(sc.true_depth.min() * 0.7), float(sc.true_depth.max() * 1.3)
+    r = R.sgm_run(0, 1, 0, D, dmin, dmax, volumes=True)
+    M, t = R.reprojection(0, 1, w, h, w, h)
+    g = api.sgm(sc.images[0], sc.images[1], M, t, dmin, dmax, D, volumes=True)
+    assert np.array_equal(g["cost"], r["cost"])
+    assert np.array_equal(g["sgm"], r["sgm"])
+    assert np.array_equal(g["depth"], r["depth"])
+    R.close()
+
+
+@needs_ref
+def test_live_sgm_low_texture_and_behind_camera():
+    """Zero / dark pixels (census skipped, luminance < 25 rejected) and a depth
+    range that puts planes behind the neighbour camera."""
+    sc = synth.make_scene(256, 192, 1, seed_index=10)
+    sc.images[0][40:80, 50:120] = 0
+    sc.images[0][100:140, 30:90] = 12
+    sc.images[1][60:100, 100:200] = 0
+    R = oref.RefScene(sc)
+    r = R.sgm_run(0, 1, 0, 64, 0.05, 40.0, volumes=True)
+    M, t = R.reprojection(0, 1, 256, 192, 256, 192)
+    g = api.sgm(sc.images[0], sc.images[1], M, t, 0.05, 40.0, 64, volumes=True)
+    assert np.array_equal(g["cost"], r["cost"])
+    assert np.array_equal(g["sgm"], r["sgm"])
+    assert np.array_equal(g["depth"], r["depth"])
+    R.close()
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json sizes: size-independent properties + one live comparison
+# ---------------------------------------------------------------------------
+
+def test_full_size_properties():
+    """1920x1080, 6 neighbours, scale 2: H symmetric, SpMV linear, CG
+    solution satisfies the reference's stopping rule, deterministic rerun."""
+    from bench import build_workload
+    wl = build_workload(1920, 1080, 6, scale=2, shading=False)
+    with api.Context(0) as ctx:
+        wl.push(ctx)
+        ctx.gn_construct(None, None, 0.01, 0.0)
+        rng = np.random.default_rng(0)
+        n = ctx.n_nodes * 4
+        x, y = rng.standard_normal(n), rng.standard_normal(n)
+        Hx, Hy = ctx.debug_spmv(x), ctx.debug_spmv(y)
+        assert abs(np.dot(y, Hx) - np.dot(x, Hy)) < 1e-9 * abs(np.dot(y, Hx))
+        assert rel_err(ctx.debug_spmv(2.0 * x - 3.0 * y), 2.0 * Hx - 3.0 * Hy) < 1e-12
+        assert np.dot(x, Hx) > 0.0                       # J^T J is PSD
+        it, info = ctx.cg_solve()
+        d1 = ctx.get_delta()
+        g = ctx.debug_get_system()["g"]
+        res = ctx.debug_spmv(d1) + g
+        assert np.linalg.norm(res) < np.linalg.norm(g)
+        it2, _ = ctx.cg_solve()
+        assert it2 == it and np.array_equal(ctx.get_delta(), d1)   # deterministic
