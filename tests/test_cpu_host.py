@@ -1,0 +1,150 @@
+"""CPU-side tests: the C ABI library loads and exports what the header
+declares, fails loudly without a GPU, and the host-side mirrors (set_scale,
+workload builder, sharding) behave like the reference."""
+import ctypes as C
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from smvs_b200 import api, sharding, stereo_view, synth, workload
+from oracle import ref as oref
+
+
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "smvs_b200.h")).read()
+    declared = set(re.findall(r"\b(smvsb_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"smvsb_ctx", "smvsb_status"}
+    assert declared == set(api.EXPORTS)
+    L = api.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.smvsb_version()
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure path")
+def test_no_cpu_fallback():
+    h = C.c_void_p()
+    rc = api.lib().smvsb_create(0, C.byref(h))
+    assert rc == -2 and not h
+    assert b"no CPU fallback" in api.lib().smvsb_last_error(None)
+    with pytest.raises(api.SmvsbError):
+        api.Context(0)
+    with pytest.raises(api.SmvsbError):
+        z = np.zeros((64, 64), np.uint8)
+        api.sgm(z, z, np.eye(3).ravel(), np.zeros(3), 1.0, 2.0, 64)
+
+
+def test_null_context_is_rejected():
+    L = api.lib()
+    assert L.smvsb_cg_solve(None, 10, C.c_double(0), C.c_double(0), None, None) == -1
+    assert L.smvsb_get_nodes(None, None) == -1
+
+
+def test_synth_is_seeded():
+    a = synth.make_scene(96, 64, 2, seed_index=3)
+    b = synth.make_scene(96, 64, 2, seed_index=3)
+    c = synth.make_scene(96, 64, 2, seed_index=4)
+    assert all(np.array_equal(x, y) for x, y in zip(a.images, b.images))
+    assert not np.array_equal(a.images[0], c.images[0])
+
+
+@pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")
+def test_set_scale_mirror_matches_reference_bitwise():
+    sc = synth.make_scene(160, 120, 1, seed_index=2, shading=True)
+    R = oref.RefScene(sc, init_linear=True)
+    for scale in (2, 4):
+        R.set_scale(scale)
+        for v in (0, 1):
+            b, g, h = stereo_view.set_scale(sc.images[v], scale)
+            assert np.array_equal(b, R.scaleimage(v))
+            assert np.array_equal(g, R.gradients(v))
+            assert np.array_equal(h, R.hessian(v))
+    s_img, s_grad = R.shading()
+    a, b = stereo_view.shading_inputs(sc.images[0])
+    assert np.array_equal(a, s_img) and np.array_equal(b, s_grad)
+    # Mi / ti, flen as the reference computes them (fp32, widened)
+    wl = workload.build_workload(160, 120, 1, scale=2, scene=sc, shading=True)
+    Mi, ti = R.Mt()
+    assert np.array_equal(wl.Mi, Mi) and np.array_equal(wl.ti, ti)
+    assert wl.flen_px == R.flen(0) and wl.inv_flen == R.inverse_flen(0)
+    R.close()
+
+
+@pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")
+def test_surface_grid_matches_reference():
+    for (w, h, scale) in ((640, 480, 2), (640, 480, 4), (417, 311, 3), (1920, 1080, 5)):
+        sc = synth.make_scene(w, h, 1, seed_index=1) if w < 1000 else None
+        if sc is None:
+            continue
+        R = oref.RefScene(sc)
+        R.surface_create(scale, sc.init_depth)
+        i = R.surface_info()
+        ps, npx, npy, sx, sy = synth.surface_grid(w, h, scale)
+        assert (i["patchsize"], i["npx"], i["npy"], i["start_x"], i["start_y"]) == \
+            (ps, npx, npy, sx, sy)
+        R.close()
+
+
+def test_workload_restrict_keeps_csr_consistent():
+    wl = workload.build_workload(256, 192, 3, scale=2, seed_index=1)
+    sub = wl.restrict(5, 4, 10, 8)
+    assert sub.patch_valid.sum() <= 80 and sub.patch_valid.sum() > 0
+    assert sub.vis_off[-1] == len(sub.vis_ids)
+    pv = sub.patch_valid.reshape(sub.npy, sub.npx)
+    assert pv[:4].sum() == 0 and pv[:, :5].sum() == 0
+    cnt = np.diff(sub.vis_off.astype(np.int64))
+    assert np.all(cnt[sub.patch_valid == 0] == 0)
+    full_cnt = np.diff(wl.vis_off.astype(np.int64))
+    assert np.array_equal(cnt[sub.patch_valid != 0], full_cnt[sub.patch_valid != 0])
+    # every node of a valid patch is valid
+    nv = sub.node_valid.reshape(sub.npy + 1, sub.npx + 1)
+    ys, xs = np.nonzero(pv)
+    assert nv[ys, xs].all() and nv[ys + 1, xs + 1].all()
+
+
+def test_round_robin_sharding():
+    got = [sharding.views_of_rank(32, r, 8) for r in range(8)]
+    assert all(len(g) == 4 for g in got)
+    assert sorted(sum(got, [])) == list(range(32))
+    assert sharding.views_of_rank(3, 5, 8) == []
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    views = sharding.views_of_rank(5, rank, world)
+    pix, secs = sharding.reduce_job_stats(100.0 * len(views), 1.0 + rank)
+    Ab = np.full(272, float(rank + 1))
+    tot = sharding.allreduce_lighting_normal_equations(Ab)
+    if rank == 0:
+        out.put((pix, secs, float(tot[0]), float(tot[271])))
+    dist.destroy_process_group()
+
+
+def test_gloo_world_size_2():
+    """The N > 1 path on CPU: view sharding, job statistics (sum of work, max
+    of time) and the opt-in lighting reduction over a 2-rank gloo group."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == (500.0, 2.0, 3.0, 3.0)
