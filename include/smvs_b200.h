@@ -79,6 +79,9 @@ const char* smvsb_last_error (const smvsb_ctx* ctx);
 const char* smvsb_version (void);
 /* Number of kernel launches issued on this context since creation. */
 uint64_t smvsb_launch_count (const smvsb_ctx* ctx);
+/* Kernel launches issued by this library in this process (all contexts and
+ * smvsb_sgm calls); lets a host prove that the GPU path did the work. */
+uint64_t smvsb_global_launch_count (void);
 
 /* ---- inputs --------------------------------------------------------- */
 

@@ -13,26 +13,36 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libsmvs_ref.so")
 
-_lib = None
+# The same C driver (oracle/ref_driver.cc) is also linked into
+# integration/_build/libsmvs_ref_b200.so, where the reference's host code runs
+# with the GPU hot path patched in (integration/Makefile).
+INTEGRATION_LIB_PATH = os.path.join(os.path.dirname(_HERE), "integration", "_build",
+                                    "libsmvs_ref_b200.so")
+_libs = {}
 
 
 def available() -> bool:
     return os.path.exists(LIB_PATH)
 
 
+def load(path=None):
+    path = path or LIB_PATH
+    if path not in _libs:
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not built (run `make -C oracle ref` / "
+                               "`make -C integration` where /root/reference exists)")
+        L = C.CDLL(path)
+        L.ref_scene_create.restype = C.c_void_p
+        L.ref_view_get_flen.restype = C.c_float
+        L.ref_view_get_inverse_flen.restype = C.c_float
+        L.ref_gn_construct.restype = C.c_int64
+        L.ref_get_visibility.restype = C.c_uint64
+        _libs[path] = L
+    return _libs[path]
+
+
 def lib():
-    global _lib
-    if _lib is None:
-        if not available():
-            raise RuntimeError("oracle/_ref/libsmvs_ref.so not built "
-                               "(run `make -C oracle ref` where /root/reference exists)")
-        _lib = C.CDLL(LIB_PATH)
-        _lib.ref_scene_create.restype = C.c_void_p
-        _lib.ref_view_get_flen.restype = C.c_float
-        _lib.ref_view_get_inverse_flen.restype = C.c_float
-        _lib.ref_gn_construct.restype = C.c_int64
-        _lib.ref_get_visibility.restype = C.c_uint64
-    return _lib
+    return load(None)
 
 
 def _p(a, t=None):
@@ -44,8 +54,8 @@ def _p(a, t=None):
 class RefScene:
     """The reference's StereoViews + DepthOptimizer over a synthetic scene."""
 
-    def __init__(self, scene, init_linear=False):
-        L = lib()
+    def __init__(self, scene, init_linear=False, lib_path=None):
+        L = self.L = load(lib_path)
         n = 1 + scene.n_sub
         self.scene = scene
         self.n_sub = scene.n_sub
@@ -64,7 +74,7 @@ class RefScene:
 
     def close(self):
         if self.h_:
-            lib().ref_scene_destroy(self.h_)
+            self.L.ref_scene_destroy(self.h_)
             self.h_ = None
 
     def __del__(self):
@@ -75,60 +85,60 @@ class RefScene:
 
     # -- views ---------------------------------------------------------
     def set_scale(self, scale):
-        lib().ref_scene_set_scale(self.h_, int(scale))
+        self.L.ref_scene_set_scale(self.h_, int(scale))
 
     def gradients(self, v):
         out = np.empty((self.h, self.w, 2), dtype=np.float32)
-        lib().ref_view_get_gradients(self.h_, v, _p(out))
+        self.L.ref_view_get_gradients(self.h_, v, _p(out))
         return out
 
     def hessian(self, v):
         out = np.empty((self.h, self.w, 3), dtype=np.float32)
-        lib().ref_view_get_hessian(self.h_, v, _p(out))
+        self.L.ref_view_get_hessian(self.h_, v, _p(out))
         return out
 
     def scaleimage(self, v):
         out = np.empty((self.h, self.w), dtype=np.float32)
-        lib().ref_view_get_scaleimage(self.h_, v, _p(out))
+        self.L.ref_view_get_scaleimage(self.h_, v, _p(out))
         return out
 
     def shading(self):
         img = np.empty((self.h, self.w), dtype=np.float32)
         grad = np.empty((self.h, self.w, 2), dtype=np.float32)
-        if lib().ref_view_get_shading(self.h_, _p(img), _p(grad)) != 0:
+        if self.L.ref_view_get_shading(self.h_, _p(img), _p(grad)) != 0:
             return None, None
         return img, grad
 
     def set_arrays(self, v, grad, hess):
         grad = np.ascontiguousarray(grad, dtype=np.float32)
         hess = None if hess is None else np.ascontiguousarray(hess, dtype=np.float32)
-        lib().ref_view_set_arrays(self.h_, v, _p(grad), _p(hess))
+        self.L.ref_view_set_arrays(self.h_, v, _p(grad), _p(hess))
 
     def set_shading(self, img, grad):
         img = np.ascontiguousarray(img, dtype=np.float32)
         grad = np.ascontiguousarray(grad, dtype=np.float32)
-        lib().ref_view_set_shading(self.h_, _p(img), _p(grad))
+        self.L.ref_view_set_shading(self.h_, _p(img), _p(grad))
 
     def flen(self, v=0):
-        return float(lib().ref_view_get_flen(self.h_, v))
+        return float(self.L.ref_view_get_flen(self.h_, v))
 
     def inverse_flen(self, v=0):
-        return float(lib().ref_view_get_inverse_flen(self.h_, v))
+        return float(self.L.ref_view_get_inverse_flen(self.h_, v))
 
     def Mt(self):
         Mi = np.empty((self.n_sub, 9), dtype=np.float64)
         ti = np.empty((self.n_sub, 3), dtype=np.float64)
-        lib().ref_scene_get_Mt(self.h_, _p(Mi), _p(ti))
+        self.L.ref_scene_get_Mt(self.h_, _p(Mi), _p(ti))
         return Mi, ti
 
     # -- surface -------------------------------------------------------
     def surface_create(self, scale, init_depth):
         d = np.ascontiguousarray(init_depth, dtype=np.float32)
-        lib().ref_surface_create(self.h_, int(scale), _p(d))
+        self.L.ref_surface_create(self.h_, int(scale), _p(d))
 
     def surface_info(self):
         info = (C.c_int * 6)()
-        lib().ref_surface_info(self.h_, info)
+        self.L.ref_surface_info(self.h_, info)
         return dict(scale=info[0], npx=info[1], npy=info[2], start_x=info[3],
                     start_y=info[4], patchsize=info[5])
 
@@ -139,65 +149,65 @@ class RefScene:
         nodes = np.empty((nn, 4), dtype=np.float64)
         nv = np.empty(nn, dtype=np.uint8)
         pv = np.empty(npatch, dtype=np.uint8)
-        lib().ref_surface_get(self.h_, _p(nodes), _p(nv), _p(pv))
+        self.L.ref_surface_get(self.h_, _p(nodes), _p(nv), _p(pv))
         return nodes, nv, pv
 
     def surface_set(self, nodes, node_valid, patch_valid):
         nodes = np.ascontiguousarray(nodes, dtype=np.float64)
         nv = np.ascontiguousarray(node_valid, dtype=np.uint8)
         pv = np.ascontiguousarray(patch_valid, dtype=np.uint8)
-        lib().ref_surface_set(self.h_, _p(nodes), _p(nv), _p(pv))
+        self.L.ref_surface_set(self.h_, _p(nodes), _p(nv), _p(pv))
 
     def surface_subdivide(self):
-        lib().ref_surface_subdivide(self.h_)
+        self.L.ref_surface_subdivide(self.h_)
 
     def surface_depth(self):
         out = np.empty((self.h, self.w), dtype=np.float32)
-        lib().ref_surface_get_depth(self.h_, _p(out))
+        self.L.ref_surface_get_depth(self.h_, _p(out))
         return out
 
     def surface_normals(self):
         out = np.empty((self.h, self.w, 3), dtype=np.float32)
-        lib().ref_surface_get_normals(self.h_, _p(out))
+        self.L.ref_surface_get_normals(self.h_, _p(out))
         return out
 
     def node_derivative_table(self):
         ps = self.surface_info()["patchsize"]
         out = np.empty((ps * ps, 96), dtype=np.float64)
-        lib().ref_node_derivative_table(self.h_, _p(out))
+        self.L.ref_node_derivative_table(self.h_, _p(out))
         return out
 
     # -- visibility ----------------------------------------------------
     def compute_visibility(self):
-        return int(lib().ref_compute_visibility(self.h_))
+        return int(self.L.ref_compute_visibility(self.h_))
 
     def get_visibility(self):
         i = self.surface_info()
         npatch = i["npx"] * i["npy"]
         off = np.empty(npatch + 1, dtype=np.uint32)
-        total = int(lib().ref_get_visibility(self.h_, _p(off), None))
+        total = int(self.L.ref_get_visibility(self.h_, _p(off), None))
         ids = np.empty(max(total, 1), dtype=np.uint8)
-        lib().ref_get_visibility(self.h_, _p(off), _p(ids))
+        self.L.ref_get_visibility(self.h_, _p(off), _p(ids))
         return off, ids[:total]
 
     def set_visibility(self, off, ids):
         off = np.ascontiguousarray(off, dtype=np.uint32)
         ids = np.ascontiguousarray(ids, dtype=np.uint8)
         self._vis_keep = (off, ids)
-        lib().ref_set_visibility(self.h_, _p(off), _p(ids))
+        self.L.ref_set_visibility(self.h_, _p(off), _p(ids))
 
     # -- Gauss-Newton --------------------------------------------------
     def gn_construct(self, active, light16=None, regularization=0.01,
                      light_surf_regularization=0.0):
         active = np.ascontiguousarray(active, dtype=np.uint8)
         l = None if light16 is None else np.ascontiguousarray(light16, dtype=np.float64)
-        return int(lib().ref_gn_construct(self.h_, _p(active), _p(l),
+        return int(self.L.ref_gn_construct(self.h_, _p(active), _p(l),
                                           C.c_double(regularization),
                                           C.c_double(light_surf_regularization)))
 
     def get_system(self):
         sz = (C.c_uint64 * 3)()
-        lib().ref_get_system_sizes(self.h_, sz)
+        self.L.ref_get_system_sizes(self.h_, sz)
         n, nh, npc = int(sz[0]), int(sz[1]), int(sz[2])
         g = np.empty(n, dtype=np.float64)
         Hv = np.empty((nh, 16), dtype=np.float64)
@@ -206,21 +216,21 @@ class RefScene:
         Pv = np.empty((npc, 16), dtype=np.float64)
         Po = np.empty(n // 4 + 1, dtype=np.uint64)
         Pi = np.empty(npc, dtype=np.uint64)
-        lib().ref_get_system(self.h_, _p(g), _p(Hv), _p(Ho), _p(Hi), _p(Pv), _p(Po), _p(Pi))
+        self.L.ref_get_system(self.h_, _p(g), _p(Hv), _p(Ho), _p(Hi), _p(Pv), _p(Po), _p(Pi))
         return dict(g=g, Hvals=Hv, Houter=Ho, Hinner=Hi, Pvals=Pv, Pouter=Po, Pinner=Pi)
 
     def hessian_multiply(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.empty_like(x)
-        lib().ref_hessian_multiply(self.h_, _p(x), _p(y))
+        self.L.ref_hessian_multiply(self.h_, _p(x), _p(y))
         return y
 
     def cg_solve(self, max_iter=200, err_tol=-1.0, q_tol=1e-3):
         sz = (C.c_uint64 * 3)()
-        lib().ref_get_system_sizes(self.h_, sz)
+        self.L.ref_get_system_sizes(self.h_, sz)
         x = np.empty(int(sz[0]), dtype=np.float64)
         it, info = C.c_int(0), C.c_int(0)
-        lib().ref_cg_solve(self.h_, int(max_iter), C.c_double(err_tol),
+        self.L.ref_cg_solve(self.h_, int(max_iter), C.c_double(err_tol),
                            C.c_double(q_tol), _p(x), C.byref(it), C.byref(info))
         return x, it.value, info.value
 
@@ -229,7 +239,7 @@ class RefScene:
         act = np.array(active, dtype=np.uint8, copy=True)
         n_active = C.c_uint64(0)
         mean_shift = C.c_double(0)
-        lib().ref_update_nodes(self.h_, _p(delta), C.c_double(reproj_thresh),
+        self.L.ref_update_nodes(self.h_, _p(delta), C.c_double(reproj_thresh),
                                int(full_opt), _p(act), C.byref(n_active),
                                C.byref(mean_shift))
         return act, int(n_active.value), float(mean_shift.value)
@@ -238,7 +248,7 @@ class RefScene:
                     light_surf_regularization=0.0, max_steps=200):
         l = None if light16 is None else np.ascontiguousarray(light16, dtype=np.float64)
         st = np.zeros(8, dtype=np.float64)
-        lib().ref_newton_loop(self.h_, _p(l), C.c_double(regularization),
+        self.L.ref_newton_loop(self.h_, _p(l), C.c_double(regularization),
                               C.c_double(light_surf_regularization), int(max_steps), _p(st))
         return dict(newton_steps=int(st[0]), cg_iterations=int(st[1]),
                     pixel_iterations=float(st[2]), t_construct=float(st[3]),
@@ -247,7 +257,7 @@ class RefScene:
 
     def fit_lighting(self):
         p = np.zeros(16, dtype=np.float64)
-        if lib().ref_fit_lighting(self.h_, _p(p)) != 0:
+        if self.L.ref_fit_lighting(self.h_, _p(p)) != 0:
             return None
         return p
 
@@ -257,7 +267,7 @@ class RefScene:
         depth = np.empty((self.h, self.w), dtype=np.float32)
         normals = np.empty((self.h, self.w, 3), dtype=np.float32)
         light = np.zeros(16, dtype=np.float64)
-        lib().ref_optimize(self.h_, _p(d), C.c_double(regularization),
+        self.L.ref_optimize(self.h_, _p(d), C.c_double(regularization),
                            int(num_iterations), int(min_scale), int(use_shading),
                            int(debug_lvl), _p(depth), _p(normals), _p(light))
         return depth, normals, light
@@ -265,7 +275,7 @@ class RefScene:
     # -- SGM -------------------------------------------------------------
     def sgm_dims(self, v, scale):
         info = (C.c_int * 2)()
-        lib().ref_sgm_dims(self.h_, v, scale, info)
+        self.L.ref_sgm_dims(self.h_, v, scale, info)
         return info[0], info[1]
 
     def sgm_run(self, a, b, scale, num_steps, min_depth, max_depth,
@@ -275,7 +285,7 @@ class RefScene:
         cost = np.empty((h, w, num_steps), dtype=np.uint16) if volumes else None
         sgm = np.empty((h, w, num_steps), dtype=np.uint16) if volumes else None
         times = np.zeros(3, dtype=np.float64)
-        lib().ref_sgm_run(self.h_, a, b, scale, num_steps, C.c_float(min_depth),
+        self.L.ref_sgm_run(self.h_, a, b, scale, num_steps, C.c_float(min_depth),
                           C.c_float(max_depth), penalty1, penalty2, _p(depth),
                           _p(cost), _p(sgm), _p(times))
         return dict(depth=depth, cost=cost, sgm=sgm, times=times)
@@ -283,14 +293,14 @@ class RefScene:
     def sgm_reconstruct(self, a, b, scale, num_steps, min_depth, max_depth):
         w, h = self.sgm_dims(a, scale)
         depth = np.empty((h, w), dtype=np.float32)
-        lib().ref_sgm_reconstruct(self.h_, a, b, scale, num_steps,
+        self.L.ref_sgm_reconstruct(self.h_, a, b, scale, num_steps,
                                   C.c_float(min_depth), C.c_float(max_depth), _p(depth))
         return depth
 
     def reprojection(self, a, b, aw, ah, bw, bh):
         M = np.empty(9, dtype=np.float32)
         t = np.empty(3, dtype=np.float32)
-        lib().ref_reprojection(self.h_, a, b, aw, ah, bw, bh, _p(M), _p(t))
+        self.L.ref_reprojection(self.h_, a, b, aw, ah, bw, bh, _p(M), _p(t))
         return M, t
 
 

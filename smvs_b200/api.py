@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libsmvs_b200.so")
 
 EXPORTS = [
     "smvsb_create", "smvsb_destroy", "smvsb_last_error", "smvsb_version",
-    "smvsb_launch_count", "smvsb_set_views", "smvsb_set_surface",
+    "smvsb_launch_count", "smvsb_global_launch_count", "smvsb_set_views", "smvsb_set_surface",
     "smvsb_set_nodes", "smvsb_gn_construct", "smvsb_cg_solve",
     "smvsb_get_delta", "smvsb_set_delta", "smvsb_update_nodes",
     "smvsb_newton_loop", "smvsb_get_nodes", "smvsb_get_depth",
@@ -56,6 +56,7 @@ def lib():
         L.smvsb_version.restype = C.c_char_p
         L.smvsb_launch_count.restype = C.c_uint64
         L.smvsb_launch_count.argtypes = [C.c_void_p]
+        L.smvsb_global_launch_count.restype = C.c_uint64
         L.smvsb_destroy.argtypes = [C.c_void_p]
         L.smvsb_destroy.restype = None
         _lib = L

@@ -6,6 +6,7 @@
  * closes the lighting fit (lib/light_optimizer.cc:50-52), a 16x16 SVD.
  */
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <dlfcn.h>
@@ -20,6 +21,10 @@ int sgm_run (int device, int w, int h, uint8_t const* main_lum, int nw, int nh,
     float min_depth, float max_depth, int num_steps, uint16_t penalty1,
     uint16_t penalty2, float* depth_out, uint16_t* cost_out,
     uint16_t* sgm_out, double* ms_out);
+}
+
+namespace smvsb {
+std::atomic<uint64_t> g_launches(0);
 }
 
 namespace {
@@ -220,6 +225,12 @@ uint64_t
 smvsb_launch_count (const smvsb_ctx* ctx)
 {
     return ctx ? ctx->launches : 0;
+}
+
+uint64_t
+smvsb_global_launch_count (void)
+{
+    return smvsb::g_launches.load();
 }
 
 int
@@ -739,6 +750,8 @@ smvsb_sgm (int device, int w, int h, const uint8_t* main_lum, int nw, int nh,
         cost_out, sgm_out, ms_out);
     if (rc != SMVSB_OK)
         g_last_error = smvsb::sgm_last_error();
+    else
+        smvsb::g_launches += 11;    /* cost + 8 paths + corners + WTA */
     return rc;
 }
 

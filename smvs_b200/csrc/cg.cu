@@ -302,7 +302,7 @@ launch_spmv (smvsb_ctx* c, double const* x, double* y)
     CgArgs a = make_args(c);
     int const n = c->n_nodes * 4;
     spmv_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(a, x, y);
-    c->launches += 1;
+    smvsb::count_launches(c, 1);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -335,7 +335,7 @@ run_cg (smvsb_ctx* c, int max_iter, double err_tol, double q_tol, int* iters,
     CUDA_CHECK(cudaLaunchCooperativeKernel((void const*)cg_kernel, dim3(grid),
         dim3(CG_THREADS), params, 0, c->stream));
     cg_finish_kernel<<<1, 1, 0, c->stream>>>(c->x.p, c->cg_result.p);
-    c->launches += 2;
+    smvsb::count_launches(c, 2);
     CUDA_CHECK(cudaGetLastError());
 
     double res[3];

@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -159,6 +160,16 @@ struct smvsb_ctx
 };
 
 namespace smvsb {
+
+/* process-wide launch counter (smvsb_global_launch_count) */
+extern std::atomic<uint64_t> g_launches;
+
+inline void
+count_launches (smvsb_ctx* c, int n)
+{
+    c->launches += n;
+    g_launches += n;
+}
 
 inline SurfaceDev
 surface_args (smvsb_ctx* c)

@@ -94,7 +94,7 @@ launch_pack_subview (smvsb_ctx* c, float const* grad, float const* hess,
     int const n = w * h;
     pack_subview_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(grad, hess,
         texels, n);
-    c->launches += 1;
+    smvsb::count_launches(c, 1);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -607,7 +607,7 @@ launch_construct (smvsb_ctx* c, bool use_light, double reg, double light_reg)
     gn_precond_kernel<<<(c->n_nodes + 127) / 128, 128, 0, c->stream>>>(a.s,
         c->H.p, c->P.p);
     CUDA_CHECK(cudaGetLastError());
-    c->launches += 3;
+    smvsb::count_launches(c, 3);
 }
 
 } /* namespace smvsb */

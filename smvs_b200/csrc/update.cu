@@ -335,7 +335,7 @@ launch_update (smvsb_ctx* c, double thresh, bool full_opt,
     update_reduce_kernel<<<1, 256, 0, c->stream>>>(c->n_patches,
         c->patch_shift.p, c->n_nodes, c->active.p, c->cg_result.p);
     CUDA_CHECK(cudaGetLastError());
-    c->launches += 3;
+    smvsb::count_launches(c, 3);
     double res[3];
     CUDA_CHECK(cudaMemcpyAsync(res, c->cg_result.p, sizeof(res),
         cudaMemcpyDeviceToHost, c->stream));
@@ -353,7 +353,7 @@ launch_count_processed (smvsb_ctx* c, unsigned long long* n_proc_host)
         c->stream));
     count_processed_kernel<<<(c->n_patches + 255) / 256, 256, 0,
         c->stream>>>(sf, c->counters.p);
-    c->launches += 1;
+    smvsb::count_launches(c, 1);
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaMemcpyAsync(n_proc_host, c->counters.p,
         sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
@@ -371,7 +371,7 @@ launch_render (smvsb_ctx* c, float* out_dev, int normals)
     dim3 const grid((c->npx * c->ps + 31) / 32, (c->npy * c->ps + 7) / 8);
     if (grid.x > 0 && grid.y > 0)
         render_kernel<<<grid, block, 0, c->stream>>>(sf, out_dev, normals);
-    c->launches += 1;
+    smvsb::count_launches(c, 1);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -400,7 +400,7 @@ run_fit_lighting (smvsb_ctx* c, double* A_b_host)
     c->light_partials.reserve(static_cast<size_t>(grid) * LIGHT_VALUES);
     light_partials_kernel<<<grid, LIGHT_THREADS, 0, c->stream>>>(npix,
         c->image_out.p, c->main_shading.p, c->light_partials.p);
-    c->launches += 1;
+    smvsb::count_launches(c, 1);
     CUDA_CHECK(cudaGetLastError());
     std::vector<double> part(static_cast<size_t>(grid) * LIGHT_VALUES);
     CUDA_CHECK(cudaMemcpyAsync(part.data(), c->light_partials.p,
