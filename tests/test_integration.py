@@ -35,7 +35,7 @@ def test_optimize_depth_parity_config0(shading):
     d_gpu, n_gpu, _ = _run(sc, oref.INTEGRATION_LIB_PATH, shading)
     # the patched build links the very libsmvs_b200.so api.lib() has loaded:
     # its kernels bumped the process-wide launch counter
-    assert api.lib().smvsb_global_launch_count() - before > 100
+    assert api.lib().smvsb_global_launch_count() - before > 20
     assert np.array_equal(d_cpu > 0, d_gpu > 0)
     m = d_cpu > 0
     assert m.mean() > 0.5
