@@ -1,0 +1,1372 @@
+/*
+ * oracle/oracle_port.cc -- plain C++ restatement of the SMVS hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle/__init__.py). No MVE, no reference
+ * headers, no SIMD: scalar loops that follow the reference function by
+ * function (every function cites the file:line it restates). It is pinned
+ * (tests/test_known_answers.py, tests/test_oracle_port.py) against
+ *   - the reference's own unit-test assertions, and
+ *   - the outputs of oracle/_ref (the reference's sources compiled verbatim),
+ * and exists so that a checker can be built where /root/reference is absent.
+ * Parity caveat shared with oracle/_ref: mve::Image::linear_at semantics are
+ * restated from memory of MVE (clamped coordinates, fp32 weights, +0.5
+ * rounding for bytes) -- "unpinned" at that seam.
+ *
+ * Deliberately written in the reference's formulation (16-column Jacobian
+ * rows, rank-1 updates, std::map block assembly, O(D^2) SGM minimum), NOT in
+ * the restructured form the CUDA kernels use, so it is an independent check.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <vector>
+
+namespace {
+
+double const R_FACTOR = 1e-4;   /* lib/gauss_newton_step.cc:17 */
+
+/* lib/bicubic_patch.cc:20-38 */
+double const coefficient_matrix[256] = {
+    1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    -3, 3, 0, 0, -2, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    2, -2, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0,
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0,
+    0, 0, 0, 0, 0, 0, 0, 0, -3, 3, 0, 0, -2, -1, 0, 0,
+    0, 0, 0, 0, 0, 0, 0, 0, 2, -2, 0, 0, 1, 1, 0, 0,
+    -3, 0, 3, 0, 0, 0, 0, 0, -2, 0, -1, 0, 0, 0, 0, 0,
+    0, 0, 0, 0, -3, 0, 3, 0, 0, 0, 0, 0, -2, 0, -1, 0,
+    9, -9, -9, 9, 6, 3, -6, -3, 6, -6, 3, -3, 4, 2, 2, 1,
+    -6, 6, 6, -6, -3, -3, 3, 3, -4, 4, -2, 2, -2, -2, -1, -1,
+    2, 0, -2, 0, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0,
+    0, 0, 0, 0, 2, 0, -2, 0, 0, 0, 0, 0, 1, 0, 1, 0,
+    -6, 6, 6, -6, -4, -2, 4, 2, -3, 3, -3, 3, -2, -1, -2, -1,
+    4, -4, -4, 4, 2, 2, -2, -2, 2, -2, 2, -2, 1, 1, 1, 1
+};
+
+/* ------------------------------------------------------------------ */
+/* BicubicPatch                                                       */
+/* ------------------------------------------------------------------ */
+
+/* nodes16: 4 nodes (n00, n10, n01, n11) x (f, dx, dy, dxy).
+ * compute_coefficients, lib/bicubic_patch.cc:56-86. */
+void
+patch_coefficients (double const* nodes16, double coeffs[4][4])
+{
+    double x[16];
+    for (int c = 0; c < 4; ++c)
+        for (int n = 0; n < 4; ++n)
+            x[4 * c + n] = nodes16[n * 4 + c];
+    double a[16];
+    for (int r = 0; r < 16; ++r)
+    {
+        double s = 0.0;
+        for (int k = 0; k < 16; ++k)
+            s += coefficient_matrix[r * 16 + k] * x[k];
+        a[r] = s;
+    }
+    for (int k = 0, j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i, ++k)
+            coeffs[i][j] = a[k];
+}
+
+/* evaluate_f/dx/dy/dxy/dxx/dyy, lib/bicubic_patch.cc:121-187 */
+void
+patch_evaluate (double const coeffs[4][4], double px, double py, double* out6)
+{
+    double ex[4] = { 1.0, px, px * px, px * px * px };
+    double ey[4] = { 1.0, py, py * py, py * py * py };
+    double f = 0, dx = 0, dy = 0, dxy = 0, dxx = 0, dyy = 0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            f += coeffs[i][j] * ex[i] * ey[j];
+    for (int i = 1; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            dx += coeffs[i][j] * i * ex[i - 1] * ey[j];
+    for (int i = 2; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            dxx += coeffs[i][j] * i * (i - 1) * ex[i - 2] * ey[j];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 1; j < 4; ++j)
+            dy += coeffs[i][j] * ex[i] * j * ey[j - 1];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 2; j < 4; ++j)
+            dyy += coeffs[i][j] * ex[i] * j * (j - 1) * ey[j - 2];
+    for (int i = 1; i < 4; ++i)
+        for (int j = 1; j < 4; ++j)
+            dxy += coeffs[i][j] * i * ex[i - 1] * j * ey[j - 1];
+    out6[0] = f; out6[1] = dx; out6[2] = dy; out6[3] = dxy;
+    out6[4] = dxx; out6[5] = dyy;
+}
+
+/* node_deriv + node_derivatives, lib/bicubic_patch.cc:258-316; out[96] =
+ * 4 nodes x [d_f(4) d_dx(4) d_dy(4) d_dxy(4) d_dxx(4) d_dyy(4)]. patchsize
+ * > 0 applies the 1/ps, 1/ps^2 scaling of :318-340 / lib/surface.cc:929-955. */
+void
+node_derivatives (double px, double py, double patchsize, double* out)
+{
+    double x[4] = { 1.0, px, px * px, px * px * px };
+    double y[4] = { 1.0, py, py * py, py * py * py };
+    std::fill(out, out + 96, 0.0);
+    for (int node = 0; node < 4; ++node)
+    {
+        double* d = out + 24 * node;
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j)
+                for (int c = 0; c < 4; ++c)
+                {
+                    double const m = coefficient_matrix[16 * (j * 4 + i)
+                        + 4 * c + node];
+                    d[0 + c] += m * x[i] * y[j];
+                    if (i > 0) d[4 + c] += m * i * x[i - 1] * y[j];
+                    if (j > 0) d[8 + c] += m * x[i] * j * y[j - 1];
+                    if (i > 0 && j > 0)
+                        d[12 + c] += m * i * x[i - 1] * j * y[j - 1];
+                    if (i > 1) d[16 + c] += m * i * (i - 1) * x[i - 2] * y[j];
+                    if (j > 1) d[20 + c] += m * x[i] * j * (j - 1) * y[j - 2];
+                }
+    }
+    if (patchsize > 0.0)
+    {
+        double const p2p = 1.0 / patchsize;
+        for (int node = 0; node < 4; ++node)
+        {
+            for (int i = 4; i < 24; ++i) out[24 * node + i] *= p2p;
+            for (int i = 12; i < 24; ++i) out[24 * node + i] *= p2p;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* Correspondence, lib/correspondence.cc                              */
+/* ------------------------------------------------------------------ */
+
+struct Corr
+{
+    double p, q, r, t[3], w, wp[2], a, b, d, d2;
+    double pp[2], qp[2], rp[2];
+
+    /* update, :20-44 */
+    void update (double const* M, double const* tt, double u, double v,
+        double w_, double wdx, double wdy)
+    {
+        t[0] = tt[0]; t[1] = tt[1]; t[2] = tt[2];
+        w = w_;
+        pp[0] = M[0]; pp[1] = M[1];
+        qp[0] = M[3]; qp[1] = M[4];
+        rp[0] = M[6]; rp[1] = M[7];
+        wp[0] = wdx; wp[1] = wdy;
+        p = M[0] * u + M[1] * v + M[2];
+        q = M[3] * u + M[4] * v + M[5];
+        r = M[6] * u + M[7] * v + M[8];
+        a = w * p + t[0];
+        b = w * q + t[1];
+        d = w * r + t[2];
+        d2 = d * d;
+    }
+    /* fill, :46-51 */
+    void fill (double* c) const { c[0] = a / d; c[1] = b / d; }
+    /* fill_jacobian, :88-100 */
+    void fill_jacobian (double* jac) const
+    {
+        jac[0] = (wp[0] * p + w * pp[0]) / d;
+        jac[2] = (wp[1] * p + w * pp[1]) / d;
+        jac[0] -= a * (wp[0] * r + w * rp[0]) / d2;
+        jac[2] -= a * (wp[1] * r + w * rp[1]) / d2;
+        jac[1] = (wp[0] * q + w * qp[0]) / d;
+        jac[3] = (wp[1] * q + w * qp[1]) / d;
+        jac[1] -= b * (wp[0] * r + w * rp[0]) / d2;
+        jac[3] -= b * (wp[1] * r + w * rp[1]) / d2;
+    }
+    /* fill_derivative, :74-86 (c_dn[16][2]) */
+    void fill_derivative (double const* dn, double* c_dn) const
+    {
+        double const du_w = (p * d - r * a) / d2;
+        double const dv_w = (q * d - r * b) / d2;
+        for (int n = 0; n < 4; ++n)
+            for (int i = 0; i < 4; ++i)
+            {
+                c_dn[(n * 4 + i) * 2 + 0] = du_w * dn[n * 24 + i];
+                c_dn[(n * 4 + i) * 2 + 1] = dv_w * dn[n * 24 + i];
+            }
+    }
+    /* fill_jacobian_derivative_grad, :102-187 (jac_dn[16][2]) */
+    void fill_jacobian_derivative_grad (double const* grad, double const* dn,
+        double* jac_dn) const
+    {
+        double const d4 = d2 * d2;
+        double const d_prime = 2.0 * d * r;
+        double du_a_temp[2], du_a_prime[2], du_b_prime[2], du_c[2];
+        double dv_a_temp[2], dv_a_prime[2], dv_b_prime[2], dv_c[2];
+        double const du_c_prime = p * t[2] - r * t[0];
+        double const dv_c_prime = q * t[2] - r * t[1];
+        double du_x[2], dv_x[2];
+        for (int k = 0; k < 2; ++k)
+        {
+            du_a_temp[k] = w * (pp[k] * r - p * rp[k]);
+            du_a_prime[k] = 2.0 * du_a_temp[k];
+            du_b_prime[k] = pp[k] * t[2] - rp[k] * t[0];
+            du_c[k] = wp[k] * du_c_prime;
+            dv_a_temp[k] = w * (qp[k] * r - q * rp[k]);
+            dv_a_prime[k] = 2.0 * dv_a_temp[k];
+            dv_b_prime[k] = qp[k] * t[2] - rp[k] * t[1];
+            dv_c[k] = wp[k] * dv_c_prime;
+            double const du_a_b_c = w * (du_a_temp[k] + du_b_prime[k]) + du_c[k];
+            double const dv_a_b_c = w * (dv_a_temp[k] + dv_b_prime[k]) + dv_c[k];
+            du_x[k] = (du_a_prime[k] + du_b_prime[k]) / d2
+                - du_a_b_c * d_prime / d4;
+            dv_x[k] = (dv_a_prime[k] + dv_b_prime[k]) / d2
+                - dv_a_b_c * d_prime / d4;
+        }
+        double const du_c_prime_d = du_c_prime / d2;
+        double const dv_c_prime_d = dv_c_prime / d2;
+        for (int n = 0; n < 4; ++n)
+            for (int i = 0; i < 4; ++i)
+            {
+                int const o = n * 24;
+                double const du0 = du_x[0] * dn[o + i], du1 = du_x[1] * dn[o + i];
+                double const dv0 = dv_x[0] * dn[o + i], dv1 = dv_x[1] * dn[o + i];
+                jac_dn[(n * 4 + i) * 2 + 0] =
+                    (du0 + du_c_prime_d * dn[o + 4 + i]) * grad[0]
+                    + (dv0 + dv_c_prime_d * dn[o + 4 + i]) * grad[1];
+                jac_dn[(n * 4 + i) * 2 + 1] =
+                    (du1 + du_c_prime_d * dn[o + 8 + i]) * grad[0]
+                    + (dv1 + dv_c_prime_d * dn[o + 8 + i]) * grad[1];
+            }
+    }
+};
+
+/* ------------------------------------------------------------------ */
+/* surfderiv, lib/surface_derivative.cc                               */
+/* ------------------------------------------------------------------ */
+
+/* fill_normal, :17-28 */
+void
+fill_normal (double x, double y, double inv_flen, double w, double dx,
+    double dy, double* n)
+{
+    double v[3] = { dx, -dy, (x * dx + y * dy + w) * inv_flen };
+    double const len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    n[0] = v[0] / len; n[1] = v[1] / len; n[2] = v[2] / len;
+}
+
+/* normal_derivative, :31-65 (deriv[48]) */
+void
+normal_derivative (double const* d_node, double x, double y, double f,
+    double w, double dx, double dy, double* deriv)
+{
+    double const f_sqr_inv = 1.0 / (f * f);
+    double const a = w + x * dx + y * dy;
+    double const t = dx * dx + dy * dy + a * a * f_sqr_inv;
+    double const n = std::sqrt(t);
+    for (int node = 0; node < 4; ++node)
+        for (int i = 0; i < 4; ++i)
+        {
+            double const* dn = d_node + 24 * node;
+            double const w_p = dn[i], dx_p = dn[4 + i], dy_p = dn[8 + i];
+            double const a_p = w_p + x * dx_p + y * dy_p;
+            double const t_p2 = dx * dx_p + dy * dy_p + f_sqr_inv * a * a_p;
+            double const n_p = t_p2 / n;
+            deriv[0 + node * 4 + i] = (dx_p * n - dx * n_p) / t;
+            deriv[16 + node * 4 + i] = (-dy_p * n + dy * n_p) / t;
+            deriv[32 + node * 4 + i] = (a_p * n - a * n_p) / (t * f);
+        }
+}
+
+/* normal_divergence, :69-107 (div[6]) */
+void
+normal_divergence (double x, double y, double f, double w, double dx,
+    double dy, double dxy, double dxx, double dyy, double* div)
+{
+    double const a = w + x * dx + y * dy;
+    double const ax = 2.0 * dx + x * dxx + y * dxy;
+    double const ay = 2.0 * dy + y * dyy + x * dxy;
+    double t = a / f;
+    t = t * t;
+    t += dx * dx + dy * dy;
+    double const n = std::sqrt(t);
+    double nx = dx * dxx + dy * dxy;
+    nx += (1.0 / (f * f)) * (w + x * dx + y * dy)
+        * (dx + dx + x * dxx + y * dxy);
+    nx /= n;
+    double ny = dx * dxy + dy * dyy;
+    ny += (1.0 / (f * f)) * (w + x * dx + y * dy)
+        * (dy + dy + x * dxy + y * dyy);
+    ny /= n;
+    div[0] = (dxx * n - dx * nx) / t;
+    div[1] = -((dxy * n - dy * nx) / t);
+    div[2] = (ax * n - a * nx) / (t * f);
+    div[3] = (dxy * n - dx * ny) / t;
+    div[4] = -((dyy * n - dy * ny) / t);
+    div[5] = (ay * n - a * ny) / (t * f);
+}
+
+/* normal_divergence_deriv, :109-190 (full_deriv[96]) */
+void
+normal_divergence_deriv (double const* d_node, double x, double y, double f,
+    double w, double dx, double dy, double dxy, double dxx, double dyy,
+    double* full)
+{
+    double const f_sqr_inv = 1.0 / (f * f);
+    double const a = w + x * dx + y * dy;
+    double const ax = 2.0 * dx + x * dxx + y * dxy;
+    double const ay = 2.0 * dy + y * dyy + x * dxy;
+    double const a_f2 = a * f_sqr_inv;
+    double const t = dx * dx + dy * dy + a * a_f2;
+    double const n = std::sqrt(t);
+    double const b = dx * dxx + dy * dxy + a_f2 * ax;
+    double const c = dx * dxy + dy * dyy + a_f2 * ay;
+    double const nx = b / n, ny = c / n;
+    for (int node = 0; node < 4; ++node)
+        for (int i = 0; i < 4; ++i)
+        {
+            double const* dn = d_node + 24 * node;
+            double const w_p = dn[i], dx_p = dn[4 + i], dy_p = dn[8 + i];
+            double const dxy_p = dn[12 + i], dxx_p = dn[16 + i];
+            double const dyy_p = dn[20 + i];
+            double const a_p = w_p + x * dx_p + y * dy_p;
+            double const ax_p = 2.0 * dx_p + x * dxx_p + y * dxy_p;
+            double const ay_p = 2.0 * dy_p + y * dyy_p + x * dxy_p;
+            double const t_p2 = dx * dx_p + dy * dy_p + f_sqr_inv * a * a_p;
+            double const n_p = t_p2 / n;
+            double const b_p = (dx_p * dxx + dx * dxx_p)
+                + (dy_p * dxy + dy * dxy_p)
+                + f_sqr_inv * (a_p * ax + a * ax_p);
+            double const c_p = (dx_p * dxy + dx * dxy_p)
+                + (dy_p * dyy + dy * dyy_p)
+                + f_sqr_inv * (a_p * ay + a * ay_p);
+            double const nx_p = (b_p * n - b * n_p) / t;
+            double const ny_p = (c_p * n - c * n_p) / t;
+            double const tt = t * t;
+            double const xx_p = ((dxx_p * n + dxx * n_p - dx_p * nx
+                - dx * nx_p) * t - (dxx * n - dx * nx) * t_p2 * 2.0) / tt;
+            double const yy_p = ((dyy_p * n + dyy * n_p - dy_p * ny
+                - dy * ny_p) * t - (dyy * n - dy * ny) * t_p2 * 2.0) / tt;
+            double const xy_p = ((dxy_p * n + dxy * n_p - dx_p * ny
+                - dx * ny_p) * t - (dxy * n - dx * ny) * t_p2 * 2.0) / tt;
+            double const yx_p = ((dxy_p * n + dxy * n_p - dy_p * nx
+                - dy * nx_p) * t - (dxy * n - dy * nx) * t_p2 * 2.0) / tt;
+            double const zx_p = ((ax_p * n + ax * n_p - a_p * nx - a * nx_p)
+                * t - (ax * n - a * nx) * t_p2 * 2.0) / (tt * f);
+            double const zy_p = ((ay_p * n + ay * n_p - a_p * ny - a * ny_p)
+                * t - (ay * n - a * ny) * t_p2 * 2.0) / (tt * f);
+            int const o = node * 4 + i;
+            full[0 + o] = xx_p;
+            full[16 + o] = -yx_p;
+            full[32 + o] = zx_p;
+            full[48 + o] = xy_p;
+            full[64 + o] = -yy_p;
+            full[80 + o] = zy_p;
+        }
+}
+
+/* ------------------------------------------------------------------ */
+/* spherical harmonics, lib/spherical_harmonics.h:62-201              */
+/* ------------------------------------------------------------------ */
+
+void
+sh_evaluate_4_band (double const* n, double* sh)
+{
+    double const x = n[0], y = n[1], z = n[2];
+    double const x2 = x * x, y2 = y * y, z2 = z * z;
+    sh[0] = 1.0; sh[1] = y; sh[2] = z; sh[3] = x;
+    sh[4] = x * y; sh[5] = y * z;
+    sh[6] = -x2 - y2 + 2.0 * z2;
+    sh[7] = x * z; sh[8] = x * x - y * y;
+    sh[9] = (3.0 * x2 - y2) * y;
+    sh[10] = x * y * z;
+    sh[11] = (4.0 * z2 - x2 - y2) * y;
+    sh[12] = (2.0 * z2 - 3.0 * x2 - 3.0 * y2) * z;
+    sh[13] = (4.0 * z2 - x2 - y2) * x;
+    sh[14] = (x2 - y2) * z;
+    sh[15] = (x2 - 3.0 * y2) * x;
+}
+
+void
+sh_derivative_4_band (double const* n, double* d)
+{
+    double const x = n[0], y = n[1], z = n[2];
+    double const x2 = x * x, y2 = y * y, z2 = z * z;
+    double const v[48] = {
+        0, 0, 0,   0, 1, 0,   0, 0, 1,   1, 0, 0,
+        y, x, 0,   0, z, y,   -2 * x, -2 * y, 4 * z,
+        z, 0, x,   2 * x, -2 * y, 0,
+        6 * x * y, 3 * (x2 - y2), 0,
+        y * z, x * z, x * y,
+        -2 * x * y, 4 * z2 - x2 - 3 * y2, 8 * y * z,
+        -6 * x * z, -6 * y * z, 6 * z2 - 3 * (x2 + y2),
+        4 * z2 - 3 * x2 - y2, -2 * x * y, 8 * x * z,
+        2 * x * z, -2 * y * z, x2 - y2,
+        3 * (x2 - y2), -6 * x * y, 0 };
+    std::copy(v, v + 48, d);
+}
+
+/* ------------------------------------------------------------------ */
+/* ldl_inverse, lib/ldl_decomposition.h:43-92                         */
+/* ------------------------------------------------------------------ */
+
+void
+ldl_inverse (double* A, int const size)
+{
+    std::vector<double> L(size * size, 0.0), D(size, 0.0);
+    for (int j = 0; j < size; ++j)
+    {
+        D[j] = A[j * size + j];
+        L[j * size + j] = 1.0;
+        for (int k = 0; k < j; ++k)
+            D[j] -= (L[j * size + k] * L[j * size + k]) * D[k];
+        if (D[j] == 0.0)
+            return;
+        for (int i = j + 1; i < size; ++i)
+        {
+            L[i * size + j] = A[i * size + j];
+            for (int k = 0; k < j; ++k)
+                L[i * size + j] -= L[i * size + k] * D[k] * L[j * size + k];
+            L[i * size + j] /= D[j];
+        }
+    }
+    for (int i = 0; i < size; ++i)
+        for (int j = i + 1; j < size; ++j)
+        {
+            double sum = 0.0;
+            for (int k = i; k < j; ++k)
+                sum -= L[j * size + k] * L[k * size + i];
+            L[j * size + i] = sum;
+        }
+    for (int i = 0; i < size; ++i)
+        D[i] = 1.0 / D[i];
+    std::fill(A, A + size * size, 0.0);
+    for (int r = 0; r < size; ++r)
+        for (int c1 = 0; c1 < size; ++c1)
+            for (int c2 = 0; c2 < size; ++c2)
+                A[c1 * size + c2] += L[r * size + c2] * L[r * size + c1] * D[r];
+}
+
+/* ------------------------------------------------------------------ */
+/* images                                                             */
+/* ------------------------------------------------------------------ */
+
+/* mve::Image<float>::linear_at (restated, see header) */
+float
+linear_at_f (float const* img, int w, int h, int c, float x, float y, int ch)
+{
+    x = std::max(0.0f, std::min(static_cast<float>(w - 1), x));
+    y = std::max(0.0f, std::min(static_cast<float>(h - 1), y));
+    int const fx = static_cast<int>(x), fy = static_cast<int>(y);
+    int const fx1 = std::min(fx + 1, w - 1), fy1 = std::min(fy + 1, h - 1);
+    float const w1 = x - static_cast<float>(fx), w0 = 1.0f - w1;
+    float const w3 = y - static_cast<float>(fy), w2 = 1.0f - w3;
+    float const v00 = img[(fy * w + fx) * c + ch];
+    float const v10 = img[(fy * w + fx1) * c + ch];
+    float const v01 = img[(fy1 * w + fx) * c + ch];
+    float const v11 = img[(fy1 * w + fx1) * c + ch];
+    return v00 * (w0 * w2) + v10 * (w1 * w2) + v01 * (w0 * w3)
+        + v11 * (w1 * w3);
+}
+
+uint8_t
+linear_at_u8 (uint8_t const* img, int w, int h, float x, float y)
+{
+    x = std::max(0.0f, std::min(static_cast<float>(w - 1), x));
+    y = std::max(0.0f, std::min(static_cast<float>(h - 1), y));
+    int const fx = static_cast<int>(x), fy = static_cast<int>(y);
+    int const fx1 = std::min(fx + 1, w - 1), fy1 = std::min(fy + 1, h - 1);
+    float const w1 = x - static_cast<float>(fx), w0 = 1.0f - w1;
+    float const w3 = y - static_cast<float>(fy), w2 = 1.0f - w3;
+    float const v = (float)img[fy * w + fx] * (w0 * w2)
+        + (float)img[fy * w + fx1] * (w1 * w2)
+        + (float)img[fy1 * w + fx] * (w0 * w3)
+        + (float)img[fy1 * w + fx1] * (w1 * w3) + 0.5f;
+    return static_cast<uint8_t>(v);
+}
+
+/* ------------------------------------------------------------------ */
+/* scene state                                                        */
+/* ------------------------------------------------------------------ */
+
+struct Block { double v[16]; Block() { std::fill(v, v + 16, 0.0); } };
+
+struct Port
+{
+    int w, h, n_sub;
+    double flen, inv_flen;
+    std::vector<float> main_grad, shading, shading_grad;
+    std::vector<int> sub_w, sub_h;
+    std::vector<std::vector<float> > sub_grad, sub_hess;
+    std::vector<double> Mi, ti;
+
+    int scale, ps, npx, npy, sx, sy;
+    std::vector<double> nodes;
+    std::vector<uint8_t> node_valid, patch_valid, vis_ids;
+    std::vector<uint32_t> vis_off;
+
+    /* system in the reference's BSC layout */
+    std::vector<double> g, Hvals, Pvals;
+    std::vector<uint64_t> Houter, Hinner, Pouter, Pinner;
+
+    int n_nodes () const { return (npx + 1) * (npy + 1); }
+    void node_ids (int patch, int* ids) const
+    {
+        /* Surface::fill_node_ids_for_patch, lib/surface.cc:286-295 */
+        int const idx = patch % npx, idy = patch / npx, ns = npx + 1;
+        ids[0] = idy * ns + idx; ids[1] = ids[0] + 1;
+        ids[2] = (idy + 1) * ns + idx; ids[3] = ids[2] + 1;
+    }
+    void patch_nodes16 (int patch, double* n16) const
+    {
+        int ids[4];
+        node_ids(patch, ids);
+        for (int n = 0; n < 4; ++n)
+            for (int c = 0; c < 4; ++c)
+                n16[n * 4 + c] = nodes[ids[n] * 4 + c];
+    }
+};
+
+int
+sampling_for_scale (int scale)
+{
+    int s = 4;
+    if (scale < 5) s = 2;
+    if (scale < 3) s = 1;
+    return s;
+}
+
+/* SurfacePatch::fill_values_at_pixels sample order, lib/surface_patch.cc:
+ * 86-119: pid steps by `sub`, rows that are not multiples of `sub` skipped. */
+void
+sample_pids (int size, int sub, std::vector<int>* pids)
+{
+    pids->clear();
+    for (int pid = 0; pid < size * size;)
+    {
+        pids->push_back(pid);
+        if (sub > 1)
+        {
+            pid += sub;
+            if ((pid / size) % sub == 1)
+                pid += size * (sub - 1);
+        }
+        else
+            pid += 1;
+    }
+}
+
+/* GaussNewtonStep::construct, lib/gauss_newton_step.cc:33-143, with
+ * jacobian_entries_for_patch (:145-244) and
+ * fill_gradient_and_hessian_entries (:246-518, scalar branch :334-383). */
+void
+gn_construct (Port& P, uint8_t const* active, double const* light,
+    double regularization, double light_surf_reg)
+{
+    int const nn = P.n_nodes();
+    std::size_t const num_params = static_cast<std::size_t>(nn) * 4;
+    int const ps = P.ps;
+    int const sampling = sampling_for_scale(P.scale);
+    std::vector<double> table(static_cast<std::size_t>(ps) * ps * 96);
+    for (int i = 0; i < ps * ps; ++i)
+        node_derivatives(((i % ps) + 0.5) / ps, ((i / ps) + 0.5) / ps,
+            static_cast<double>(ps), &table[i * 96]);
+    std::vector<int> pids;
+    sample_pids(ps, sampling, &pids);
+
+    P.g.assign(num_params, 0.0);
+    std::map<std::size_t, Block> blocks;
+    std::vector<double> jac_entries, j_grad;
+
+    for (int patch = 0; patch < P.npx * P.npy; ++patch)
+    {
+        if (!P.patch_valid[patch])
+            continue;
+        int ids[4];
+        P.node_ids(patch, ids);
+        if (!active[ids[0]] && !active[ids[1]] && !active[ids[2]]
+            && !active[ids[3]])
+            continue;
+
+        double sub_g[16], sub_h[256];
+        std::fill(sub_g, sub_g + 16, 0.0);
+        std::fill(sub_h, sub_h + 256, 0.0);
+        double n16[16], coeffs[4][4];
+        P.patch_nodes16(patch, n16);
+        patch_coefficients(n16, coeffs);
+        uint32_t const v0 = P.vis_off[patch];
+        int const num_subs = static_cast<int>(P.vis_off[patch + 1] - v0);
+        jac_entries.assign(static_cast<std::size_t>(num_subs) * 32, 0.0);
+        j_grad.assign(static_cast<std::size_t>(num_subs) * 2, 0.0);
+        int const px0 = P.sx + (patch % P.npx) * ps;
+        int const py0 = P.sy + (patch / P.npx) * ps;
+
+        for (std::size_t s = 0; s < pids.size(); ++s)
+        {
+            int const pid = pids[s];
+            int const i = pid % ps, j = pid / ps;
+            double const pixx = i + px0, pixy = j + py0;
+            double e[6];
+            patch_evaluate(coeffs, (i + 0.5) / ps, (j + 0.5) / ps, e);
+            double const depth = e[0];
+            double const ddx = e[1] / ps, ddy = e[2] / ps;
+            double const d2xy = e[3] / (ps * ps), d2xx = e[4] / (ps * ps);
+            double const d2yy = e[5] / (ps * ps);
+            std::size_t const pix = static_cast<std::size_t>(pixy) * P.w
+                + static_cast<std::size_t>(pixx);
+            double const gm[2] = { P.main_grad[pix * 2], P.main_grad[pix * 2 + 1] };
+            double const* dn00 = &table[pid * 96];
+
+            for (int jn = 0; jn < num_subs; ++jn)
+            {
+                int const sub = P.vis_ids[v0 + jn];
+                Corr C;
+                C.update(&P.Mi[sub * 9], &P.ti[sub * 3], pixx + 0.5,
+                    pixy + 0.5, depth, ddx, ddy);
+                double proj[2], jac[4];
+                C.fill(proj);
+                C.fill_jacobian(jac);
+                proj[0] -= 0.5; proj[1] -= 0.5;
+                float const* sg = P.sub_grad[sub].data();
+                float const* sh = P.sub_hess[sub].data();
+                int const sw = P.sub_w[sub], shh = P.sub_h[sub];
+                double gs[2], hs[4];
+                gs[0] = linear_at_f(sg, sw, shh, 2, (float)proj[0], (float)proj[1], 0);
+                gs[1] = linear_at_f(sg, sw, shh, 2, (float)proj[0], (float)proj[1], 1);
+                hs[0] = linear_at_f(sh, sw, shh, 3, (float)proj[0], (float)proj[1], 0);
+                hs[1] = linear_at_f(sh, sw, shh, 3, (float)proj[0], (float)proj[1], 1);
+                hs[2] = hs[1];
+                hs[3] = linear_at_f(sh, sw, shh, 3, (float)proj[0], (float)proj[1], 2);
+                j_grad[jn * 2 + 0] = jac[0] * gs[0] + jac[1] * gs[1];
+                j_grad[jn * 2 + 1] = jac[2] * gs[0] + jac[3] * gs[1];
+                double c_dn[32], jac_dn[32];
+                C.fill_derivative(dn00, c_dn);
+                C.fill_jacobian_derivative_grad(gs, dn00, jac_dn);
+                double const jh[4] = {
+                    jac[0] * hs[0] + jac[1] * hs[2], jac[0] * hs[1] + jac[1] * hs[3],
+                    jac[2] * hs[0] + jac[3] * hs[2], jac[2] * hs[1] + jac[3] * hs[3] };
+                for (int col = 0; col < 16; ++col)
+                {
+                    jac_entries[(jn * 16 + col) * 2 + 0] = jac_dn[col * 2]
+                        + jh[0] * c_dn[col * 2] + jh[1] * c_dn[col * 2 + 1];
+                    jac_entries[(jn * 16 + col) * 2 + 1] = jac_dn[col * 2 + 1]
+                        + jh[2] * c_dn[col * 2] + jh[3] * c_dn[col * 2 + 1];
+                }
+            }
+
+            double div[6], div_deriv[96], normal_deriv[48];
+            double basic = 0.0;
+            double const x = pixx + 0.5 - static_cast<double>(P.w) / 2.0;
+            double const y = pixy + 0.5 - static_cast<double>(P.h) / 2.0;
+            if (regularization > 0.0)
+            {
+                basic = regularization * 0.005
+                    / std::max(0.03, std::abs(gm[0]) + std::abs(gm[1]));
+                normal_divergence(x, y, P.flen, depth, ddx, ddy, d2xy, d2xx,
+                    d2yy, div);
+                normal_divergence_deriv(dn00, x, y, P.flen, depth, ddx, ddy,
+                    d2xy, d2xx, d2yy, div_deriv);
+                normal_derivative(dn00, x, y, P.flen, depth, ddx, ddy,
+                    normal_deriv);
+            }
+
+            /* photometric terms (scalar branch) */
+            for (int jn = 0; jn < num_subs; ++jn)
+            {
+                double diff[2], wt[2];
+                for (int k = 0; k < 2; ++k)
+                {
+                    diff[k] = j_grad[jn * 2 + k] - gm[k];
+                    wt[k] = 1.0 / (R_FACTOR + std::abs(diff[k]));
+                }
+                double const* je = &jac_entries[jn * 32];
+                for (int col = 0; col < 16; ++col)
+                {
+                    sub_g[col] += diff[0] * wt[0] * je[col * 2]
+                        + diff[1] * wt[1] * je[col * 2 + 1];
+                    for (int col2 = col; col2 < 16; ++col2)
+                        sub_h[col * 16 + col2] +=
+                            je[col * 2] * wt[0] * je[col2 * 2]
+                            + je[col * 2 + 1] * wt[1] * je[col2 * 2 + 1];
+                }
+                for (int j2 = jn + 1; j2 < num_subs; ++j2)
+                {
+                    double sd[2], sw2[2];
+                    for (int k = 0; k < 2; ++k)
+                    {
+                        sd[k] = j_grad[jn * 2 + k] - j_grad[j2 * 2 + k];
+                        sw2[k] = 1.0 / (R_FACTOR + std::abs(sd[k]));
+                    }
+                    double const* j2e = &jac_entries[j2 * 32];
+                    for (int col = 0; col < 16; ++col)
+                    {
+                        double const jace0 = (je[col * 2] - j2e[col * 2]) * sw2[0];
+                        double const jace1 = (je[col * 2 + 1] - j2e[col * 2 + 1])
+                            * sw2[1];
+                        sub_g[col] += jace0 * sd[0] + jace1 * sd[1];
+                        for (int col2 = col; col2 < 16; ++col2)
+                            sub_h[col * 16 + col2] +=
+                                jace0 * (je[col2 * 2] - j2e[col2 * 2])
+                                + jace1 * (je[col2 * 2 + 1] - j2e[col2 * 2 + 1]);
+                    }
+                }
+            }
+            if (regularization <= 0.0)
+                continue;
+
+            double const num_diffs = (num_subs * (num_subs + 1)) / 2;
+            basic *= num_diffs;
+            if (light == nullptr || light_surf_reg > 0.0)
+            {
+                double geom_weight = 1.0;
+                if (light != nullptr)
+                    geom_weight *= light_surf_reg / 100;
+                for (int v = 0; v < 6; ++v)
+                {
+                    double const weight = geom_weight
+                        / (R_FACTOR + std::abs(div[v]));
+                    for (int col = 0; col < 16; ++col)
+                    {
+                        sub_g[col] += div_deriv[16 * v + col] * div[v] * basic
+                            * weight;
+                        for (int col2 = col; col2 < 16; ++col2)
+                            sub_h[col * 16 + col2] += div_deriv[v * 16 + col]
+                                * div_deriv[v * 16 + col2] * basic * weight;
+                    }
+                }
+                if (light == nullptr)
+                    continue;
+            }
+
+            /* shading term, :419-515 */
+            double normal[3], sh_d[48], sh[16];
+            fill_normal(x, y, P.inv_flen, depth, ddx, ddy, normal);
+            sh_derivative_4_band(normal, sh_d);
+            sh_evaluate_4_band(normal, sh);
+            double shading = 0.0;
+            for (int l = 0; l < 16; ++l) shading += light[l] * sh[l];
+            double lig[2] = { P.shading_grad[pix * 2], P.shading_grad[pix * 2 + 1] };
+            double const liv = P.shading[pix];
+            double const shading_weight = 0.001 * num_diffs
+                / (R_FACTOR + std::abs(lig[0]) + std::abs(lig[1]));
+            if (std::sqrt(lig[0] * lig[0] + lig[1] * lig[1]) < 1e-10)
+                continue;
+            if (shading * shading < 1e-10 || liv * liv < 1e-10)
+                continue;
+            double sgrad[2] = { 0.0, 0.0 };
+            for (int l = 1; l < 16; ++l)
+            {
+                sgrad[0] += light[l] * (sh_d[l * 3] * div[0]
+                    + sh_d[l * 3 + 1] * div[1] + sh_d[l * 3 + 2] * div[2]);
+                sgrad[1] += light[l] * (sh_d[l * 3] * div[3]
+                    + sh_d[l * 3 + 1] * div[4] + sh_d[l * 3 + 2] * div[5]);
+            }
+            double const render[2] = { sgrad[0] / shading, sgrad[1] / shading };
+            lig[0] *= 1.0 / liv; lig[1] *= 1.0 / liv;
+            double const err[2] = { render[0] - lig[0], render[1] - lig[1] };
+            double rd[32];
+            for (int col = 0; col < 16; ++col)
+            {
+                double sd = 0.0, gd0 = 0.0, gd1 = 0.0;
+                for (int l = 1; l < 16; ++l)
+                {
+                    sd += light[l] * (sh_d[l * 3] * normal_deriv[col]
+                        + sh_d[l * 3 + 1] * normal_deriv[16 + col]
+                        + sh_d[l * 3 + 2] * normal_deriv[32 + col]);
+                    gd0 += light[l] * (sh_d[l * 3] * div_deriv[col]
+                        + sh_d[l * 3 + 1] * div_deriv[16 + col]
+                        + sh_d[l * 3 + 2] * div_deriv[32 + col]);
+                    gd1 += light[l] * (sh_d[l * 3] * div_deriv[48 + col]
+                        + sh_d[l * 3 + 1] * div_deriv[64 + col]
+                        + sh_d[l * 3 + 2] * div_deriv[80 + col]);
+                }
+                rd[col * 2] = (gd0 * shading - sgrad[0] * sd)
+                    / (shading * shading);
+                rd[col * 2 + 1] = (gd1 * shading - sgrad[1] * sd)
+                    / (shading * shading);
+            }
+            double const w0 = shading_weight / (R_FACTOR + std::abs(err[0]));
+            double const w1 = shading_weight / (R_FACTOR + std::abs(err[1]));
+            for (int col = 0; col < 16; ++col)
+            {
+                sub_g[col] += err[0] * rd[col * 2] * w0
+                    + err[1] * rd[col * 2 + 1] * w1;
+                for (int col2 = col; col2 < 16; ++col2)
+                    sub_h[col * 16 + col2] += rd[col * 2] * rd[col2 * 2] * w0
+                        + rd[col * 2 + 1] * rd[col2 * 2 + 1] * w1;
+            }
+        }
+
+        /* scatter, :88-121 */
+        for (int node = 0; node < 4; ++node)
+        {
+            if (!active[ids[node]]) continue;
+            for (int v = 0; v < 4; ++v)
+                P.g[ids[node] * 4 + v] += sub_g[node * 4 + v];
+        }
+        for (std::size_t n1 = 0; n1 < 16; ++n1)
+        {
+            if (!active[ids[n1 / 4]]) continue;
+            for (std::size_t n2 = n1; n2 < 16; ++n2)
+            {
+                if (!active[ids[n2 / 4]]) continue;
+                std::size_t const id1 = ids[n1 / 4] * num_params + ids[n2 / 4];
+                std::size_t const id2 = ids[n1 / 4] + num_params * ids[n2 / 4];
+                std::size_t const ox = n1 % 4, oy = n2 % 4;
+                blocks[id1].v[ox + 4 * oy] += sub_h[n1 * 16 + n2];
+                if (n1 != n2)
+                    blocks[id2].v[ox * 4 + oy] += sub_h[n1 * 16 + n2];
+            }
+        }
+    }
+
+    /* set_from_blocks + transpose = column-major block order, :123-142,
+     * lib/block_sparse_matrix.h:155-190,241-274 */
+    struct E { std::size_t row, col; Block const* b; };
+    std::vector<E> es;
+    for (auto const& kv : blocks)
+        es.push_back(E{ 4 * kv.first % num_params, 4 * kv.first / num_params,
+            &kv.second });
+    std::stable_sort(es.begin(), es.end(), [](E const& a, E const& b)
+        { return a.col != b.col ? a.col < b.col : a.row < b.row; });
+    P.Hvals.clear(); P.Hinner.clear(); P.Houter.assign(nn + 1, 0);
+    P.Pvals.clear(); P.Pinner.clear(); P.Pouter.assign(nn + 1, 0);
+    for (E const& e : es)
+    {
+        P.Houter[e.col / 4 + 1] += 1;
+        P.Hinner.push_back(e.row);
+        P.Hvals.insert(P.Hvals.end(), e.b->v, e.b->v + 16);
+        if (e.row == e.col)
+        {
+            P.Pouter[e.col / 4 + 1] += 1;
+            P.Pinner.push_back(e.row);
+            /* invert_blocks_inplace, block_sparse_matrix.h:300-316 */
+            double b[16];
+            std::copy(e.b->v, e.b->v + 16, b);
+            ldl_inverse(b, 4);
+            bool nan = false;
+            for (int i = 0; i < 16; ++i) nan = nan || std::isnan(b[i]);
+            if (nan) std::copy(e.b->v, e.b->v + 16, b);
+            P.Pvals.insert(P.Pvals.end(), b, b + 16);
+        }
+    }
+    for (int i = 0; i < nn; ++i)
+    {
+        P.Houter[i + 1] += P.Houter[i];
+        P.Pouter[i + 1] += P.Pouter[i];
+    }
+}
+
+/* BlockSparseMatrix::multiply, lib/block_sparse_matrix.h:276-298 */
+void
+bsm_multiply (std::vector<double> const& vals,
+    std::vector<uint64_t> const& outer, std::vector<uint64_t> const& inner,
+    std::vector<double> const& x, std::vector<double>* y)
+{
+    y->assign(x.size(), 0.0);
+    for (std::size_t i = 0; i + 1 < outer.size(); ++i)
+        for (uint64_t id = outer[i]; id < outer[i + 1]; ++id)
+        {
+            std::size_t ret_id = inner[id];
+            int bid = 0;
+            for (int br = 0; br < 4; ++br, ++ret_id)
+                for (int bc = 0; bc < 4; ++bc)
+                    (*y)[ret_id] += vals[id * 16 + bid++] * x[i * 4 + bc];
+        }
+}
+
+double
+dot (std::vector<double> const& a, std::vector<double> const& b)
+{
+    double s = 0.0;
+    for (std::size_t i = 0; i < a.size(); ++i) s += a[i] * b[i];
+    return s;
+}
+
+/* ConjugateGradient::solve, lib/conjugate_gradient.h:72-202 (b = -g) */
+void
+cg_solve (Port const& P, int max_iter, double err_tol, double q_tol,
+    std::vector<double>* x, int* iters, int* info)
+{
+    std::size_t const n = P.g.size();
+    std::vector<double> b(n), r, d, z, Ad, tmp(n);
+    for (std::size_t i = 0; i < n; ++i) b[i] = -P.g[i];
+    if (err_tol < 0.0)
+        err_tol = std::sqrt(dot(P.g, P.g)) * 0.01;
+    x->assign(n, 0.0);
+    r = b;
+    bsm_multiply(P.Pvals, P.Pouter, P.Pinner, r, &z);
+    double r_dot_r = dot(z, r);
+    d = z;
+    for (std::size_t i = 0; i < n; ++i) tmp[i] = b[i] + r[i];
+    double Q0 = -1.0 * dot(*x, tmp);
+    int it = 1;
+    for (; it < max_iter; ++it)
+    {
+        bsm_multiply(P.Hvals, P.Houter, P.Hinner, d, &Ad);
+        double const alpha = r_dot_r / dot(d, Ad);
+        for (std::size_t i = 0; i < n; ++i) (*x)[i] += d[i] * alpha;
+        for (std::size_t i = 0; i < n; ++i) r[i] -= Ad[i] * alpha;
+        double new_r_dot_r = dot(r, r);
+        if (new_r_dot_r < err_tol) { *iters = it; *info = 0; return; }
+        for (std::size_t i = 0; i < n; ++i) tmp[i] = b[i] + r[i];
+        double const Q1 = -1.0 * dot(*x, tmp);
+        double const zeta = it * (Q1 - Q0) / Q1;
+        if (zeta < q_tol) { *iters = it; *info = 0; return; }
+        Q0 = Q1;
+        bsm_multiply(P.Pvals, P.Pouter, P.Pinner, r, &z);
+        new_r_dot_r = dot(z, r);
+        double const beta = new_r_dot_r / r_dot_r;
+        for (std::size_t i = 0; i < n; ++i) d[i] = z[i] + d[i] * beta;
+        r_dot_r = new_r_dot_r;
+    }
+    *iters = it; *info = 1;
+}
+
+/* fill_node_reprojections, lib/depth_optimizer.cc:647-677 */
+void
+node_reprojections (Port const& P, uint8_t const* active,
+    std::vector<int>* node_of, std::vector<double>* proj)
+{
+    node_of->clear(); proj->clear();
+    for (int patch = 0; patch < P.npx * P.npy; ++patch)
+    {
+        if (!P.patch_valid[patch]) continue;
+        int ids[4];
+        P.node_ids(patch, ids);
+        if (active[ids[0]] + active[ids[1]] + active[ids[2]] + active[ids[3]] == 0)
+            continue;
+        double n16[16], coeffs[4][4];
+        P.patch_nodes16(patch, n16);
+        patch_coefficients(n16, coeffs);
+        int const px0 = P.sx + (patch % P.npx) * P.ps;
+        int const py0 = P.sy + (patch / P.npx) * P.ps;
+        for (uint32_t k = P.vis_off[patch]; k < P.vis_off[patch + 1]; ++k)
+            for (int pid = 0; pid < P.ps * P.ps; ++pid)
+            {
+                int const i = pid % P.ps, j = pid / P.ps;
+                double e[6];
+                patch_evaluate(coeffs, (i + 0.5) / P.ps, (j + 0.5) / P.ps, e);
+                int const sub = P.vis_ids[k];
+                Corr C;
+                C.update(&P.Mi[sub * 9], &P.ti[sub * 3], i + px0, j + py0,
+                    e[0], 0.0, 0.0);
+                double pr[2];
+                C.fill(pr);
+                for (int n = 0; n < 4; ++n)
+                {
+                    node_of->push_back(ids[n]);
+                    proj->push_back(pr[0]);
+                    proj->push_back(pr[1]);
+                }
+            }
+    }
+}
+
+/* lib/depth_optimizer.cc:271-303 */
+void
+update_nodes (Port& P, std::vector<double> const& delta, double thresh,
+    bool full_opt, std::vector<uint8_t>* active, uint64_t* n_active,
+    double* mean_shift)
+{
+    std::vector<int> node_of, dummy;
+    std::vector<double> p1, p2;
+    node_reprojections(P, active->data(), &node_of, &p1);
+    for (int i = 0; i < P.n_nodes(); ++i)       /* Surface::update_nodes */
+        if (P.node_valid[i])
+            for (int c = 0; c < 4; ++c)
+                P.nodes[i * 4 + c] += delta[i * 4 + c];
+    node_reprojections(P, active->data(), &dummy, &p2);
+    double sum = 0.0;
+    std::vector<double> diffs(node_of.size());
+    for (std::size_t k = 0; k < node_of.size(); ++k)
+    {
+        double const ex = p1[2 * k] - p2[2 * k], ey = p1[2 * k + 1] - p2[2 * k + 1];
+        diffs[k] = std::sqrt(ex * ex + ey * ey);
+        sum += diffs[k];
+    }
+    if (mean_shift) *mean_shift = sum / static_cast<double>(node_of.size());
+    if (!full_opt)
+    {
+        std::fill(active->begin(), active->end(), 0);
+        for (std::size_t k = 0; k < node_of.size(); ++k)
+            if (diffs[k] > thresh)
+                (*active)[node_of[k]] = 1;
+    }
+    uint64_t cnt = 0;
+    for (uint8_t a : *active) cnt += (a == 1);
+    if (n_active) *n_active = cnt;
+}
+
+/* SGM, lib/sgm_stereo.cc (SSE branch semantics) -------------------- */
+
+void
+census_filter (uint8_t const* img, int w, int h, int c, uint64_t* out)
+{
+    /* :126-148 */
+    std::fill(out, out + static_cast<std::size_t>(w) * h * c, 0);
+    for (int x = 4; x < w - 5; ++x)
+        for (int y = 3; y < h - 4; ++y)
+            for (int d = 0; d < c; ++d)
+            {
+                uint8_t const thr = img[(static_cast<std::size_t>(y) * w + x) * c + d];
+                if (thr == 0) continue;
+                uint64_t census = 0;
+                for (int i = x - 4; i < x + 5; ++i)
+                    for (int j = y - 3; j < y + 4; ++j)
+                    {
+                        census *= 2;
+                        if (thr < img[(static_cast<std::size_t>(j) * w + i) * c + d])
+                            census += 1;
+                    }
+                out[(static_cast<std::size_t>(y) * w + x) * c + d] = census;
+            }
+}
+
+} /* namespace */
+
+extern "C" {
+
+/* ---- unit-level entry points (same signatures as oracle/ref_driver.cc) -- */
+
+void
+port_bicubic_eval (double const* nodes16, double x, double y, double* out)
+{
+    double c[4][4];
+    patch_coefficients(nodes16, c);
+    patch_evaluate(c, x, y, out);
+}
+
+void
+port_bicubic_node_derivatives (double x, double y, double patchsize, double* out)
+{
+    node_derivatives(x, y, patchsize, out);
+}
+
+void
+port_correspondence (double const* M9, double const* t3, double u, double v,
+    double w, double wx, double wy, double const* grad2, double const* dn96,
+    double* proj, double* jac, double* c_dn, double* jac_dn, double* depth)
+{
+    Corr C;
+    C.update(M9, t3, u, v, w, wx, wy);
+    C.fill(proj);
+    C.fill_jacobian(jac);
+    C.fill_derivative(dn96, c_dn);
+    C.fill_jacobian_derivative_grad(grad2, dn96, jac_dn);
+    *depth = C.d;
+}
+
+void
+port_surface_derivatives (double const* dn96, double x, double y, double f,
+    double w, double dx, double dy, double dxy, double dxx, double dyy,
+    double* normal, double* div, double* div_deriv, double* normal_deriv)
+{
+    fill_normal(x, y, 1.0 / f, w, dx, dy, normal);
+    normal_divergence(x, y, f, w, dx, dy, dxy, dxx, dyy, div);
+    normal_divergence_deriv(dn96, x, y, f, w, dx, dy, dxy, dxx, dyy, div_deriv);
+    normal_derivative(dn96, x, y, f, w, dx, dy, normal_deriv);
+}
+
+void
+port_sh_4band (double const* normal, double* sh16, double* deriv48)
+{
+    sh_evaluate_4_band(normal, sh16);
+    sh_derivative_4_band(normal, deriv48);
+}
+
+void
+port_ldl_inverse (double* A, int n)
+{
+    ldl_inverse(A, n);
+}
+
+/* ---- path-level entry points ------------------------------------------- */
+
+void*
+port_create (int w, int h, double flen, double inv_flen,
+    float const* main_grad, float const* shading, float const* shading_grad,
+    int n_sub, int const* sub_w, int const* sub_h,
+    float const* const* sub_grad, float const* const* sub_hess,
+    double const* Mi, double const* ti)
+{
+    Port* P = new Port();
+    P->w = w; P->h = h; P->flen = flen; P->inv_flen = inv_flen;
+    P->n_sub = n_sub;
+    std::size_t const np = static_cast<std::size_t>(w) * h;
+    P->main_grad.assign(main_grad, main_grad + np * 2);
+    if (shading)
+    {
+        P->shading.assign(shading, shading + np);
+        P->shading_grad.assign(shading_grad, shading_grad + np * 2);
+    }
+    for (int k = 0; k < n_sub; ++k)
+    {
+        std::size_t const n = static_cast<std::size_t>(sub_w[k]) * sub_h[k];
+        P->sub_w.push_back(sub_w[k]); P->sub_h.push_back(sub_h[k]);
+        P->sub_grad.emplace_back(sub_grad[k], sub_grad[k] + n * 2);
+        P->sub_hess.emplace_back(sub_hess[k], sub_hess[k] + n * 3);
+    }
+    P->Mi.assign(Mi, Mi + 9 * n_sub);
+    P->ti.assign(ti, ti + 3 * n_sub);
+    P->npx = P->npy = 0;
+    return P;
+}
+
+void
+port_destroy (void* p)
+{
+    delete static_cast<Port*>(p);
+}
+
+void
+port_set_surface (void* p, int scale, int npx, int npy, int sx, int sy,
+    double const* nodes, uint8_t const* node_valid, uint8_t const* patch_valid,
+    uint32_t const* vis_off, uint8_t const* vis_ids)
+{
+    Port* P = static_cast<Port*>(p);
+    P->scale = scale; P->ps = 1 << scale; P->npx = npx; P->npy = npy;
+    P->sx = sx; P->sy = sy;
+    int const nn = (npx + 1) * (npy + 1), np = npx * npy;
+    P->nodes.assign(nodes, nodes + nn * 4);
+    P->node_valid.assign(node_valid, node_valid + nn);
+    P->patch_valid.assign(patch_valid, patch_valid + np);
+    P->vis_off.assign(vis_off, vis_off + np + 1);
+    P->vis_ids.assign(vis_ids, vis_ids + vis_off[np]);
+}
+
+int64_t
+port_gn_construct (void* p, uint8_t const* active, double const* light16,
+    double regularization, double light_surf_regularization)
+{
+    Port* P = static_cast<Port*>(p);
+    gn_construct(*P, active, light16, regularization, light_surf_regularization);
+    return static_cast<int64_t>(P->Hinner.size());
+}
+
+void
+port_get_system_sizes (void* p, uint64_t* sizes)
+{
+    Port* P = static_cast<Port*>(p);
+    sizes[0] = P->g.size(); sizes[1] = P->Hinner.size();
+    sizes[2] = P->Pinner.size();
+}
+
+void
+port_get_system (void* p, double* g, double* Hvals, uint64_t* Houter,
+    uint64_t* Hinner, double* Pvals, uint64_t* Pouter, uint64_t* Pinner)
+{
+    Port* P = static_cast<Port*>(p);
+    if (g) std::copy(P->g.begin(), P->g.end(), g);
+    if (Hvals) std::copy(P->Hvals.begin(), P->Hvals.end(), Hvals);
+    if (Houter) std::copy(P->Houter.begin(), P->Houter.end(), Houter);
+    if (Hinner) std::copy(P->Hinner.begin(), P->Hinner.end(), Hinner);
+    if (Pvals) std::copy(P->Pvals.begin(), P->Pvals.end(), Pvals);
+    if (Pouter) std::copy(P->Pouter.begin(), P->Pouter.end(), Pouter);
+    if (Pinner) std::copy(P->Pinner.begin(), P->Pinner.end(), Pinner);
+}
+
+int
+port_cg_solve (void* p, int max_iter, double err_tol, double q_tol,
+    double* x_out, int* iters, int* info)
+{
+    Port* P = static_cast<Port*>(p);
+    std::vector<double> x;
+    cg_solve(*P, max_iter, err_tol, q_tol, &x, iters, info);
+    std::copy(x.begin(), x.end(), x_out);
+    return 0;
+}
+
+int
+port_update_nodes (void* p, double const* delta, double thresh, int full_opt,
+    uint8_t* active_inout, uint64_t* n_active, double* mean_shift)
+{
+    Port* P = static_cast<Port*>(p);
+    std::vector<uint8_t> act(active_inout, active_inout + P->n_nodes());
+    std::vector<double> d(delta, delta + P->n_nodes() * 4);
+    update_nodes(*P, d, thresh, full_opt != 0, &act, n_active, mean_shift);
+    std::copy(act.begin(), act.end(), active_inout);
+    return 0;
+}
+
+void
+port_get_nodes (void* p, double* nodes)
+{
+    Port* P = static_cast<Port*>(p);
+    std::copy(P->nodes.begin(), P->nodes.end(), nodes);
+}
+
+/* lib/depth_optimizer.cc:204-304. stats[8] as ref_newton_loop; times 0. */
+int
+port_newton_loop (void* p, double const* light16, double regularization,
+    double light_surf_regularization, int max_steps, double* stats)
+{
+    Port* P = static_cast<Port*>(p);
+    int const nn = P->n_nodes();
+    std::vector<uint8_t> active(P->node_valid.begin(), P->node_valid.end());
+    uint64_t num_initial = 0;
+    for (uint8_t a : active) num_initial += (a != 0);
+    uint64_t num_active = num_initial;
+    int const sampling = sampling_for_scale(P->scale);
+    double const spp = double(P->ps * P->ps) / (sampling * sampling);
+    double steps = 0, cg_iters = 0, pix = 0, nan = 0;
+    for (; steps < max_steps && num_active > num_initial / 20;)
+    {
+        steps += 1;
+        for (int patch = 0; patch < P->npx * P->npy; ++patch)
+        {
+            if (!P->patch_valid[patch]) continue;
+            int ids[4];
+            P->node_ids(patch, ids);
+            if (active[ids[0]] || active[ids[1]] || active[ids[2]] || active[ids[3]])
+                pix += spp;
+        }
+        gn_construct(*P, active.data(), light16, regularization,
+            light_surf_regularization);
+        std::vector<double> x;
+        int it = 0, info = 0;
+        cg_solve(*P, 200, -1.0, 1e-3, &x, &it, &info);
+        cg_iters += it;
+        if (std::isnan(x[0])) { nan = 1; break; }
+        update_nodes(*P, x, 0.15, false, &active, &num_active, nullptr);
+    }
+    (void)nn;
+    stats[0] = steps; stats[1] = cg_iters; stats[2] = pix;
+    stats[3] = stats[4] = stats[5] = 0.0;
+    stats[6] = (double)num_active; stats[7] = nan;
+    return 0;
+}
+
+/* SGMStereo::run_sgm, lib/sgm_stereo.cc:98-124 with create_cost_volume
+ * (:192-244), aggregate_sgm_costs (:429-667, SSE semantics) and
+ * depth_from_sgm_volume (:274-306). cost_out / sgm_out: w*h*D uint16. */
+int
+port_sgm (int w, int h, uint8_t const* main_img, int nw, int nh,
+    uint8_t const* neigh, float const* M, float const* t, float min_depth,
+    float max_depth, int D, int P1, int P2, float* depth_out,
+    uint16_t* cost_out, uint16_t* sgm_out)
+{
+    std::size_t const npix = static_cast<std::size_t>(w) * h;
+    std::vector<float> depths(D);
+    {
+        float inv_depth = 1.0f / max_depth;
+        float const inc = (1.0f / min_depth - inv_depth) / (D - 1);
+        for (int i = 0; i < D; ++i) { depths[i] = 1.0f / inv_depth; inv_depth += inc; }
+    }
+    /* warped_neighbors_for_depth, :150-190 */
+    std::vector<uint8_t> warped(npix * D, 0);
+    for (int x = 0; x < w; ++x)
+        for (int y = 0; y < h; ++y)
+        {
+            float const px = 0.5f + x, py = 0.5f + y;
+            float tp[3];
+            for (int r = 0; r < 3; ++r)
+            {
+                float s = 0.0f;
+                s += M[3 * r] * px; s += M[3 * r + 1] * py; s += M[3 * r + 2] * 1.f;
+                tp[r] = s;
+            }
+            for (int d = 0; d < D; ++d)
+            {
+                float q0 = tp[0] * depths[d] + t[0];
+                float q1 = tp[1] * depths[d] + t[1];
+                float const q2 = tp[2] * depths[d] + t[2];
+                if (q2 < 0) continue;
+                q0 /= q2; q1 /= q2; q0 -= 0.5f; q1 -= 0.5f;
+                if (q0 < 0 || q1 < 0 || q0 > nw - 1 || q1 > nh - 1) continue;
+                warped[(static_cast<std::size_t>(y) * w + x) * D + d] =
+                    linear_at_u8(neigh, nw, nh, q0, q1);
+            }
+        }
+    std::vector<uint64_t> main_census(npix), warped_census(npix * D);
+    census_filter(main_img, w, h, 1, main_census.data());
+    census_filter(warped.data(), w, h, D, warped_census.data());
+    std::vector<uint16_t> C(npix * D, 255);
+    for (std::size_t p = 0; p < npix; ++p)
+        for (int i = 0; i < D; ++i)
+        {
+            if (warped[p * D + i] == 0) continue;
+            C[p * D + i] = static_cast<uint8_t>(__builtin_popcountll(
+                main_census[p] ^ warped_census[p * D + i]));
+        }
+
+    /* aggregation */
+    std::vector<uint16_t> S(npix * D, 0);
+    std::vector<uint16_t> L0(npix * D), L1(npix * D), L2(npix * D);
+    auto copy_add = [&](std::vector<uint16_t>& L, std::size_t base) {
+        for (int i = 0; i < D; ++i)
+        {
+            L[base + i] = C[base + i];
+            S[base + i] = static_cast<uint16_t>(S[base + i] + C[base + i]);
+        }
+    };
+    auto path = [&](std::vector<uint16_t>& L, std::size_t base, std::size_t pbase) {
+        /* fill_path_cost_sse, :361-406, O(D^2) as in the reference */
+        uint16_t min_prev = 0xffff;
+        for (int i = 0; i < D; ++i) min_prev = std::min(min_prev, L[pbase + i]);
+        std::vector<uint16_t> upd(D);
+        for (int idx = 0; idx < D; ++idx)
+        {
+            uint16_t best = 0xffff;
+            for (int j = 0; j < D; ++j)
+            {
+                uint16_t c = static_cast<uint16_t>(L[pbase + j] + P2);
+                if (j == idx) c = L[pbase + j];
+                else if (j == idx - 1 || j == idx + 1)
+                    c = static_cast<uint16_t>(L[pbase + j] + P1);
+                best = std::min(best, c);
+            }
+            upd[idx] = best;
+        }
+        for (int i = 0; i < D; ++i)
+        {
+            uint16_t v = static_cast<uint16_t>(C[base + i] + upd[i]);
+            v = static_cast<uint16_t>(v - min_prev);
+            L[base + i] = v;
+            S[base + i] = static_cast<uint16_t>(S[base + i] + v);
+        }
+    };
+    auto B = [&](int x, int y) { return (static_cast<std::size_t>(y) * w + x) * D; };
+    /* left-to-right, right-to-left, :456-503 */
+    std::fill(L0.begin(), L0.end(), 0);
+    for (int y = 0; y < h; ++y) copy_add(L0, B(0, y));
+    for (int x = 1; x < w; ++x)
+        for (int y = 0; y < h; ++y) path(L0, B(x, y), B(x - 1, y));
+    std::fill(L0.begin(), L0.end(), 0);
+    for (int y = 0; y < h; ++y) copy_add(L0, B(w - 1, y));
+    for (int x = w - 2; x >= 0; --x)
+        for (int y = 0; y < h; ++y) path(L0, B(x, y), B(x + 1, y));
+    /* top-to-bottom with both diagonals, :505-548 */
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        int const y0 = pass == 0 ? 0 : h - 1, dy = pass == 0 ? 1 : -1;
+        std::fill(L0.begin(), L0.end(), 0);
+        std::fill(L1.begin(), L1.end(), 0);
+        std::fill(L2.begin(), L2.end(), 0);
+        for (int x = 0; x < w; ++x)
+        {
+            copy_add(L0, B(x, y0)); copy_add(L1, B(x, y0)); copy_add(L2, B(x, y0));
+        }
+        for (int y = 0; y < h; ++y) copy_add(L1, B(0, y));
+        for (int y = 0; y < h; ++y) copy_add(L2, B(w - 1, y));
+        for (int y = y0 + dy; y >= 0 && y < h; y += dy)
+            for (int x = 0; x < w; ++x)
+            {
+                if (x > 0) path(L1, B(x, y), B(x - 1, y - dy));
+                if (x < w - 1) path(L2, B(x, y), B(x + 1, y - dy));
+                path(L0, B(x, y), B(x, y - dy));
+            }
+    }
+    /* depth_from_sgm_volume */
+    for (std::size_t p = 0; p < npix; ++p)
+    {
+        uint16_t min_error = 0xffff;
+        int min_index = 0;
+        for (int i = 0; i < D; ++i)
+            if (S[p * D + i] < min_error) { min_error = S[p * D + i]; min_index = i; }
+        depth_out[p] = (min_index < 2 || main_img[p] < 25) ? 0.0f : depths[min_index];
+    }
+    if (cost_out) std::copy(C.begin(), C.end(), cost_out);
+    if (sgm_out) std::copy(S.begin(), S.end(), sgm_out);
+    return 0;
+}
+
+} /* extern "C" */

@@ -1,0 +1,93 @@
+"""Pins the plain restatement (oracle/oracle_port.cc) against the committed
+golden fixtures, which are outputs of the compiled-verbatim reference
+(tests/golden/make_golden.py), and against oracle/_ref run live."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import port as oport
+from oracle import ref as oref
+from smvs_b200 import synth
+
+pytestmark = pytest.mark.skipif(not oport.available(), reason="oracle port not built")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300))
+
+
+def scene_from_golden(G):
+    n = int(G["n_sub"])
+    P = oport.PortScene(G["main_grad"], [G[f"sub_grad{k}"] for k in range(n)],
+                        [G[f"sub_hess{k}"] for k in range(n)], G["Mi"], G["ti"],
+                        float(G["flen"]), float(G["inv_flen"]),
+                        G["shading"] if "shading" in G else None,
+                        G["shading_grad"] if "shading_grad" in G else None)
+    P.set_surface(int(G["scale"]), int(G["npx"]), int(G["npy"]), int(G["start_x"]),
+                  int(G["start_y"]), G["nodes"], G["node_valid"], G["patch_valid"],
+                  G["vis_off"], G["vis_ids"])
+    return P
+
+
+@pytest.mark.parametrize("fixture", ["gn_s2.npz", "gn_s4.npz"])
+def test_port_matches_reference_fixtures(fixture):
+    G = np.load(os.path.join(GOLD, fixture))
+    P = scene_from_golden(G)
+    for tag in G["variants"]:
+        light = G["light"] if tag in ("lit", "litR") else None
+        P.gn_construct(G[f"{tag}_active"], light, float(G["regularization"]),
+                       float(G[f"{tag}_lreg"]))
+        s = P.get_system()
+        assert np.array_equal(s["Houter"], G[f"{tag}_Houter"])
+        assert np.array_equal(s["Hinner"], G[f"{tag}_Hinner"])
+        assert np.array_equal(s["Pinner"], G[f"{tag}_Pinner"])
+        assert rel(s["g"], G[f"{tag}_g"]) < 1e-10
+        assert rel(s["Hvals"], G[f"{tag}_Hvals"]) < 1e-10
+        assert rel(s["Pvals"], G[f"{tag}_Pvals"]) < 1e-10
+        x, it, info = P.cg_solve()
+        assert it == int(G[f"{tag}_cg_iters"]) and info == int(G[f"{tag}_cg_info"])
+        assert rel(x, G[f"{tag}_x"]) < 1e-6   # CG amplifies 1e-13 input noise
+    P.gn_construct(G["full_active"], None, float(G["regularization"]), 0.0)
+    x, _, _ = P.cg_solve()
+    act, n_act, shift = P.update_nodes(x, G["full_active"])
+    assert np.array_equal(act, G["upd_active"]) and n_act == int(G["upd_n_active"])
+    assert abs(shift - float(G["upd_mean_shift"])) < 1e-9
+    assert rel(P.get_nodes(), G["upd_nodes"]) < 1e-10
+    P.close()
+
+
+def test_port_newton_loop_fixture():
+    G = np.load(os.path.join(GOLD, "gn_s4.npz"))
+    P = scene_from_golden(G)
+    st = P.newton_loop(None, float(G["regularization"]), 0.0)
+    assert st["newton_steps"] == int(G["loop_newton_steps"])
+    assert st["cg_iterations"] == int(G["loop_cg_iterations"])
+    assert st["pixel_iterations"] == float(G["loop_pixel_iterations"])
+    assert rel(P.get_nodes(), G["loop_nodes"]) < 1e-8
+    P.close()
+
+
+def test_port_sgm_fixture_bit_exact():
+    G = np.load(os.path.join(GOLD, "sgm.npz"))
+    r = oport.sgm(G["main"], G["neigh"], G["M"], G["t"], float(G["min_depth"]),
+                  float(G["max_depth"]), int(G["D"]))
+    assert np.array_equal(r["cost"], G["cost"].astype(np.uint16))
+    assert np.array_equal(r["sgm"], G["sgm"])
+    assert np.array_equal(r["depth"], G["depth"])
+
+
+@pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")
+def test_port_sgm_live_dark_regions():
+    sc = synth.make_scene(120, 90, 1, seed_index=30)
+    sc.images[0][20:40, 30:70] = 0
+    sc.images[1][50:70, 10:60] = 10
+    R = oref.RefScene(sc)
+    r = R.sgm_run(0, 1, 0, 32, 0.05, 30.0, volumes=True)
+    M, t = R.reprojection(0, 1, 120, 90, 120, 90)
+    p = oport.sgm(sc.images[0], sc.images[1], M, t, 0.05, 30.0, 32)
+    assert np.array_equal(p["cost"], r["cost"])
+    assert np.array_equal(p["sgm"], r["sgm"])
+    assert np.array_equal(p["depth"], r["depth"])
+    R.close()
