@@ -239,6 +239,16 @@ def run_product(args):
         torch.cuda.synchronize()
 
     wl = build_workload(WIDTH, HEIGHT, N_SUB, SCALE, shading=False, seed_index=rank)
+
+    def pin(a):
+        # page-locked host copies: the e2e arm copies from pinned memory
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy()
+
+    wl.main_grad = pin(wl.main_grad)
+    wl.sub_grads = [pin(a) for a in wl.sub_grads]
+    wl.sub_hess = [pin(a) for a in wl.sub_hess]
+    wl.nodes = pin(wl.nodes)
     ctx = api.Context(local)
     nodes_out = None
 

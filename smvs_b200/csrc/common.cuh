@@ -143,7 +143,7 @@ struct smvsb_ctx
     smvsb::DevBuf<double> light;        /* 16 */
 
     /* CG */
-    smvsb::DevBuf<double> x, r, d, z, Ad;
+    smvsb::DevBuf<double> x, r, d, d2, z, Ad;
     smvsb::DevBuf<double> cg_partials;
     smvsb::DevBuf<unsigned int> cg_sync;
     smvsb::DevBuf<double> cg_result;    /* iters, info, ... */

@@ -151,21 +151,26 @@ apply_delta_kernel (int n_nodes, uint8_t const* __restrict__ node_valid,
         nodes[i] += delta[i];
 }
 
-/* sums patch_shift (fixed order) and counts active nodes; one block. */
-__global__ void
+/* Stage 1: each block sums a fixed slice of patch_shift and of the active
+ * flags; stage 2 (one block) sums the per-block results in block order. Fixed
+ * grid -> deterministic. */
+constexpr int RED_BLOCKS = 128;
+
+__global__ void __launch_bounds__(256)
 update_reduce_kernel (int n_patches, double const* __restrict__ patch_shift,
     int n_nodes, uint8_t const* __restrict__ active,
-    double* __restrict__ out /* [0] sum, [1] count, [2] n_active */)
+    double* __restrict__ partial /* [RED_BLOCKS][3] */)
 {
     __shared__ double s_a[256], s_b[256], s_c[256];
     int const tid = threadIdx.x;
+    int const gid = blockIdx.x * 256 + tid, gstride = gridDim.x * 256;
     double a = 0.0, b = 0.0, c = 0.0;
-    for (int i = tid; i < n_patches; i += 256)
+    for (int i = gid; i < n_patches; i += gstride)
     {
         a += patch_shift[2 * i];
         b += patch_shift[2 * i + 1];
     }
-    for (int i = tid; i < n_nodes; i += 256)
+    for (int i = gid; i < n_nodes; i += gstride)
         c += (active[i] == 1) ? 1.0 : 0.0;
     s_a[tid] = a; s_b[tid] = b; s_c[tid] = c;
     __syncthreads();
@@ -181,9 +186,22 @@ update_reduce_kernel (int n_patches, double const* __restrict__ patch_shift,
     }
     if (tid == 0)
     {
-        out[0] = s_a[0];
-        out[1] = s_b[0];
-        out[2] = s_c[0];
+        partial[3 * blockIdx.x + 0] = s_a[0];
+        partial[3 * blockIdx.x + 1] = s_b[0];
+        partial[3 * blockIdx.x + 2] = s_c[0];
+    }
+}
+
+__global__ void
+update_reduce_final_kernel (int nblocks, double const* __restrict__ partial,
+    double* __restrict__ out /* [0] sum, [1] count, [2] n_active */)
+{
+    if (threadIdx.x < 3)
+    {
+        double v = 0.0;
+        for (int b = 0; b < nblocks; ++b)
+            v += partial[3 * b + threadIdx.x];
+        out[threadIdx.x] = v;
     }
 }
 
@@ -317,7 +335,7 @@ launch_update (smvsb_ctx* c, double thresh, bool full_opt,
     SurfaceDev const sf = surface_args(c);
     c->patch_shift.reserve(static_cast<size_t>(c->n_patches) * 2);
     c->active_new.reserve(c->n_nodes);
-    c->cg_result.reserve(4);
+    c->cg_result.reserve(16);
     CUDA_CHECK(cudaMemsetAsync(c->active_new.p, 0, c->n_nodes, c->stream));
     reproj_kernel<<<c->n_patches, UPD_THREADS, 0, c->stream>>>(sf, c->x.p,
         thresh, c->active_new.p, c->patch_shift.p);
@@ -332,10 +350,14 @@ launch_update (smvsb_ctx* c, double thresh, bool full_opt,
         CUDA_CHECK(cudaMemcpyAsync(c->active.p, c->active_new.p, c->n_nodes,
             cudaMemcpyDeviceToDevice, c->stream));
     }
-    update_reduce_kernel<<<1, 256, 0, c->stream>>>(c->n_patches,
-        c->patch_shift.p, c->n_nodes, c->active.p, c->cg_result.p);
+    c->light_partials.reserve(3 * RED_BLOCKS);
+    update_reduce_kernel<<<RED_BLOCKS, 256, 0, c->stream>>>(c->n_patches,
+        c->patch_shift.p, c->n_nodes, c->active.p, c->light_partials.p);
     CUDA_CHECK(cudaGetLastError());
-    smvsb::count_launches(c, 3);
+    update_reduce_final_kernel<<<1, 32, 0, c->stream>>>(RED_BLOCKS,
+        c->light_partials.p, c->cg_result.p);
+    CUDA_CHECK(cudaGetLastError());
+    smvsb::count_launches(c, 4);
     double res[3];
     CUDA_CHECK(cudaMemcpyAsync(res, c->cg_result.p, sizeof(res),
         cudaMemcpyDeviceToHost, c->stream));
