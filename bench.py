@@ -11,10 +11,11 @@ sample of one processed patch in one Newton step.
 
   value  pixel-iterations / device time of the loop (CUDA events on the
          library's stream, inputs resident in HBM)
-  e2e    the same loop through the C ABI from HOST buffers: smvsb_set_views +
-         smvsb_set_surface (H2D of all images and the surface) +
-         smvsb_newton_loop + smvsb_get_nodes (D2H), wall clock around the
-         calls with a device synchronize on both sides
+  e2e    the same loop through the C ABI from HOST buffers, every step:
+         smvsb_set_views_u8 (H2D of the 7 byte images from pinned memory +
+         StereoView::set_scale on the device) + smvsb_set_surface (H2D of nodes,
+         validity, visibility) + smvsb_newton_loop + smvsb_get_nodes (D2H),
+         wall clock around the calls with a device synchronize on both sides
 
 N > 1 (torchrun, one rank per GPU): reference views are independent units
 (app/smvsrecon.cc:658-733), so every rank refines its own view (seed = rank);
@@ -245,18 +246,25 @@ def run_product(args):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t.numpy()
 
-    wl.main_grad = pin(wl.main_grad)
-    wl.sub_grads = [pin(a) for a in wl.sub_grads]
-    wl.sub_hess = [pin(a) for a in wl.sub_hess]
+    wl.scene.images = [pin(a) for a in wl.scene.images]
     wl.nodes = pin(wl.nodes)
     ctx = api.Context(local)
     nodes_out = None
 
+    e2e_parts = np.zeros(4)
+
     def e2e_step():
-        wl.push_views(ctx)
+        t = [time.perf_counter()]
+        wl.push_views_u8(ctx)        # byte images; set_scale runs on the device
+        t.append(time.perf_counter())
         wl.push_surface(ctx)
+        t.append(time.perf_counter())
         st = ctx.newton_loop(None, REGULARIZATION, 0.0)
-        return st, ctx.get_nodes()
+        t.append(time.perf_counter())
+        nodes = ctx.get_nodes()
+        t.append(time.perf_counter())
+        e2e_parts[:] += np.diff(t)
+        return st, nodes
 
     def resident_step():
         ctx.set_nodes(wl.nodes)             # reset; not part of the timed loop
@@ -290,6 +298,7 @@ def run_product(args):
 
     # ---- end-to-end arm ---------------------------------------------------
     barrier()
+    e2e_parts[:] = 0.0
     t0 = time.perf_counter()
     pix_e2e = 0.0
     for _ in range(args.steps):
@@ -359,9 +368,11 @@ def run_product(args):
                                                      for x in t_split]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": wl.h2d_bytes(),
+                    "h2d_bytes_per_step": wl.h2d_bytes_u8(),
                     "d2h_bytes_per_step": int(nodes_out.nbytes),
-                    "ms_per_step": 1e3 * wall_e2e / max(args.steps, 1)},
+                    "ms_per_step": 1e3 * wall_e2e / max(args.steps, 1),
+                    "ms_set_views_set_surface_loop_get_nodes":
+                        [1e3 * float(x) / max(args.steps, 1) for x in e2e_parts]},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_base,

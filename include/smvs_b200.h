@@ -106,6 +106,23 @@ int smvsb_set_views (smvsb_ctx* ctx, int w, int h, double flen_px,
     const float* const* sub_hess, const double* Mi, const double* ti);
 
 /*
+ * Same as smvsb_set_views, but from the views' BYTE images: StereoView::
+ * set_scale (Gaussian blur with sigma = 0.12 * 2^scale + 0.2, then gradient
+ * and Hessian; lib/stereo_view.cc:24-46, 97-188) and, with with_shading != 0,
+ * StereoView::initialize_linear without gamma (:64-84) run on the device.
+ * Images are single-channel (luminance) uint8, w*h each. Bit-identical to the
+ * reference's CPU result, 20x less host-to-device traffic.
+ */
+int smvsb_set_views_u8 (smvsb_ctx* ctx, int scale, int w, int h,
+    double flen_px, double inv_flen, const uint8_t* main_img,
+    int with_shading, int n_sub, const int* sub_w, const int* sub_h,
+    const uint8_t* const* sub_img, const double* Mi, const double* ti);
+
+/* Parity-test access to the device-side images: view 0 = main (grad w*h*2,
+ * hess ignored), view k >= 1 = neighbour k-1 (grad, hess w*h*3). */
+int smvsb_debug_get_view (smvsb_ctx* ctx, int view, float* grad, float* hess);
+
+/*
  * The Surface and the per-patch visibility lists (DepthOptimizer::subsurfaces).
  *   scale, npx, npy, start_x, start_y   grid of lib/surface.cc:28-37: patch
  *       (idx, idy) has id idy*npx+idx, covers pixels start + id*2^scale;

@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(_HERE, "libsmvs_b200.so")
 
 EXPORTS = [
     "smvsb_create", "smvsb_destroy", "smvsb_last_error", "smvsb_version",
-    "smvsb_launch_count", "smvsb_global_launch_count", "smvsb_set_views", "smvsb_set_surface",
+    "smvsb_launch_count", "smvsb_global_launch_count", "smvsb_set_views",
+    "smvsb_set_views_u8", "smvsb_debug_get_view", "smvsb_set_surface",
     "smvsb_set_nodes", "smvsb_gn_construct", "smvsb_cg_solve",
     "smvsb_get_delta", "smvsb_set_delta", "smvsb_update_nodes",
     "smvsb_newton_loop", "smvsb_get_nodes", "smvsb_get_depth",
@@ -136,6 +137,34 @@ class Context:
             self._h, w, h, C.c_double(flen_px), C.c_double(inv_flen), _p(main_grad),
             _p(ms), _p(msg), n, sw, shh, gp, hp, _p(Mi), _p(ti)))
         self.w, self.h = w, h
+
+    def set_views_u8(self, scale, main_img, sub_imgs, Mi, ti, flen_px, inv_flen,
+                     with_shading=False):
+        """StereoView::set_scale on the device from the byte images."""
+        main_img = _u8(main_img)
+        h, w = main_img.shape
+        n = len(sub_imgs)
+        si = [_u8(a) for a in sub_imgs]
+        sw = (C.c_int * max(n, 1))(*[a.shape[1] for a in si])
+        shh = (C.c_int * max(n, 1))(*[a.shape[0] for a in si])
+        ip = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in si])
+        Mi, ti = _f64(Mi), _f64(ti)
+        self._check(lib().smvsb_set_views_u8(
+            self._h, int(scale), w, h, C.c_double(flen_px), C.c_double(inv_flen),
+            _p(main_img), int(with_shading), n, sw, shh, ip, _p(Mi), _p(ti)))
+        self.w, self.h = w, h
+        self._sub_shapes = [a.shape for a in si]
+
+    def debug_get_view(self, view):
+        if view == 0:
+            g = np.empty((self.h, self.w, 2), dtype=np.float32)
+            self._check(lib().smvsb_debug_get_view(self._h, 0, _p(g), None))
+            return g, None
+        hh, ww = self._sub_shapes[view - 1]
+        g = np.empty((hh, ww, 2), dtype=np.float32)
+        hs = np.empty((hh, ww, 3), dtype=np.float32)
+        self._check(lib().smvsb_debug_get_view(self._h, int(view), _p(g), _p(hs)))
+        return g, hs
 
     def set_surface(self, scale, npx, npy, start_x, start_y, nodes, node_valid,
                     patch_valid, vis_off, vis_ids):

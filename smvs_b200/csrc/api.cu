@@ -15,6 +15,12 @@
 
 namespace smvsb {
 void fill_basis_table (std::vector<double>& tab, int ps, int step);
+void device_set_scale (smvsb_ctx* c, uint8_t const* img_dev, int w, int h,
+    int scale, float* tmp_a, float* tmp_b, int mode, float* out_dev);
+void device_shading_inputs (smvsb_ctx* c, uint8_t const* img_dev, int w, int h,
+    float* shading_dev, float* shading_grad_dev);
+void device_unpack_texels (smvsb_ctx* c, float const* texels, int n,
+    float* grad, float* hess);
 std::string const& sgm_last_error (void);
 int sgm_run (int device, int w, int h, uint8_t const* main_lum, int nw, int nh,
     uint8_t const* neigh_lum, float const* M, float const* t,
@@ -312,7 +318,8 @@ smvsb_set_views (smvsb_ctx* ctx, int w, int h, double flen_px,
         std::vector<float const*> ptrs(std::max(n_sub, 1), nullptr);
         std::vector<int> dims(std::max(2 * n_sub, 2), 0);
         std::vector<double> mt(std::max(12 * n_sub, 12), 0.0);
-        smvsb::DevBuf<float> stage_g, stage_h;
+        smvsb::DevBuf<float>& stage_g = c->stage_a;
+        smvsb::DevBuf<float>& stage_h = c->stage_b;
         for (int k = 0; k < n_sub; ++k)
         {
             require(sub_w[k] > 0 && sub_h[k] > 0 && sub_grad[k]
@@ -336,6 +343,103 @@ smvsb_set_views (smvsb_ctx* ctx, int w, int h, double flen_px,
         CUDA_CHECK(cudaStreamSynchronize(c->stream));   /* staging buffers */
         c->have_views = true;
         c->have_system = false;
+    });
+}
+
+int
+smvsb_set_views_u8 (smvsb_ctx* ctx, int scale, int w, int h, double flen_px,
+    double inv_flen, const uint8_t* main_img, int with_shading, int n_sub,
+    const int* sub_w, const int* sub_h, const uint8_t* const* sub_img,
+    const double* Mi, const double* ti)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(w > 2 && h > 2 && main_img != nullptr, SMVSB_ERR_INVALID,
+            "main view missing");
+        require(scale >= 0 && scale <= 8, SMVSB_ERR_INVALID,
+            "scale out of range");
+        require(n_sub >= 0 && n_sub <= SMVSB_MAX_SUBS, SMVSB_ERR_INVALID,
+            "n_sub out of range (max 32)");
+        require(n_sub == 0 || (sub_w && sub_h && sub_img && Mi && ti),
+            SMVSB_ERR_INVALID, "neighbour arrays missing");
+        smvsb_ctx* c = ctx;
+        c->w = w; c->h = h; c->flen = flen_px; c->inv_flen = inv_flen;
+        size_t max_pix = static_cast<size_t>(w) * h;
+        for (int k = 0; k < n_sub; ++k)
+        {
+            require(sub_w[k] > 2 && sub_h[k] > 2 && sub_img[k],
+                SMVSB_ERR_INVALID, "neighbour image missing");
+            max_pix = std::max(max_pix, static_cast<size_t>(sub_w[k])
+                * sub_h[k]);
+        }
+        c->stage_u8.reserve(max_pix);
+        c->stage_a.reserve(max_pix);
+        c->stage_b.reserve(max_pix);
+        size_t const npix = static_cast<size_t>(w) * h;
+        c->main_grad.reserve(npix * 2);
+        upload(c, c->stage_u8, main_img, npix);
+        smvsb::device_set_scale(c, c->stage_u8.p, w, h, scale, c->stage_a.p,
+            c->stage_b.p, 0, c->main_grad.p);
+        c->have_shading = (with_shading != 0);
+        if (c->have_shading)
+        {
+            c->main_shading.reserve(npix);
+            c->main_shading_grad.reserve(npix * 2);
+            smvsb::device_shading_inputs(c, c->stage_u8.p, w, h,
+                c->main_shading.p, c->main_shading_grad.p);
+        }
+        c->n_sub = n_sub;
+        std::vector<float const*> ptrs(std::max(n_sub, 1), nullptr);
+        std::vector<int> dims(std::max(2 * n_sub, 2), 0);
+        std::vector<double> mt(std::max(12 * n_sub, 12), 0.0);
+        for (int k = 0; k < n_sub; ++k)
+        {
+            size_t const n = static_cast<size_t>(sub_w[k]) * sub_h[k];
+            smvsb::SubViewDev& sv = c->subs[k];
+            sv.w = sub_w[k]; sv.h = sub_h[k];
+            sv.texels.reserve(n * SMVSB_NB_STRIDE);
+            upload(c, c->stage_u8, sub_img[k], n);
+            smvsb::device_set_scale(c, c->stage_u8.p, sv.w, sv.h, scale,
+                c->stage_a.p, c->stage_b.p, 1, sv.texels.p);
+            ptrs[k] = sv.texels.p;
+            dims[2 * k] = sv.w; dims[2 * k + 1] = sv.h;
+            std::copy(Mi + 9 * k, Mi + 9 * k + 9, mt.begin() + 12 * k);
+            std::copy(ti + 3 * k, ti + 3 * k + 3, mt.begin() + 12 * k + 9);
+        }
+        upload(c, c->sub_ptrs, ptrs.data(), ptrs.size());
+        upload(c, c->sub_dims, dims.data(), dims.size());
+        upload(c, c->Mt, mt.data(), mt.size());
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->have_views = true;
+        c->have_system = false;
+    });
+}
+
+int
+smvsb_debug_get_view (smvsb_ctx* ctx, int view, float* grad, float* hess)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        smvsb_ctx* c = ctx;
+        require(c->have_views && grad != nullptr, SMVSB_ERR_STATE,
+            "views not set");
+        require(view >= 0 && view <= c->n_sub, SMVSB_ERR_INVALID,
+            "view index out of range");
+        if (view == 0)
+        {
+            download(c, grad, c->main_grad.p,
+                static_cast<size_t>(c->w) * c->h * 2);
+            return;
+        }
+        require(hess != nullptr, SMVSB_ERR_INVALID, "hess missing");
+        smvsb::SubViewDev& sv = c->subs[view - 1];
+        size_t const n = static_cast<size_t>(sv.w) * sv.h;
+        smvsb::DevBuf<float> g, hs;
+        g.reserve(n * 2); hs.reserve(n * 3);
+        smvsb::device_unpack_texels(c, sv.texels.p, static_cast<int>(n), g.p,
+            hs.p);
+        download(c, grad, g.p, n * 2);
+        download(c, hess, hs.p, n * 3);
     });
 }
 

@@ -119,6 +119,8 @@ struct smvsb_ctx
     smvsb::DevBuf<float const*> sub_ptrs;
     smvsb::DevBuf<int> sub_dims;
     smvsb::DevBuf<double> Mt;
+    smvsb::DevBuf<uint8_t> stage_u8;       /* upload staging (reused) */
+    smvsb::DevBuf<float> stage_a, stage_b;
 
     /* surface */
     bool have_surface = false;

@@ -58,6 +58,18 @@ class Workload:
         ctx.set_views(self.main_grad, self.sub_grads, self.sub_hess, self.Mi, self.ti,
                       self.flen_px, self.inv_flen, self.shading, self.shading_grad)
 
+    def push_views_u8(self, ctx):
+        """Byte images up, StereoView::set_scale on the device."""
+        ctx.set_views_u8(self.scale, self.scene.images[0], self.scene.images[1:],
+                         self.Mi, self.ti, self.flen_px, self.inv_flen,
+                         with_shading=self.shading is not None)
+
+    def h2d_bytes_u8(self):
+        n = sum(im.nbytes for im in self.scene.images) + self.Mi.nbytes + self.ti.nbytes
+        n += self.nodes.nbytes + self.node_valid.nbytes + self.patch_valid.nbytes \
+            + self.vis_off.nbytes + self.vis_ids.nbytes
+        return int(n)
+
     def push_surface(self, ctx):
         ctx.set_surface(self.scale, self.npx, self.npy, self.start_x, self.start_y,
                         self.nodes, self.node_valid, self.patch_valid, self.vis_off,

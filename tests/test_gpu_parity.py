@@ -102,6 +102,34 @@ def test_golden_sgm_bit_exact():
     assert np.array_equal(r["depth"], G["depth"])
 
 
+def test_device_set_scale_bitwise():
+    """smvsb_set_views_u8 (StereoView::set_scale on the device) against the
+    numpy mirror, which tests/test_cpu_host.py pins bitwise to the reference."""
+    from smvs_b200 import stereo_view, workload
+    sc = synth.make_scene(333, 207, 2, seed_index=4, shading=True)
+    for scale in (2, 3, 5):
+        wl = workload.build_workload(333, 207, 2, scale=scale, scene=sc, shading=True)
+        with api.Context(0) as ctx:
+            wl.push_views_u8(ctx)
+            g, _ = ctx.debug_get_view(0)
+            assert np.array_equal(g, wl.main_grad)
+            for k in range(2):
+                g, h = ctx.debug_get_view(k + 1)
+                assert np.array_equal(g, wl.sub_grads[k])
+                assert np.array_equal(h, wl.sub_hess[k])
+            # the Gauss-Newton system built from device-made inputs is the one
+            # built from host-made inputs, bit for bit (shading path included)
+            wl.push_surface(ctx)
+            light = np.linspace(1.0, -0.2, 16)
+            ctx.gn_construct(None, light, 0.01, 0.0)
+            a = ctx.debug_get_system()
+            wl.push_views(ctx)
+            wl.push_surface(ctx)
+            ctx.gn_construct(None, light, 0.01, 0.0)
+            b = ctx.debug_get_system()
+            assert np.array_equal(a["g"], b["g"]) and np.array_equal(a["Hvals"], b["Hvals"])
+
+
 # ---------------------------------------------------------------------------
 # live reference, larger / odd shapes
 # ---------------------------------------------------------------------------
