@@ -855,7 +855,7 @@ smvsb_sgm (int device, int w, int h, const uint8_t* main_lum, int nw, int nh,
     if (rc != SMVSB_OK)
         g_last_error = smvsb::sgm_last_error();
     else
-        smvsb::g_launches += 11;    /* cost + 8 paths + corners + WTA */
+        smvsb::g_launches += 3;     /* cost volume, 8-path aggregation, sum + WTA */
     return rc;
 }
 

@@ -12,20 +12,26 @@
  *                           2.1 GB at 2 MP x 128); here a block keeps one
  *                           warped tile with halo in shared memory per plane
  *                           and only the uint8 cost leaves the SM.
- *   K7  sgm_path_kernel     aggregate_sgm_costs (:429-667), SSE branch
+ *   K7  sgm_paths_kernel    aggregate_sgm_costs (:429-667), SSE branch
  *                           (constant P2, uint16 arithmetic): one warp per
- *                           scan line of a direction, disparities across the
- *                           lanes, L_r carried in registers, min over
- *                           disparities by warp shuffles. Diagonals follow the
- *                           line with wrap-around at the image border, where
- *                           the reference restarts the path (:515-534).
- *   K8  sgm_wta_kernel      depth_from_sgm_volume (:274-306).
+ *                           scan line of a direction, all 8 directions in one
+ *                           launch; disparities across the lanes, L_r carried
+ *                           in registers, min over disparities by warp
+ *                           shuffles. Diagonals follow the line with
+ *                           wrap-around at the image border, where the
+ *                           reference restarts the path (:515-534). Each
+ *                           direction writes L_r - C (a byte) to its own volume.
+ *   K8  sgm_sum_wta_kernel  S = 8 C + sum_r (L_r - C) (+ the reference's
+ *                           corner extras) and depth_from_sgm_volume
+ *                           (:274-306) in one pass; S is only materialised
+ *                           when the caller asks for the volume.
  *
  * Layouts: cost C[pixel][disp] uint8, sum S[pixel][disp] uint16 (pixel-major,
  * disparity contiguous, like the reference's sse_*_volume), so a warp's
  * access to one pixel is one coalesced 128 B / 256 B segment.
  */
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -175,55 +181,63 @@ enum PathKind
 };
 
 /*
- * One warp per line. DPL = disparities per lane (D = 32 * DPL).
+ * All eight path directions in ONE launch: warp -> (direction, scan line),
+ * 2h + 6w warps in flight (13 680 at 1920x1080) instead of h or w per
+ * sequential launch. DPL = disparities per lane (D = 32 * DPL).
  * fill_path_cost_sse (:361-406):
  *   L(p,i) = C(p,i) + min(L(q,i), L(q,i-1)+P1, L(q,i+1)+P1, min_k L(q,k)+P2)
  *            - min_k L(q,k)            (all uint16, wrap-around)
- * and copy_cost_and_add_to_sgm (:408-426) where a path starts.
- * `first` = this pass initialises S (no read of S).
+ * and copy_cost_and_add_to_sgm (:408-426) where a path starts (L = C).
+ * The directions cannot share one read-modify-write sum volume without
+ * racing, so each writes its own byte volume of L - C, which lies in [0, P2]
+ * (P2 <= 255): 1 B/voxel/direction. sgm_sum_wta_kernel adds them up.
  */
 template <int DPL>
 __global__ void __launch_bounds__(128)
-sgm_path_kernel (int w, int h, int kind, unsigned P1, unsigned P2,
-    uint8_t const* __restrict__ cost, uint16_t* __restrict__ S, int first)
+sgm_paths_kernel (int w, int h, unsigned P1, unsigned P2,
+    uint8_t const* __restrict__ cost, uint8_t* __restrict__ Dvol)
 {
     int const D = 32 * DPL;
-    int const line = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int const lane = threadIdx.x & 31;
-    bool const horizontal = (kind == PATH_L2R || kind == PATH_R2L);
-    int const n_lines = horizontal ? h : w;
-    if (line >= n_lines)
-        return;
-    int const steps = horizontal ? w : h;
-    unsigned Lp[DPL];
-#pragma unroll
-    for (int i = 0; i < DPL; ++i) Lp[i] = 0;
-
-    for (int s = 0; s < steps; ++s)
+    int kind, line;
+    if (gw < 2 * h)
     {
-        int x, y;
-        bool start;
-        switch (kind)
-        {
-        case PATH_L2R: x = s; y = line; start = (s == 0); break;
-        case PATH_R2L: x = w - 1 - s; y = line; start = (s == 0); break;
-        case PATH_T2B: x = line; y = s; start = (s == 0); break;
-        case PATH_B2T: x = line; y = h - 1 - s; start = (s == 0); break;
-        case PATH_T2B_D1:   /* predecessor (x-1, y-1) */
-            x = (line + s) % w; y = s; start = (s == 0 || x == 0); break;
-        case PATH_T2B_D2:   /* predecessor (x+1, y-1) */
-            x = ((line - s) % w + w) % w; y = s;
-            start = (s == 0 || x == w - 1); break;
-        case PATH_B2T_D1:   /* predecessor (x-1, y+1) */
-            x = (line + s) % w; y = h - 1 - s;
-            start = (s == 0 || x == 0); break;
-        default:            /* PATH_B2T_D2: predecessor (x+1, y+1) */
-            x = ((line - s) % w + w) % w; y = h - 1 - s;
-            start = (s == 0 || x == w - 1); break;
-        }
-        size_t const base = (static_cast<size_t>(y) * w + x) * D + lane * DPL;
+        kind = gw / h;                  /* PATH_L2R, PATH_R2L */
+        line = gw % h;
+    }
+    else
+    {
+        gw -= 2 * h;
+        if (gw >= 6 * w)
+            return;
+        kind = 2 + gw / w;              /* PATH_T2B .. PATH_B2T_D2 */
+        line = gw % w;
+    }
+    bool const horizontal = (kind < 2);
+    int const steps = horizontal ? w : h;
+    size_t const nvox = static_cast<size_t>(w) * h * D;
+    uint8_t* __restrict__ Dr = Dvol + static_cast<size_t>(kind) * nvox;
 
-        unsigned C[DPL];
+    /* start pixel and per-step increments; diagonals wrap around in x,
+     * where the reference restarts the path (:515-534) */
+    int x, y, dx, dy;
+    switch (kind)
+    {
+    case PATH_L2R: x = 0; y = line; dx = 1; dy = 0; break;
+    case PATH_R2L: x = w - 1; y = line; dx = -1; dy = 0; break;
+    case PATH_T2B: x = line; y = 0; dx = 0; dy = 1; break;
+    case PATH_T2B_D1: x = line; y = 0; dx = 1; dy = 1; break;
+    case PATH_T2B_D2: x = line; y = 0; dx = -1; dy = 1; break;
+    case PATH_B2T: x = line; y = h - 1; dx = 0; dy = -1; break;
+    case PATH_B2T_D1: x = line; y = h - 1; dx = 1; dy = -1; break;
+    default: x = line; y = h - 1; dx = -1; dy = -1; break;   /* B2T_D2 */
+    }
+    int const restart_x = (dx > 0) ? 0 : w - 1;   /* diagonals only */
+    bool const diagonal = (!horizontal && dx != 0);
+
+    auto load_cost = [&](size_t base, unsigned* C)
+    {
         if (DPL == 4)
         {
             uchar4 const c4 = *reinterpret_cast<uchar4 const*>(cost + base);
@@ -234,12 +248,33 @@ sgm_path_kernel (int w, int h, int kind, unsigned P1, unsigned P2,
 #pragma unroll
             for (int i = 0; i < DPL; ++i) C[i] = cost[base + i];
         }
+    };
 
-        unsigned L[DPL];
+    unsigned Lp[DPL], C[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) Lp[i] = 0;
+    size_t base = (static_cast<size_t>(y) * w + x) * D + lane * DPL;
+    load_cost(base, C);
+    bool start = true;
+
+    for (int s = 0; s < steps; ++s)
+    {
+        /* next pixel: its cost is fetched while this one is computed */
+        int xn = x + dx, yn = y + dy;
+        if (xn < 0) xn = w - 1;
+        if (xn >= w) xn = 0;
+        bool const startn = diagonal && (xn == restart_x);
+        size_t const basen = (static_cast<size_t>(yn) * w + xn) * D
+            + lane * DPL;
+        unsigned Cn[DPL];
+        if (s + 1 < steps)
+            load_cost(basen, Cn);
+
+        unsigned Dv[DPL];
         if (start)
         {
 #pragma unroll
-            for (int i = 0; i < DPL; ++i) L[i] = C[i];
+            for (int i = 0; i < DPL; ++i) { Lp[i] = C[i]; Dv[i] = 0; }
         }
         else
         {
@@ -251,6 +286,7 @@ sgm_path_kernel (int w, int h, int kind, unsigned P1, unsigned P2,
             unsigned const below = __shfl_up_sync(0xffffffffu, Lp[DPL - 1], 1);
             unsigned const above = __shfl_down_sync(0xffffffffu, Lp[0], 1);
             unsigned const far = (mn + P2) & 0xffffu;
+            unsigned Ln[DPL];
 #pragma unroll
             for (int i = 0; i < DPL; ++i)
             {
@@ -261,87 +297,83 @@ sgm_path_kernel (int w, int h, int kind, unsigned P1, unsigned P2,
                 unsigned const hi = (i < DPL - 1) ? Lp[i + 1] : above;
                 if (has_lo) best = min(best, (lo + P1) & 0xffffu);
                 if (has_hi) best = min(best, (hi + P1) & 0xffffu);
-                L[i] = (((C[i] + best) & 0xffffu) - mn) & 0xffffu;
+                Dv[i] = (best - mn) & 0xffffu;           /* = L - C, <= P2 */
+                Ln[i] = (C[i] + Dv[i]) & 0xffffu;
             }
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) Lp[i] = Ln[i];
         }
-
-        /* S += L */
         if (DPL == 4)
-        {
-            uint2* sp = reinterpret_cast<uint2*>(S + base);
-            uint2 v = make_uint2(0u, 0u);
-            if (!first)
-                v = *sp;
-            unsigned const s0 = ((v.x & 0xffffu) + L[0]) & 0xffffu;
-            unsigned const s1 = ((v.x >> 16) + L[1]) & 0xffffu;
-            unsigned const s2 = ((v.y & 0xffffu) + L[2]) & 0xffffu;
-            unsigned const s3 = ((v.y >> 16) + L[3]) & 0xffffu;
-            *sp = make_uint2(s0 | (s1 << 16), s2 | (s3 << 16));
-        }
+            *reinterpret_cast<uchar4*>(Dr + base) = make_uchar4(
+                (unsigned char)Dv[0], (unsigned char)Dv[1],
+                (unsigned char)Dv[2], (unsigned char)Dv[3]);
         else
         {
 #pragma unroll
             for (int i = 0; i < DPL; ++i)
-            {
-                unsigned const old = first ? 0u : S[base + i];
-                S[base + i] = static_cast<uint16_t>((old + L[i]) & 0xffffu);
-            }
+                Dr[base + i] = static_cast<uint8_t>(Dv[i]);
         }
 #pragma unroll
-        for (int i = 0; i < DPL; ++i) Lp[i] = L[i];
+        for (int i = 0; i < DPL; ++i) C[i] = Cn[i];
+        x = xn; y = yn; base = basen; start = startn;
     }
 }
 
-/* The extra copy_cost_and_add_to_sgm calls at the corners: column 0 of the
- * d1 volume and column w-1 of the d2 volume are (re)initialised for ALL y
- * after row 0 / row h-1 already were (:521-534, :600-613), so those four
- * corner pixels receive C once more per vertical sweep. */
-__global__ void
-sgm_corner_kernel (int w, int h, int D, uint8_t const* __restrict__ cost,
-    uint16_t* __restrict__ S)
-{
-    int const i = threadIdx.x;
-    if (i >= D)
-        return;
-    size_t const px[4] = { 0, static_cast<size_t>(w - 1),
-        static_cast<size_t>(h - 1) * w,
-        static_cast<size_t>(h - 1) * w + w - 1 };
-    for (int k = 0; k < 4; ++k)
-    {
-        size_t const o = px[k] * D + i;
-        S[o] = static_cast<uint16_t>((S[o] + cost[o]) & 0xffffu);
-    }
-}
-
-/* depth_from_sgm_volume, :274-306: first minimum over the planes. */
+/*
+ * S(p,i) = sum over the 8 directions of L_r(p,i) = 8 C + sum_r (L_r - C),
+ * plus C once more at the four image corners: column 0 of the d1 volume and
+ * column w-1 of the d2 volume are (re)initialised for ALL y after row 0 /
+ * row h-1 already were (:521-534, :600-613). Then depth_from_sgm_volume
+ * (:274-306): first minimum over the planes. One warp per pixel.
+ */
 template <int DPL>
 __global__ void
-sgm_wta_kernel (int npix, uint16_t const* __restrict__ S,
-    uint8_t const* __restrict__ main_img, float const* __restrict__ depths,
+sgm_sum_wta_kernel (int w, int h, uint8_t const* __restrict__ cost,
+    uint8_t const* __restrict__ Dvol, uint8_t const* __restrict__ main_img,
+    float const* __restrict__ depths, uint16_t* __restrict__ S_out,
     float* __restrict__ out)
 {
     int const D = 32 * DPL;
+    int const npix = w * h;
     int const p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int const lane = threadIdx.x & 31;
     if (p >= npix)
         return;
+    size_t const nvox = static_cast<size_t>(npix) * D;
+    size_t const base = static_cast<size_t>(p) * D + lane * DPL;
+    int const px = p % w, py = p / w;
+    unsigned const mult = 8u + (((px == 0 || px == w - 1)
+        && (py == 0 || py == h - 1)) ? 1u : 0u);
+    unsigned Sv[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i)
+        Sv[i] = (mult * cost[base + i]) & 0xffffu;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+    {
+        uint8_t const* Dr = Dvol + r * nvox + base;
+#pragma unroll
+        for (int i = 0; i < DPL; ++i)
+            Sv[i] = (Sv[i] + Dr[i]) & 0xffffu;
+    }
+    if (S_out != nullptr)
+    {
+#pragma unroll
+        for (int i = 0; i < DPL; ++i)
+            S_out[base + i] = static_cast<uint16_t>(Sv[i]);
+    }
     unsigned best = 0xffffu;    /* numeric_limits<uint16_t>::max() */
     int best_i = 0;
     bool found = false;
 #pragma unroll
     for (int i = 0; i < DPL; ++i)
-    {
-        unsigned const v = S[static_cast<size_t>(p) * D + lane * DPL + i];
-        if (v < best)
+        if (Sv[i] < best)
         {
-            best = v;
+            best = Sv[i];
             best_i = lane * DPL + i;
             found = true;
         }
-    }
-    /* key = value << 16 | index: min picks the lowest value, then index;
-     * lanes without a strict improvement over 0xffff report index 0 only
-     * if nobody found anything (min_index stays 0 in the reference). */
+    /* key = value << 16 | index: min picks the lowest value, then index */
     unsigned key = found ? ((best << 16) | best_i) : 0xffffffffu;
     for (int off = 16; off > 0; off >>= 1)
         key = min(key, __shfl_xor_sync(0xffffffffu, key, off));
@@ -366,31 +398,23 @@ u8_to_u16_kernel (size_t n, uint8_t const* __restrict__ in,
 template <int DPL>
 void
 run_paths (int w, int h, unsigned P1, unsigned P2, uint8_t const* cost,
-    uint16_t* S, cudaStream_t st)
+    uint8_t* Dvol, cudaStream_t st)
 {
-    int const order[8] = { PATH_L2R, PATH_R2L, PATH_T2B, PATH_T2B_D1,
-        PATH_T2B_D2, PATH_B2T, PATH_B2T_D1, PATH_B2T_D2 };
-    for (int k = 0; k < 8; ++k)
-    {
-        bool const horizontal = (order[k] == PATH_L2R || order[k] == PATH_R2L);
-        int const lines = horizontal ? h : w;
-        int const blocks = (lines * 32 + 127) / 128;
-        sgm_path_kernel<DPL><<<blocks, 128, 0, st>>>(w, h, order[k], P1, P2,
-            cost, S, k == 0 ? 1 : 0);
-        CUDA_CHECK(cudaGetLastError());
-    }
-    sgm_corner_kernel<<<1, 32 * DPL, 0, st>>>(w, h, 32 * DPL, cost, S);
+    int const warps = 2 * h + 6 * w;
+    sgm_paths_kernel<DPL><<<(warps * 32 + 127) / 128, 128, 0, st>>>(w, h, P1,
+        P2, cost, Dvol);
     CUDA_CHECK(cudaGetLastError());
 }
 
 template <int DPL>
 void
-run_wta (int npix, uint16_t const* S, uint8_t const* main_img,
-    float const* depths, float* out, cudaStream_t st)
+run_wta (int w, int h, uint8_t const* cost, uint8_t const* Dvol,
+    uint8_t const* main_img, float const* depths, uint16_t* S_out, float* out,
+    cudaStream_t st)
 {
-    int const blocks = (npix * 32 + 255) / 256;
-    sgm_wta_kernel<DPL><<<blocks, 256, 0, st>>>(npix, S, main_img, depths,
-        out);
+    int const blocks = (w * h * 32 + 255) / 256;
+    sgm_sum_wta_kernel<DPL><<<blocks, 256, 0, st>>>(w, h, cost, Dvol, main_img,
+        depths, S_out, out);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -426,9 +450,9 @@ sgm_run (int device, int w, int h, uint8_t const* main_lum, int nw, int nh,
                 "smvsb_sgm: num_steps must be 32, 64, 128 or 256");
         /* the O(D) recurrence equals the reference's O(D^2) minimum only
          * for P1 <= P2 and without uint16 wrap-around */
-        if (penalty1 > penalty2 || penalty2 > 16384)
+        if (penalty1 > penalty2 || penalty2 > 255)
             throw Error(SMVSB_ERR_INVALID,
-                "smvsb_sgm: need penalty1 <= penalty2 <= 16384");
+                "smvsb_sgm: need penalty1 <= penalty2 <= 255");
         int count = 0;
         if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
             throw Error(SMVSB_ERR_CUDA, "no CUDA device (no CPU fallback)");
@@ -454,13 +478,15 @@ sgm_run (int device, int w, int h, uint8_t const* main_lum, int nw, int nh,
 
         size_t const npix = static_cast<size_t>(w) * h;
         size_t const nvox = npix * num_steps;
-        DevBuf<uint8_t> d_main, d_neigh, d_cost;
+        DevBuf<uint8_t> d_main, d_neigh, d_cost, d_D;
         DevBuf<uint16_t> d_S;
         DevBuf<float> d_depths, d_out;
         d_main.reserve(npix);
         d_neigh.reserve(static_cast<size_t>(nw) * nh);
         d_cost.reserve(nvox);
-        d_S.reserve(nvox);
+        d_D.reserve(nvox * 8);                 /* L - C per direction */
+        if (sgm_out || cost_out)
+            d_S.reserve(nvox);
         d_depths.reserve(num_steps);
         d_out.reserve(npix);
         CUDA_CHECK(cudaMemcpyAsync(d_main.p, main_lum, npix,
@@ -486,18 +512,19 @@ sgm_run (int device, int w, int h, uint8_t const* main_lum, int nw, int nh,
         int const dpl = num_steps / 32;
         switch (dpl)
         {
-        case 1: run_paths<1>(w, h, penalty1, penalty2, d_cost.p, d_S.p, st); break;
-        case 2: run_paths<2>(w, h, penalty1, penalty2, d_cost.p, d_S.p, st); break;
-        case 4: run_paths<4>(w, h, penalty1, penalty2, d_cost.p, d_S.p, st); break;
-        default: run_paths<8>(w, h, penalty1, penalty2, d_cost.p, d_S.p, st); break;
+        case 1: run_paths<1>(w, h, penalty1, penalty2, d_cost.p, d_D.p, st); break;
+        case 2: run_paths<2>(w, h, penalty1, penalty2, d_cost.p, d_D.p, st); break;
+        case 4: run_paths<4>(w, h, penalty1, penalty2, d_cost.p, d_D.p, st); break;
+        default: run_paths<8>(w, h, penalty1, penalty2, d_cost.p, d_D.p, st); break;
         }
         CUDA_CHECK(cudaEventRecord(ev[2], st));
+        uint16_t* const S_dev = sgm_out ? d_S.p : nullptr;
         switch (dpl)
         {
-        case 1: run_wta<1>((int)npix, d_S.p, d_main.p, d_depths.p, d_out.p, st); break;
-        case 2: run_wta<2>((int)npix, d_S.p, d_main.p, d_depths.p, d_out.p, st); break;
-        case 4: run_wta<4>((int)npix, d_S.p, d_main.p, d_depths.p, d_out.p, st); break;
-        default: run_wta<8>((int)npix, d_S.p, d_main.p, d_depths.p, d_out.p, st); break;
+        case 1: run_wta<1>(w, h, d_cost.p, d_D.p, d_main.p, d_depths.p, S_dev, d_out.p, st); break;
+        case 2: run_wta<2>(w, h, d_cost.p, d_D.p, d_main.p, d_depths.p, S_dev, d_out.p, st); break;
+        case 4: run_wta<4>(w, h, d_cost.p, d_D.p, d_main.p, d_depths.p, S_dev, d_out.p, st); break;
+        default: run_wta<8>(w, h, d_cost.p, d_D.p, d_main.p, d_depths.p, S_dev, d_out.p, st); break;
         }
         CUDA_CHECK(cudaEventRecord(ev[3], st));
 
