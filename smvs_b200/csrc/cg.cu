@@ -117,6 +117,13 @@ all_sum (double const* partials, int slot, double* s_bcast)
 }
 
 /*
+ * Plain (weak, L1-cached) loads are correct for the vectors other CTAs wrote
+ * in the previous phase: the grid barrier is a release (fence + atomic) /
+ * acquire (ld.acquire.gpu + fence) pair extended to the CTA by bar.sync, so
+ * causality order covers them, and the gpu-scope fence after the spin drops
+ * the SM's L1 lines. Each vector entry is used by up to nine rows, most of
+ * them in the same CTA pass: L1 serves the re-use instead of L2.
+ *
  * VecOp: the vector the matrix is applied to. For CG it is the NEW search
  * direction z + beta * d_old, formed on the fly for the nine neighbours, so
  * the direction update (lib/conjugate_gradient.h:192-198) needs no pass and
@@ -127,10 +134,10 @@ struct PlainVec
     double const* v;
     __device__ __forceinline__ void load (int node, double* out) const
     {
-        double2 const a = __ldcg(reinterpret_cast<double2 const*>(
-            v + static_cast<size_t>(node) * 4));
-        double2 const b = __ldcg(reinterpret_cast<double2 const*>(
-            v + static_cast<size_t>(node) * 4 + 2));
+        double2 const a = *reinterpret_cast<double2 const*>(
+            v + static_cast<size_t>(node) * 4);
+        double2 const b = *reinterpret_cast<double2 const*>(
+            v + static_cast<size_t>(node) * 4 + 2);
         out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
     }
 };
@@ -142,14 +149,14 @@ struct DirVec
     double beta;
     __device__ __forceinline__ void load (int node, double* out) const
     {
-        double2 const z0 = __ldcg(reinterpret_cast<double2 const*>(
-            z + static_cast<size_t>(node) * 4));
-        double2 const z1 = __ldcg(reinterpret_cast<double2 const*>(
-            z + static_cast<size_t>(node) * 4 + 2));
-        double2 const d0 = __ldcg(reinterpret_cast<double2 const*>(
-            d_old + static_cast<size_t>(node) * 4));
-        double2 const d1 = __ldcg(reinterpret_cast<double2 const*>(
-            d_old + static_cast<size_t>(node) * 4 + 2));
+        double2 const z0 = *reinterpret_cast<double2 const*>(
+            z + static_cast<size_t>(node) * 4);
+        double2 const z1 = *reinterpret_cast<double2 const*>(
+            z + static_cast<size_t>(node) * 4 + 2);
+        double2 const d0 = *reinterpret_cast<double2 const*>(
+            d_old + static_cast<size_t>(node) * 4);
+        double2 const d1 = *reinterpret_cast<double2 const*>(
+            d_old + static_cast<size_t>(node) * 4 + 2);
         out[0] = z0.x + d0.x * beta; out[1] = z0.y + d0.y * beta;
         out[2] = z1.x + d1.x * beta; out[3] = z1.y + d1.y * beta;
     }
