@@ -198,7 +198,9 @@ spmv_row (CgArgs const& a, VecOp const& vec, int node, int rp, double* own)
     return acc;
 }
 
-__global__ void __launch_bounds__(CG_THREADS)
+/* 2 CTAs / SM: measured faster than 3 at 80 registers (fewer loads hoisted,
+ * more barrier participants). */
+__global__ void __launch_bounds__(CG_THREADS, 2)
 cg_kernel (CgArgs const a)
 {
     __shared__ double s_red[CG_THREADS / 32];
@@ -451,7 +453,7 @@ run_cg (smvsb_ctx* c, int max_iter, double err_tol, double q_tol, int* iters,
         cg_kernel, CG_THREADS, 0));
     if (per_sm < 1)
         throw Error(SMVSB_ERR_CUDA, "cg_kernel does not fit on an SM");
-    int grid = c->num_sms * per_sm;
+    int grid = c->num_sms * std::min(per_sm, 2);
     int const need = static_cast<int>((n + CG_THREADS - 1) / CG_THREADS);
     grid = std::max(1, std::min(std::min(grid, need), CG_MAX_BLOCKS));
 
