@@ -453,8 +453,8 @@ smvsb_set_surface (smvsb_ctx* ctx, int scale, int npx, int npy, int start_x,
     return guarded(ctx, [&]() {
         require(ctx->have_views, SMVSB_ERR_STATE,
             "smvsb_set_views must precede smvsb_set_surface");
-        require(scale >= 0 && scale <= 8, SMVSB_ERR_INVALID,
-            "scale out of range");
+        require(scale >= 0 && scale <= 6, SMVSB_ERR_INVALID,
+            "scale out of range (0..6)");
         require(npx > 0 && npy > 0, SMVSB_ERR_INVALID, "empty patch grid");
         require(nodes && node_valid && patch_valid && vis_off && vis_ids,
             SMVSB_ERR_INVALID, "surface arrays missing");
@@ -463,8 +463,8 @@ smvsb_set_surface (smvsb_ctx* ctx, int scale, int npx, int npy, int start_x,
         require(ps % sampling == 0, SMVSB_ERR_INVALID,
             "patch size below sampling");
         int const npos = ps / sampling;
-        require(npos == 4 || npos == 8, SMVSB_ERR_INVALID,
-            "this build handles scales 2..5 (16 or 64 samples per patch)");
+        require(npos == 1 || npos == 2 || npos == 4 || npos == 8
+            || npos == 16, SMVSB_ERR_INVALID, "unsupported samples per patch");
         require(start_x >= 0 && start_y >= 0
             && start_x + npx * ps <= ctx->w && start_y + npy * ps <= ctx->h,
             SMVSB_ERR_INVALID, "patch grid exceeds the main image");

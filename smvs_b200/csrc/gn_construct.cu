@@ -112,8 +112,10 @@ struct ConstructArgs
 };
 
 /*
- * S = samples per patch (16 at scales 2 and 3, 64 at scales 4 and 5;
+ * S = samples per patch (1 / 4 / 16 / 16 / 64 / 64 / 256 at scales 0..6;
  * lib/gauss_newton_step.cc:157-161 with lib/surface_patch.cc:57-120).
+ * S >= 16: groups of 16 samples; a 256-sample patch takes two chunks of 128.
+ * S < 16: 8 patches per block, 8 * S threads busy in phase 1.
  */
 /* 3 CTAs / SM (168 registers, a few spills) beats 2 CTAs at 248 registers by
  * 13 % on B200: the kernel is fp64-latency bound and wants the warps. */
@@ -121,13 +123,18 @@ template <int S>
 __global__ void __launch_bounds__(K1_THREADS, 3)
 gn_patch_kernel (ConstructArgs const args)
 {
-    constexpr int PPB = K1_THREADS / S;          /* patches per block */
-    constexpr int GPP = S / 16;                  /* 16-sample groups / patch */
+    /* samples of one patch per chunk, chunks per patch, patches per block,
+     * samples per phase-2 group, groups per patch and chunk */
+    constexpr int SPC = (S < K1_THREADS) ? S : K1_THREADS;
+    constexpr int CHUNKS = S / SPC;
+    constexpr int PPB = (S >= 16) ? K1_THREADS / SPC : 8;
+    constexpr int GSZ = (S >= 16) ? 16 : S;
+    constexpr int GPP = (S >= 16) ? SPC / 16 : 1;
     SurfaceDev const& sf = args.s;
 
     __shared__ double s_theta[PPB][16];
     __shared__ double s_as[K1_THREADS * AS_STRIDE];
-    __shared__ double s_basis[3 * 8 * 4];        /* npos <= 8 */
+    __shared__ double s_basis[3 * 16 * 4];       /* npos <= 16 */
     __shared__ double s_part[(GPP > 1) ? K1_THREADS * 17 : 1];
     __shared__ int s_proc[PPB];
 
@@ -170,10 +177,24 @@ gn_patch_kernel (ConstructArgs const args)
     }
     __syncthreads();
 
-    /* ---------------- phase 1: one thread per sample ---------------- */
+    /* phase-2 accumulators live across the chunks of a patch */
+    int const q = tid / 16;                  /* group in block */
+    int const row = tid % 16;
+    int const pl2 = q / GPP;
+    int const patch2 = blockIdx.x * PPB + pl2;
+    bool const proc2 = s_proc[pl2] != 0;
+    double hrow[16];
+    double grow = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) hrow[i] = 0.0;
+
+    for (int chunk = 0; chunk < CHUNKS; ++chunk)
     {
-        int const pl = tid / S;
-        int const s = tid % S;
+    /* ---------------- phase 1: one thread per sample ---------------- */
+    if (tid < PPB * SPC)
+    {
+        int const pl = tid / SPC;
+        int const s = chunk * SPC + tid % SPC;
         int const patch = blockIdx.x * PPB + pl;
         double A[21], b[6];
 #pragma unroll
@@ -343,27 +364,17 @@ gn_patch_kernel (ConstructArgs const args)
     }
     __syncthreads();
 
-    /* ------- phase 2: one thread per (16-sample group, row) -------- */
-    int const q = tid / 16;                  /* group in block */
-    int const row = tid % 16;
-    int const pl2 = q / GPP;
-    int const patch2 = blockIdx.x * PPB + pl2;
-    bool const proc2 = s_proc[pl2] != 0;
-
-    double hrow[16];
-    double grow = 0.0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) hrow[i] = 0.0;
-
+    /* ------- phase 2: one thread per (sample group, row) ----------- */
     if (proc2)
     {
         int const rbx = ((row >> 2) & 1) + 2 * (row & 1);
         int const rby = ((row >> 3) & 1) + 2 * ((row >> 1) & 1);
-        for (int ss = 0; ss < 16; ++ss)
+        for (int ss = 0; ss < GSZ; ++ss)
         {
-            int const s = (q % GPP) * 16 + ss;       /* sample in patch */
+            int const sl = (q % GPP) * GSZ + ss;     /* sample in chunk */
+            int const s = chunk * SPC + sl;          /* sample in patch */
             int const ix = s % npos, iy = s / npos;
-            double const* as = s_as + (pl2 * S + s) * AS_STRIDE;
+            double const* as = s_as + (pl2 * SPC + sl) * AS_STRIDE;
             double const* X0 = s_basis + (0 * npos + ix) * 4;
             double const* X1 = s_basis + (1 * npos + ix) * 4;
             double const* X2 = s_basis + (2 * npos + ix) * 4;
@@ -412,6 +423,9 @@ gn_patch_kernel (ConstructArgs const args)
             }
         }
     }
+    if (CHUNKS > 1)
+        __syncthreads();     /* s_as is rewritten by the next chunk */
+    } /* chunk */
 
     if (GPP == 1)
     {
@@ -585,21 +599,25 @@ launch_construct (smvsb_ctx* c, bool use_light, double reg, double light_reg)
     a.patch_g = c->patch_g.p;
     a.patch_proc = c->patch_proc.p;
 
+    /* samples per patch: 1 (scale 0), 4 (scale 1), 16 (scales 2, 3),
+     * 64 (scales 4, 5), 256 (scale 6), lib/gauss_newton_step.cc:157-161 */
     int const S = c->npos * c->npos;
-    if (S == 16)
+    auto blocks = [&](int ppb) { return (c->n_patches + ppb - 1) / ppb; };
+    switch (S)
     {
-        int const ppb = K1_THREADS / 16;
-        gn_patch_kernel<16><<<(c->n_patches + ppb - 1) / ppb, K1_THREADS, 0,
-            c->stream>>>(a);
-    }
-    else if (S == 64)
-    {
-        int const ppb = K1_THREADS / 64;
-        gn_patch_kernel<64><<<(c->n_patches + ppb - 1) / ppb, K1_THREADS, 0,
-            c->stream>>>(a);
-    }
-    else
+    case 1:
+        gn_patch_kernel<1><<<blocks(8), K1_THREADS, 0, c->stream>>>(a); break;
+    case 4:
+        gn_patch_kernel<4><<<blocks(8), K1_THREADS, 0, c->stream>>>(a); break;
+    case 16:
+        gn_patch_kernel<16><<<blocks(8), K1_THREADS, 0, c->stream>>>(a); break;
+    case 64:
+        gn_patch_kernel<64><<<blocks(2), K1_THREADS, 0, c->stream>>>(a); break;
+    case 256:
+        gn_patch_kernel<256><<<blocks(1), K1_THREADS, 0, c->stream>>>(a); break;
+    default:
         throw Error(SMVSB_ERR_INVALID, "unsupported samples per patch");
+    }
     CUDA_CHECK(cudaGetLastError());
 
     int const n_thr = c->n_nodes * 36;

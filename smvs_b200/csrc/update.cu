@@ -44,7 +44,7 @@ reproj_kernel (SurfaceDev const sf, double const* __restrict__ delta,
     double* __restrict__ patch_shift)
 {
     __shared__ double s_theta[16], s_dtheta[16];
-    __shared__ double s_b0[32 * 4];
+    __shared__ double s_b0[64 * 4];
     __shared__ double s_sum[UPD_THREADS / 32];
     __shared__ int s_flag[UPD_THREADS / 32];
 

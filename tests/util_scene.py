@@ -21,7 +21,13 @@ class Pair:
         self.R = oref.RefScene(self.scene, init_linear=shading)
         self.scale = scale
         self.R.set_scale(scale)
-        self.R.surface_create(scale, self.scene.init_depth)
+        if scale == 0:
+            # a scale-0 surface only ever arises by subdividing a scale-1 one
+            # (initialize_node_from_depth has an empty window at patch size 1)
+            self.R.surface_create(1, self.scene.init_depth)
+            self.R.surface_subdivide()
+        else:
+            self.R.surface_create(scale, self.scene.init_depth)
         self.R.compute_visibility()
         self.info = self.R.surface_info()
         self.nodes, self.node_valid, self.patch_valid = self.R.surface_get()
