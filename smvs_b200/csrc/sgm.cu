@@ -250,6 +250,70 @@ sgm_paths_kernel (int w, int h, unsigned P1, unsigned P2,
         }
     };
 
+    if (DPL == 4)
+    {
+        /* Fast path for 128 planes: the four disparities of a lane live in
+         * two registers as 16-bit pairs; the minima are DPX instructions
+         * (VIMNMX3 / VIADDMNMX on 16x2). L <= C + P2 <= 510 never overflows a
+         * half, so packed adds / subtracts are plain 32-bit ones. */
+        unsigned const P1x2 = P1 | (P1 << 16), P2x2 = P2 | (P2 << 16);
+        unsigned const BIG = 0x7000u;      /* "no neighbour" sentinel */
+        unsigned P01 = 0, P23 = 0;
+        size_t base = (static_cast<size_t>(y) * w + x) * D + lane * 4;
+        unsigned c4 = *reinterpret_cast<unsigned const*>(cost + base);
+        bool start = true;
+        for (int s = 0; s < steps; ++s)
+        {
+            int xn = x + dx, yn = y + dy;
+            if (xn < 0) xn = w - 1;
+            if (xn >= w) xn = 0;
+            bool const startn = diagonal && (xn == restart_x);
+            size_t const basen = (static_cast<size_t>(yn) * w + xn) * D
+                + lane * 4;
+            unsigned c4n = 0;
+            if (s + 1 < steps)
+                c4n = *reinterpret_cast<unsigned const*>(cost + basen);
+
+            unsigned const C01 = __byte_perm(c4, 0, 0x4140);
+            unsigned const C23 = __byte_perm(c4, 0, 0x4342);
+            unsigned D01 = 0, D23 = 0;
+            if (start)
+            {
+                P01 = C01; P23 = C23;
+            }
+            else
+            {
+                unsigned const m2 = __vminu2(P01, P23);
+                unsigned mn = min(m2 & 0xffffu, m2 >> 16);
+                for (int off = 16; off > 0; off >>= 1)
+                    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+                unsigned below = __shfl_up_sync(0xffffffffu, P23, 1) >> 16;
+                unsigned above = __shfl_down_sync(0xffffffffu, P01, 1)
+                    & 0xffffu;
+                if (lane == 0) below = BIG;
+                if (lane == 31) above = BIG;
+                unsigned const mid = (P01 >> 16) | (P23 << 16);   /* L1, L2 */
+                unsigned const lo01 = below | (P01 << 16);        /* -, L0 */
+                unsigned const hi23 = (P23 >> 16) | (above << 16);/* L3, - */
+                unsigned const mn2 = mn * 0x10001u;
+                unsigned const far2 = mn2 + P2x2;
+                unsigned const b01 = __vimin3_u16x2(P01, far2,
+                    __viaddmin_u16x2(mid, P1x2, lo01 + P1x2));
+                unsigned const b23 = __vimin3_u16x2(P23, far2,
+                    __viaddmin_u16x2(hi23, P1x2, mid + P1x2));
+                D01 = b01 - mn2;          /* = L - C, in [0, P2] per half */
+                D23 = b23 - mn2;
+                P01 = C01 + D01;
+                P23 = C23 + D23;
+            }
+            *reinterpret_cast<unsigned*>(Dr + base) =
+                __byte_perm(D01, D23, 0x6420);
+            c4 = c4n;
+            x = xn; y = yn; base = basen; start = startn;
+        }
+        return;
+    }
+
     unsigned Lp[DPL], C[DPL];
 #pragma unroll
     for (int i = 0; i < DPL; ++i) Lp[i] = 0;

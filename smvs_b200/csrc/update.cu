@@ -38,97 +38,113 @@ eval_depth (double const* theta, double const* X0, double const* Y0)
     return w;
 }
 
+/*
+ * G = threads per patch (a power of two <= UPD_THREADS, = min(ps^2, 64));
+ * a block holds UPD_THREADS / G patches, so at scale 2 (16 pixels per patch)
+ * four patches share a block instead of leaving 48 of 64 threads idle.
+ */
+template <int G>
 __global__ void __launch_bounds__(UPD_THREADS)
 reproj_kernel (SurfaceDev const sf, double const* __restrict__ delta,
     double thresh, uint8_t* __restrict__ active_new,
     double* __restrict__ patch_shift)
 {
-    __shared__ double s_theta[16], s_dtheta[16];
+    constexpr int PPB = UPD_THREADS / G;
+    __shared__ double s_theta[PPB][16], s_dtheta[PPB][16];
     __shared__ double s_b0[64 * 4];
     __shared__ double s_sum[UPD_THREADS / 32];
     __shared__ int s_flag[UPD_THREADS / 32];
 
-    int const patch = blockIdx.x;
     int const tid = threadIdx.x;
-    int const idx = patch % sf.npx, idy = patch / sf.npx;
-    int const n0 = idy * (sf.npx + 1) + idx;
-    bool proc = sf.patch_valid[patch] != 0;
-    if (proc)
-        proc = (sf.active[n0] | sf.active[n0 + 1]
-            | sf.active[n0 + sf.npx + 1] | sf.active[n0 + sf.npx + 2]) != 0;
-    if (!proc)
+    int const pl = tid / G, lt = tid % G;
+    int const patch = blockIdx.x * PPB + pl;
+    int idx = 0, idy = 0, n0 = 0;
+    bool proc = false;
+    if (patch < sf.n_patches)
     {
-        if (tid == 0)
-        {
-            patch_shift[2 * patch] = 0.0;
-            patch_shift[2 * patch + 1] = 0.0;
-        }
-        return;
-    }
-
-    if (tid < 16)
-    {
-        int const node = (idy + ((tid >> 3) & 1)) * (sf.npx + 1)
-            + idx + ((tid >> 2) & 1);
-        s_theta[tid] = sf.nodes[node * 4 + (tid & 3)];
-        s_dtheta[tid] = delta[node * 4 + (tid & 3)];
+        idx = patch % sf.npx; idy = patch / sf.npx;
+        n0 = idy * (sf.npx + 1) + idx;
+        proc = sf.patch_valid[patch] != 0;
+        if (proc)
+            proc = (sf.active[n0] | sf.active[n0 + 1]
+                | sf.active[n0 + sf.npx + 1] | sf.active[n0 + sf.npx + 2]) != 0;
     }
     for (int i = tid; i < sf.ps * 4; i += UPD_THREADS)
         s_b0[i] = sf.basis_f[i];
+    for (int c = lt; c < 16 && proc; c += G)
+    {
+        int const node = (idy + ((c >> 3) & 1)) * (sf.npx + 1)
+            + idx + ((c >> 2) & 1);
+        s_theta[pl][c] = sf.nodes[node * 4 + (c & 3)];
+        s_dtheta[pl][c] = delta[node * 4 + (c & 3)];
+    }
     __syncthreads();
 
-    uint32_t const v0 = sf.vis_off[patch];
-    int const n = static_cast<int>(sf.vis_off[patch + 1] - v0);
-    int const npix = sf.ps * sf.ps;
     double sum = 0.0;
     int flag = 0;
-    for (int p = tid; p < npix; p += UPD_THREADS)
+    int const npix = sf.ps * sf.ps;
+    int n = 0;
+    if (proc)
     {
-        int const i = p % sf.ps, j = p / sf.ps;
-        double const w1 = eval_depth(s_theta, s_b0 + i * 4, s_b0 + j * 4);
-        double const w2 = w1 + eval_depth(s_dtheta, s_b0 + i * 4,
-            s_b0 + j * 4);
-        /* no +0.5 here: lib/depth_optimizer.cc:669-670 */
-        double const u = sf.start_x + idx * sf.ps + i;
-        double const v = sf.start_y + idy * sf.ps + j;
-        for (int k = 0; k < n; ++k)
+        uint32_t const v0 = sf.vis_off[patch];
+        n = static_cast<int>(sf.vis_off[patch + 1] - v0);
+        for (int p = lt; p < npix; p += G)
         {
-            double const* Mt = sf.Mt + sf.vis_ids[v0 + k] * 12;
-            double const pp = Mt[0] * u + Mt[1] * v + Mt[2];
-            double const qq = Mt[3] * u + Mt[4] * v + Mt[5];
-            double const rr = Mt[6] * u + Mt[7] * v + Mt[8];
-            double const d1 = w1 * rr + Mt[11], d2 = w2 * rr + Mt[11];
-            double const ex = (w1 * pp + Mt[9]) / d1 - (w2 * pp + Mt[9]) / d2;
-            double const ey = (w1 * qq + Mt[10]) / d1
-                - (w2 * qq + Mt[10]) / d2;
-            double const diff = sqrt(ex * ex + ey * ey);
-            sum += diff;
-            flag |= (diff > thresh);
+            int const i = p % sf.ps, j = p / sf.ps;
+            double const w1 = eval_depth(s_theta[pl], s_b0 + i * 4,
+                s_b0 + j * 4);
+            double const w2 = w1 + eval_depth(s_dtheta[pl], s_b0 + i * 4,
+                s_b0 + j * 4);
+            /* no +0.5 here: lib/depth_optimizer.cc:669-670 */
+            double const u = sf.start_x + idx * sf.ps + i;
+            double const v = sf.start_y + idy * sf.ps + j;
+            for (int k = 0; k < n; ++k)
+            {
+                double const* Mt = sf.Mt + sf.vis_ids[v0 + k] * 12;
+                double const pp = Mt[0] * u + Mt[1] * v + Mt[2];
+                double const qq = Mt[3] * u + Mt[4] * v + Mt[5];
+                double const rr = Mt[6] * u + Mt[7] * v + Mt[8];
+                double const d1 = w1 * rr + Mt[11], d2 = w2 * rr + Mt[11];
+                double const ex = (w1 * pp + Mt[9]) / d1
+                    - (w2 * pp + Mt[9]) / d2;
+                double const ey = (w1 * qq + Mt[10]) / d1
+                    - (w2 * qq + Mt[10]) / d2;
+                double const diff = sqrt(ex * ex + ey * ey);
+                sum += diff;
+                flag |= (diff > thresh);
+            }
         }
     }
-    for (int off = 16; off > 0; off >>= 1)
+    /* reduce over the G threads of the patch (fixed order) */
+    constexpr int W = (G < 32) ? G : 32;
+    for (int off = W / 2; off > 0; off >>= 1)
     {
-        sum += __shfl_down_sync(0xffffffffu, sum, off);
-        flag |= __shfl_down_sync(0xffffffffu, flag, off);
+        sum += __shfl_down_sync(0xffffffffu, sum, off, W);
+        flag |= __shfl_down_sync(0xffffffffu, flag, off, W);
     }
-    if ((tid & 31) == 0)
+    if (G > 32)
     {
-        s_sum[tid >> 5] = sum;
-        s_flag[tid >> 5] = flag;
-    }
-    __syncthreads();
-    if (tid == 0)
-    {
-        double tot = 0.0;
-        int f = 0;
-        for (int i = 0; i < UPD_THREADS / 32; ++i)
+        if ((tid & 31) == 0)
         {
-            tot += s_sum[i];
-            f |= s_flag[i];
+            s_sum[tid >> 5] = sum;
+            s_flag[tid >> 5] = flag;
         }
-        patch_shift[2 * patch] = tot;
-        patch_shift[2 * patch + 1] = double(npix) * n;
-        if (f)
+        __syncthreads();
+        if (tid == 0)
+        {
+            sum = 0.0; flag = 0;
+            for (int i = 0; i < UPD_THREADS / 32; ++i)
+            {
+                sum += s_sum[i];
+                flag |= s_flag[i];
+            }
+        }
+    }
+    if (lt == 0 && patch < sf.n_patches)
+    {
+        patch_shift[2 * patch] = proc ? sum : 0.0;
+        patch_shift[2 * patch + 1] = proc ? double(npix) * n : 0.0;
+        if (proc && flag)
         {
             /* every entry of the patch carries all four node ids,
              * lib/depth_optimizer.cc:674-675 */
@@ -337,8 +353,21 @@ launch_update (smvsb_ctx* c, double thresh, bool full_opt,
     c->active_new.reserve(c->n_nodes);
     c->cg_result.reserve(16);
     CUDA_CHECK(cudaMemsetAsync(c->active_new.p, 0, c->n_nodes, c->stream));
-    reproj_kernel<<<c->n_patches, UPD_THREADS, 0, c->stream>>>(sf, c->x.p,
-        thresh, c->active_new.p, c->patch_shift.p);
+    int const npix_patch = c->ps * c->ps;
+    auto grid_for = [&](int g) { int const ppb = UPD_THREADS / g;
+        return (c->n_patches + ppb - 1) / ppb; };
+    if (npix_patch >= 64)
+        reproj_kernel<64><<<grid_for(64), UPD_THREADS, 0, c->stream>>>(sf,
+            c->x.p, thresh, c->active_new.p, c->patch_shift.p);
+    else if (npix_patch == 16)
+        reproj_kernel<16><<<grid_for(16), UPD_THREADS, 0, c->stream>>>(sf,
+            c->x.p, thresh, c->active_new.p, c->patch_shift.p);
+    else if (npix_patch == 4)
+        reproj_kernel<4><<<grid_for(4), UPD_THREADS, 0, c->stream>>>(sf,
+            c->x.p, thresh, c->active_new.p, c->patch_shift.p);
+    else
+        reproj_kernel<1><<<grid_for(1), UPD_THREADS, 0, c->stream>>>(sf,
+            c->x.p, thresh, c->active_new.p, c->patch_shift.p);
     CUDA_CHECK(cudaGetLastError());
     int const n4 = c->n_nodes * 4;
     apply_delta_kernel<<<(n4 + 255) / 256, 256, 0, c->stream>>>(c->n_nodes,
