@@ -9,9 +9,11 @@
  *                           slice, Hamming distance; 255 where the warped
  *                           pixel is 0. The reference materialises the warped
  *                           volume (uint8) and its census volume (uint64,
- *                           2.1 GB at 2 MP x 128); here a block keeps one
- *                           warped tile with halo in shared memory per plane
- *                           and only the uint8 cost leaves the SM.
+ *                           2.1 GB at 2 MP x 128); here a block keeps the
+ *                           warped tile (with halo) of four planes in shared
+ *                           memory, compares two pixels per integer add
+ *                           (16-bit fields) and only the uint8 cost leaves
+ *                           the SM.
  *   K7  sgm_paths_kernel    aggregate_sgm_costs (:429-667), SSE branch
  *                           (constant P2, uint16 arithmetic): one warp per
  *                           scan line of a direction, all 8 directions in one
@@ -39,9 +41,6 @@ namespace smvsb {
 
 namespace {
 
-constexpr int CT_X = 32, CT_Y = 8;             /* cost kernel pixel tile */
-constexpr int CH_X = CT_X + 8, CH_Y = CT_Y + 6; /* with census halo */
-
 struct SgmParams
 {
     int w, h, nw, nh, D;
@@ -49,35 +48,51 @@ struct SgmParams
     float t[3];
 };
 
-/* warped_neighbors_for_depth for one pixel / plane, :150-190 */
+/*
+ * Cost volume, SWAR formulation. A thread owns two horizontally adjacent
+ * pixels and works on four depth planes at a time.
+ *
+ *  - Pixels are kept as 16-bit fields, two per register. For centre pair A
+ *    and neighbour pair B, R = B + 0x00FF00FF - A has bit 8 of each field
+ *    set iff A < B (field value B - A + 255 in [0, 510], no borrow between
+ *    the fields): ONE integer add per two census comparisons.
+ *  - The Hamming distance of two census words does not depend on the bit
+ *    order, so no 63-bit word is ever assembled: per offset the comparison
+ *    bits of the warped slice are XORed with the main image's bits for the
+ *    same offset (precomputed once per block into shared memory, reused for
+ *    all planes) and accumulated in the fields: 3 instructions per 2
+ *    comparisons instead of ~8.
+ *  - The warped slice of a 32 x 16 pixel tile with its 9x7 halo is computed
+ *    once per plane into shared memory by the whole block (fp32 steps
+ *    restated with explicit round-to-nearest ops, so bit-identical to the
+ *    CPU); M * (x, y, 1) does not depend on the plane and is kept in
+ *    registers.
+ * Semantics restated from census_filter / create_cost_volume
+ * (lib/sgm_stereo.cc:126-148, 192-244): census only for pixels with
+ * 4 <= x < w-5, 3 <= y < h-4 and a non-zero centre; cost 255 where the
+ * warped pixel is 0.
+ */
+constexpr int CT_W = 32, CT_H = 16;              /* pixel tile per block */
+constexpr int CT_THREADS = (CT_W / 2) * CT_H;    /* 256: one pixel pair each */
+constexpr int HALO_W = CT_W + 8, HALO_H = CT_H + 6;
+constexpr int HALO_N = HALO_W * HALO_H;          /* 880 */
+constexpr int HALO_PER_THREAD = (HALO_N + CT_THREADS - 1) / CT_THREADS;
+constexpr int PLANES = 4;                        /* planes per iteration */
+
 __device__ __forceinline__ uint8_t
-warp_pixel (SgmParams const& p, uint8_t const* __restrict__ neigh, int x,
-    int y, float depth)
+warp_from_tp (SgmParams const& p, uint8_t const* __restrict__ neigh,
+    float const* tp, float depth)
 {
-    float const px = 0.5f + static_cast<float>(x);
-    float const py = 0.5f + static_cast<float>(y);
-    float tp[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-    {
-        float s = __fmul_rn(p.M[3 * r], px);
-        s = __fadd_rn(s, __fmul_rn(p.M[3 * r + 1], py));
-        s = __fadd_rn(s, p.M[3 * r + 2]);      /* * 1.f */
-        tp[r] = s;
-    }
     float q0 = __fadd_rn(__fmul_rn(tp[0], depth), p.t[0]);
     float q1 = __fadd_rn(__fmul_rn(tp[1], depth), p.t[1]);
     float const q2 = __fadd_rn(__fmul_rn(tp[2], depth), p.t[2]);
     if (q2 < 0)
         return 0;
-    q0 = __fdiv_rn(q0, q2);
-    q1 = __fdiv_rn(q1, q2);
-    q0 = __fsub_rn(q0, 0.5f);
-    q1 = __fsub_rn(q1, 0.5f);
+    q0 = __fsub_rn(__fdiv_rn(q0, q2), 0.5f);
+    q1 = __fsub_rn(__fdiv_rn(q1, q2), 0.5f);
     if (q0 < 0 || q1 < 0 || q0 > static_cast<float>(p.nw - 1)
         || q1 > static_cast<float>(p.nh - 1))
         return 0;
-
     /* mve::Image<uint8_t>::linear_at */
     float const xx = fmaxf(0.0f, fminf(static_cast<float>(p.nw - 1), q0));
     float const yy = fmaxf(0.0f, fminf(static_cast<float>(p.nh - 1), q1));
@@ -97,80 +112,163 @@ warp_pixel (SgmParams const& p, uint8_t const* __restrict__ neigh, int x,
     return static_cast<uint8_t>(s);
 }
 
-/* 9x7 census around tile-local (lx, ly) of a CH_X x CH_Y byte tile; bit
- * order as census_filter builds it (x outer, y inner, MSB first). */
-__device__ __forceinline__ unsigned long long
-census63 (uint8_t const* tile, int lx, int ly)
-{
-    uint8_t const thr = tile[(ly + 3) * CH_X + lx + 4];
-    unsigned long long c = 0;
-#pragma unroll
-    for (int i = 0; i < 9; ++i)
-#pragma unroll
-        for (int j = 0; j < 7; ++j)
-        {
-            c <<= 1;
-            c |= (thr < tile[(ly + j) * CH_X + lx + i]) ? 1ull : 0ull;
-        }
-    return c;
-}
+/* Pair of 16-bit fields at element offset e (0..8) of the five words
+ * wd[0..4] that hold elements 0..9 of a tile row. */
+#define SMVSB_WINDOW(wd, e) (((e) & 1) ? __funnelshift_r((wd)[(e) >> 1],   \
+    (wd)[((e) >> 1) + 1], 16) : (wd)[(e) >> 1])
 
-__global__ void __launch_bounds__(CT_X * CT_Y)
+__global__ void __launch_bounds__(CT_THREADS)
 sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
     uint8_t const* __restrict__ neigh, float const* __restrict__ depths,
     uint8_t* __restrict__ cost)
 {
-    __shared__ uint8_t s_tile[CH_X * CH_Y];
+    /* tile of 16-bit pixels, HALO_W even; as words: HALO_W / 2 per row */
+    __shared__ unsigned s_tile[PLANES][HALO_H][HALO_W / 2];
+    /* main comparison bits, [63][CT_THREADS] words = 63 KB: dynamic */
+    extern __shared__ unsigned s_mask_dyn[];
+    unsigned (*s_mask)[CT_THREADS] =
+        reinterpret_cast<unsigned (*)[CT_THREADS]>(s_mask_dyn);
     __shared__ float s_depths[256];
-    int const tid = threadIdx.y * CT_X + threadIdx.x;
-    int const x0 = blockIdx.x * CT_X, y0 = blockIdx.y * CT_Y;
-    int const x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    bool const inside = (x < p.w && y < p.h);
-    bool const interior = inside && x >= 4 && x < p.w - 5 && y >= 3
-        && y < p.h - 4;
 
-    for (int i = tid; i < p.D; i += CT_X * CT_Y)
+    int const tid = threadIdx.x;
+    int const tx = tid % (CT_W / 2), ty = tid / (CT_W / 2);
+    int const x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+    int const px = x0 + 2 * tx, py = y0 + ty;        /* left pixel of the pair */
+
+    for (int i = tid; i < p.D; i += CT_THREADS)
         s_depths[i] = depths[i];
 
-    /* main census, once */
-    for (int i = tid; i < CH_X * CH_Y; i += CT_X * CT_Y)
+    /* plane-independent part of the warp for this thread's halo pixels */
+    float tp[HALO_PER_THREAD][3];
+    bool in_img[HALO_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < HALO_PER_THREAD; ++k)
     {
-        int const gx = x0 - 4 + i % CH_X, gy = y0 - 3 + i / CH_X;
-        s_tile[i] = (gx >= 0 && gx < p.w && gy >= 0 && gy < p.h)
-            ? main_img[gy * p.w + gx] : 0;
+        int const i = tid + k * CT_THREADS;
+        int const gx = x0 - 4 + i % HALO_W, gy = y0 - 3 + i / HALO_W;
+        in_img[k] = (i < HALO_N && gx >= 0 && gx < p.w && gy >= 0 && gy < p.h);
+        float const fx = 0.5f + static_cast<float>(gx);
+        float const fy = 0.5f + static_cast<float>(gy);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+        {
+            float s = __fmul_rn(p.M[3 * r], fx);
+            s = __fadd_rn(s, __fmul_rn(p.M[3 * r + 1], fy));
+            tp[k][r] = __fadd_rn(s, p.M[3 * r + 2]);      /* * 1.f */
+        }
+    }
+
+    /* main image tile -> comparison bits per offset */
+    unsigned short* tile16 = reinterpret_cast<unsigned short*>(&s_tile[0][0][0]);
+#pragma unroll
+    for (int k = 0; k < HALO_PER_THREAD; ++k)
+    {
+        int const i = tid + k * CT_THREADS;
+        if (i < HALO_N)
+        {
+            int const gx = x0 - 4 + i % HALO_W, gy = y0 - 3 + i / HALO_W;
+            tile16[i] = in_img[k] ? main_img[gy * p.w + gx] : 0;
+        }
     }
     __syncthreads();
-    unsigned long long main_census = 0;
-    if (interior && s_tile[(threadIdx.y + 3) * CH_X + threadIdx.x + 4] != 0)
-        main_census = census63(s_tile, threadIdx.x, threadIdx.y);
+    bool const in0 = (px < p.w && py < p.h), in1 = (px + 1 < p.w && py < p.h);
+    bool const int0 = in0 && px >= 4 && px < p.w - 5 && py >= 3 && py < p.h - 4;
+    bool const int1 = in1 && px + 1 >= 4 && px + 1 < p.w - 5 && py >= 3
+        && py < p.h - 4;
+    {
+        unsigned const A = s_tile[0][ty + 3][tx + 2];
+        /* fields of pixels without a census (border, zero centre) stay 0 */
+        unsigned keep = 0;
+        if (int0 && (A & 0xffffu) != 0) keep |= 0x00000100u;
+        if (int1 && (A >> 16) != 0) keep |= 0x01000000u;
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+        {
+            unsigned wd[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) wd[q] = s_tile[0][ty + j][tx + q];
+#pragma unroll
+            for (int e = 0; e < 9; ++e)
+            {
+                unsigned const B = SMVSB_WINDOW(wd, e);
+                s_mask[j * 9 + e][tid] = (B + 0x00FF00FFu - A) & keep;
+            }
+        }
+    }
 
-    size_t const pix = static_cast<size_t>(y) * p.w + x;
-    for (int d = 0; d < p.D; ++d)
+    for (int d0 = 0; d0 < p.D; d0 += PLANES)
     {
         __syncthreads();
-        float const depth = s_depths[d];
-        for (int i = tid; i < CH_X * CH_Y; i += CT_X * CT_Y)
+#pragma unroll
+        for (int k = 0; k < HALO_PER_THREAD; ++k)
         {
-            int const gx = x0 - 4 + i % CH_X, gy = y0 - 3 + i / CH_X;
-            s_tile[i] = (gx >= 0 && gx < p.w && gy >= 0 && gy < p.h)
-                ? warp_pixel(p, neigh, gx, gy, depth) : 0;
+            int const i = tid + k * CT_THREADS;
+            if (i < HALO_N)
+            {
+#pragma unroll
+                for (int pl = 0; pl < PLANES; ++pl)
+                {
+                    unsigned short v = 0;
+                    if (in_img[k])
+                        v = warp_from_tp(p, neigh, tp[k], s_depths[d0 + pl]);
+                    reinterpret_cast<unsigned short*>(
+                        &s_tile[pl][0][0])[i] = v;
+                }
+            }
         }
         __syncthreads();
-        if (!inside)
-            continue;
-        uint8_t const centre =
-            s_tile[(threadIdx.y + 3) * CH_X + threadIdx.x + 4];
-        uint8_t c = 255;
-        if (centre != 0)
+
+        unsigned A[PLANES], acc[PLANES];
+#pragma unroll
+        for (int pl = 0; pl < PLANES; ++pl)
         {
-            unsigned long long wc = 0;
-            if (interior)
-                wc = census63(s_tile, threadIdx.x, threadIdx.y);
-            c = static_cast<uint8_t>(__popcll(main_census ^ wc));
+            A[pl] = s_tile[pl][ty + 3][tx + 2];
+            acc[pl] = 0;
         }
-        cost[pix * p.D + d] = c;
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+        {
+            unsigned wd[PLANES][5];
+#pragma unroll
+            for (int pl = 0; pl < PLANES; ++pl)
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                    wd[pl][q] = s_tile[pl][ty + j][tx + q];
+#pragma unroll
+            for (int e = 0; e < 9; ++e)
+            {
+                unsigned const mm = s_mask[j * 9 + e][tid];
+#pragma unroll
+                for (int pl = 0; pl < PLANES; ++pl)
+                {
+                    unsigned const B = SMVSB_WINDOW(wd[pl], e);
+                    acc[pl] += ((B + 0x00FF00FFu - A[pl]) ^ mm) & 0x01000100u;
+                }
+            }
+        }
+        /* cost bytes of the four planes for each of the two pixels */
+        unsigned out0 = 0, out1 = 0;
+#pragma unroll
+        for (int pl = 0; pl < PLANES; ++pl)
+        {
+            unsigned const w0v = A[pl] & 0xffffu, w1v = A[pl] >> 16;
+            /* border pixels have no census on either side: distance 0 */
+            unsigned c0 = int0 ? ((acc[pl] >> 8) & 0xffu) : 0u;
+            unsigned c1 = int1 ? (acc[pl] >> 24) : 0u;
+            if (w0v == 0) c0 = 255u;
+            if (w1v == 0) c1 = 255u;
+            out0 |= c0 << (8 * pl);
+            out1 |= c1 << (8 * pl);
+        }
+        if (in0)
+            *reinterpret_cast<unsigned*>(cost + (static_cast<size_t>(py) * p.w
+                + px) * p.D + d0) = out0;
+        if (in1)
+            *reinterpret_cast<unsigned*>(cost + (static_cast<size_t>(py) * p.w
+                + px + 1) * p.D + d0) = out1;
     }
 }
+#undef SMVSB_WINDOW
 
 /* ------------------------------------------------------------------ */
 
@@ -566,9 +664,13 @@ sgm_run (int device, int w, int h, uint8_t const* main_lum, int nw, int nh,
         std::copy(t, t + 3, p.t);
 
         CUDA_CHECK(cudaEventRecord(ev[0], st));
-        dim3 const cb(CT_X, CT_Y);
-        dim3 const cg((w + CT_X - 1) / CT_X, (h + CT_Y - 1) / CT_Y);
-        sgm_cost_kernel<<<cg, cb, 0, st>>>(p, d_main.p, d_neigh.p, d_depths.p,
+        dim3 const cb(CT_THREADS);
+        dim3 const cg((w + CT_W - 1) / CT_W, (h + CT_H - 1) / CT_H);
+        size_t const mask_bytes = 63 * CT_THREADS * sizeof(unsigned);
+        CUDA_CHECK(cudaFuncSetAttribute(sgm_cost_kernel,
+            cudaFuncAttributeMaxDynamicSharedMemorySize,
+            static_cast<int>(mask_bytes)));
+        sgm_cost_kernel<<<cg, cb, mask_bytes, st>>>(p, d_main.p, d_neigh.p, d_depths.p,
             d_cost.p);
         CUDA_CHECK(cudaGetLastError());
         CUDA_CHECK(cudaEventRecord(ev[1], st));
