@@ -339,7 +339,12 @@ def run_product(args):
         roofline = {"bound": "hbm", "kernel": "cg_kernel (persistent PCG)",
                     "achieved": achieved, "peak": hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
-                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                    "unit": "GB/s", "frac": achieved / hbm_peak,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full
+                    # capture (profiles/r1b_cg.txt: 33.55 GB for a 200-iteration launch
+                    # = 167.8 MB per CG iteration), scaled to this run's iterations/launch
+                    "traffic": 167.8e6 * cg / max(newton, 1),
+                    "traffic_source": "profiles/r1b_cg.txt",
                     "algorithmic_bytes_per_launch": bytes_per_iter * cg / max(newton, 1),
                     "launches_timed": newton}
 
