@@ -141,42 +141,45 @@ def _windows(wl, n, frac_x=4, frac_y=4):
     return out
 
 
-def cpu_reference_run(wl, threads, repeats=1):
-    """Newton loops of the reference on `threads` bounded windows (1/16 of the
-    patch grid each) run concurrently, one per host thread. Returns
-    (pixel_iterations, seconds, description)."""
-    from oracle import ref as oref
-    if not oref.available():
-        raise RuntimeError("oracle/_ref missing")
-    wins = _windows(wl, threads)
-    scenes = []
-    for (x0, y0, nx, ny) in wins:
-        scenes.append((_ref_scene_for(wl.restrict(x0, y0, nx, ny)),
-                       wl.restrict(x0, y0, nx, ny)))
-    results = [None] * threads
+class ReferenceWorkers:
+    """`threads` reference optimizers, each on its own bounded window (1/16 of
+    the patch grid) of the same workload; run() lets every one do `repeats`
+    Newton loops concurrently, one host thread each (the reference's
+    ThreadPool model: one view per thread, app/smvsrecon.cc:558)."""
 
-    def work(i):
-        R, sub = scenes[i]
-        tot = 0.0
-        for _ in range(repeats):
-            R.surface_set(sub.nodes, sub.node_valid, sub.patch_valid)
-            st = R.newton_loop(None, REGULARIZATION, 0.0)
-            tot += st["pixel_iterations"]
-        results[i] = tot
+    def __init__(self, wl, threads):
+        from oracle import ref as oref
+        if not oref.available():
+            raise RuntimeError("oracle/_ref missing")
+        self.threads = threads
+        self.wins = _windows(wl, threads)
+        self.subs = [wl.restrict(*w) for w in self.wins]
+        self.scenes = [_ref_scene_for(sub) for sub in self.subs]
+        self.desc = (f"{threads} thread(s), each Newton loop on a "
+                     f"{self.wins[0][2]}x{self.wins[0][3]}-patch window (1/16 of the "
+                     f"{wl.npx}x{wl.npy} grid) of the same 2 MP / 6-neighbour scale-2 workload")
 
-    t0 = time.perf_counter()
-    th = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
-    for t in th:
-        t.start()
-    for t in th:
-        t.join()
-    dt = time.perf_counter() - t0
-    for R, _ in scenes:
-        R.close()
-    desc = (f"{threads} thread(s) x {repeats} Newton loop(s), each on a "
-            f"{wins[0][2]}x{wins[0][3]}-patch window (1/16 of the {wl.npx}x{wl.npy} grid) "
-            f"of the same 2 MP / 6-neighbour scale-2 workload")
-    return float(sum(results)), dt, desc
+    def run(self, repeats=1):
+        results = [0.0] * self.threads
+
+        def work(i):
+            R, sub = self.scenes[i], self.subs[i]
+            for _ in range(repeats):
+                R.surface_set(sub.nodes, sub.node_valid, sub.patch_valid)
+                st = R.newton_loop(None, REGULARIZATION, 0.0)
+                results[i] += st["pixel_iterations"]
+
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(i,)) for i in range(self.threads)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return float(sum(results)), time.perf_counter() - t0
+
+    def close(self):
+        for R in self.scenes:
+            R.close()
 
 
 # ---------------------------------------------------------------------------
@@ -194,14 +197,16 @@ def run_reference(args):
         return 0
     threads = max(1, min(os.cpu_count() or 1, 16))
     wl = build_workload(WIDTH, HEIGHT, N_SUB, SCALE, shading=False, seed_index=0)
+    workers = ReferenceWorkers(wl, threads)
+    desc = workers.desc
     for _ in range(args.warmup):
-        cpu_reference_run(wl, threads)
+        workers.run()
     pix, secs = 0.0, 0.0
-    desc = ""
     for _ in range(args.steps):
-        p, s, desc = cpu_reference_run(wl, threads)
+        p, s = workers.run()
         pix += p
         secs += s
+    workers.close()
     value = pix / secs / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
@@ -351,9 +356,12 @@ def run_product(args):
         cpu_base = None
         if not args.no_cpu_baseline:
             try:
-                p, s, desc = cpu_reference_run(wl, 1, repeats=2)
+                workers = ReferenceWorkers(wl, 1)
+                p, s = workers.run(repeats=3)
+                workers.close()
                 cpu_base = {"value": p / s / 1e6, "unit": UNIT, "cores": 1,
-                            "kind": "reference", "sample": desc}
+                            "kind": "reference",
+                            "sample": "3 loops: " + workers.desc}
             except Exception as exc:      # noqa: BLE001
                 cpu_base = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                             "sample": f"unavailable: {exc}"}
