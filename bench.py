@@ -71,7 +71,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                 "-i", str(self.index), "-lms", "100"],
+                 "-i", str(self.index), "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -147,16 +147,16 @@ class ReferenceWorkers:
     Newton loops concurrently, one host thread each (the reference's
     ThreadPool model: one view per thread, app/smvsrecon.cc:558)."""
 
-    def __init__(self, wl, threads):
+    def __init__(self, wl, threads, frac=4):
         from oracle import ref as oref
         if not oref.available():
             raise RuntimeError("oracle/_ref missing")
         self.threads = threads
-        self.wins = _windows(wl, threads)
+        self.wins = _windows(wl, threads, frac, frac)
         self.subs = [wl.restrict(*w) for w in self.wins]
         self.scenes = [_ref_scene_for(sub) for sub in self.subs]
         self.desc = (f"{threads} thread(s), each Newton loop on a "
-                     f"{self.wins[0][2]}x{self.wins[0][3]}-patch window (1/16 of the "
+                     f"{self.wins[0][2]}x{self.wins[0][3]}-patch window (1/{frac * frac} of the "
                      f"{wl.npx}x{wl.npy} grid) of the same 2 MP / 6-neighbour scale-2 workload")
 
     def run(self, repeats=1):
@@ -195,9 +195,15 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
-    threads = max(1, min(os.cpu_count() or 1, 16))
+    # one optimizer per host thread, like the reference's ThreadPool
+    # (hardware_concurrency() workers, one view each); capped at 64 so that the
+    # set-up (0.7 GB and ~1 s per worker) stays bounded
+    threads = max(1, min(os.cpu_count() or 1, 64))
     wl = build_workload(WIDTH, HEIGHT, N_SUB, SCALE, shading=False, seed_index=0)
-    workers = ReferenceWorkers(wl, threads)
+    # bounded sample per step: a 1/16 window (~5 s per step) for short runs, a
+    # 1/64 window when many steps are requested, so the run ends within minutes
+    frac = 4 if (args.steps + args.warmup) <= 25 else 8
+    workers = ReferenceWorkers(wl, threads, frac)
     desc = workers.desc
     for _ in range(args.warmup):
         workers.run()
