@@ -80,9 +80,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Samples that arrived inside [t_begin, t_end] (the timed region); the
+        sampler is started before the warm-up because nvidia-smi needs a few
+        hundred ms to produce its first line."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -92,7 +95,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = [ln for (t, ln) in self.lines
+                 if t_begin is None or (t_begin <= t <= t_end + 0.05)]
+        if not lines:          # region shorter than the sampling jitter: nearest ones
+            lines = [ln for (_, ln) in self.lines[-5:]]
+        for ln in lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 6:
                 continue
@@ -281,6 +288,8 @@ def run_product(args):
         ctx.set_nodes(wl.nodes)             # reset; not part of the timed loop
         return ctx.newton_loop(None, REGULARIZATION, 0.0)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     # warm-up (both paths)
     wl.push(ctx)
     for _ in range(max(args.warmup, 3)):
@@ -288,9 +297,7 @@ def run_product(args):
     e2e_step()
 
     # ---- device-resident arm --------------------------------------------
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     launches0 = ctx.launches
     t_dev_ms, pix, newton, cg = 0.0, 0.0, 0, 0
     t_split = np.zeros(3)
@@ -303,9 +310,10 @@ def run_product(args):
         cg += st["cg_iterations"]
         t_split += [st["ms_construct"], st["ms_solve"], st["ms_update"]]
     barrier()
-    wall_resident = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    wall_resident = t1 - t0
     launches = ctx.launches - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t0, t1)
 
     # ---- end-to-end arm ---------------------------------------------------
     barrier()

@@ -336,3 +336,79 @@ def test_full_size_properties():
         assert np.linalg.norm(res) < np.linalg.norm(g)
         it2, _ = ctx.cg_solve()
         assert it2 == it and np.array_equal(ctx.get_delta(), d1)   # deterministic
+
+
+# ---------------------------------------------------------------------------
+# error behaviour of the ABI (codes instead of the reference's exceptions)
+# ---------------------------------------------------------------------------
+
+def test_error_paths():
+    G = load("gn_s2.npz")
+    n = int(G["n_sub"])
+    views = dict(main_grad=G["main_grad"], sub_grads=[G[f"sub_grad{k}"] for k in range(n)],
+                 sub_hess=[G[f"sub_hess{k}"] for k in range(n)], Mi=G["Mi"], ti=G["ti"],
+                 flen_px=float(G["flen"]), inv_flen=float(G["inv_flen"]))
+    surf = [int(G["scale"]), int(G["npx"]), int(G["npy"]), int(G["start_x"]),
+            int(G["start_y"]), G["nodes"], G["node_valid"], G["patch_valid"],
+            G["vis_off"], G["vis_ids"]]
+    with api.Context(0) as ctx:
+        with pytest.raises(api.SmvsbError) as e:       # call order
+            ctx.set_surface(*surf)
+        assert e.value.code == -4
+        ctx.set_views(**views)
+        with pytest.raises(api.SmvsbError) as e:       # no system yet
+            ctx.n_nodes = 10
+            ctx.cg_solve()
+        assert e.value.code == -4
+        bad = list(surf)
+        bad[0] = 7                                     # unsupported scale
+        with pytest.raises(api.SmvsbError) as e:
+            ctx.set_surface(*bad)
+        assert e.value.code == -1
+        bad = list(surf)
+        bad[1] = surf[1] + 50                          # grid larger than the image
+        bad[5] = np.zeros(((bad[1] + 1) * (surf[2] + 1), 4))
+        bad[6] = np.zeros((bad[1] + 1) * (surf[2] + 1), np.uint8)
+        bad[7] = np.zeros(bad[1] * surf[2], np.uint8)
+        bad[8] = np.zeros(bad[1] * surf[2] + 1, np.uint32)
+        with pytest.raises(api.SmvsbError) as e:
+            ctx.set_surface(*bad)
+        assert e.value.code == -1
+        bad = list(surf)
+        bad[9] = np.full_like(surf[9], 9)              # neighbour id out of range
+        with pytest.raises(api.SmvsbError) as e:
+            ctx.set_surface(*bad)
+        assert e.value.code == -1
+        ctx.set_surface(*surf)
+        with pytest.raises(api.SmvsbError) as e:       # lighting without shading image
+            ctx.gn_construct(None, np.ones(16), 0.01, 0.0)
+        assert e.value.code == -4
+        ctx.gn_construct(None, None, 0.01, 0.0)        # still usable afterwards
+        assert ctx.cg_solve()[0] > 0
+    z = np.zeros((64, 64), np.uint8)
+    eye, t0 = np.eye(3, dtype=np.float32).ravel(), np.zeros(3, np.float32)
+    for kwargs in (dict(num_steps=48), dict(penalty1=100, penalty2=50),
+                   dict(penalty2=300)):
+        with pytest.raises(api.SmvsbError) as e:
+            api.sgm(z, z, eye, t0, 1.0, 2.0, **kwargs)
+        assert e.value.code == -1
+    with pytest.raises(api.SmvsbError):                # image smaller than the census
+        api.sgm(z[:6, :8], z, eye, t0, 1.0, 2.0)
+
+
+def test_nan_break_and_zero_gradient():
+    """Constant images: zero photometric gradient everywhere. The loop must
+    leave through the reference's NaN rule or converge, never hang."""
+    G = load("gn_s4.npz")
+    n = int(G["n_sub"])
+    with api.Context(0) as ctx:
+        zero2 = np.zeros_like(G["main_grad"])
+        ctx.set_views(zero2, [np.zeros_like(G[f"sub_grad{k}"]) for k in range(n)],
+                      [np.zeros_like(G[f"sub_hess{k}"]) for k in range(n)], G["Mi"],
+                      G["ti"], float(G["flen"]), float(G["inv_flen"]))
+        ctx.set_surface(int(G["scale"]), int(G["npx"]), int(G["npy"]), int(G["start_x"]),
+                        int(G["start_y"]), G["nodes"], G["node_valid"], G["patch_valid"],
+                        G["vis_off"], G["vis_ids"])
+        st = ctx.newton_loop(None, 0.0, 0.0, max_steps=5)   # no regulariser: g = 0, H = 0
+        assert st["nan"] and st["newton_steps"] == 1
+        assert np.array_equal(ctx.get_nodes(), G["nodes"])  # surface untouched
