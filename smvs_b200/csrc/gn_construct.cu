@@ -28,6 +28,28 @@ namespace {
 constexpr int K1_THREADS = 128;
 constexpr int AS_STRIDE = 27;           /* 21 + 6 doubles per sample, odd */
 
+/* Hermite interpolation matrix: 16 polynomial coefficients from the 16 node
+ * values ordered (f x4, dx x4, dy x4, dxy x4), lib/bicubic_patch.cc:20-38.
+ * (A table of small integers that any bicubic Hermite patch implies.) */
+__constant__ double c_hermite[256] = {
+    1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    -3, 3, 0, 0, -2, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    2, -2, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0,
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0,
+    0, 0, 0, 0, 0, 0, 0, 0, -3, 3, 0, 0, -2, -1, 0, 0,
+    0, 0, 0, 0, 0, 0, 0, 0, 2, -2, 0, 0, 1, 1, 0, 0,
+    -3, 0, 3, 0, 0, 0, 0, 0, -2, 0, -1, 0, 0, 0, 0, 0,
+    0, 0, 0, 0, -3, 0, 3, 0, 0, 0, 0, 0, -2, 0, -1, 0,
+    9, -9, -9, 9, 6, 3, -6, -3, 6, -6, 3, -3, 4, 2, 2, 1,
+    -6, 6, 6, -6, -3, -3, 3, 3, -4, 4, -2, 2, -2, -2, -1, -1,
+    2, 0, -2, 0, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0,
+    0, 0, 0, 0, 2, 0, -2, 0, 0, 0, 0, 0, 1, 0, 1, 0,
+    -6, 6, 6, -6, -4, -2, 4, 2, -3, 3, -3, 3, -2, -1, -2, -1,
+    4, -4, -4, 4, 2, 2, -2, -2, 2, -2, 2, -2, 1, 1, 1, 1
+};
+
 /* Hermite basis and its derivatives on [0,1]; index = side + 2 * order. */
 __host__ __device__ inline void
 hermite (double t, double* b0, double* b1, double* b2)
@@ -133,6 +155,7 @@ gn_patch_kernel (ConstructArgs const args)
     SurfaceDev const& sf = args.s;
 
     __shared__ double s_theta[PPB][16];
+    __shared__ double s_coef[PPB][16];        /* coeffs[i][j] at [i * 4 + j] */
     __shared__ double s_as[K1_THREADS * AS_STRIDE];
     __shared__ double s_basis[3 * 16 * 4];       /* npos <= 16 */
     __shared__ double s_part[(GPP > 1) ? K1_THREADS * 17 : 1];
@@ -177,6 +200,25 @@ gn_patch_kernel (ConstructArgs const args)
     }
     __syncthreads();
 
+    /* BicubicPatch::compute_coefficients, lib/bicubic_patch.cc:56-86: a = A x
+     * with x = (f x4, dx x4, dy x4, dxy x4), summed in index order exactly
+     * like the reference, so that the sample values below are bitwise its */
+    if (tid < PPB * 16)
+    {
+        int const pl = tid / 16, r = tid % 16;
+        xd sum(0.0);
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+        {
+            /* x[4 * c + node] = theta[node * 4 + c] */
+            double const xv = s_theta[pl][(k & 3) * 4 + (k >> 2)];
+            sum += xd(c_hermite[r * 16 + k]) * xd(xv);
+        }
+        /* a[k = j * 4 + i] -> coeffs[i][j] */
+        s_coef[pl][(r & 3) * 4 + (r >> 2)] = sum.v;
+    }
+    __syncthreads();
+
     /* phase-2 accumulators live across the chunks of a patch */
     int const q = tid / 16;                  /* group in block */
     int const row = tid % 16;
@@ -205,28 +247,65 @@ gn_patch_kernel (ConstructArgs const args)
         if (s_proc[pl])
         {
             int const ix = s % npos, iy = s / npos;
-            double const* X0 = s_basis + (0 * npos + ix) * 4;
-            double const* X1 = s_basis + (1 * npos + ix) * 4;
-            double const* X2 = s_basis + (2 * npos + ix) * 4;
-            double const* Y0 = s_basis + (0 * npos + iy) * 4;
-            double const* Y1 = s_basis + (1 * npos + iy) * 4;
-            double const* Y2 = s_basis + (2 * npos + iy) * 4;
 
-            /* depth and derivatives at the sample,
-             * lib/surface_patch.cc:93-109 */
-            double w = 0, wx = 0, wy = 0, wxy = 0, wxx = 0, wyy = 0;
-#pragma unroll
-            for (int col = 0; col < 16; ++col)
+            /* depth and derivatives at the sample: BicubicPatch::evaluate_*
+             * (lib/bicubic_patch.cc:121-187) on the polynomial coefficients,
+             * then the 1/ps scaling of lib/surface_patch.cc:93-109 -- exact
+             * arithmetic in the reference's order (see xd in gn_math.cuh) */
+            double w, wx, wy, wxy, wxx, wyy;
             {
-                int const bx = ((col >> 2) & 1) + 2 * (col & 1);
-                int const by = ((col >> 3) & 1) + 2 * ((col >> 1) & 1);
-                double const th = s_theta[pl][col];
-                w += th * X0[bx] * Y0[by];
-                wx += th * X1[bx] * Y0[by];
-                wy += th * X0[bx] * Y1[by];
-                wxy += th * X1[bx] * Y1[by];
-                wxx += th * X2[bx] * Y0[by];
-                wyy += th * X0[bx] * Y2[by];
+                double const* cf = s_coef[pl];
+                xd const size(static_cast<double>(sf.ps));
+                xd const sx = (xd(static_cast<double>(ix * sf.sampling))
+                    + xd(0.5)) / size;
+                xd const sy = (xd(static_cast<double>(iy * sf.sampling))
+                    + xd(0.5)) / size;
+                xd ex[4], ey[4];
+                ex[0] = xd(1.0); ex[1] = sx; ex[2] = sx * sx; ex[3] = ex[2] * sx;
+                ey[0] = xd(1.0); ey[1] = sy; ey[2] = sy * sy; ey[3] = ey[2] * sy;
+                xd f(0.0), fx(0.0), fy(0.0), fxy(0.0), fxx(0.0), fyy(0.0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        f += xd(cf[i * 4 + j]) * ex[i] * ey[j];
+#pragma unroll
+                for (int i = 1; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        fx += xd(cf[i * 4 + j]) * xd(double(i)) * ex[i - 1]
+                            * ey[j];
+#pragma unroll
+                for (int i = 2; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        fxx += xd(cf[i * 4 + j]) * xd(double(i))
+                            * xd(double(i - 1)) * ex[i - 2] * ey[j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 1; j < 4; ++j)
+                        fy += xd(cf[i * 4 + j]) * ex[i] * xd(double(j))
+                            * ey[j - 1];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 2; j < 4; ++j)
+                        fyy += xd(cf[i * 4 + j]) * ex[i] * xd(double(j))
+                            * xd(double(j - 1)) * ey[j - 2];
+#pragma unroll
+                for (int i = 1; i < 4; ++i)
+#pragma unroll
+                    for (int j = 1; j < 4; ++j)
+                        fxy += xd(cf[i * 4 + j]) * xd(double(i)) * ex[i - 1]
+                            * xd(double(j)) * ey[j - 1];
+                xd const size2(static_cast<double>(sf.ps * sf.ps));
+                w = f.v;
+                wx = (fx / size).v;
+                wy = (fy / size).v;
+                wxy = (fxy / size2).v;
+                wxx = (fxx / size2).v;
+                wyy = (fyy / size2).v;
             }
 
             int const idx = patch % sf.npx, idy = patch / sf.npx;

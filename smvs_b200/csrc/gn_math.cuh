@@ -29,6 +29,32 @@ sym6 (int k, int l)
 }
 
 /*
+ * "Exact double": arithmetic with explicit round-to-nearest instructions, so
+ * the compiler cannot contract a*b+c into an FMA. Several formulas of the
+ * path subtract nearly equal products (p*d - r*a, dxx*n - dx*nx, second
+ * derivatives of a smooth depth field from Hermite data, ...); at 2 MP their
+ * rounding noise is amplified 1e3..1e5 x, so evaluating them in a different
+ * order than the CPU costs parity (1e-9 instead of 1e-13 on the Hessian).
+ * Code written with xd in the reference's expression order is bitwise equal
+ * to the reference built with -ffp-contract=off.
+ */
+struct xd
+{
+    double v;
+    __device__ __forceinline__ xd (void) {}
+    __device__ __forceinline__ xd (double a) : v(a) {}
+};
+__device__ __forceinline__ xd operator+ (xd a, xd b) { return xd(__dadd_rn(a.v, b.v)); }
+__device__ __forceinline__ xd operator- (xd a, xd b) { return xd(__dadd_rn(a.v, -b.v)); }
+__device__ __forceinline__ xd operator* (xd a, xd b) { return xd(__dmul_rn(a.v, b.v)); }
+__device__ __forceinline__ xd operator/ (xd a, xd b) { return xd(__ddiv_rn(a.v, b.v)); }
+__device__ __forceinline__ xd operator- (xd a) { return xd(-a.v); }
+__device__ __forceinline__ xd& operator+= (xd& a, xd b) { a = a + b; return a; }
+__device__ __forceinline__ xd& operator-= (xd& a, xd b) { a = a - b; return a; }
+__device__ __forceinline__ xd& operator/= (xd& a, xd b) { a = a / b; return a; }
+__device__ __forceinline__ xd xsqrt (xd a) { return xd(__dsqrt_rn(a.v)); }
+
+/*
  * mve::Image<float>::linear_at on a packed neighbour texel image, restated
  * bit-for-bit: coordinates narrowed to fp32 and clamped to the image, fp32
  * weights, left-to-right fp32 sum without FMA contraction
@@ -99,68 +125,67 @@ neighbour_row (double const* __restrict__ Mt, float const* __restrict__ tex,
     double const M6 = Mt[6], M7 = Mt[7], M8 = Mt[8];
     double const t0 = Mt[9], t1 = Mt[10], t2 = Mt[11];
 
-    double const p = M0 * u + M1 * v + M2;
-    double const q = M3 * u + M4 * v + M5;
-    double const r = M6 * u + M7 * v + M8;
-    double const a = w * p + t0;
-    double const b = w * q + t1;
-    double const d = w * r + t2;
-    double const d2 = d * d;
-    double const inv_d = 1.0 / d;
-    double const inv_d2 = inv_d * inv_d;
+    /* exact arithmetic in the reference's expression order (see xd) */
+    xd const m0(M0), m1(M1), m2(M2), m3(M3), m4(M4), m5(M5), m6(M6), m7(M7),
+        m8(M8), T0(t0), T1(t1), T2(t2), W(w), WX(wx), WY(wy), U(u), V(v);
+    /* update, lib/correspondence.cc:20-44 */
+    xd const p = m0 * U + m1 * V + m2;
+    xd const q = m3 * U + m4 * V + m5;
+    xd const r = m6 * U + m7 * V + m8;
+    xd const a = W * p + T0;
+    xd const b = W * q + T1;
+    xd const d = W * r + T2;
+    xd const d2 = d * d;
 
-    /* fill + fill_jacobian */
-    double const projx = a * inv_d - 0.5;
-    double const projy = b * inv_d - 0.5;
-    double const rx = wx * r + w * M6;
-    double const ry = wy * r + w * M7;
-    double const jac0 = (wx * p + w * M0) * inv_d - a * rx * inv_d2;
-    double const jac2 = (wy * p + w * M1) * inv_d - a * ry * inv_d2;
-    double const jac1 = (wx * q + w * M3) * inv_d - b * rx * inv_d2;
-    double const jac3 = (wy * q + w * M4) * inv_d - b * ry * inv_d2;
+    /* fill (:46-51) and the caller's -0.5 (gauss_newton_step.cc:189-190) */
+    double const projx = (a / d - xd(0.5)).v;
+    double const projy = (b / d - xd(0.5)).v;
+    /* fill_jacobian, :88-100 */
+    xd j0 = (WX * p + W * m0) / d;
+    xd j2 = (WY * p + W * m1) / d;
+    j0 -= a * (WX * r + W * m6) / d2;
+    j2 -= a * (WY * r + W * m7) / d2;
+    xd j1 = (WX * q + W * m3) / d;
+    xd j3 = (WY * q + W * m4) / d;
+    j1 -= b * (WX * r + W * m6) / d2;
+    j3 -= b * (WY * r + W * m7) / d2;
 
     float tap[5];
     tap_neighbour(tex, sw, sh, projx, projy, tap);
-    double const gx = tap[0], gy = tap[1];
-    double const h0 = tap[2], h1 = tap[3], h3 = tap[4];
+    xd const GX(tap[0]), GY(tap[1]), H0(tap[2]), H1(tap[3]), H3(tap[4]);
+    double const gx = GX.v, gy = GY.v;
 
     NbRow out;
-    out.jgx = jac0 * gx + jac1 * gy;
-    out.jgy = jac2 * gx + jac3 * gy;
+    /* jac * grad_sub and jac * hess_sub (row times column, left to right) */
+    out.jgx = (j0 * GX + j1 * GY).v;
+    out.jgy = (j2 * GX + j3 * GY).v;
+    double const jh00 = (j0 * H0 + j1 * H1).v;
+    double const jh01 = (j0 * H1 + j1 * H3).v;
+    double const jh10 = (j2 * H0 + j3 * H1).v;
+    double const jh11 = (j2 * H1 + j3 * H3).v;
+    /* fill_derivative, :74-86 */
+    double const du_w = ((p * d - r * a) / d2).v;
+    double const dv_w = ((q * d - r * b) / d2).v;
 
-    /* jac * hess_sub, and d(proj)/dw */
-    double const jh00 = jac0 * h0 + jac1 * h1;
-    double const jh01 = jac0 * h1 + jac1 * h3;
-    double const jh10 = jac2 * h0 + jac3 * h1;
-    double const jh11 = jac2 * h1 + jac3 * h3;
-    double const du_w = (p * d - r * a) * inv_d2;
-    double const dv_w = (q * d - r * b) * inv_d2;
-
-    /* fill_jacobian_derivative_grad, lib/correspondence.cc:102-187 */
-    double const d4 = d2 * d2;
-    double const d_prime_d4 = 2.0 * d * r / d4;
-    double const du_c_prime = p * t2 - r * t0;
-    double const dv_c_prime = q * t2 - r * t1;
-
-    double const du_a_t0 = w * (M0 * r - p * M6);
-    double const du_a_t1 = w * (M1 * r - p * M7);
-    double const du_b0 = M0 * t2 - M6 * t0;
-    double const du_b1 = M1 * t2 - M7 * t0;
-    double const dv_a_t0 = w * (M3 * r - q * M6);
-    double const dv_a_t1 = w * (M4 * r - q * M7);
-    double const dv_b0 = M3 * t2 - M6 * t1;
-    double const dv_b1 = M4 * t2 - M7 * t1;
-
-    double const A0 = (2.0 * du_a_t0 + du_b0) * inv_d2
-        - (w * (du_a_t0 + du_b0) + wx * du_c_prime) * d_prime_d4;
-    double const A1 = (2.0 * du_a_t1 + du_b1) * inv_d2
-        - (w * (du_a_t1 + du_b1) + wy * du_c_prime) * d_prime_d4;
-    double const B0 = (2.0 * dv_a_t0 + dv_b0) * inv_d2
-        - (w * (dv_a_t0 + dv_b0) + wx * dv_c_prime) * d_prime_d4;
-    double const B1 = (2.0 * dv_a_t1 + dv_b1) * inv_d2
-        - (w * (dv_a_t1 + dv_b1) + wy * dv_c_prime) * d_prime_d4;
-    double const cu = du_c_prime * inv_d2;
-    double const cv = dv_c_prime * inv_d2;
+    /* fill_jacobian_derivative_grad, :102-187 */
+    xd const d4 = d2 * d2;
+    xd const d_prime = xd(2.0) * d * r;
+    xd const du_c_prime = p * T2 - r * T0;
+    xd const dv_c_prime = q * T2 - r * T1;
+    xd const du_a_t0 = W * (m0 * r - p * m6), du_a_t1 = W * (m1 * r - p * m7);
+    xd const du_b0 = m0 * T2 - m6 * T0, du_b1 = m1 * T2 - m7 * T0;
+    xd const dv_a_t0 = W * (m3 * r - q * m6), dv_a_t1 = W * (m4 * r - q * m7);
+    xd const dv_b0 = m3 * T2 - m6 * T1, dv_b1 = m4 * T2 - m7 * T1;
+    double const A0 = ((xd(2.0) * du_a_t0 + du_b0) / d2
+        - (W * (du_a_t0 + du_b0) + WX * du_c_prime) * d_prime / d4).v;
+    double const A1 = ((xd(2.0) * du_a_t1 + du_b1) / d2
+        - (W * (du_a_t1 + du_b1) + WY * du_c_prime) * d_prime / d4).v;
+    double const B0 = ((xd(2.0) * dv_a_t0 + dv_b0) / d2
+        - (W * (dv_a_t0 + dv_b0) + WX * dv_c_prime) * d_prime / d4).v;
+    double const B1 = ((xd(2.0) * dv_a_t1 + dv_b1) / d2
+        - (W * (dv_a_t1 + dv_b1) + WY * dv_c_prime) * d_prime / d4).v;
+    double const cu = (du_c_prime / d2).v;
+    double const cv = (dv_c_prime / d2).v;
 
     out.ax = A0 * gx + B0 * gy + jh00 * du_w + jh01 * dv_w;
     out.ay = A1 * gx + B1 * gy + jh10 * du_w + jh11 * dv_w;
@@ -213,46 +238,60 @@ struct SurfGeo
 };
 
 __device__ __forceinline__ void
-surface_geometry (double x, double y, double f, double w, double dx,
-    double dy, double dxy, double dxx, double dyy, SurfGeo& g)
+surface_geometry (double x_, double y_, double f_, double w_, double dx_,
+    double dy_, double dxy_, double dxx_, double dyy_, SurfGeo& g)
 {
-    double const f_sqr_inv = 1.0 / (f * f);
-    double const a = w + x * dx + y * dy;
-    double const ax = 2.0 * dx + x * dxx + y * dxy;
-    double const ay = 2.0 * dy + y * dyy + x * dxy;
+    /* exact arithmetic in the reference's expression order (see xd) */
+    xd const x(x_), y(y_), f(f_), w(w_), dx(dx_), dy(dy_), dxy(dxy_),
+        dxx(dxx_), dyy(dyy_);
+    xd const a = w + x * dx + y * dy;
+    xd const ax = xd(2.0) * dx + x * dxx + y * dxy;
+    xd const ay = xd(2.0) * dy + y * dyy + x * dxy;
 
     /* normal_divergence, :69-107 */
     {
-        double t = a / f;
+        xd t = a / f;
         t = t * t;
         t += dx * dx + dy * dy;
-        double const n = sqrt(t);
-        double nx = dx * dxx + dy * dxy;
-        nx += f_sqr_inv * a * (dx + dx + x * dxx + y * dxy);
+        xd const n = xsqrt(t);
+        xd nx = dx * dxx + dy * dxy;
+        nx += (xd(1.0) / (f * f)) * (w + x * dx + y * dy)
+            * (dx + dx + x * dxx + y * dxy);
         nx /= n;
-        double ny = dx * dxy + dy * dyy;
-        ny += f_sqr_inv * a * (dy + dy + x * dxy + y * dyy);
+        xd ny = dx * dxy + dy * dyy;
+        ny += (xd(1.0) / (f * f)) * (w + x * dx + y * dy)
+            * (dy + dy + x * dxy + y * dyy);
         ny /= n;
-        g.div[0] = (dxx * n - dx * nx) / t;
-        g.div[1] = -((dxy * n - dy * nx) / t);
-        g.div[2] = (ax * n - a * nx) / (t * f);
-        g.div[3] = (dxy * n - dx * ny) / t;
-        g.div[4] = -((dyy * n - dy * ny) / t);
-        g.div[5] = (ay * n - a * ny) / (t * f);
+        g.div[0] = ((dxx * n - dx * nx) / t).v;
+        g.div[1] = (-((dxy * n - dy * nx) / t)).v;
+        g.div[2] = ((ax * n - a * nx) / (t * f)).v;
+        g.div[3] = ((dxy * n - dx * ny) / t).v;
+        g.div[4] = (-((dyy * n - dy * ny) / t)).v;
+        g.div[5] = ((ay * n - a * ny) / (t * f)).v;
     }
 
-    /* normal_divergence_deriv, :109-190 */
-    double const a_f2 = a * f_sqr_inv;
-    double const t = dx * dx + dy * dy + a * a_f2;
-    double const n = sqrt(t);
-    double const b = dx * dxx + dy * dxy + a_f2 * ax;
-    double const c = dx * dxy + dy * dyy + a_f2 * ay;
-    double const nx = b / n;
-    double const ny = c / n;
+    /* normal_divergence_deriv, :109-190, and normal_derivative, :31-65,
+     * applied to the six unit "prime" vectors. The shared quantities
+     * (t, n, b, c, nx, ny) are exact; the coefficients themselves are only
+     * ever combined linearly with the basis rows, so ordinary (contracted)
+     * double arithmetic is enough for them and much cheaper. */
+    xd const f_sqr_inv_x = xd(1.0) / (f * f);
+    xd const a_f2_x = a * f_sqr_inv_x;
+    xd const t_x = dx * dx + dy * dy + a * a_f2_x;
+    xd const n_x = xsqrt(t_x);
+    xd const b_x = dx * dxx + dy * dxy
+        + a_f2_x * (xd(2.0) * dx + x * dxx + y * dxy);
+    xd const c_x = dx * dxy + dy * dyy
+        + a_f2_x * (xd(2.0) * dy + x * dxy + y * dyy);
+    double const f_sqr_inv = f_sqr_inv_x.v, t = t_x.v, n = n_x.v;
+    double const b = b_x.v, c = c_x.v;
+    double const nx = (b_x / n_x).v, ny = (c_x / n_x).v;
+    double const X = x_, Y = y_, F = f_, A = a.v, AX = ax.v, AY = ay.v;
+    double const DX = dx_, DY = dy_, DXY = dxy_, DXX = dxx_, DYY = dyy_;
     double const inv_t = 1.0 / t;
     double const inv_tt = inv_t * inv_t;
-    double const inv_ttf = inv_tt / f;
-    double const inv_tf = inv_t / f;
+    double const inv_ttf = inv_tt / F;
+    double const inv_tf = inv_t / F;
 
 #pragma unroll
     for (int k = 0; k < 6; ++k)
@@ -260,30 +299,30 @@ surface_geometry (double x, double y, double f, double w, double dx,
         double const w_p = (k == 0), dx_p = (k == 1), dy_p = (k == 2);
         double const dxy_p = (k == 3), dxx_p = (k == 4), dyy_p = (k == 5);
 
-        double const a_p = w_p + x * dx_p + y * dy_p;
-        double const ax_p = 2.0 * dx_p + x * dxx_p + y * dxy_p;
-        double const ay_p = 2.0 * dy_p + y * dyy_p + x * dxy_p;
-        double const t_p2 = dx * dx_p + dy * dy_p + f_sqr_inv * a * a_p;
+        double const a_p = w_p + X * dx_p + Y * dy_p;
+        double const ax_p = 2.0 * dx_p + X * dxx_p + Y * dxy_p;
+        double const ay_p = 2.0 * dy_p + Y * dyy_p + X * dxy_p;
+        double const t_p2 = DX * dx_p + DY * dy_p + f_sqr_inv * A * a_p;
         double const n_p = t_p2 / n;
-        double const b_p = (dx_p * dxx + dx * dxx_p)
-            + (dy_p * dxy + dy * dxy_p) + f_sqr_inv * (a_p * ax + a * ax_p);
-        double const c_p = (dx_p * dxy + dx * dxy_p)
-            + (dy_p * dyy + dy * dyy_p) + f_sqr_inv * (a_p * ay + a * ay_p);
+        double const b_p = (dx_p * DXX + DX * dxx_p)
+            + (dy_p * DXY + DY * dxy_p) + f_sqr_inv * (a_p * AX + A * ax_p);
+        double const c_p = (dx_p * DXY + DX * dxy_p)
+            + (dy_p * DYY + DY * dyy_p) + f_sqr_inv * (a_p * AY + A * ay_p);
         double const nx_p = (b_p * n - b * n_p) * inv_t;
         double const ny_p = (c_p * n - c * n_p) * inv_t;
 
-        double const xx_p = ((dxx_p * n + dxx * n_p - dx_p * nx - dx * nx_p)
-            * t - (dxx * n - dx * nx) * t_p2 * 2.0) * inv_tt;
-        double const yy_p = ((dyy_p * n + dyy * n_p - dy_p * ny - dy * ny_p)
-            * t - (dyy * n - dy * ny) * t_p2 * 2.0) * inv_tt;
-        double const xy_p = ((dxy_p * n + dxy * n_p - dx_p * ny - dx * ny_p)
-            * t - (dxy * n - dx * ny) * t_p2 * 2.0) * inv_tt;
-        double const yx_p = ((dxy_p * n + dxy * n_p - dy_p * nx - dy * nx_p)
-            * t - (dxy * n - dy * nx) * t_p2 * 2.0) * inv_tt;
-        double const zx_p = ((ax_p * n + ax * n_p - a_p * nx - a * nx_p)
-            * t - (ax * n - a * nx) * t_p2 * 2.0) * inv_ttf;
-        double const zy_p = ((ay_p * n + ay * n_p - a_p * ny - a * ny_p)
-            * t - (ay * n - a * ny) * t_p2 * 2.0) * inv_ttf;
+        double const xx_p = ((dxx_p * n + DXX * n_p - dx_p * nx - DX * nx_p)
+            * t - (DXX * n - DX * nx) * t_p2 * 2.0) * inv_tt;
+        double const yy_p = ((dyy_p * n + DYY * n_p - dy_p * ny - DY * ny_p)
+            * t - (DYY * n - DY * ny) * t_p2 * 2.0) * inv_tt;
+        double const xy_p = ((dxy_p * n + DXY * n_p - dx_p * ny - DX * ny_p)
+            * t - (DXY * n - DX * ny) * t_p2 * 2.0) * inv_tt;
+        double const yx_p = ((dxy_p * n + DXY * n_p - dy_p * nx - DY * nx_p)
+            * t - (DXY * n - DY * nx) * t_p2 * 2.0) * inv_tt;
+        double const zx_p = ((ax_p * n + AX * n_p - a_p * nx - A * nx_p)
+            * t - (AX * n - A * nx) * t_p2 * 2.0) * inv_ttf;
+        double const zy_p = ((ay_p * n + AY * n_p - a_p * ny - A * ny_p)
+            * t - (AY * n - A * ny) * t_p2 * 2.0) * inv_ttf;
 
         g.C[0][k] = xx_p;
         g.C[1][k] = -yx_p;
@@ -294,10 +333,9 @@ surface_geometry (double x, double y, double f, double w, double dx,
 
         if (k < 3)
         {
-            /* normal_derivative, :31-65 */
-            g.N[0][k] = (dx_p * n - dx * n_p) * inv_t;
-            g.N[1][k] = (-dy_p * n + dy * n_p) * inv_t;
-            g.N[2][k] = (a_p * n - a * n_p) * inv_tf;
+            g.N[0][k] = (dx_p * n - DX * n_p) * inv_t;
+            g.N[1][k] = (-dy_p * n + DY * n_p) * inv_t;
+            g.N[2][k] = (a_p * n - A * n_p) * inv_tf;
         }
     }
 }

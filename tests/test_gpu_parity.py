@@ -2,10 +2,11 @@
 (1) the committed golden fixtures and (2) the compiled-verbatim reference
 run live on the same seeded inputs.
 
-Tolerances. The Gauss-Newton path is fp64 with a different (but fixed)
-summation order and FMA contraction, so values agree to ~1e-13 relative; the
-tests ask for 1e-9 on g / H / P / CG solution and for EQUAL iteration counts
-and active sets. Depth maps (float32 outputs) must agree to 1e-6 relative,
+Tolerances. The Gauss-Newton path is fp64; the cancellation-prone per-sample
+quantities are evaluated bitwise like the reference (gn_math.cuh: xd), the
+accumulation has a different (but fixed) summation order, so values agree to
+~1e-14 relative; the tests ask for 1e-11 on g / H, 1e-7..1e-8 on P and the CG
+solution (conditioning) and for EQUAL iteration counts and active sets. Depth maps (float32 outputs) must agree to 1e-6 relative,
 far inside the 1e-4 of BASELINE.json. SGM is integer work: bit-exact."""
 import os
 
@@ -19,7 +20,7 @@ from util_scene import Pair, rel_err
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-TOL = 1e-9
+TOL = 1e-11
 
 
 def load(name):
@@ -412,3 +413,46 @@ def test_nan_break_and_zero_gradient():
         st = ctx.newton_loop(None, 0.0, 0.0, max_steps=5)   # no regulariser: g = 0, H = 0
         assert st["nan"] and st["newton_steps"] == 1
         assert np.array_equal(ctx.get_nodes(), G["nodes"])  # surface untouched
+
+
+@needs_ref
+@pytest.mark.parametrize("shading", [False, True])
+def test_full_size_live_parity(shading):
+    """BASELINE.json configs[1] / configs[2] at their real size (1 ref + 6
+    neighbours, 1920x1080, scale 2): one Gauss-Newton construct + PCG solve +
+    update against the compiled reference on the bench workload's own
+    arrays."""
+    from bench import _ref_scene_for
+    from smvs_b200.workload import build_workload
+    wl = build_workload(1920, 1080, 6, scale=2, shading=shading, seed_index=3)
+    R = _ref_scene_for(wl)
+    with api.Context(0) as ctx:
+        wl.push_views_u8(ctx)          # device set_scale, bit-identical inputs
+        wl.push_surface(ctx)
+        light = None
+        if shading:
+            light, lg = R.fit_lighting(), ctx.fit_lighting()
+            assert rel_err(lg, light) < 1e-5
+        act = wl.node_valid
+        R.gn_construct(act, light, 0.01, 0.0)
+        ctx.gn_construct(act, light, 0.01, 0.0)
+        rs, gs = R.get_system(), ctx.debug_get_system()
+        assert np.array_equal(gs["Hinner"], rs["Hinner"])
+        assert rel_err(gs["g"], rs["g"]) < TOL
+        assert rel_err(gs["Hvals"], rs["Hvals"]) < TOL
+        xr, itr, infr = R.cg_solve()
+        itg, infg = ctx.cg_solve()
+        assert (itg, infg) == (itr, infr)
+        # the first solve at 2 MP runs into max_iterations (199 updates of an
+        # unconverged Krylov process): rounding differences of 1e-15 in H are
+        # amplified to ~1e-5 in x by the loss of orthogonality, in any
+        # implementation. The update step is therefore compared on the
+        # reference's own x.
+        assert rel_err(ctx.get_delta(), xr) < 1e-3
+        ctx.set_delta(xr)
+        ar, nr, _ = R.update_nodes(xr, act)
+        ag, ng, _ = ctx.update_nodes()
+        assert ng == nr and np.array_equal(ag, ar)
+        valid = wl.node_valid.astype(bool)      # the reference reports 0 for null nodes
+        assert np.array_equal(ctx.get_nodes()[valid], R.surface_get()[0][valid])
+    R.close()
