@@ -360,10 +360,11 @@ def run_product(args):
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
                     "unit": "GB/s", "frac": achieved / hbm_peak,
                     # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full
-                    # capture (profiles/r1b_cg.txt: 33.55 GB for a 200-iteration launch
-                    # = 167.8 MB per CG iteration), scaled to this run's iterations/launch
-                    "traffic": 167.8e6 * cg / max(newton, 1),
-                    "traffic_source": "profiles/r1b_cg.txt",
+                    # capture (profiles/r1c_cg.txt: 29.45 GB for a 200-iteration launch
+                    # = 147.3 MB per CG iteration: H only -- P and the vectors stay in
+                    # L2), scaled to this run's iterations/launch
+                    "traffic": 147.3e6 * cg / max(newton, 1),
+                    "traffic_source": "profiles/r1c_cg.txt",
                     "algorithmic_bytes_per_launch": bytes_per_iter * cg / max(newton, 1),
                     "launches_timed": newton}
 

@@ -19,6 +19,16 @@
  * d = z + beta d is folded into the next SpMV (formed on the fly for the nine
  * neighbours), the block-diagonal preconditioner into the residual update
  * (quad shuffles).
+ *
+ * Measured and NOT kept (1920x1080 scale 2, B200): parking what only the
+ * owning thread touches (x, r, A d, its row of P) in shared memory for the
+ * whole solve. It shortens the vector-update phase (5.1 -> 3.9 us) but every
+ * KB of shared memory is a KB less L1, and the SpMV needs L1 both for the
+ * vector entries nine rows share and as landing space for ~150 KB of loads in
+ * flight per SM: 22.3 -> 24.2 us with 86 KB of shared memory, 37 us with
+ * 200 KB. Likewise cp.async.bulk.prefetch.L2 of the rows a CTA reads first,
+ * issued while HBM idles in the vector-update phase: the SpMV gains 1.3 us,
+ * the update phase and the barriers lose more.
  */
 #include <cstdlib>
 
@@ -30,6 +40,7 @@ namespace {
 
 constexpr int CG_THREADS = 256;
 constexpr int CG_MAX_BLOCKS = 1024;
+constexpr int CG_UF = 4;          /* entries per thread in flight, update phase */
 
 struct CgArgs
 {
@@ -79,41 +90,111 @@ now_ns (void)
     return t;
 }
 
-/* Sum of `v` over the block in a fixed order; valid in thread 0. */
-__device__ __forceinline__ double
-block_sum (double v, double* s_red)
+/* Streaming load of the four Hessian entries of one block row: one 256-bit
+ * request per thread (LDG.E.NA.EFL2.256), not allocated in L1 -- L1 is left
+ * to the vector entries the nine rows around a node share -- and marked
+ * evict-first in L2 (H is 148 MB, read once per iteration). */
+__device__ __forceinline__ void
+ld_stream (double const* p, double2& h01, double2& h23)
 {
-    for (int off = 16; off > 0; off >>= 1)
-        v += __shfl_down_sync(0xffffffffu, v, off);
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.L1::no_allocate.L2::evict_first.v4.b64 "
+        "{%0, %1, %2, %3}, [%4];"
+        : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    h01.x = __longlong_as_double(a); h01.y = __longlong_as_double(b);
+    h23.x = __longlong_as_double(c); h23.y = __longlong_as_double(d);
+}
+
+/* 16-byte load of a vector entry pair other rows re-use from L1. */
+__device__ __forceinline__ double2
+ld_vec (double const* p)
+{
+    return *reinterpret_cast<double2 const*>(p);
+}
+
+/* 16-byte load with an L2 eviction-priority hint (P: keep resident). */
+__device__ __forceinline__ double2
+ld_hint (double const* p, unsigned long long policy)
+{
+    double2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+        : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy));
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long
+policy_evict_last (void)
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;"
+        : "=l"(pol));
+    return pol;
+}
+
+/* Sums of NV values over the block, each in a fixed order (warp shuffle
+ * tree, then the warps' results left to right); valid in thread 0. */
+template <int NV>
+__device__ __forceinline__ void
+block_sums (double (&v)[NV], double* s_red)
+{
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+        for (int off = 16; off > 0; off >>= 1)
+            v[j] += __shfl_down_sync(0xffffffffu, v[j], off);
     int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __syncthreads();
     if (lane == 0)
-        s_red[warp] = v;
-    __syncthreads();
-    double total = 0.0;
-    if (threadIdx.x == 0)
-        for (int i = 0; i < CG_THREADS / 32; ++i)
-            total += s_red[i];
-    return total;
-}
-
-/* Every block sums all per-block partials of `slot` in the same order. */
-__device__ __forceinline__ double
-all_sum (double const* partials, int slot, double* s_bcast)
-{
-    __syncthreads();
-    if (threadIdx.x < 32)
     {
-        double v = 0.0;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += 32)
-            v += __ldcg(partials + slot * CG_MAX_BLOCKS + i);
-        for (int off = 16; off > 0; off >>= 1)
-            v += __shfl_down_sync(0xffffffffu, v, off);
-        if (threadIdx.x == 0)
-            *s_bcast = v;
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+            s_red[j * (CG_THREADS / 32) + warp] = v[j];
     }
     __syncthreads();
-    return *s_bcast;
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+        {
+            double total = 0.0;
+            for (int i = 0; i < CG_THREADS / 32; ++i)
+                total += s_red[j * (CG_THREADS / 32) + i];
+            v[j] = total;
+        }
+    }
+}
+
+/* Every block sums all per-block partials of slots first .. first+NV-1 in
+ * the same order: warp j takes slot first+j, lane l adds partials l, l+32,
+ * ... in sequence (loads issued in batches ahead of the adds), then the
+ * shuffle tree. Results in s_bcast[0..NV-1], valid for all threads. */
+template <int NV>
+__device__ __forceinline__ void
+all_sums (double const* partials, int first, double* s_bcast)
+{
+    __syncthreads();
+    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < NV)
+    {
+        double const* p = partials + (first + warp) * CG_MAX_BLOCKS;
+        int const nb = gridDim.x;
+        double v = 0.0;
+        for (int base = lane; base < nb; base += 32 * 8)
+        {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                t[u] = (base + 32 * u < nb) ? __ldcg(p + base + 32 * u) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (base + 32 * u < nb)
+                    v += t[u];
+        }
+        for (int off = 16; off > 0; off >>= 1)
+            v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0)
+            s_bcast[warp] = v;
+    }
+    __syncthreads();
 }
 
 /*
@@ -149,14 +230,10 @@ struct DirVec
     double beta;
     __device__ __forceinline__ void load (int node, double* out) const
     {
-        double2 const z0 = *reinterpret_cast<double2 const*>(
-            z + static_cast<size_t>(node) * 4);
-        double2 const z1 = *reinterpret_cast<double2 const*>(
-            z + static_cast<size_t>(node) * 4 + 2);
-        double2 const d0 = *reinterpret_cast<double2 const*>(
-            d_old + static_cast<size_t>(node) * 4);
-        double2 const d1 = *reinterpret_cast<double2 const*>(
-            d_old + static_cast<size_t>(node) * 4 + 2);
+        double2 const z0 = ld_vec(z + static_cast<size_t>(node) * 4);
+        double2 const z1 = ld_vec(z + static_cast<size_t>(node) * 4 + 2);
+        double2 const d0 = ld_vec(d_old + static_cast<size_t>(node) * 4);
+        double2 const d1 = ld_vec(d_old + static_cast<size_t>(node) * 4 + 2);
         out[0] = z0.x + d0.x * beta; out[1] = z0.y + d0.y * beta;
         out[2] = z1.x + d1.x * beta; out[3] = z1.y + d1.y * beta;
     }
@@ -180,10 +257,8 @@ spmv_row (CgArgs const& a, VecOp const& vec, int node, int rp, double* own)
         if (jx < 0 || jx > a.npx || jy < 0 || jy > a.npy)
             continue;
         int const nj = jy * ns + jx;
-        double2 const h01 = __ldcs(reinterpret_cast<double2 const*>(
-            hrow + k * 16));
-        double2 const h23 = __ldcs(reinterpret_cast<double2 const*>(
-            hrow + k * 16 + 2));
+        double2 h01, h23;
+        ld_stream(hrow + k * 16, h01, h23);
         double v[4];
         vec.load(nj, v);
         if (k == 4)
@@ -203,8 +278,9 @@ spmv_row (CgArgs const& a, VecOp const& vec, int node, int rp, double* own)
 __global__ void __launch_bounds__(CG_THREADS, 2)
 cg_kernel (CgArgs const a)
 {
-    __shared__ double s_red[CG_THREADS / 32];
-    __shared__ double s_bcast;
+    unsigned long long const keep = policy_evict_last();
+    __shared__ double s_red[3 * CG_THREADS / 32];
+    __shared__ double s_bcast[3];
     unsigned int epoch = 0;
     int const n = a.n_nodes * 4;
     int const stride = gridDim.x * CG_THREADS;
@@ -212,7 +288,8 @@ cg_kernel (CgArgs const a)
     int const quad = threadIdx.x & 28;      /* first lane of the node's quad */
     int const rp = threadIdx.x & 3;
     /* bound rounded up: whole warps iterate together (shuffles below) */
-    int const n_round = ((n + 2 * stride - 1) / (2 * stride)) * (2 * stride);
+    int const n_round = ((n + CG_UF * stride - 1) / (CG_UF * stride))
+        * (CG_UF * stride);
 
     /* r = b = -g; x = 0; z = P r; r_dot_r = z.r; ||g||^2
      * (lib/conjugate_gradient.h:85-117). d_old = 0 with beta = 0 makes the
@@ -231,8 +308,9 @@ cg_kernel (CgArgs const a)
         if (!ok)
             continue;
         double const* prow = a.P + static_cast<size_t>(i >> 2) * 16 + rp * 4;
-        double const zi = prow[0] * r0 + prow[1] * r1 + prow[2] * r2
-            + prow[3] * r3;
+        double2 const p01 = *reinterpret_cast<double2 const*>(prow);
+        double2 const p23 = *reinterpret_cast<double2 const*>(prow + 2);
+        double const zi = p01.x * r0 + p01.y * r1 + p23.x * r2 + p23.y * r3;
         a.r[i] = ri;
         a.x[i] = 0.0;
         a.z[i] = zi;
@@ -240,13 +318,19 @@ cg_kernel (CgArgs const a)
         p_gg += gi * gi;
         p_zr += zi * ri;
     }
-    double tot = block_sum(p_zr, s_red);
-    if (threadIdx.x == 0) a.partials[0 * CG_MAX_BLOCKS + blockIdx.x] = tot;
-    tot = block_sum(p_gg, s_red);
-    if (threadIdx.x == 0) a.partials[1 * CG_MAX_BLOCKS + blockIdx.x] = tot;
+    {
+        double v[2] = { p_zr, p_gg };
+        block_sums<2>(v, s_red);
+        if (threadIdx.x == 0)
+        {
+            a.partials[0 * CG_MAX_BLOCKS + blockIdx.x] = v[0];
+            a.partials[1 * CG_MAX_BLOCKS + blockIdx.x] = v[1];
+        }
+    }
     grid_barrier(a.sync, epoch);
-    double r_dot_r = all_sum(a.partials, 0, &s_bcast);
-    double const gg = all_sum(a.partials, 1, &s_bcast);
+    all_sums<2>(a.partials, 0, s_bcast);
+    double r_dot_r = s_bcast[0];
+    double const gg = s_bcast[1];
     double const tol = (a.err_tol < 0.0) ? sqrt(gg) * 0.01 : a.err_tol;
     double Q0 = 0.0;     /* -x.(b + r) with x = 0 */
     double beta = 0.0;
@@ -274,93 +358,84 @@ cg_kernel (CgArgs const a)
             d_new[i] = di;
             p_dAd += v * di;
         }
-        tot = block_sum(p_dAd, s_red);
         int const slot = 2 + 4 * (iter & 1);
-        if (threadIdx.x == 0)
-            a.partials[slot * CG_MAX_BLOCKS + blockIdx.x] = tot;
+        {
+            double v[1] = { p_dAd };
+            block_sums<1>(v, s_red);
+            if (threadIdx.x == 0)
+                a.partials[slot * CG_MAX_BLOCKS + blockIdx.x] = v[0];
+        }
         unsigned long long const t_b = now_ns();
         grid_barrier(a.sync, epoch);
         unsigned long long const t_c = now_ns();
         tm[0] += t_b - t_a; tm[1] += t_c - t_b;
-        double const dAd = all_sum(a.partials, slot, &s_bcast);
+        all_sums<1>(a.partials, slot, s_bcast);
+        double const dAd = s_bcast[0];
         double const alpha = r_dot_r / dAd;
 
         /* x += alpha d; r -= alpha Ad; r.r; Q1 = -x.(b + r); z = P r; z.r
          * (:130-181) */
         double p_rr = 0.0, p_q = 0.0, p_zr2 = 0.0;
-        /* two elements per thread in flight: the pass is latency bound */
-        for (int i0 = t0; i0 < n_round; i0 += 2 * stride)
+        /* CG_UF entries per thread in flight: the pass is latency bound */
+        for (int i0 = t0; i0 < n_round; i0 += CG_UF * stride)
         {
-            int const i1 = i0 + stride;
-            bool const ok0 = i0 < n, ok1 = i1 < n;
-            double x0 = 0.0, ra = 0.0, x1 = 0.0, rb = 0.0;
-            double g0 = 0.0, g1 = 0.0;
-            double2 pa01 = make_double2(0, 0), pa23 = pa01, pb01 = pa01,
-                pb23 = pa01;
-            if (ok0)
+            double xv[CG_UF], rv[CG_UF], gv[CG_UF];
+            double2 p01[CG_UF], p23[CG_UF];
+#pragma unroll
+            for (int u = 0; u < CG_UF; ++u)
             {
-                x0 = a.x[i0]; ra = a.r[i0];
-                double const dn = d_new[i0], ad = a.Ad[i0];
-                g0 = a.g[i0];
-                pa01 = __ldcs(reinterpret_cast<double2 const*>(
-                    a.P + static_cast<size_t>(i0 >> 2) * 16 + rp * 4));
-                pa23 = __ldcs(reinterpret_cast<double2 const*>(
-                    a.P + static_cast<size_t>(i0 >> 2) * 16 + rp * 4 + 2));
-                x0 += dn * alpha; ra -= ad * alpha;
+                int const i = i0 + u * stride;
+                xv[u] = 0.0; rv[u] = 0.0; gv[u] = 0.0;
+                p01[u] = make_double2(0, 0); p23[u] = p01[u];
+                if (i < n)
+                {
+                    double const dn = d_new[i], ad = a.Ad[i];
+                    gv[u] = a.g[i];
+                    xv[u] = a.x[i]; rv[u] = a.r[i];
+                    double const* prow = a.P + static_cast<size_t>(i >> 2) * 16
+                        + rp * 4;
+                    p01[u] = ld_hint(prow, keep);
+                    p23[u] = ld_hint(prow + 2, keep);
+                    xv[u] += dn * alpha; rv[u] -= ad * alpha;
+                }
             }
-            if (ok1)
+#pragma unroll
+            for (int u = 0; u < CG_UF; ++u)
             {
-                x1 = a.x[i1]; rb = a.r[i1];
-                double const dn = d_new[i1], ad = a.Ad[i1];
-                g1 = a.g[i1];
-                pb01 = __ldcs(reinterpret_cast<double2 const*>(
-                    a.P + static_cast<size_t>(i1 >> 2) * 16 + rp * 4));
-                pb23 = __ldcs(reinterpret_cast<double2 const*>(
-                    a.P + static_cast<size_t>(i1 >> 2) * 16 + rp * 4 + 2));
-                x1 += dn * alpha; rb -= ad * alpha;
-            }
-            double const a0 = __shfl_sync(0xffffffffu, ra, quad);
-            double const a1 = __shfl_sync(0xffffffffu, ra, quad + 1);
-            double const a2 = __shfl_sync(0xffffffffu, ra, quad + 2);
-            double const a3 = __shfl_sync(0xffffffffu, ra, quad + 3);
-            double const b0 = __shfl_sync(0xffffffffu, rb, quad);
-            double const b1 = __shfl_sync(0xffffffffu, rb, quad + 1);
-            double const b2 = __shfl_sync(0xffffffffu, rb, quad + 2);
-            double const b3 = __shfl_sync(0xffffffffu, rb, quad + 3);
-            if (ok0)
-            {
-                double const zi = pa01.x * a0 + pa01.y * a1 + pa23.x * a2
-                    + pa23.y * a3;
-                a.x[i0] = x0; a.r[i0] = ra; a.z[i0] = zi;
-                p_rr += ra * ra;
-                p_q += x0 * (ra - g0);
-                p_zr2 += zi * ra;
-            }
-            if (ok1)
-            {
-                double const zi = pb01.x * b0 + pb01.y * b1 + pb23.x * b2
-                    + pb23.y * b3;
-                a.x[i1] = x1; a.r[i1] = rb; a.z[i1] = zi;
-                p_rr += rb * rb;
-                p_q += x1 * (rb - g1);
-                p_zr2 += zi * rb;
+                int const i = i0 + u * stride;
+                double const q0 = __shfl_sync(0xffffffffu, rv[u], quad);
+                double const q1 = __shfl_sync(0xffffffffu, rv[u], quad + 1);
+                double const q2 = __shfl_sync(0xffffffffu, rv[u], quad + 2);
+                double const q3 = __shfl_sync(0xffffffffu, rv[u], quad + 3);
+                if (i < n)
+                {
+                    double const zi = p01[u].x * q0 + p01[u].y * q1
+                        + p23[u].x * q2 + p23[u].y * q3;
+                    a.x[i] = xv[u]; a.r[i] = rv[u];
+                    a.z[i] = zi;
+                    p_rr += rv[u] * rv[u];
+                    p_q += xv[u] * (rv[u] - gv[u]);
+                    p_zr2 += zi * rv[u];
+                }
             }
         }
-        tot = block_sum(p_rr, s_red);
-        if (threadIdx.x == 0)
-            a.partials[(slot + 1) * CG_MAX_BLOCKS + blockIdx.x] = tot;
-        tot = block_sum(p_q, s_red);
-        if (threadIdx.x == 0)
-            a.partials[(slot + 2) * CG_MAX_BLOCKS + blockIdx.x] = tot;
-        tot = block_sum(p_zr2, s_red);
-        if (threadIdx.x == 0)
-            a.partials[(slot + 3) * CG_MAX_BLOCKS + blockIdx.x] = tot;
+        {
+            double v[3] = { p_rr, p_q, p_zr2 };
+            block_sums<3>(v, s_red);
+            if (threadIdx.x == 0)
+            {
+                a.partials[(slot + 1) * CG_MAX_BLOCKS + blockIdx.x] = v[0];
+                a.partials[(slot + 2) * CG_MAX_BLOCKS + blockIdx.x] = v[1];
+                a.partials[(slot + 3) * CG_MAX_BLOCKS + blockIdx.x] = v[2];
+            }
+        }
         unsigned long long const t_d = now_ns();
         grid_barrier(a.sync, epoch);
+        all_sums<3>(a.partials, slot + 1, s_bcast);
         tm[2] += t_d - t_c; tm[3] += now_ns() - t_d;
-        double const new_rr = all_sum(a.partials, slot + 1, &s_bcast);
-        double const xbr = all_sum(a.partials, slot + 2, &s_bcast);
-        double const new_zr = all_sum(a.partials, slot + 3, &s_bcast);
+        double const new_rr = s_bcast[0];
+        double const xbr = s_bcast[1];
+        double const new_zr = s_bcast[2];
 
         if (new_rr < tol)
         {
