@@ -131,7 +131,8 @@ int smvsb_debug_get_view (smvsb_ctx* ctx, int view, float* grad, float* hess);
  *   node_valid   (npx+1)*(npy+1)     0 where Surface::nodes[i] == nullptr
  *   patch_valid  npx*npy             0 where Surface::patches[i] == nullptr
  *   vis_off      npx*npy+1, vis_ids  CSR of subsurfaces[patch] (neighbour ids,
- *                                    in the reference's order)
+ *                                    in the reference's order); both NULL =
+ *                                    nothing visible yet (see smvsb_visibility)
  */
 int smvsb_set_surface (smvsb_ctx* ctx, int scale, int npx, int npy,
     int start_x, int start_y, const double* nodes, const uint8_t* node_valid,
@@ -189,6 +190,40 @@ int smvsb_update_nodes (smvsb_ctx* ctx, double reproj_thresh, int full_opt,
 int smvsb_newton_loop (smvsb_ctx* ctx, const double* light16,
     double regularization, double light_surf_regularization, int max_steps,
     int full_opt, smvsb_newton_stats* stats);
+
+/* ---- visibility and boundary cutting (the callers' side of the loop) ---- */
+
+/*
+ * DepthOptimizer::create_subview_surfaces (lib/depth_optimizer.cc:433-604) in
+ * the use_sgm mode, on the surface set by smvsb_set_surface (whose visibility
+ * lists may be NULL): z-buffer of every neighbour from the surface's depth map
+ * and `sgm_depth` (w*h floats, 0 = no depth), then per (patch, neighbour) the
+ * 3 % border test, the 0.95 depth test and the warp-anisotropy test (> 8).
+ * Patches no neighbour sees are deleted, nodes without a patch removed, the
+ * context's visibility lists replaced. sgm_depth == NULL (the use_sgm = false
+ * mode with its NCC filter) -> SMVSB_ERR_INVALID.
+ */
+int smvsb_visibility (smvsb_ctx* ctx, const float* sgm_depth,
+    uint64_t* removed_patches);
+
+/*
+ * One DepthOptimizer::cut_boundaries() (lib/depth_optimizer.cc:360-431):
+ * patches across a depth discontinuity, then rim patches with mse_for_patch
+ * (:747-793) > 0.05, are deleted; nodes without a patch removed. inv_calib9 =
+ * the main camera's fill_inverse_calibration(w, h) (row-major 3x3 floats).
+ * Callers repeat while *deleted > 10, like the reference (:192-195).
+ */
+int smvsb_cut_boundaries (smvsb_ctx* ctx, const float* inv_calib9,
+    int* deleted);
+
+/*
+ * The context's node / patch validity and visibility lists (what the two
+ * calls above and smvsb_set_surface left). Any pointer may be NULL; vis_ids
+ * needs room for vis_capacity entries (n_patches * n_sub always suffices).
+ */
+int smvsb_get_surface_state (smvsb_ctx* ctx, uint8_t* node_valid,
+    uint8_t* patch_valid, uint32_t* vis_off, uint8_t* vis_ids,
+    uint64_t vis_capacity);
 
 /* ---- outputs -------------------------------------------------------- */
 

@@ -1,16 +1,22 @@
 /*
  * integration/b200_depth_optimizer.cc
  *
- * Drop-in body for smvs::DepthOptimizer::run_newton_iterations
- * (reference: lib/depth_optimizer.cc:164-358) that runs the inner Newton loop
- * (:204-304) on the GPU through the C ABI of libsmvs_b200.so. Everything that
- * is not the hot path -- visibility lists, boundary cutting, surface
- * expansion, the patch-count convergence test -- still calls the reference's
- * own member functions. lib/depth_optimizer.h is untouched: this file only
- * DEFINES the member, so it compiles against the unmodified header.
+ * Drop-in bodies for three members of smvs::DepthOptimizer that run on the
+ * GPU through the C ABI of libsmvs_b200.so:
+ *   run_newton_iterations    lib/depth_optimizer.cc:164-358 (inner Newton
+ *                            loop :204-304 -> smvsb_newton_loop)
+ *   create_subview_surfaces  :433-604 -> smvsb_visibility (use_sgm mode; the
+ *                            use_sgm = false mode keeps the reference's body)
+ *   cut_boundaries           :360-431 -> smvsb_cut_boundaries
+ * Everything else -- surface expansion / subdivision, isolated-patch removal,
+ * the patch-count convergence test -- still calls the reference's own member
+ * functions, and the host Surface stays the owner of the state (uploaded
+ * before, read back after every call). lib/depth_optimizer.h is untouched:
+ * this file only DEFINES members, so it compiles against the unmodified
+ * header.
  *
  * Built by integration/Makefile together with the reference's unmodified
- * objects (its own definition of this one symbol weakened with objcopy) into
+ * objects (its own definitions of these symbols weakened with objcopy) into
  * integration/_build/libsmvs_ref_b200.so, which tests/test_integration.py
  * drives side by side with the pure-CPU build.
  */
@@ -19,6 +25,8 @@
 #include <iostream>
 #include <limits>
 #include <memory>
+#include <chrono>
+#include <cstdlib>
 #include <vector>
 
 #include "depth_optimizer.h"
@@ -48,6 +56,203 @@ namespace
             n += (p != nullptr);
         return n;
     }
+
+    /* Which optimizer / scale the context's views belong to. */
+    struct ViewsKey
+    {
+        void const* owner = nullptr;
+        void const* gradients = nullptr;
+        int scale = -1;
+    };
+    ViewsKey&
+    views_key (void)
+    {
+        static thread_local ViewsKey key;
+        return key;
+    }
+
+    /* StereoView images + reprojections -> smvsb_set_views. */
+    void
+    upload_views (smvsb::Context& gpu, void const* owner, int scale,
+        StereoView::Ptr main_view, std::vector<StereoView::Ptr> const& subs,
+        std::vector<math::Matrix3d> const& Mi,
+        std::vector<math::Vec3d> const& ti)
+    {
+        std::size_t const n = subs.size();
+        std::vector<int> sw(n), sh(n);
+        std::vector<float const*> sg(n), shess(n);
+        std::vector<double> M(9 * n), t(3 * n);
+        for (std::size_t k = 0; k < n; ++k)
+        {
+            sw[k] = subs[k]->get_width();
+            sh[k] = subs[k]->get_height();
+            sg[k] = subs[k]->get_image_gradients()->begin();
+            shess[k] = subs[k]->get_image_hessian()->begin();
+            for (int j = 0; j < 9; ++j) M[9 * k + j] = Mi[k][j];
+            for (int j = 0; j < 3; ++j) t[3 * k + j] = ti[k][j];
+        }
+        bool const lit = (main_view->get_shading_image() != nullptr);
+        gpu.check(smvsb_set_views(gpu.get(), main_view->get_width(),
+            main_view->get_height(), main_view->get_flen(),
+            main_view->get_inverse_flen(),
+            main_view->get_image_gradients()->begin(),
+            lit ? main_view->get_shading_image()->begin() : nullptr,
+            lit ? main_view->get_shading_gradients()->begin() : nullptr,
+            static_cast<int>(n), sw.data(), sh.data(), sg.data(),
+            shess.data(), M.data(), t.data()));
+        views_key().owner = owner;
+        views_key().gradients = main_view->get_image_gradients().get();
+        views_key().scale = scale;
+    }
+
+    bool
+    views_current (void const* owner, int scale, StereoView::Ptr main_view)
+    {
+        ViewsKey const& k = views_key();
+        return k.owner == owner && k.scale == scale
+            && k.gradients == main_view->get_image_gradients().get();
+    }
+
+    /* Surface (+ visibility lists, if given) -> smvsb_set_surface. */
+    struct PackedSurface
+    {
+        int npx = 0, npy = 0;
+        std::vector<double> node_values;
+        std::vector<uint8_t> node_valid, patch_valid;
+    };
+
+    void
+    upload_surface (smvsb::Context& gpu, Surface::Ptr surface,
+        std::vector<std::vector<std::size_t>> const* subsurfaces,
+        PackedSurface* out)
+    {
+        Surface::NodeList const& nodes = surface->get_nodes();
+        Surface::PatchList const& patches = surface->get_patches();
+        std::size_t ids[4];
+        surface->fill_node_ids_for_patch(0, ids);
+        int const npx = static_cast<int>(ids[2]) - 1;
+        int const npy = static_cast<int>(patches.size()) / npx;
+        int const ps = surface->get_patchsize();
+        out->npx = npx;
+        out->npy = npy;
+        out->node_values.assign(nodes.size() * 4, 0.0);
+        out->node_valid.assign(nodes.size(), 0);
+        out->patch_valid.assign(patches.size(), 0);
+        std::vector<uint32_t> vis_off(patches.size() + 1, 0);
+        std::vector<uint8_t> vis_ids;
+        for (std::size_t i = 0; i < nodes.size(); ++i)
+        {
+            if (nodes[i] == nullptr)
+                continue;
+            out->node_valid[i] = 1;
+            out->node_values[4 * i + 0] = nodes[i]->f;
+            out->node_values[4 * i + 1] = nodes[i]->dx;
+            out->node_values[4 * i + 2] = nodes[i]->dy;
+            out->node_values[4 * i + 3] = nodes[i]->dxy;
+        }
+        int start_x = 0, start_y = 0;
+        for (std::size_t p = 0; p < patches.size(); ++p)
+        {
+            vis_off[p] = static_cast<uint32_t>(vis_ids.size());
+            if (patches[p] == nullptr)
+                continue;
+            out->patch_valid[p] = 1;
+            start_x = patches[p]->get_x() - static_cast<int>(p % npx) * ps;
+            start_y = patches[p]->get_y() - static_cast<int>(p / npx) * ps;
+            if (subsurfaces != nullptr && p < subsurfaces->size())
+                for (std::size_t id : (*subsurfaces)[p])
+                    vis_ids.push_back(static_cast<uint8_t>(id));
+        }
+        vis_off[patches.size()] = static_cast<uint32_t>(vis_ids.size());
+        if (vis_ids.empty())
+            vis_ids.push_back(0);
+        gpu.check(smvsb_set_surface(gpu.get(), surface->get_scale(),
+            npx, npy, start_x, start_y, out->node_values.data(),
+            out->node_valid.data(), out->patch_valid.data(),
+            subsurfaces != nullptr ? vis_off.data() : nullptr,
+            subsurfaces != nullptr ? vis_ids.data() : nullptr));
+    }
+
+    /* Patches the device deleted -> Surface::delete_patch, then the
+     * reference's own node clean-up. Returns the number deleted. */
+    int
+    apply_deletions (smvsb::Context& gpu, Surface::Ptr surface,
+        PackedSurface const& before)
+    {
+        std::vector<uint8_t> now(before.patch_valid.size());
+        gpu.check(smvsb_get_surface_state(gpu.get(), nullptr, now.data(),
+            nullptr, nullptr, 0));
+        int deleted = 0;
+        for (std::size_t p = 0; p < now.size(); ++p)
+            if (before.patch_valid[p] && !now[p])
+            {
+                surface->delete_patch(p);
+                deleted += 1;
+            }
+        if (deleted > 0)
+            surface->remove_nodes_without_patch();
+        return deleted;
+    }
+}
+
+/* The reference's own create_subview_surfaces, kept under this name by
+ * integration/Makefile (objcopy --redefine-sym on a private copy of the
+ * object) for the use_sgm = false mode. */
+extern "C" void smvs_ref_create_subview_surfaces (DepthOptimizer* self);
+
+void
+DepthOptimizer::create_subview_surfaces (void)
+{
+    if (!this->opts.use_sgm)
+    {
+        smvs_ref_create_subview_surfaces(this);
+        return;
+    }
+    smvsb::Context& gpu = thread_context();
+    int const scale = this->surface->get_scale();
+    if (!views_current(this, scale, this->main_view))
+        upload_views(gpu, this, scale, this->main_view, this->sub_views,
+            this->Mi, this->ti);
+
+    PackedSurface packed;
+    upload_surface(gpu, this->surface, nullptr, &packed);
+    uint64_t removed = 0;
+    gpu.check(smvsb_visibility(gpu.get(), this->sgm_depth->begin(),
+        &removed));
+
+    std::size_t const np = packed.patch_valid.size();
+    std::vector<uint32_t> vis_off(np + 1);
+    std::vector<uint8_t> vis_ids(np * this->sub_views.size() + 1);
+    gpu.check(smvsb_get_surface_state(gpu.get(), nullptr, nullptr,
+        vis_off.data(), vis_ids.data(), vis_ids.size()));
+    this->subsurfaces.clear();
+    this->subsurfaces.resize(np);
+    for (std::size_t p = 0; p < np; ++p)
+        for (uint32_t k = vis_off[p]; k < vis_off[p + 1]; ++k)
+            this->subsurfaces[p].push_back(vis_ids[k]);
+    int const deleted = apply_deletions(gpu, this->surface, packed);
+    if (this->opts.debug_lvl > 0)
+        std::cout << "Removed " << deleted << " patches "
+            "due to occlusions." << std::endl;
+}
+
+int
+DepthOptimizer::cut_boundaries (void)
+{
+    smvsb::Context& gpu = thread_context();
+    int const scale = this->surface->get_scale();
+    if (!views_current(this, scale, this->main_view))
+        upload_views(gpu, this, scale, this->main_view, this->sub_views,
+            this->Mi, this->ti);
+    PackedSurface packed;
+    upload_surface(gpu, this->surface, &this->subsurfaces, &packed);
+    math::Matrix3f invproj;
+    this->main_view->get_camera().fill_inverse_calibration(*invproj,
+        this->main_view->get_width(), this->main_view->get_height());
+    int deleted = 0;
+    gpu.check(smvsb_cut_boundaries(gpu.get(), *invproj, &deleted));
+    apply_deletions(gpu, this->surface, packed);
+    return deleted;
 }
 
 void
@@ -57,85 +262,43 @@ DepthOptimizer::run_newton_iterations (int num_iters)
     this->main_gradients = this->main_view->get_image_gradients();
 
     /* ---- images of this scale: once per call (set_scale precedes it) ---- */
-    {
-        std::size_t const n = this->sub_views.size();
-        std::vector<int> sw(n), sh(n);
-        std::vector<float const*> sg(n), shess(n);
-        std::vector<double> M(9 * n), t(3 * n);
-        for (std::size_t k = 0; k < n; ++k)
-        {
-            sw[k] = this->sub_views[k]->get_width();
-            sh[k] = this->sub_views[k]->get_height();
-            sg[k] = this->sub_views[k]->get_image_gradients()->begin();
-            shess[k] = this->sub_views[k]->get_image_hessian()->begin();
-            for (int j = 0; j < 9; ++j) M[9 * k + j] = this->Mi[k][j];
-            for (int j = 0; j < 3; ++j) t[3 * k + j] = this->ti[k][j];
-        }
-        bool const lit = (this->main_view->get_shading_image() != nullptr);
-        gpu.check(smvsb_set_views(gpu.get(), this->main_view->get_width(),
-            this->main_view->get_height(), this->main_view->get_flen(),
-            this->main_view->get_inverse_flen(),
-            this->main_gradients->begin(),
-            lit ? this->main_view->get_shading_image()->begin() : nullptr,
-            lit ? this->main_view->get_shading_gradients()->begin() : nullptr,
-            static_cast<int>(n), sw.data(), sh.data(), sg.data(),
-            shess.data(), M.data(), t.data()));
-    }
+    upload_views(gpu, this, this->surface->get_scale(), this->main_view,
+        this->sub_views, this->Mi, this->ti);
+
+    /* SMVSB_TIMING=1: where this call's wall time goes (host code of the
+     * reference vs. the path on the GPU), one line per call */
+    typedef std::chrono::steady_clock Clock;
+    double t_vis = 0, t_cut = 0, t_pack = 0, t_gpu = 0, t_unpack = 0, t_topo = 0;
+    Clock::time_point tick = Clock::now();
+    auto lap = [&tick] (double& acc) {
+        Clock::time_point const now = Clock::now();
+        acc += std::chrono::duration<double>(now - tick).count();
+        tick = now;
+    };
+    lap(t_pack);   /* smvsb_set_views above */
 
     bool converged = false;
     for (int iter = 0; iter < num_iters; ++iter)
     {
         int const patches_before = count_patches(this->surface);
+        tick = Clock::now();
         if (iter == 0)
         {
             /* :189-195, reference code */
             this->create_subview_surfaces();
+            lap(t_vis);
             for (int del = std::numeric_limits<int>::max(); del > 10;)
                 del = this->cut_boundaries();
+            lap(t_cut);
         }
 
         /* ---- Surface + visibility -> device (replaces :197-213) -------- */
         Surface::NodeList const& nodes = this->surface->get_nodes();
-        Surface::PatchList const& patches = this->surface->get_patches();
-        std::size_t ids[4];
-        this->surface->fill_node_ids_for_patch(0, ids);
-        int const npx = static_cast<int>(ids[2]) - 1;
-        int const npy = static_cast<int>(patches.size()) / npx;
-        int const ps = this->surface->get_patchsize();
-        std::vector<double> node_values(nodes.size() * 4, 0.0);
-        std::vector<uint8_t> node_valid(nodes.size(), 0);
-        std::vector<uint8_t> patch_valid(patches.size(), 0);
-        std::vector<uint32_t> vis_off(patches.size() + 1, 0);
-        std::vector<uint8_t> vis_ids;
-        for (std::size_t i = 0; i < nodes.size(); ++i)
-        {
-            if (nodes[i] == nullptr)
-                continue;
-            node_valid[i] = 1;
-            node_values[4 * i + 0] = nodes[i]->f;
-            node_values[4 * i + 1] = nodes[i]->dx;
-            node_values[4 * i + 2] = nodes[i]->dy;
-            node_values[4 * i + 3] = nodes[i]->dxy;
-        }
-        int start_x = 0, start_y = 0;
-        for (std::size_t p = 0; p < patches.size(); ++p)
-        {
-            vis_off[p] = static_cast<uint32_t>(vis_ids.size());
-            if (patches[p] == nullptr)
-                continue;
-            patch_valid[p] = 1;
-            start_x = patches[p]->get_x() - static_cast<int>(p % npx) * ps;
-            start_y = patches[p]->get_y() - static_cast<int>(p / npx) * ps;
-            for (std::size_t id : this->subsurfaces[p])
-                vis_ids.push_back(static_cast<uint8_t>(id));
-        }
-        vis_off[patches.size()] = static_cast<uint32_t>(vis_ids.size());
-        if (vis_ids.empty())
-            vis_ids.push_back(0);
-        gpu.check(smvsb_set_surface(gpu.get(), this->surface->get_scale(),
-            npx, npy, start_x, start_y, node_values.data(), node_valid.data(),
-            patch_valid.data(), vis_off.data(), vis_ids.data()));
+        PackedSurface packed;
+        upload_surface(gpu, this->surface, &this->subsurfaces, &packed);
+        std::vector<double>& node_values = packed.node_values;
 
+        lap(t_pack);
         /* ---- the inner Newton loop, :219-304, on the GPU ---------------- */
         double light[16];
         if (this->lighting != nullptr)
@@ -156,6 +319,7 @@ DepthOptimizer::run_newton_iterations (int num_iters)
                 << " construct/solve/update ms: " << st.ms_construct << " / "
                 << st.ms_solve << " / " << st.ms_update << std::endl;
 
+        lap(t_gpu);
         /* ---- nodes back into the Surface (Surface::update_nodes' job) --- */
         gpu.check(smvsb_get_nodes(gpu.get(), node_values.data()));
         std::vector<double> delta(node_values.size(), 0.0), unused;
@@ -179,19 +343,25 @@ DepthOptimizer::run_newton_iterations (int num_iters)
             nodes[i]->dxy = node_values[4 * i + 3];
         }
 
+        lap(t_unpack);
         /* ---- :318-356, reference code ---------------------------------- */
         if (converged)
             break;
         for (int del = std::numeric_limits<int>::max(); del > 10;)
             del = this->cut_boundaries();
+        lap(t_cut);
         if (!this->opts.use_sgm)
         {
             this->surface->expand();
+            lap(t_topo);
             this->create_subview_surfaces();
+            lap(t_vis);
             for (int del = std::numeric_limits<int>::max(); del > 10;)
                 del = this->cut_boundaries();
+            lap(t_cut);
         }
         this->surface->remove_isolated_patches();
+        lap(t_topo);
         int const patches_after = count_patches(this->surface);
         double const change = 1.0
             - static_cast<double>(std::min(patches_after, patches_before))
@@ -200,6 +370,12 @@ DepthOptimizer::run_newton_iterations (int num_iters)
             || change < 0.05 * this->surface->get_scale()))
             converged = true;
     }
+    if (std::getenv("SMVSB_TIMING") != nullptr)
+        std::cerr << "[b200] scale " << this->surface->get_scale()
+            << ": create_subview_surfaces " << t_vis << " s, cut_boundaries "
+            << t_cut << " s, expand/remove_isolated " << t_topo
+            << " s, pack+upload " << t_pack << " s, GPU newton loops "
+            << t_gpu << " s, download+unpack " << t_unpack << " s" << std::endl;
 }
 
 SMVS_NAMESPACE_END

@@ -181,6 +181,23 @@ class RefScene:
     def compute_visibility(self):
         return int(self.L.ref_compute_visibility(self.h_))
 
+    def create_subview_surfaces(self, use_sgm=True):
+        """DepthOptimizer::create_subview_surfaces alone; returns patches left."""
+        return int(self.L.ref_create_subview_surfaces(self.h_, int(bool(use_sgm))))
+
+    def cut_boundaries(self):
+        """One DepthOptimizer::cut_boundaries(); returns patches deleted."""
+        return int(self.L.ref_cut_boundaries(self.h_))
+
+    def set_sgm_depth(self, depth):
+        d = np.ascontiguousarray(depth, dtype=np.float32)
+        self.L.ref_set_sgm_depth(self.h_, d.ctypes.data_as(C.c_void_p))
+
+    def inverse_calibration(self):
+        out = np.empty(9, dtype=np.float32)
+        self.L.ref_main_inverse_calibration(self.h_, out.ctypes.data_as(C.c_void_p))
+        return out
+
     def get_visibility(self):
         i = self.surface_info()
         npatch = i["npx"] * i["npy"]

@@ -393,6 +393,54 @@ ref_compute_visibility (void* scene)
     return valid;
 }
 
+/* DepthOptimizer::create_subview_surfaces alone (lib/depth_optimizer.cc:433-604);
+ * returns the number of patches left. */
+int
+ref_create_subview_surfaces (void* scene, int use_sgm)
+{
+    RefScene* s = static_cast<RefScene*>(scene);
+    s->opts.use_sgm = (use_sgm != 0);
+    s->optimizer->main_gradients = s->main_view->get_image_gradients();
+    silence_cout(true);
+    s->optimizer->create_subview_surfaces();
+    silence_cout(false);
+    int valid = 0;
+    for (auto const& p : s->optimizer->surface->get_patches())
+        valid += (p != nullptr);
+    return valid;
+}
+
+/* One DepthOptimizer::cut_boundaries() (lib/depth_optimizer.cc:360-431);
+ * returns its return value (patches deleted). */
+int
+ref_cut_boundaries (void* scene)
+{
+    RefScene* s = static_cast<RefScene*>(scene);
+    s->optimizer->main_gradients = s->main_view->get_image_gradients();
+    return s->optimizer->cut_boundaries();
+}
+
+/* The depth image create_subview_surfaces adds to the z-buffers in the
+ * use_sgm mode (DepthOptimizer::sgm_depth). */
+void
+ref_set_sgm_depth (void* scene, float const* depth)
+{
+    RefScene* s = static_cast<RefScene*>(scene);
+    int const w = s->main_view->get_width(), h = s->main_view->get_height();
+    mve::FloatImage::Ptr img = mve::FloatImage::create(w, h, 1);
+    std::copy(depth, depth + (std::size_t)w * h, img->begin());
+    s->optimizer->sgm_depth = img;
+}
+
+/* The matrix cut_boundaries builds at lib/depth_optimizer.cc:377-379. */
+void
+ref_main_inverse_calibration (void* scene, float* out9)
+{
+    RefScene* s = static_cast<RefScene*>(scene);
+    s->main_view->get_camera().fill_inverse_calibration(out9,
+        s->main_view->get_width(), s->main_view->get_height());
+}
+
 /* vis_off has num_patches + 1 entries; pass vis_ids = NULL to query size. */
 uint64_t
 ref_get_visibility (void* scene, uint32_t* vis_off, uint8_t* vis_ids)

@@ -23,7 +23,8 @@ EXPORTS = [
     "smvsb_get_delta", "smvsb_set_delta", "smvsb_update_nodes",
     "smvsb_newton_loop", "smvsb_get_nodes", "smvsb_get_depth",
     "smvsb_get_normals", "smvsb_debug_get_system", "smvsb_debug_spmv",
-    "smvsb_fit_lighting", "smvsb_sgm",
+    "smvsb_fit_lighting", "smvsb_sgm", "smvsb_visibility",
+    "smvsb_cut_boundaries", "smvsb_get_surface_state",
 ]
 
 
@@ -170,15 +171,45 @@ class Context:
                     patch_valid, vis_off, vis_ids):
         nodes = _f64(nodes)
         nv, pv = _u8(node_valid), _u8(patch_valid)
-        vo = np.ascontiguousarray(vis_off, dtype=np.uint32)
-        vi = _u8(vis_ids)
-        if vi.size == 0:
-            vi = np.zeros(1, dtype=np.uint8)
+        if vis_off is None:
+            vo, vi = None, None          # no lists yet: smvsb_visibility makes them
+        else:
+            vo = np.ascontiguousarray(vis_off, dtype=np.uint32)
+            vi = _u8(vis_ids)
+            if vi.size == 0:
+                vi = np.zeros(1, dtype=np.uint8)
         self._check(lib().smvsb_set_surface(
             self._h, int(scale), int(npx), int(npy), int(start_x), int(start_y),
             _p(nodes), _p(nv), _p(pv), _p(vo), _p(vi)))
         self.n_nodes = (npx + 1) * (npy + 1)
         self.n_patches = npx * npy
+
+    # -- visibility / boundary cutting --------------------------------------
+    def visibility(self, sgm_depth):
+        """DepthOptimizer::create_subview_surfaces (use_sgm mode) on the
+        context's surface; returns the number of patches it deleted."""
+        d = None if sgm_depth is None else np.ascontiguousarray(sgm_depth, dtype=np.float32)
+        removed = C.c_uint64(0)
+        self._check(lib().smvsb_visibility(self._h, _p(d), C.byref(removed)))
+        return removed.value
+
+    def cut_boundaries(self, inv_calib9):
+        """One DepthOptimizer::cut_boundaries(); returns the patches deleted."""
+        k = np.ascontiguousarray(inv_calib9, dtype=np.float32).reshape(9)
+        deleted = C.c_int(0)
+        self._check(lib().smvsb_cut_boundaries(self._h, _p(k), C.byref(deleted)))
+        return deleted.value
+
+    def surface_state(self):
+        """(node_valid, patch_valid, vis_off, vis_ids) as the context holds them."""
+        nv = np.empty(self.n_nodes, dtype=np.uint8)
+        pv = np.empty(self.n_patches, dtype=np.uint8)
+        vo = np.empty(self.n_patches + 1, dtype=np.uint32)
+        cap = self.n_patches * 32 + 1
+        vi = np.empty(cap, dtype=np.uint8)
+        self._check(lib().smvsb_get_surface_state(self._h, _p(nv), _p(pv), _p(vo), _p(vi),
+                                                  C.c_uint64(cap)))
+        return nv, pv, vo, vi[:vo[-1]].copy()
 
     def set_nodes(self, nodes):
         nodes = _f64(nodes)

@@ -456,8 +456,10 @@ smvsb_set_surface (smvsb_ctx* ctx, int scale, int npx, int npy, int start_x,
         require(scale >= 0 && scale <= 6, SMVSB_ERR_INVALID,
             "scale out of range (0..6)");
         require(npx > 0 && npy > 0, SMVSB_ERR_INVALID, "empty patch grid");
-        require(nodes && node_valid && patch_valid && vis_off && vis_ids,
-            SMVSB_ERR_INVALID, "surface arrays missing");
+        require(nodes && node_valid && patch_valid, SMVSB_ERR_INVALID,
+            "surface arrays missing");
+        require((vis_off == nullptr) == (vis_ids == nullptr),
+            SMVSB_ERR_INVALID, "vis_off and vis_ids go together");
         int const ps = 1 << scale;
         int const sampling = sampling_for_scale(scale);
         require(ps % sampling == 0, SMVSB_ERR_INVALID,
@@ -473,6 +475,15 @@ smvsb_set_surface (smvsb_ctx* ctx, int scale, int npx, int npy, int start_x,
         c->npx = npx; c->npy = npy; c->start_x = start_x; c->start_y = start_y;
         c->n_patches = npx * npy;
         c->n_nodes = (npx + 1) * (npy + 1);
+        /* no lists: nothing visible yet (smvsb_visibility fills them) */
+        std::vector<uint32_t> no_off;
+        uint8_t const no_id = 0;
+        if (vis_off == nullptr)
+        {
+            no_off.assign(static_cast<size_t>(c->n_patches) + 1, 0);
+            vis_off = no_off.data();
+            vis_ids = &no_id;
+        }
         size_t const total_vis = vis_off[c->n_patches];
         for (size_t i = 0; i < total_vis; ++i)
             require(vis_ids[i] < c->n_sub, SMVSB_ERR_INVALID,
@@ -481,7 +492,7 @@ smvsb_set_surface (smvsb_ctx* ctx, int scale, int npx, int npy, int start_x,
         upload(c, c->node_valid, node_valid, c->n_nodes);
         upload(c, c->patch_valid, patch_valid, c->n_patches);
         upload(c, c->vis_off, vis_off, static_cast<size_t>(c->n_patches) + 1);
-        upload(c, c->vis_ids, vis_ids, total_vis);
+        upload(c, c->vis_ids, vis_ids, std::max<size_t>(total_vis, 1));
         c->h_node_valid.assign(node_valid, node_valid + c->n_nodes);
         c->h_patch_valid.assign(patch_valid, patch_valid + c->n_patches);
         std::vector<double> tab;
@@ -665,6 +676,79 @@ smvsb_get_nodes (smvsb_ctx* ctx, double* nodes_out)
             "no surface set");
         download(ctx, nodes_out, ctx->nodes.p,
             static_cast<size_t>(ctx->n_nodes) * 4);
+    });
+}
+
+/* Host mirrors of the validity flags after the device changed them. */
+static void
+refresh_validity (smvsb_ctx* c)
+{
+    c->h_node_valid.resize(c->n_nodes);
+    c->h_patch_valid.resize(c->n_patches);
+    download(c, c->h_node_valid.data(), c->node_valid.p, c->n_nodes);
+    download(c, c->h_patch_valid.data(), c->patch_valid.p, c->n_patches);
+    set_active(c, nullptr);
+    c->have_system = false;
+}
+
+int
+smvsb_visibility (smvsb_ctx* ctx, const float* sgm_depth,
+    uint64_t* removed_patches)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_views && ctx->have_surface, SMVSB_ERR_STATE,
+            "views / surface not set");
+        require(sgm_depth != nullptr, SMVSB_ERR_INVALID,
+            "sgm_depth missing (the use_sgm = false mode, with its NCC "
+            "occlusion filter, is not offered on the device)");
+        require(ctx->n_sub <= 32, SMVSB_ERR_INVALID,
+            "more than 32 neighbours");
+        uint64_t const removed = smvsb::run_visibility(ctx, sgm_depth);
+        refresh_validity(ctx);
+        if (removed_patches) *removed_patches = removed;
+    });
+}
+
+int
+smvsb_cut_boundaries (smvsb_ctx* ctx, const float* inv_calib9, int* deleted)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_views && ctx->have_surface, SMVSB_ERR_STATE,
+            "views / surface not set");
+        require(inv_calib9 != nullptr, SMVSB_ERR_INVALID,
+            "inverse calibration missing");
+        uint64_t const n = smvsb::run_cut_boundaries(ctx, inv_calib9);
+        refresh_validity(ctx);
+        if (deleted) *deleted = static_cast<int>(n);
+    });
+}
+
+int
+smvsb_get_surface_state (smvsb_ctx* ctx, uint8_t* node_valid,
+    uint8_t* patch_valid, uint32_t* vis_off, uint8_t* vis_ids,
+    uint64_t vis_capacity)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        smvsb_ctx* c = ctx;
+        require(c->have_surface, SMVSB_ERR_STATE, "no surface set");
+        if (node_valid)
+            download(c, node_valid, c->node_valid.p, c->n_nodes);
+        if (patch_valid)
+            download(c, patch_valid, c->patch_valid.p, c->n_patches);
+        std::vector<uint32_t> off(static_cast<size_t>(c->n_patches) + 1);
+        download(c, off.data(), c->vis_off.p, off.size());
+        if (vis_off)
+            std::copy(off.begin(), off.end(), vis_off);
+        if (vis_ids)
+        {
+            require(off.back() <= vis_capacity, SMVSB_ERR_INVALID,
+                "vis_ids capacity too small");
+            if (off.back() > 0)
+                download(c, vis_ids, c->vis_ids.p, off.back());
+        }
     });
 }
 

@@ -154,6 +154,12 @@ struct smvsb_ctx
     smvsb::DevBuf<double> patch_shift;  /* n_patches * 2: sum, count */
     smvsb::DevBuf<unsigned long long> counters;
 
+    /* visibility / cutting */
+    smvsb::DevBuf<unsigned int> zbuf, vis_mask;
+    smvsb::DevBuf<unsigned long long> zoff;
+    smvsb::DevBuf<float> sgm_depth;
+    smvsb::DevBuf<uint32_t> vis_counts;
+
     /* lighting */
     smvsb::DevBuf<double> light_partials;
 
@@ -211,6 +217,8 @@ void launch_render_depth (smvsb_ctx* c, float* out_dev);
 void launch_render_normals (smvsb_ctx* c, float* out_dev);
 void run_fit_lighting (smvsb_ctx* c, double* A_b_host /*272*/);
 void launch_count_processed (smvsb_ctx* c, unsigned long long* n_proc_host);
+uint64_t run_visibility (smvsb_ctx* c, float const* sgm_depth_host);
+uint64_t run_cut_boundaries (smvsb_ctx* c, float const* inv_calib9);
 
 } /* namespace smvsb */
 

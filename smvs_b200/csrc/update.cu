@@ -16,6 +16,7 @@
  *                        (lib/light_optimizer.cc:22-55)
  */
 #include "gn_math.cuh"
+#include "patch_eval.cuh"
 
 namespace smvsb {
 
@@ -251,23 +252,15 @@ render_kernel (SurfaceDev const sf, float* __restrict__ out, int normals)
     if (!sf.patch_valid[patch])
         return;
     int const i = gx % sf.ps, j = gy % sf.ps;
-    double const* X0 = sf.basis_f + (0 * sf.ps + i) * 4;
-    double const* X1 = sf.basis_f + (1 * sf.ps + i) * 4;
-    double const* Y0 = sf.basis_f + (0 * sf.ps + j) * 4;
-    double const* Y1 = sf.basis_f + (1 * sf.ps + j) * 4;
-    double w = 0.0, wx = 0.0, wy = 0.0;
-#pragma unroll
-    for (int col = 0; col < 16; ++col)
-    {
-        int const bx = ((col >> 2) & 1) + 2 * (col & 1);
-        int const by = ((col >> 3) & 1) + 2 * ((col >> 1) & 1);
-        int const node = (idy + ((col >> 3) & 1)) * (sf.npx + 1)
-            + idx + ((col >> 2) & 1);
-        double const th = sf.nodes[node * 4 + (col & 3)];
-        w += th * X0[bx] * Y0[by];
-        wx += th * X1[bx] * Y0[by];
-        wy += th * X0[bx] * Y1[by];
-    }
+    /* BicubicPatch::evaluate_f / _dx / _dy on the polynomial coefficients,
+     * bitwise the reference's values (patch_eval.cuh): the depth map feeds
+     * the visibility z-buffer, where decisions hang on the last bit */
+    double theta[16], cf[16];
+    load_patch_theta(sf.nodes, sf.npx, idx, idy, theta);
+    patch_coefficients(theta, cf);
+    PatchSample const smp = normals ? patch_sample<true>(cf, i, j, sf.ps)
+        : patch_sample<false>(cf, i, j, sf.ps);
+    double const w = smp.w, wx = smp.wx, wy = smp.wy;
     int const px = sf.start_x + gx, py = sf.start_y + gy;
     size_t const pix = static_cast<size_t>(py) * sf.w + px;
     if (!normals)

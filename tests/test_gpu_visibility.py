@@ -1,0 +1,105 @@
+"""Visibility lists and boundary cutting on the device against the reference's
+DepthOptimizer::create_subview_surfaces / cut_boundaries (compiled verbatim,
+oracle/_ref): yes/no decisions, so everything is compared for EQUALITY."""
+import numpy as np
+import pytest
+
+from smvs_b200 import api, synth
+from oracle import ref as oref
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")]
+
+
+def occluded_scene(width, height, n_sub, seed_index):
+    """A scene whose initial depth has a raised block (depth discontinuities,
+    wrong photometry at its rim) and whose SGM depth has a foreground disc
+    and holes (occlusions in the neighbours' z-buffers)."""
+    sc = synth.make_scene(width, height, n_sub, seed_index=seed_index)
+    init = sc.init_depth.copy()
+    init[height // 3:height // 2, width // 3:width // 2] *= 0.8
+    yy, xx = np.mgrid[0:height, 0:width]
+    sgm = sc.init_depth.copy()
+    disc = (xx - 0.7 * width) ** 2 + (yy - 0.6 * height) ** 2 < (0.12 * height) ** 2
+    sgm[disc] *= 0.6
+    sgm[(xx + 2 * yy) % 17 == 0] = 0.0
+    return sc, init.astype(np.float32), sgm.astype(np.float32)
+
+
+def lists_of(off, ids, valid):
+    return [tuple(ids[off[p]:off[p + 1]]) if valid[p] else () for p in range(len(valid))]
+
+
+def run_pair(width, height, n_sub, scale, seed_index):
+    sc, init, sgm = occluded_scene(width, height, n_sub, seed_index)
+    R = oref.RefScene(sc)
+    R.set_scale(scale)
+    R.surface_create(scale, init)
+    R.set_sgm_depth(sgm)
+    info = R.surface_info()
+    nodes, nv, pv = R.surface_get()
+    Mi, ti = R.Mt()
+    with api.Context(0) as ctx:
+        ctx.set_views(R.gradients(0), [R.gradients(k + 1) for k in range(n_sub)],
+                      [R.hessian(k + 1) for k in range(n_sub)], Mi, ti,
+                      R.flen(0), R.inverse_flen(0))
+        ctx.set_surface(info["scale"], info["npx"], info["npy"], info["start_x"],
+                        info["start_y"], nodes, nv, pv, None, None)
+        # the depth map the z-buffer is filled from: bit-exact
+        assert np.array_equal(ctx.get_depth(), R.surface_depth())
+
+        left = R.create_subview_surfaces(True)
+        removed = ctx.visibility(sgm)
+        _, nv_r, pv_r = R.surface_get()
+        off_r, ids_r = R.get_visibility()
+        nv_g, pv_g, off_g, ids_g = ctx.surface_state()
+        assert np.array_equal(pv_g, pv_r)
+        assert np.array_equal(nv_g, nv_r)
+        assert int(pv.sum()) - removed == left == int(pv_g.sum())
+        lr, lg = lists_of(off_r, ids_r, pv_r), lists_of(off_g, ids_g, pv_g)
+        assert lr == lg
+        stats = dict(patches=int(pv.sum()), removed=int(removed),
+                     partial=sum(1 for l in lg if 0 < len(l) < n_sub), cuts=[])
+
+        K = R.inverse_calibration()
+        for _ in range(12):
+            d_r = R.cut_boundaries()
+            d_g = ctx.cut_boundaries(K)
+            _, nv_r, pv_r = R.surface_get()
+            nv_g, pv_g, _, _ = ctx.surface_state()
+            assert d_g == d_r
+            assert np.array_equal(pv_g, pv_r)
+            assert np.array_equal(nv_g, nv_r)
+            stats["cuts"].append(d_r)
+            if d_r <= 10:
+                break
+    R.close()
+    return stats
+
+
+@pytest.mark.parametrize("width,height,n_sub,scale,seed", [
+    (320, 240, 3, 2, 41), (320, 240, 3, 3, 42), (320, 240, 2, 4, 43),
+    (640, 480, 4, 5, 44), (320, 240, 3, 1, 45)])
+def test_visibility_and_cut_parity(width, height, n_sub, scale, seed):
+    st = run_pair(width, height, n_sub, scale, seed)
+    # the scene must actually exercise the rules
+    assert st["removed"] > 0 or st["partial"] > 0
+    assert sum(st["cuts"]) > 0
+
+
+def test_visibility_requires_sgm_depth():
+    sc = synth.make_scene(160, 120, 1, seed_index=46)
+    R = oref.RefScene(sc)
+    R.set_scale(3)
+    R.surface_create(3, sc.init_depth)
+    info = R.surface_info()
+    nodes, nv, pv = R.surface_get()
+    Mi, ti = R.Mt()
+    with api.Context(0) as ctx:
+        ctx.set_views(R.gradients(0), [R.gradients(1)], [R.hessian(1)], Mi, ti,
+                      R.flen(0), R.inverse_flen(0))
+        ctx.set_surface(info["scale"], info["npx"], info["npy"], info["start_x"],
+                        info["start_y"], nodes, nv, pv, None, None)
+        with pytest.raises(api.SmvsbError):
+            ctx.visibility(None)
+    R.close()

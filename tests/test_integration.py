@@ -56,3 +56,60 @@ def test_sgm_reconstruct_parity():
         R.close()
     assert np.array_equal(out[0], out[1])
     assert (out[0] > 0).mean() > 0.3
+
+
+def _vis_state(R):
+    _, nv, pv = R.surface_get()
+    off, ids = R.get_visibility()
+    lists = [tuple(ids[off[p]:off[p + 1]]) if pv[p] else () for p in range(len(pv))]
+    return nv, pv, lists
+
+
+def test_visibility_and_cut_members_on_gpu():
+    """DepthOptimizer::create_subview_surfaces / cut_boundaries as members of
+    the patched build (host Surface in, host Surface out) against the CPU
+    build: same patches, nodes and visibility lists after every call."""
+    from test_gpu_visibility import occluded_scene
+    sc, init, sgm = occluded_scene(320, 240, 3, 47)
+    R = [oref.RefScene(sc, lib_path=p) for p in (None, oref.INTEGRATION_LIB_PATH)]
+    for r in R:
+        r.set_scale(2)
+        r.surface_create(2, init)
+        r.set_sgm_depth(sgm)
+    before = api.lib().smvsb_global_launch_count()
+    left = [r.create_subview_surfaces(True) for r in R]
+    assert api.lib().smvsb_global_launch_count() - before >= 7
+    assert left[0] == left[1]
+    a, b = _vis_state(R[0]), _vis_state(R[1])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    for _ in range(12):
+        d = [r.cut_boundaries() for r in R]
+        assert d[0] == d[1]
+        a, b = _vis_state(R[0]), _vis_state(R[1])
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        if d[0] <= 10:
+            break
+    for r in R:
+        r.close()
+
+
+def test_visibility_without_sgm_keeps_reference_body():
+    """use_sgm = false (NCC occlusion filter on colour images) is not offered
+    on the device: the patched build must run the reference's own body."""
+    import copy
+    sc = synth.make_scene(320, 240, 2, seed_index=48)
+    col = copy.copy(sc)
+    col.images = [np.repeat(im[:, :, None], 3, axis=2) if im.ndim == 2 else im
+                  for im in sc.images]
+    out = []
+    for path in (None, oref.INTEGRATION_LIB_PATH):
+        r = oref.RefScene(col, lib_path=path)
+        r.set_scale(3)
+        r.surface_create(3, sc.init_depth)
+        before = api.lib().smvsb_global_launch_count()
+        left = r.create_subview_surfaces(False)
+        assert api.lib().smvsb_global_launch_count() == before
+        out.append((left,) + _vis_state(r))
+        r.close()
+    assert out[0][0] == out[1][0] > 0
+    assert np.array_equal(out[0][2], out[1][2]) and out[0][3] == out[1][3]
