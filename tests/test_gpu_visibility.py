@@ -103,3 +103,53 @@ def test_visibility_requires_sgm_depth():
         with pytest.raises(api.SmvsbError):
             ctx.visibility(None)
     R.close()
+
+
+def test_full_size_visibility_and_cut_parity():
+    """BASELINE.json configs[1] size: 1920x1080, 6 neighbours, scale 2
+    (128 104 patches, 12.3 M pixel x neighbour warps)."""
+    from smvs_b200.workload import build_workload
+    wl = build_workload(1920, 1080, 6, 2, shading=False, seed_index=3)
+    sc = wl.scene
+    yy, xx = np.mgrid[0:1080, 0:1920]
+    sgm = sc.init_depth.astype(np.float32).copy()
+    sgm[(xx - 1300) ** 2 + (yy - 600) ** 2 < 150 ** 2] *= 0.6
+    R = oref.RefScene(sc)
+    R.set_scale(2)
+    R.surface_create(2, sc.init_depth)
+    nodes = wl.nodes.copy().reshape(-1, 4)
+    # a slightly raised block: its rim crosses the depth-discontinuity
+    # threshold without tripping the anisotropy test first
+    ns = wl.npx + 1
+    for iy in range(80, 120):
+        nodes[iy * ns + 150:iy * ns + 210, 0] *= 0.97
+    R.surface_set(nodes.reshape(-1), wl.node_valid, wl.patch_valid)
+    R.set_sgm_depth(sgm)
+    with api.Context(0) as ctx:
+        wl.push_views(ctx)
+        ctx.set_surface(2, wl.npx, wl.npy, wl.start_x, wl.start_y, nodes.reshape(-1),
+                        wl.node_valid, wl.patch_valid, None, None)
+        assert np.array_equal(ctx.get_depth(), R.surface_depth())
+        left = R.create_subview_surfaces(True)
+        removed = ctx.visibility(sgm)
+        _, nv_r, pv_r = R.surface_get()
+        off_r, ids_r = R.get_visibility()
+        nv_g, pv_g, off_g, ids_g = ctx.surface_state()
+        assert removed > 100 and int(pv_g.sum()) == left
+        assert np.array_equal(pv_g, pv_r) and np.array_equal(nv_g, nv_r)
+        m = pv_r.astype(bool)
+        assert np.array_equal(np.diff(off_g)[m], np.diff(off_r)[m])
+        assert lists_of(off_r, ids_r, pv_r) == lists_of(off_g, ids_g, pv_g)
+        K = R.inverse_calibration()
+        total = 0
+        for _ in range(12):
+            d_r, d_g = R.cut_boundaries(), ctx.cut_boundaries(K)
+            _, nv_r, pv_r = R.surface_get()
+            nv_g, pv_g, _, _ = ctx.surface_state()
+            assert d_g == d_r
+            assert np.array_equal(pv_g, pv_r) and np.array_equal(nv_g, nv_r)
+            total += d_r
+            if d_r <= 10:
+                break
+        assert total > 50
+    R.close()
