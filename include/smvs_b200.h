@@ -191,6 +191,18 @@ int smvsb_newton_loop (smvsb_ctx* ctx, const double* light16,
     double regularization, double light_surf_regularization, int max_steps,
     int full_opt, smvsb_newton_stats* stats);
 
+/*
+ * StereoView::set_scale (lib/stereo_view.cc:24-46, 97-188) for ONE view whose
+ * float image (w*h, single channel, what byte_to_float_image made) is on the
+ * host: Gaussian blur with sigma = 0.12 * 2^scale + 0.2, then the 3x3
+ * quadratic-fit gradient (w*h*2) and Hessian (w*h*3), bit-identical to the
+ * reference; results go back to the host arrays a StereoView holds
+ * (scaleimage, image_grad, image_hessian; any may be NULL). Needs no views or
+ * surface in the context.
+ */
+int smvsb_view_set_scale (smvsb_ctx* ctx, int w, int h, const float* image,
+    int scale, float* scaleimage, float* grad, float* hess);
+
 /* ---- visibility and boundary cutting (the callers' side of the loop) ---- */
 
 /*

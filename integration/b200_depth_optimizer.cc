@@ -31,22 +31,13 @@
 
 #include "depth_optimizer.h"
 
-#include "smvs_b200.hpp"
+#include "b200_context.h"
 
 SMVS_NAMESPACE_BEGIN
 
 namespace
 {
-    /* One GPU context per host thread: the reference runs one DepthOptimizer
-     * per pool thread (app/smvsrecon.cc:658-733). */
-    smvsb::Context&
-    thread_context (void)
-    {
-        static thread_local std::unique_ptr<smvsb::Context> ctx;
-        if (!ctx)
-            ctx.reset(new smvsb::Context(0));
-        return *ctx;
-    }
+    using smvs_b200_integration::thread_context;
 
     int
     count_patches (Surface::Ptr surface)

@@ -24,7 +24,7 @@ EXPORTS = [
     "smvsb_newton_loop", "smvsb_get_nodes", "smvsb_get_depth",
     "smvsb_get_normals", "smvsb_debug_get_system", "smvsb_debug_spmv",
     "smvsb_fit_lighting", "smvsb_sgm", "smvsb_visibility",
-    "smvsb_cut_boundaries", "smvsb_get_surface_state",
+    "smvsb_cut_boundaries", "smvsb_get_surface_state", "smvsb_view_set_scale",
 ]
 
 
@@ -183,6 +183,18 @@ class Context:
             _p(nodes), _p(nv), _p(pv), _p(vo), _p(vi)))
         self.n_nodes = (npx + 1) * (npy + 1)
         self.n_patches = npx * npy
+
+    def view_set_scale(self, image, scale):
+        """StereoView::set_scale of one single-channel float image:
+        (scaleimage, gradients, hessian) as host arrays."""
+        img = np.ascontiguousarray(image, dtype=np.float32)
+        h, w = img.shape
+        blur = np.empty((h, w), dtype=np.float32)
+        grad = np.empty((h, w, 2), dtype=np.float32)
+        hess = np.empty((h, w, 3), dtype=np.float32)
+        self._check(lib().smvsb_view_set_scale(self._h, w, h, _p(img), int(scale),
+                                               _p(blur), _p(grad), _p(hess)))
+        return blur, grad, hess
 
     # -- visibility / boundary cutting --------------------------------------
     def visibility(self, sgm_depth):

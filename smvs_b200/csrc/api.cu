@@ -19,6 +19,8 @@ void device_set_scale (smvsb_ctx* c, uint8_t const* img_dev, int w, int h,
     int scale, float* tmp_a, float* tmp_b, int mode, float* out_dev);
 void device_shading_inputs (smvsb_ctx* c, uint8_t const* img_dev, int w, int h,
     float* shading_dev, float* shading_grad_dev);
+void device_set_scale_float (smvsb_ctx* c, float const* img_dev, int w, int h,
+    int scale, float* tmp_a, float* tmp_b, float* out_dev);
 void device_unpack_texels (smvsb_ctx* c, float const* texels, int n,
     float* grad, float* hess);
 std::string const& sgm_last_error (void);
@@ -440,6 +442,45 @@ smvsb_debug_get_view (smvsb_ctx* ctx, int view, float* grad, float* hess)
             hs.p);
         download(c, grad, g.p, n * 2);
         download(c, hess, hs.p, n * 3);
+    });
+}
+
+int
+smvsb_view_set_scale (smvsb_ctx* ctx, int w, int h, const float* image,
+    int scale, float* scaleimage, float* grad, float* hess)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        smvsb_ctx* c = ctx;
+        require(w >= 3 && h >= 3 && image != nullptr, SMVSB_ERR_INVALID,
+            "image missing or smaller than 3x3");
+        require(scale >= 0 && scale <= 8, SMVSB_ERR_INVALID,
+            "scale out of range");
+        size_t const n = static_cast<size_t>(w) * h;
+        c->stage_a.reserve(n);
+        c->stage_b.reserve(n);
+        c->view_in.reserve(n);
+        c->view_texels.reserve(n * SMVSB_NB_STRIDE);
+        c->view_out.reserve(n * 5);
+        CUDA_CHECK(cudaMemcpyAsync(c->view_in.p, image, n * sizeof(float),
+            cudaMemcpyHostToDevice, c->stream));
+        smvsb::device_set_scale_float(c, c->view_in.p, w, h, scale,
+            c->stage_a.p, c->stage_b.p, c->view_texels.p);
+        if (scaleimage != nullptr)
+            CUDA_CHECK(cudaMemcpyAsync(scaleimage, c->stage_b.p,
+                n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (grad != nullptr || hess != nullptr)
+        {
+            smvsb::device_unpack_texels(c, c->view_texels.p,
+                static_cast<int>(n), c->view_out.p, c->view_out.p + 2 * n);
+            if (grad != nullptr)
+                CUDA_CHECK(cudaMemcpyAsync(grad, c->view_out.p,
+                    2 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            if (hess != nullptr)
+                CUDA_CHECK(cudaMemcpyAsync(hess, c->view_out.p + 2 * n,
+                    3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
     });
 }
 

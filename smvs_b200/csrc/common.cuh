@@ -121,6 +121,7 @@ struct smvsb_ctx
     smvsb::DevBuf<double> Mt;
     smvsb::DevBuf<uint8_t> stage_u8;       /* upload staging (reused) */
     smvsb::DevBuf<float> stage_a, stage_b;
+    smvsb::DevBuf<float> view_in, view_texels, view_out;   /* smvsb_view_set_scale */
 
     /* surface */
     bool have_surface = false;

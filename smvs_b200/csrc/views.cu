@@ -29,22 +29,36 @@ struct BlurKernel
     float wsum;
 };
 
-/* x pass: byte -> float (v / 255, clamped) -> blur along x */
+__device__ __forceinline__ float
+pixel_value (uint8_t v)
+{
+    /* mve::image::byte_to_float_image: v / 255, clamped */
+    float const f = __fdiv_rn(static_cast<float>(v), 255.0f);
+    return fminf(1.0f, fmaxf(0.0f, f));
+}
+
+__device__ __forceinline__ float
+pixel_value (float v)
+{
+    return v;
+}
+
+/* x pass: (byte -> float, v / 255, clamped ->) blur along x */
+template <typename T>
 __global__ void
-blur_x_kernel (uint8_t const* __restrict__ img, int w, int h,
+blur_x_kernel (T const* __restrict__ img, int w, int h,
     BlurKernel const k, float* __restrict__ out)
 {
     int const x = blockIdx.x * blockDim.x + threadIdx.x;
     int const y = blockIdx.y;
     if (x >= w)
         return;
-    uint8_t const* row = img + static_cast<size_t>(y) * w;
+    T const* row = img + static_cast<size_t>(y) * w;
     float acc = 0.0f;
     for (int i = -k.ks; i <= k.ks; ++i)
     {
         int const xi = min(max(x + i, 0), w - 1);
-        float v = __fdiv_rn(static_cast<float>(row[xi]), 255.0f);
-        v = fminf(1.0f, fmaxf(0.0f, v));
+        float const v = pixel_value(row[xi]);
         acc = __fadd_rn(acc, __fmul_rn(v, k.w[abs(i)]));
     }
     out[static_cast<size_t>(y) * w + x] = __fdiv_rn(acc, k.wsum);
@@ -187,12 +201,31 @@ device_set_scale (smvsb_ctx* c, uint8_t const* img_dev, int w, int h,
 {
     BlurKernel const k = make_blur_kernel(scale);
     dim3 const block(128, 1), grid((w + 127) / 128, h);
-    blur_x_kernel<<<grid, block, 0, c->stream>>>(img_dev, w, h, k, tmp_a);
+    blur_x_kernel<uint8_t><<<grid, block, 0, c->stream>>>(img_dev, w, h, k,
+        tmp_a);
     CUDA_CHECK(cudaGetLastError());
     blur_y_kernel<<<grid, block, 0, c->stream>>>(tmp_a, w, h, k, tmp_b);
     CUDA_CHECK(cudaGetLastError());
     grad_hess_kernel<<<grid, block, 0, c->stream>>>(tmp_b, w, h, mode,
         out_dev);
+    CUDA_CHECK(cudaGetLastError());
+    count_launches(c, 3);
+}
+
+/* The same from a float image on the device (StereoView::image); the blurred
+ * image is left in tmp_b, the packed gradient / Hessian texels in out_dev. */
+void
+device_set_scale_float (smvsb_ctx* c, float const* img_dev, int w, int h,
+    int scale, float* tmp_a, float* tmp_b, float* out_dev)
+{
+    BlurKernel const k = make_blur_kernel(scale);
+    dim3 const block(128, 1), grid((w + 127) / 128, h);
+    blur_x_kernel<float><<<grid, block, 0, c->stream>>>(img_dev, w, h, k,
+        tmp_a);
+    CUDA_CHECK(cudaGetLastError());
+    blur_y_kernel<<<grid, block, 0, c->stream>>>(tmp_a, w, h, k, tmp_b);
+    CUDA_CHECK(cudaGetLastError());
+    grad_hess_kernel<<<grid, block, 0, c->stream>>>(tmp_b, w, h, 1, out_dev);
     CUDA_CHECK(cudaGetLastError());
     count_launches(c, 3);
 }

@@ -151,6 +151,21 @@ def test_device_set_scale_bitwise():
             assert np.array_equal(a["g"], b["g"]) and np.array_equal(a["Hvals"], b["Hvals"])
 
 
+def test_view_set_scale_bitwise():
+    """smvsb_view_set_scale (one StereoView::set_scale, host image in, host
+    images out -- what the drop-in member calls) against the numpy mirror."""
+    from smvs_b200 import stereo_view
+    sc = synth.make_scene(333, 207, 1, seed_index=5)
+    img = sc.images[1]
+    with api.Context(0) as ctx:
+        for scale in (0, 2, 4, 6):
+            f = stereo_view.byte_to_float(img)
+            blur, grad, hess = ctx.view_set_scale(f, scale)
+            rb, rg, rh = stereo_view.set_scale(img, scale)
+            assert np.array_equal(blur, rb)
+            assert np.array_equal(grad, rg) and np.array_equal(hess, rh)
+
+
 # ---------------------------------------------------------------------------
 # live reference, larger / odd shapes
 # ---------------------------------------------------------------------------
