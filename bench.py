@@ -149,8 +149,8 @@ def _windows(wl, n, frac_x=4, frac_y=4):
 
 
 class ReferenceWorkers:
-    """`threads` reference optimizers, each on its own bounded window (1/16 of
-    the patch grid) of the same workload; run() lets every one do `repeats`
+    """`threads` reference optimizers, each on its own bounded window (1/frac^2
+    of the patch grid) of the same workload; run() lets every one do `repeats`
     Newton loops concurrently, one host thread each (the reference's
     ThreadPool model: one view per thread, app/smvsrecon.cc:558)."""
 
@@ -202,14 +202,21 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
-    # one optimizer per host thread, like the reference's ThreadPool
-    # (hardware_concurrency() workers, one view each); capped at 64 so that the
-    # set-up (0.7 GB and ~1 s per worker) stays bounded
-    threads = max(1, min(os.cpu_count() or 1, 64))
+    # one optimizer per host thread, like the reference's ThreadPool (one view
+    # each, app/smvsrecon.cc:558). The reference's throughput stops growing
+    # with threads early (every vector operation of its CG allocates, and the
+    # threads share one address space): measured on the 128-core GPU box, 8
+    # threads reach 0.70 Mpix-iters/s, 64 threads 0.43. The arm therefore runs
+    # the thread count that served the reference best there (16, or
+    # SMVSB_REF_THREADS). Each thread runs the Newton loop of a quarter of the
+    # patch grid (about 12 s a step); smaller windows would sell the reference
+    # short, because its CG vectors span the whole node grid whatever part of
+    # it is valid (measured on one core: 0.109 Mpix-iters/s on a quarter,
+    # 0.078 on 1/16, 0.029 on 1/64). Long runs (> 16 steps) fall back to 1/16.
+    threads = int(os.environ.get("SMVSB_REF_THREADS", "0")) or min(os.cpu_count() or 1, 16)
+    threads = max(1, min(threads, 64))
     wl = build_workload(WIDTH, HEIGHT, N_SUB, SCALE, shading=False, seed_index=0)
-    # bounded sample per step: a 1/16 window (~5 s per step) for short runs, a
-    # 1/64 window when many steps are requested, so the run ends within minutes
-    frac = 4 if (args.steps + args.warmup) <= 25 else 8
+    frac = 2 if (args.steps + args.warmup) <= 16 else 4
     workers = ReferenceWorkers(wl, threads, frac)
     desc = workers.desc
     for _ in range(args.warmup):
@@ -371,12 +378,11 @@ def run_product(args):
         cpu_base = None
         if not args.no_cpu_baseline:
             try:
-                workers = ReferenceWorkers(wl, 1)
-                p, s = workers.run(repeats=3)
+                workers = ReferenceWorkers(wl, 1, 2)
+                p, s = workers.run(repeats=1)
                 workers.close()
                 cpu_base = {"value": p / s / 1e6, "unit": UNIT, "cores": 1,
-                            "kind": "reference",
-                            "sample": "3 loops: " + workers.desc}
+                            "kind": "reference", "sample": workers.desc}
             except Exception as exc:      # noqa: BLE001
                 cpu_base = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                             "sample": f"unavailable: {exc}"}
