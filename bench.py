@@ -205,15 +205,15 @@ def run_reference(args):
     # one optimizer per host thread, like the reference's ThreadPool (one view
     # each, app/smvsrecon.cc:558). The reference's throughput stops growing
     # with threads early (every vector operation of its CG allocates, and the
-    # threads share one address space): measured on the 128-core GPU box, 8
-    # threads reach 0.70 Mpix-iters/s, 64 threads 0.43. The arm therefore runs
-    # the thread count that served the reference best there (16, or
-    # SMVSB_REF_THREADS). Each thread runs the Newton loop of a quarter of the
-    # patch grid (about 12 s a step); smaller windows would sell the reference
+    # threads share one address space): measured on the 128-core GPU box with
+    # quarter-grid windows, 16 threads reach 1.47 Mpix-iters/s, 32 threads 1.93
+    # (and, with 1/16 windows, 8 threads 0.70 but 64 threads only 0.43). The
+    # arm runs 32 threads (or SMVSB_REF_THREADS). Each thread runs the Newton loop of a quarter of the
+    # patch grid (12-18 s a step); smaller windows would sell the reference
     # short, because its CG vectors span the whole node grid whatever part of
     # it is valid (measured on one core: 0.109 Mpix-iters/s on a quarter,
     # 0.078 on 1/16, 0.029 on 1/64). Long runs (> 16 steps) fall back to 1/16.
-    threads = int(os.environ.get("SMVSB_REF_THREADS", "0")) or min(os.cpu_count() or 1, 16)
+    threads = int(os.environ.get("SMVSB_REF_THREADS", "0")) or min(os.cpu_count() or 1, 32)
     threads = max(1, min(threads, 64))
     wl = build_workload(WIDTH, HEIGHT, N_SUB, SCALE, shading=False, seed_index=0)
     frac = 2 if (args.steps + args.warmup) <= 16 else 4
