@@ -26,7 +26,11 @@
  * KB of shared memory is a KB less L1, and the SpMV needs L1 both for the
  * vector entries nine rows share and as landing space for ~150 KB of loads in
  * flight per SM: 22.3 -> 24.2 us with 86 KB of shared memory, 37 us with
- * 200 KB. Likewise cp.async.bulk.prefetch.L2 of the rows a CTA reads first,
+ * 200 KB. Reading the blocks left of / above the diagonal as transposes of the
+ * neighbours' mirror blocks (256-bit row load + 4x4 transpose across the quad,
+ * slots 0..3 never fetched): the second use of a line does not hit L2 often
+ * enough, SpMV 22.3 -> 43.6 us; and the assembled H is symmetric only to
+ * rounding, so x changes. Likewise cp.async.bulk.prefetch.L2 of the rows a CTA reads first,
  * issued while HBM idles in the vector-update phase: the SpMV gains 1.3 us,
  * the update phase and the barriers lose more.
  */
