@@ -203,6 +203,20 @@ int smvsb_newton_loop (smvsb_ctx* ctx, const double* light16,
 int smvsb_view_set_scale (smvsb_ctx* ctx, int w, int h, const float* image,
     int scale, float* scaleimage, float* grad, float* hess);
 
+/*
+ * DepthOptimizer::depthmap_bilateral_filter (lib/depth_optimizer.cc:957-1004):
+ * joint bilateral filter of a depth map (dm_w*dm_h, 0 = no depth) guided by
+ * the w*h*channels float image; spatial Gaussian `sigma` over a
+ * (2*kernel_size+1)^2 window, range Gaussian 0.1 per channel; out: w*h.
+ * Bit-identical to the reference (fp32, same accumulation order, expf as
+ * glibc computes it). kernel_size <= 8, channels <= 4.
+ */
+int smvsb_bilateral_filter (smvsb_ctx* ctx, int w, int h, int channels,
+    const float* guide, int dm_w, int dm_h, const float* depth, float sigma,
+    int kernel_size, float* out);
+/* Host twin of the device expf used above (tests compare it with libm). */
+float smvsb_debug_expf (float x);
+
 /* ---- visibility and boundary cutting (the callers' side of the loop) ---- */
 
 /*

@@ -1,13 +1,14 @@
 /*
  * integration/b200_depth_optimizer.cc
  *
- * Drop-in bodies for three members of smvs::DepthOptimizer that run on the
+ * Drop-in bodies for four members of smvs::DepthOptimizer that run on the
  * GPU through the C ABI of libsmvs_b200.so:
  *   run_newton_iterations    lib/depth_optimizer.cc:164-358 (inner Newton
  *                            loop :204-304 -> smvsb_newton_loop)
  *   create_subview_surfaces  :433-604 -> smvsb_visibility (use_sgm mode; the
  *                            use_sgm = false mode keeps the reference's body)
  *   cut_boundaries           :360-431 -> smvsb_cut_boundaries
+ *   depthmap_bilateral_filter :957-1004 -> smvsb_bilateral_filter
  * Everything else -- surface expansion / subdivision, isolated-patch removal,
  * the patch-count convergence test -- still calls the reference's own member
  * functions, and the host Surface stays the owner of the state (uploaded
@@ -225,6 +226,19 @@ DepthOptimizer::create_subview_surfaces (void)
     if (this->opts.debug_lvl > 0)
         std::cout << "Removed " << deleted << " patches "
             "due to occlusions." << std::endl;
+}
+
+mve::FloatImage::Ptr
+DepthOptimizer::depthmap_bilateral_filter (mve::FloatImage::ConstPtr dm,
+    mve::FloatImage::ConstPtr ci, float sigma, int kernel_size)
+{
+    smvsb::Context& gpu = thread_context();
+    mve::FloatImage::Ptr out = mve::FloatImage::create(ci->width(),
+        ci->height(), 1);
+    gpu.check(smvsb_bilateral_filter(gpu.get(), ci->width(), ci->height(),
+        ci->channels(), ci->begin(), dm->width(), dm->height(), dm->begin(),
+        sigma, kernel_size, out->begin()));
+    return out;
 }
 
 int

@@ -198,6 +198,21 @@ class RefScene:
         self.L.ref_main_inverse_calibration(self.h_, out.ctypes.data_as(C.c_void_p))
         return out
 
+    def bilateral_filter(self, depth):
+        """DepthOptimizer::depthmap_bilateral_filter(depth, main image)."""
+        d = np.ascontiguousarray(depth, dtype=np.float32)
+        out = np.empty((self.h, self.w), dtype=np.float32)
+        self.L.ref_bilateral_filter(self.h_, _p(d), d.shape[1], d.shape[0], _p(out))
+        return out
+
+    def image(self, v):
+        """StereoView::get_image(): the unblurred float image of view v."""
+        ch = int(self.L.ref_view_get_image(self.h_, v, None))
+        h, w = self.scene.images[v].shape[:2]
+        out = np.empty((h, w, ch), dtype=np.float32)
+        self.L.ref_view_get_image(self.h_, v, _p(out))
+        return out[:, :, 0] if ch == 1 else out
+
     def get_visibility(self):
         i = self.surface_info()
         npatch = i["npx"] * i["npy"]

@@ -441,6 +441,32 @@ ref_main_inverse_calibration (void* scene, float* out9)
         s->main_view->get_width(), s->main_view->get_height());
 }
 
+/* DepthOptimizer::depthmap_bilateral_filter(dm, main_view->get_image()) with
+ * its default sigma = 5, kernel_size = 5 (lib/depth_optimizer.cc:42-43,
+ * 957-1004). dm: dm_w x dm_h; out: main view size. */
+void
+ref_bilateral_filter (void* scene, float const* dm, int dm_w, int dm_h,
+    float* out)
+{
+    RefScene* s = static_cast<RefScene*>(scene);
+    mve::FloatImage::Ptr d = mve::FloatImage::create(dm_w, dm_h, 1);
+    std::copy(dm, dm + (std::size_t)dm_w * dm_h, d->begin());
+    mve::FloatImage::Ptr r = s->optimizer->depthmap_bilateral_filter(d,
+        s->main_view->get_image());
+    std::copy(r->begin(), r->end(), out);
+}
+
+/* StereoView::get_image(): the unblurred float image; returns its channels. */
+int
+ref_view_get_image (void* scene, int v, float* out)
+{
+    mve::FloatImage::ConstPtr img = view_of(static_cast<RefScene*>(scene), v)
+        ->get_image();
+    if (out != nullptr)
+        std::copy(img->begin(), img->end(), out);
+    return img->channels();
+}
+
 /* vis_off has num_patches + 1 entries; pass vis_ids = NULL to query size. */
 uint64_t
 ref_get_visibility (void* scene, uint32_t* vis_off, uint8_t* vis_ids)

@@ -25,6 +25,7 @@ EXPORTS = [
     "smvsb_get_normals", "smvsb_debug_get_system", "smvsb_debug_spmv",
     "smvsb_fit_lighting", "smvsb_sgm", "smvsb_visibility",
     "smvsb_cut_boundaries", "smvsb_get_surface_state", "smvsb_view_set_scale",
+    "smvsb_bilateral_filter", "smvsb_debug_expf",
 ]
 
 
@@ -195,6 +196,19 @@ class Context:
         self._check(lib().smvsb_view_set_scale(self._h, w, h, _p(img), int(scale),
                                                _p(blur), _p(grad), _p(hess)))
         return blur, grad, hess
+
+    def bilateral_filter(self, guide, depth, sigma=5.0, kernel_size=5):
+        """DepthOptimizer::depthmap_bilateral_filter: guide (h, w[, C]) float
+        image, depth (dm_h, dm_w) -> filtered (h, w) depth."""
+        g = np.ascontiguousarray(guide, dtype=np.float32)
+        d = np.ascontiguousarray(depth, dtype=np.float32)
+        h, w = g.shape[:2]
+        ch = 1 if g.ndim == 2 else g.shape[2]
+        out = np.empty((h, w), dtype=np.float32)
+        self._check(lib().smvsb_bilateral_filter(
+            self._h, w, h, ch, _p(g), d.shape[1], d.shape[0], _p(d),
+            C.c_float(sigma), int(kernel_size), _p(out)))
+        return out
 
     # -- visibility / boundary cutting --------------------------------------
     def visibility(self, sgm_depth):

@@ -21,6 +21,10 @@ void device_shading_inputs (smvsb_ctx* c, uint8_t const* img_dev, int w, int h,
     float* shading_dev, float* shading_grad_dev);
 void device_set_scale_float (smvsb_ctx* c, float const* img_dev, int w, int h,
     int scale, float* tmp_a, float* tmp_b, float* out_dev);
+void device_bilateral_filter (smvsb_ctx* c, float const* ci_dev, int w, int h,
+    int channels, float const* dm_dev, int dm_w, int dm_h, float sigma,
+    int kernel_size, float* out_dev);
+float host_expf_like_glibc (float x);
 void device_unpack_texels (smvsb_ctx* c, float const* texels, int n,
     float* grad, float* hess);
 std::string const& sgm_last_error (void);
@@ -482,6 +486,37 @@ smvsb_view_set_scale (smvsb_ctx* ctx, int w, int h, const float* image,
         }
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
     });
+}
+
+int
+smvsb_bilateral_filter (smvsb_ctx* ctx, int w, int h, int channels,
+    const float* guide, int dm_w, int dm_h, const float* depth, float sigma,
+    int kernel_size, float* out)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        smvsb_ctx* c = ctx;
+        require(w > 0 && h > 0 && dm_w > 0 && dm_h > 0 && guide && depth
+            && out, SMVSB_ERR_INVALID, "bilateral filter: image missing");
+        size_t const n = static_cast<size_t>(w) * h;
+        size_t const nd = static_cast<size_t>(dm_w) * dm_h;
+        c->view_texels.reserve(n * channels);
+        c->view_in.reserve(nd);
+        c->view_out.reserve(n);
+        CUDA_CHECK(cudaMemcpyAsync(c->view_texels.p, guide,
+            n * channels * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(c->view_in.p, depth, nd * sizeof(float),
+            cudaMemcpyHostToDevice, c->stream));
+        smvsb::device_bilateral_filter(c, c->view_texels.p, w, h, channels,
+            c->view_in.p, dm_w, dm_h, sigma, kernel_size, c->view_out.p);
+        download(c, out, c->view_out.p, n);
+    });
+}
+
+float
+smvsb_debug_expf (float x)
+{
+    return smvsb::host_expf_like_glibc(x);
 }
 
 int

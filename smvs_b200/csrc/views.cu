@@ -13,6 +13,7 @@
  * 6x9 matrix applied term by term.
  */
 #include <cmath>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -230,6 +231,121 @@ device_set_scale_float (smvsb_ctx* c, float const* img_dev, int w, int h,
     count_launches(c, 3);
 }
 
+/* ------------------------------------------------------------------ */
+/* DepthOptimizer::depthmap_bilateral_filter (lib/depth_optimizer.cc:957-1004):
+ * joint bilateral filter of the SGM depth with the colour image as guide.  */
+
+constexpr int BILAT_MAX_K = 8;          /* kernel_size (radius), default 5 */
+
+struct BilateralArgs
+{
+    int w, h, channels, dm_w, dm_h, ks;
+    float scale_x, scale_y;
+    float two_sigma_sq;                 /* T(2) * 0.1f * 0.1f of math::gaussian */
+    float spatial[(2 * BILAT_MAX_K + 1) * (2 * BILAT_MAX_K + 1)];
+    unsigned long long exp_tab[32];     /* 2^(i/32) table of expf */
+};
+
+/* expf as glibc computes it (sysdeps/ieee754/flt-32/e_expf.c: N = 32 table,
+ * cubic in double, one rounding to float), for -87 < x <= 0: the range weight
+ * must be the bits the CPU produces. Checked against libm on 3e7 arguments
+ * (tests/test_cpu_host.py runs the host twin of this function). */
+__host__ __device__ __forceinline__ float
+expf_like_glibc (float x, unsigned long long const* tab)
+{
+    double const n = 32.0;
+    double const c0 = 0x1.c6af84b912394p-5 / n / n / n;
+    double const c1 = 0x1.ebfce50fac4f3p-3 / n / n;
+    double const c2 = 0x1.62e42ff0c52d6p-1 / n;
+    double const inv_ln2_n = 0x1.71547652b82fep+0 * n;
+    double const shift = 0x1.8p+52;
+#ifdef __CUDA_ARCH__
+    double z = __dmul_rn(inv_ln2_n, static_cast<double>(x));
+    double kd = __dadd_rn(z, shift);
+    unsigned long long const ki = static_cast<unsigned long long>(
+        __double_as_longlong(kd));
+    kd = __dadd_rn(kd, -shift);
+    double const r = __dadd_rn(z, -kd);
+    unsigned long long const t = tab[ki % 32] + (ki << 47);
+    double const s = __longlong_as_double(static_cast<long long>(t));
+    z = __dadd_rn(__dmul_rn(c0, r), c1);
+    double const r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(c2, r), 1.0);
+    y = __dadd_rn(__dmul_rn(z, r2), y);
+    y = __dmul_rn(y, s);
+    return static_cast<float>(y);
+#else
+    volatile double z = inv_ln2_n * static_cast<double>(x);
+    volatile double kd = z + shift;
+    unsigned long long ki;
+    double const kd_copy = kd;
+    memcpy(&ki, &kd_copy, 8);
+    kd = kd - shift;
+    volatile double r = z - kd;
+    unsigned long long const t = tab[ki % 32] + (ki << 47);
+    double s;
+    memcpy(&s, &t, 8);
+    volatile double zz = c0 * r;
+    zz = zz + c1;
+    volatile double r2 = r * r;
+    volatile double y = c2 * r;
+    y = y + 1.0;
+    volatile double m = zz * r2;
+    y = m + y;
+    y = y * s;
+    return static_cast<float>(y);
+#endif
+}
+
+__global__ void __launch_bounds__(128)
+bilateral_kernel (BilateralArgs const a, float const* __restrict__ ci,
+    float const* __restrict__ dm, float* __restrict__ out)
+{
+    int const x = blockIdx.x * blockDim.x + threadIdx.x;
+    int const y = blockIdx.y;
+    if (x >= a.w)
+        return;
+    int const C = a.channels;
+    float centre[4];
+    for (int c = 0; c < C; ++c)
+        centre[c] = ci[(static_cast<size_t>(y) * a.w + x) * C + c];
+    float acc_v = 0.0f, acc_w = 0.0f;
+    int const side = 2 * a.ks + 1;
+    for (int ky = -a.ks; ky <= a.ks; ++ky)
+        for (int kx = -a.ks; kx <= a.ks; ++kx)
+        {
+            int const cx = min(max(x + kx, 0), a.w - 1);
+            int const cy = min(max(y + ky, 0), a.h - 1);
+            /* math::clamp(scale * c, 0.f, dm_size - 1.f), then truncation */
+            float fx = __fmul_rn(a.scale_x, static_cast<float>(cx));
+            float fy = __fmul_rn(a.scale_y, static_cast<float>(cy));
+            float const mx = static_cast<float>(a.dm_w) - 1.0f;
+            float const my = static_cast<float>(a.dm_h) - 1.0f;
+            fx = (fx < 0.0f) ? 0.0f : ((fx > mx) ? mx : fx);
+            fy = (fy < 0.0f) ? 0.0f : ((fy > my) ? my : fy);
+            int const dx = static_cast<int>(fx), dy = static_cast<int>(fy);
+            float const d = dm[static_cast<size_t>(dy) * a.dm_w + dx];
+            if (d == 0.0f)
+                continue;
+            float weight = 1.0f;
+            weight = __fmul_rn(weight,
+                a.spatial[(ky + a.ks) * side + (kx + a.ks)]);
+            for (int c = 0; c < C; ++c)
+            {
+                float const diff = __fadd_rn(
+                    ci[(static_cast<size_t>(cy) * a.w + cx) * C + c],
+                    -centre[c]);
+                float const arg = -__fdiv_rn(__fmul_rn(diff, diff),
+                    a.two_sigma_sq);
+                weight = __fmul_rn(weight, expf_like_glibc(arg, a.exp_tab));
+            }
+            acc_v = __fadd_rn(acc_v, __fmul_rn(d, weight));
+            acc_w = __fadd_rn(acc_w, weight);
+        }
+    out[static_cast<size_t>(y) * a.w + x] =
+        (acc_w > 0.0f) ? __fdiv_rn(acc_v, acc_w) : 0.0f;
+}
+
 /* initialize_linear without gamma (lib/stereo_view.cc:64-84): shading image =
  * byte_to_float(image), plus its gradient. */
 void
@@ -255,6 +371,63 @@ device_unpack_texels (smvsb_ctx* c, float const* texels, int n, float* grad,
         grad, hess);
     CUDA_CHECK(cudaGetLastError());
     count_launches(c, 1);
+}
+
+/* w*h*channels guide image and dm_w*dm_h depth on the device -> w*h depth. */
+void
+device_bilateral_filter (smvsb_ctx* c, float const* ci_dev, int w, int h,
+    int channels, float const* dm_dev, int dm_w, int dm_h, float sigma,
+    int kernel_size, float* out_dev)
+{
+    if (kernel_size < 0 || kernel_size > BILAT_MAX_K)
+        throw Error(SMVSB_ERR_INVALID, "bilateral kernel_size out of range");
+    if (channels < 1 || channels > 4)
+        throw Error(SMVSB_ERR_INVALID, "guide image needs 1..4 channels");
+    BilateralArgs a;
+    a.w = w; a.h = h; a.channels = channels; a.dm_w = dm_w; a.dm_h = dm_h;
+    a.ks = kernel_size;
+    a.scale_x = static_cast<float>(dm_w) / static_cast<float>(w);
+    a.scale_y = static_cast<float>(dm_h) / static_cast<float>(h);
+    float const range_sigma = 0.1f;     /* lib/depth_optimizer.cc:996 */
+    a.two_sigma_sq = 2.0f * range_sigma * range_sigma;
+    int const side = 2 * kernel_size + 1;
+    for (int ky = -kernel_size; ky <= kernel_size; ++ky)
+        for (int kx = -kernel_size; kx <= kernel_size; ++kx)
+        {
+            /* math::gaussian_2d((float)kx, (float)ky, sigma, sigma) */
+            float const fx = static_cast<float>(kx), fy = static_cast<float>(ky);
+            float const ex = -(fx * fx) / (2.0f * sigma * sigma)
+                - (fy * fy) / (2.0f * sigma * sigma);
+            a.spatial[(ky + kernel_size) * side + (kx + kernel_size)]
+                = std::exp(ex);
+        }
+    for (int i = 0; i < 32; ++i)
+    {
+        double const v = std::exp2(static_cast<double>(i) / 32.0);
+        unsigned long long bits;
+        memcpy(&bits, &v, 8);
+        a.exp_tab[i] = bits - (static_cast<unsigned long long>(i) << 47);
+    }
+    dim3 const block(128, 1), grid((w + 127) / 128, h);
+    bilateral_kernel<<<grid, block, 0, c->stream>>>(a, ci_dev, dm_dev,
+        out_dev);
+    CUDA_CHECK(cudaGetLastError());
+    count_launches(c, 1);
+}
+
+/* Host twin of the device expf (tests pin it to libm). */
+float
+host_expf_like_glibc (float x)
+{
+    unsigned long long tab[32];
+    for (int i = 0; i < 32; ++i)
+    {
+        double const v = std::exp2(static_cast<double>(i) / 32.0);
+        unsigned long long bits;
+        memcpy(&bits, &v, 8);
+        tab[i] = bits - (static_cast<unsigned long long>(i) << 47);
+    }
+    return expf_like_glibc(x, tab);
 }
 
 } /* namespace smvsb */

@@ -148,3 +148,20 @@ def test_gloo_world_size_2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == (500.0, 2.0, 3.0, 3.0)
+
+
+def test_expf_twin_matches_libm():
+    """The device bilateral filter evaluates expf the way glibc does (table +
+    cubic in double, one rounding); its host twin must give libm's bits."""
+    import ctypes as C
+    L = api.lib()
+    L.smvsb_debug_expf.restype = C.c_float
+    L.smvsb_debug_expf.argtypes = [C.c_float]
+    libm = C.CDLL("libm.so.6")
+    libm.expf.restype = C.c_float
+    libm.expf.argtypes = [C.c_float]
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([-(rng.random(20000) ** 2 * 50).astype(np.float32),
+                         np.float32([-0.0, -1e-7, -1.0, -50.0, -86.9])])
+    for x in xs:
+        assert L.smvsb_debug_expf(float(x)) == libm.expf(float(x))

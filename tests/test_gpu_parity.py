@@ -166,6 +166,26 @@ def test_view_set_scale_bitwise():
             assert np.array_equal(grad, rg) and np.array_equal(hess, rh)
 
 
+@pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")
+def test_bilateral_filter_bit_exact():
+    """smvsb_bilateral_filter against DepthOptimizer::depthmap_bilateral_filter
+    (joint bilateral filter of the SGM init): fp32 with expf in the loop --
+    bit-identical, full-resolution and half-resolution depth, with holes."""
+    sc = synth.make_scene(333, 207, 1, seed_index=6)
+    R = oref.RefScene(sc)
+    guide = R.image(0)
+    d = sc.init_depth.astype(np.float32).copy()
+    d[::7, ::5] = 0.0
+    d[40:80, 100:160] = 0.0
+    with api.Context(0) as ctx:
+        for dm in (d, d[::2, ::2].copy()):
+            out = ctx.bilateral_filter(guide, dm)
+            ref = R.bilateral_filter(dm)
+            assert np.array_equal(out, ref)
+            assert (out > 0).mean() > 0.8
+    R.close()
+
+
 # ---------------------------------------------------------------------------
 # live reference, larger / odd shapes
 # ---------------------------------------------------------------------------
