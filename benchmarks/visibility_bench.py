@@ -66,6 +66,21 @@ def main():
                     "visibility_entries": int(off[-1]),
                     "ms_visibility_abi": 1e3 * float(np.median(t_vis[1:])),
                     "ms_cut_loop_abi": 1e3 * float(np.median(t_cut[1:]))})
+        # the two image-side members of the same drop-in: joint bilateral filter
+        # of the SGM init and StereoView::set_scale of one view (host in / out)
+        from smvs_b200 import stereo_view
+        guide = stereo_view.byte_to_float(sc.images[0])
+        t_bil, t_set = [], []
+        for _ in range(a.reps + 1):
+            t0 = time.perf_counter()
+            filtered = ctx.bilateral_filter(guide, sgm)
+            t1 = time.perf_counter()
+            ctx.view_set_scale(guide, a.scale)
+            t2 = time.perf_counter()
+            t_bil.append(t1 - t0)
+            t_set.append(t2 - t1)
+        out.update({"ms_bilateral_filter_abi": 1e3 * float(np.median(t_bil[1:])),
+                    "ms_view_set_scale_abi": 1e3 * float(np.median(t_set[1:]))})
     if a.reference:
         from oracle import ref as oref
         R = oref.RefScene(sc)
@@ -88,6 +103,14 @@ def main():
                     "ref_cut_rounds": rounds, "ref_cores": 1,
                     "same_patches_as_reference": bool(np.array_equal(pv_r, pv)),
                     "same_nodes_as_reference": bool(np.array_equal(nv_r, nv))})
+        t0 = time.perf_counter()
+        ref_filtered = R.bilateral_filter(sgm)
+        t1 = time.perf_counter()
+        R.set_scale(a.scale)
+        t2 = time.perf_counter()
+        out.update({"ref_ms_bilateral_filter": 1e3 * (t1 - t0),
+                    "ref_ms_set_scale_per_view": 1e3 * (t2 - t1) / (1 + a.neighbours),
+                    "same_filtered_depth_as_reference": bool(np.array_equal(ref_filtered, filtered))})
         R.close()
     print(json.dumps(out))
 

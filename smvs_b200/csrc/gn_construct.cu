@@ -121,7 +121,7 @@ struct ConstructArgs
 /* 3 CTAs / SM (168 registers, a few spills) beats 2 CTAs at 248 registers by
  * 13 % on B200: the kernel is fp64-latency bound and wants the warps. */
 template <int S>
-__global__ void __launch_bounds__(K1_THREADS, 3)
+__global__ void __launch_bounds__(K1_THREADS, 4)
 gn_patch_kernel (ConstructArgs const args)
 {
     /* samples of one patch per chunk, chunks per patch, patches per block,
