@@ -153,3 +153,29 @@ def test_full_size_visibility_and_cut_parity():
                 break
         assert total > 50
     R.close()
+
+
+def test_error_paths_of_the_new_entry_points():
+    import ctypes as C
+    L = api.lib()
+    sc = synth.make_scene(96, 64, 1, seed_index=49)
+    with api.Context(0) as ctx:
+        # nothing set yet
+        with pytest.raises(api.SmvsbError):
+            ctx.visibility(sc.init_depth)
+        with pytest.raises(api.SmvsbError):
+            ctx.cut_boundaries(np.eye(3, dtype=np.float32))
+        # images: too small / too many channels / kernel too large
+        with pytest.raises(api.SmvsbError):
+            ctx.view_set_scale(np.zeros((2, 2), dtype=np.float32), 2)
+        with pytest.raises(api.SmvsbError):
+            ctx.bilateral_filter(np.zeros((8, 8, 5), dtype=np.float32),
+                                 np.ones((8, 8), dtype=np.float32))
+        with pytest.raises(api.SmvsbError):
+            ctx.bilateral_filter(np.zeros((8, 8), dtype=np.float32),
+                                 np.ones((8, 8), dtype=np.float32), kernel_size=9)
+        assert b"kernel_size" in L.smvsb_last_error(ctx._h)
+        # a filter over an empty depth map gives an empty depth map
+        out = ctx.bilateral_filter(np.full((8, 8), 0.5, dtype=np.float32),
+                                   np.zeros((8, 8), dtype=np.float32))
+        assert not out.any()
