@@ -307,6 +307,7 @@ def run_product(args):
     barrier()
     launches0 = ctx.launches
     t_dev_ms, pix, newton, cg = 0.0, 0.0, 0, 0
+    cg_blocks, cg_rows = 0.0, 0.0
     t_split = np.zeros(3)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -315,6 +316,8 @@ def run_product(args):
         pix += st["pixel_iterations"]
         newton += st["newton_steps"]
         cg += st["cg_iterations"]
+        cg_blocks += st["cg_block_iterations"]
+        cg_rows += st["cg_row_iterations"]
         t_split += [st["ms_construct"], st["ms_solve"], st["ms_update"]]
     barrier()
     t1 = time.perf_counter()
@@ -349,8 +352,11 @@ def run_product(args):
         e2e_value = pix_e2e / wall_e2e / 1e6
 
         # roofline of the dominant kernel: the PCG (one persistent launch per
-        # Newton step). Algorithmic bytes per CG iteration per node
-        # (DESIGN.md section 5): H 9*128 + P 128 + vector traffic 12*32.
+        # Newton step). Algorithmic bytes per CG iteration (DESIGN.md section
+        # 5): 128 per 4x4 block of the system + per block row 128 (P) and
+        # 12 * 32 (vector passes). The system of a Newton step holds the blocks
+        # whose two nodes are still active (the reference drops the others,
+        # lib/gauss_newton_step.cc:91-105); the kernel reports their number.
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -358,21 +364,34 @@ def run_product(args):
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        n_nodes = (wl.npx + 1) * (wl.npy + 1)
-        bytes_per_iter = n_nodes * (9 * 128 + 128 + 12 * 32)
+        algorithmic = cg_blocks * 128.0 + cg_rows * (128.0 + 12 * 32.0)
         cg_ms = float(t_split[1])
-        achieved = (bytes_per_iter * cg / max(cg_ms * 1e-3, 1e-12)) / 1e9
+        achieved = (algorithmic / max(cg_ms * 1e-3, 1e-12)) / 1e9
+        # blocks of the full system (every valid node active), for scaling the
+        # ncu capture of such a launch to the launches of this run
+        nv = wl.node_valid.reshape(wl.npy + 1, wl.npx + 1).astype(bool)
+        blocks_full = 0
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                a = nv[max(dy, 0):nv.shape[0] + min(dy, 0), max(dx, 0):nv.shape[1] + min(dx, 0)]
+                b = nv[max(-dy, 0):nv.shape[0] + min(-dy, 0), max(-dx, 0):nv.shape[1] + min(-dx, 0)]
+                blocks_full += int((a & b).sum())
         roofline = {"bound": "hbm", "kernel": "cg_kernel (persistent PCG)",
                     "achieved": achieved, "peak": hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
                     "unit": "GB/s", "frac": achieved / hbm_peak,
                     # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full
                     # capture (profiles/r1c_cg.txt: 29.45 GB for a 200-iteration launch
-                    # = 147.3 MB per CG iteration: H only -- P and the vectors stay in
-                    # L2), scaled to this run's iterations/launch
-                    "traffic": 147.3e6 * cg / max(newton, 1),
-                    "traffic_source": "profiles/r1c_cg.txt",
-                    "algorithmic_bytes_per_launch": bytes_per_iter * cg / max(newton, 1),
+                    # on the full system = 147.3 MB per CG iteration: H only -- P and
+                    # the vectors stay in L2), scaled by the blocks this run's launches
+                    # read
+                    "traffic": 29.45e9 / (200.0 * blocks_full) * cg_blocks / max(newton, 1),
+                    "traffic_source": "profiles/r1c_cg.txt, scaled by system blocks x iterations",
+                    "frac_dram": (29.45e9 / (200.0 * blocks_full) * cg_blocks
+                                  / max(cg_ms * 1e-3, 1e-12)) / 1e9 / hbm_peak,
+                    "algorithmic_bytes_per_launch": algorithmic / max(newton, 1),
+                    "system_blocks_full": blocks_full,
+                    "system_block_iterations_per_launch": cg_blocks / max(newton, 1),
                     "launches_timed": newton}
 
         cpu_base = None

@@ -66,6 +66,9 @@ typedef struct smvsb_newton_stats
     double ms_update;
     double ms_total;             /* first launch to last result, incl. the
                                     per-step host read-back of the scalars */
+    double cg_block_iterations;  /* sum over solves of (4x4 blocks of the
+                                    system, i.e. both nodes active) x iterations */
+    double cg_row_iterations;    /* sum over solves of active nodes x iterations */
 } smvsb_newton_stats;
 
 /* ---- lifetime ------------------------------------------------------- */

@@ -40,7 +40,8 @@ class NewtonStats(C.Structure):
                 ("nan_break", C.c_int32), ("reserved", C.c_int32),
                 ("n_active", C.c_uint64), ("pixel_iterations", C.c_double),
                 ("ms_construct", C.c_double), ("ms_solve", C.c_double),
-                ("ms_update", C.c_double), ("ms_total", C.c_double)]
+                ("ms_update", C.c_double), ("ms_total", C.c_double),
+                ("cg_block_iterations", C.c_double), ("cg_row_iterations", C.c_double)]
 
 
 _lib = None
@@ -284,7 +285,9 @@ class Context:
                     nan=bool(st.nan_break), n_active=int(st.n_active),
                     pixel_iterations=float(st.pixel_iterations),
                     ms_construct=st.ms_construct, ms_solve=st.ms_solve,
-                    ms_update=st.ms_update, ms_total=st.ms_total)
+                    ms_update=st.ms_update, ms_total=st.ms_total,
+                    cg_block_iterations=st.cg_block_iterations,
+                    cg_row_iterations=st.cg_row_iterations)
 
     # -- outputs ---------------------------------------------------------
     def get_nodes(self):

@@ -702,6 +702,8 @@ smvsb_newton_loop (smvsb_ctx* ctx, const double* light16,
             smvsb::run_cg(c, 200, -1.0, 1e-3, &iters, &info, &x0_nan);
             CUDA_CHECK(cudaEventRecord(c->ev[2], c->stream));
             st.cg_iterations += iters;
+            st.cg_block_iterations += double(c->cg_blocks) * iters;
+            st.cg_row_iterations += double(c->cg_rows) * iters;
             if (x0_nan)     /* lib/depth_optimizer.cc:267 */
             {
                 st.nan_break = 1;

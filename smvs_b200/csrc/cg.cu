@@ -55,6 +55,7 @@ struct CgArgs
     double const* H;
     double const* P;
     double const* g;         /* b = -g (lib/depth_optimizer.cc:251) */
+    uint16_t const* rowmask; /* bit k: block k of the node's row exists */
     double* x;
     double* r;
     double* d;               /* search direction, double buffered */
@@ -248,18 +249,28 @@ struct DirVec
  * lib/block_sparse_matrix.h:283-296). own[] receives v[node]. */
 template <typename VecOp>
 __device__ __forceinline__ double
-spmv_row (CgArgs const& a, VecOp const& vec, int node, int rp, double* own)
+spmv_row (CgArgs const& a, VecOp const& vec, int node, int rp,
+    unsigned int mask, double* own)
 {
     int const ns = a.npx + 1;
     int const ix = node % ns, iy = node / ns;
     double const* hrow = a.H + static_cast<size_t>(node) * 144 + rp * 4;
     double acc = 0.0;
+    own[0] = 0.0; own[1] = 0.0; own[2] = 0.0; own[3] = 0.0;
+    /* The reference drops the rows and columns of inactive nodes
+     * (lib/gauss_newton_step.cc:91,101,105); here they are zero blocks, which
+     * are neither fetched nor multiplied: as the active set shrinks from one
+     * Newton step to the next, so does the Hessian traffic. */
+    /* The mask (both nodes valid, active and inside the grid) is in a
+     * register before the row starts, so the nine loads stay independent. */
+    if (mask == 0)
+        return 0.0;
 #pragma unroll
     for (int k = 0; k < 9; ++k)
     {
-        int const jx = ix + (k % 3) - 1, jy = iy + (k / 3) - 1;
-        if (jx < 0 || jx > a.npx || jy < 0 || jy > a.npy)
+        if (!((mask >> k) & 1u))
             continue;
+        int const jx = ix + (k % 3) - 1, jy = iy + (k / 3) - 1;
         int const nj = jy * ns + jx;
         double2 h01, h23;
         ld_stream(hrow + k * 16, h01, h23);
@@ -352,10 +363,15 @@ cg_kernel (CgArgs const a)
         DirVec dir;
         dir.z = a.z; dir.d_old = d_old; dir.beta = beta;
         double p_dAd = 0.0;
+        unsigned int mask = (t0 < n) ? a.rowmask[t0 >> 2] : 0u;
         for (int i = t0; i < n; i += stride)
         {
+            /* next pass's mask travels while this pass streams its row */
+            unsigned int const mask_next = (i + stride < n)
+                ? a.rowmask[(i + stride) >> 2] : 0u;
             double own[4];
-            double const v = spmv_row(a, dir, i >> 2, rp, own);
+            double const v = spmv_row(a, dir, i >> 2, rp, mask, own);
+            mask = mask_next;
             double const di = (rp == 0) ? own[0] : (rp == 1) ? own[1]
                 : (rp == 2) ? own[2] : own[3];
             a.Ad[i] = v;
@@ -468,6 +484,42 @@ cg_kernel (CgArgs const a)
     }
 }
 
+/* bit k of rowmask[node]: block k of the node's 3x3 stencil row exists, i.e.
+ * the node and its k-th grid neighbour are both valid and active. */
+__global__ void
+cg_mark_kernel (int npx, int npy, uint8_t const* __restrict__ node_valid,
+    uint8_t const* __restrict__ active, uint16_t* __restrict__ rowmask,
+    unsigned long long* __restrict__ counts)
+{
+    int const node = blockIdx.x * blockDim.x + threadIdx.x;
+    int const ns = npx + 1;
+    if (node >= ns * (npy + 1))
+        return;
+    unsigned int m = 0;
+    if (node_valid[node] && active[node])
+    {
+        int const ix = node % ns, iy = node / ns;
+        for (int k = 0; k < 9; ++k)
+        {
+            int const jx = ix + (k % 3) - 1, jy = iy + (k / 3) - 1;
+            if (jx < 0 || jx > npx || jy < 0 || jy > npy)
+                continue;
+            int const nj = jy * ns + jx;
+            if (node_valid[nj] && active[nj])
+                m |= 1u << k;
+        }
+    }
+    rowmask[node] = static_cast<uint16_t>(m);
+    /* counts[0]: blocks of the system, counts[1]: its block rows */
+    unsigned int const blocks = __reduce_add_sync(__activemask(), __popc(m));
+    unsigned int const rows = __reduce_add_sync(__activemask(), m != 0);
+    if ((threadIdx.x & 31) == 0)
+    {
+        atomicAdd(counts, static_cast<unsigned long long>(blocks));
+        atomicAdd(counts + 1, static_cast<unsigned long long>(rows));
+    }
+}
+
 __global__ void
 cg_finish_kernel (double const* x, double* result)
 {
@@ -484,7 +536,7 @@ spmv_kernel (CgArgs const a, double const* __restrict__ x,
     PlainVec vec;
     vec.v = x;
     double own[4];
-    y[i] = spmv_row(a, vec, i >> 2, i & 3, own);
+    y[i] = spmv_row(a, vec, i >> 2, i & 3, a.rowmask[i >> 2], own);
 }
 
 CgArgs
@@ -494,6 +546,15 @@ make_args (smvsb_ctx* c)
     a.n_nodes = c->n_nodes; a.npx = c->npx; a.npy = c->npy;
     a.max_iter = 0; a.err_tol = 0; a.q_tol = 0;
     a.H = c->H.p; a.P = c->P.p; a.g = c->g.p;
+    c->cg_rowmask.reserve(c->n_nodes);
+    c->cg_counts.reserve(2);
+    a.rowmask = c->cg_rowmask.p;
+    CUDA_CHECK(cudaMemsetAsync(c->cg_counts.p, 0,
+        2 * sizeof(unsigned long long), c->stream));
+    cg_mark_kernel<<<(c->n_nodes + 255) / 256, 256, 0, c->stream>>>(c->npx,
+        c->npy, c->node_valid.p, c->active.p, c->cg_rowmask.p,
+        c->cg_counts.p);
+    smvsb::count_launches(c, 1);
     a.x = c->x.p; a.r = c->r.p; a.d = c->d.p; a.d2 = c->d2.p;
     a.Ad = c->Ad.p; a.z = c->z.p;
     a.partials = c->cg_partials.p; a.sync = c->cg_sync.p;
@@ -548,12 +609,17 @@ run_cg (smvsb_ctx* c, int max_iter, double err_tol, double q_tol, int* iters,
     double res[10];
     CUDA_CHECK(cudaMemcpyAsync(res, c->cg_result.p, sizeof(res),
         cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long counts[2] = {0, 0};
+    CUDA_CHECK(cudaMemcpyAsync(counts, c->cg_counts.p, sizeof(counts),
+        cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (getenv("SMVSB_CG_TIMING"))
         fprintf(stderr, "cg: iters %d grid %d | us/iter: spmv %.1f wait %.1f | "
             "update %.1f wait %.1f\n", (int)res[0], grid,
             res[4] / 1e3 / res[0], res[5] / 1e3 / res[0], res[6] / 1e3 / res[0],
             res[7] / 1e3 / res[0]);
+    c->cg_blocks = counts[0];
+    c->cg_rows = counts[1];
     if (iters) *iters = static_cast<int>(res[0]);
     if (info) *info = static_cast<int>(res[1]);
     if (x0_nan) *x0_nan = (res[2] != 0.0);
