@@ -56,6 +56,8 @@ struct CgArgs
     double const* P;
     double const* g;         /* b = -g (lib/depth_optimizer.cc:251) */
     uint16_t const* rowmask; /* bit k: block k of the node's row exists */
+    uint32_t const* rows;    /* nodes with a non-empty row, ascending */
+    unsigned long long const* counts;   /* [0] blocks, [1] rows of the system */
     double* x;
     double* r;
     double* d;               /* search direction, double buffered */
@@ -330,6 +332,8 @@ cg_kernel (CgArgs const a)
         a.x[i] = 0.0;
         a.z[i] = zi;
         a.d[i] = 0.0;
+        a.d2[i] = 0.0;      /* rows outside the system are never written again */
+        a.Ad[i] = 0.0;
         p_gg += gi * gi;
         p_zr += zi * ri;
     }
@@ -352,6 +356,14 @@ cg_kernel (CgArgs const a)
     double* d_old = a.d;
     double* d_new = a.d2;
 
+    /* the masks do not change during a solve: the first pass's is fetched
+     * once, the others one pass ahead */
+    int const n_rows = static_cast<int>(a.counts[1]);
+    int const quad0 = t0 >> 2, quads = stride >> 2;
+    int const node_first = (quad0 < n_rows) ? static_cast<int>(a.rows[quad0])
+        : 0;
+    unsigned int const mask_first = (quad0 < n_rows) ? a.rowmask[node_first]
+        : 0u;
     int iter = 1;
     int info = SMVSB_CG_MAX_ITERATIONS;
     unsigned long long tm[4] = {0, 0, 0, 0};
@@ -363,14 +375,20 @@ cg_kernel (CgArgs const a)
         DirVec dir;
         dir.z = a.z; dir.d_old = d_old; dir.beta = beta;
         double p_dAd = 0.0;
-        unsigned int mask = (t0 < n) ? a.rowmask[t0 >> 2] : 0u;
-        for (int i = t0; i < n; i += stride)
+        unsigned int mask = mask_first;
+        int node = node_first;
+        for (int q = quad0; q < n_rows; q += quads)
         {
-            /* next pass's mask travels while this pass streams its row */
-            unsigned int const mask_next = (i + stride < n)
-                ? a.rowmask[(i + stride) >> 2] : 0u;
+            /* next pass's row and mask travel while this pass streams */
+            int const qn = q + quads;
+            int const node_next = (qn < n_rows) ? static_cast<int>(a.rows[qn])
+                : 0;
+            unsigned int const mask_next = (qn < n_rows)
+                ? a.rowmask[node_next] : 0u;
             double own[4];
-            double const v = spmv_row(a, dir, i >> 2, rp, mask, own);
+            int const i = node * 4 + rp;
+            double const v = spmv_row(a, dir, node, rp, mask, own);
+            node = node_next;
             mask = mask_next;
             double const di = (rp == 0) ? own[0] : (rp == 1) ? own[1]
                 : (rp == 2) ? own[2] : own[3];
@@ -486,17 +504,15 @@ cg_kernel (CgArgs const a)
 
 /* bit k of rowmask[node]: block k of the node's 3x3 stencil row exists, i.e.
  * the node and its k-th grid neighbour are both valid and active. */
-__global__ void
+__global__ void __launch_bounds__(256)
 cg_mark_kernel (int npx, int npy, uint8_t const* __restrict__ node_valid,
     uint8_t const* __restrict__ active, uint16_t* __restrict__ rowmask,
-    unsigned long long* __restrict__ counts)
+    uint32_t* __restrict__ block_rows, unsigned long long* __restrict__ counts)
 {
     int const node = blockIdx.x * blockDim.x + threadIdx.x;
     int const ns = npx + 1;
-    if (node >= ns * (npy + 1))
-        return;
     unsigned int m = 0;
-    if (node_valid[node] && active[node])
+    if (node < ns * (npy + 1) && node_valid[node] && active[node])
     {
         int const ix = node % ns, iy = node / ns;
         for (int k = 0; k < 9; ++k)
@@ -509,15 +525,89 @@ cg_mark_kernel (int npx, int npy, uint8_t const* __restrict__ node_valid,
                 m |= 1u << k;
         }
     }
-    rowmask[node] = static_cast<uint16_t>(m);
+    if (node < ns * (npy + 1))
+        rowmask[node] = static_cast<uint16_t>(m);
     /* counts[0]: blocks of the system, counts[1]: its block rows */
-    unsigned int const blocks = __reduce_add_sync(__activemask(), __popc(m));
-    unsigned int const rows = __reduce_add_sync(__activemask(), m != 0);
+    unsigned int const blocks = __reduce_add_sync(0xffffffffu, __popc(m));
+    int const rows = __syncthreads_count(m != 0);
     if ((threadIdx.x & 31) == 0)
-    {
         atomicAdd(counts, static_cast<unsigned long long>(blocks));
+    if (threadIdx.x == 0)
+    {
+        block_rows[blockIdx.x] = rows;
         atomicAdd(counts + 1, static_cast<unsigned long long>(rows));
     }
+}
+
+/* exclusive prefix sum of the per-block row counts, one block */
+__global__ void __launch_bounds__(1024)
+cg_scan_kernel (uint32_t const* __restrict__ block_rows,
+    uint32_t* __restrict__ block_off, int nb)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0)
+        s_carry = 0;
+    __syncthreads();
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < nb; base += 1024)
+    {
+        int const i = base + threadIdx.x;
+        uint32_t const v = (i < nb) ? block_rows[i] : 0;
+        uint32_t inc = v;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            uint32_t const u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o)
+                inc += u;
+        }
+        if (lane == 31)
+            s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0)
+        {
+            uint32_t w = s_warp[lane];
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                uint32_t const u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o)
+                    w += u;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        uint32_t const before = s_carry + (warp > 0 ? s_warp[warp - 1] : 0)
+            + inc - v;
+        if (i < nb)
+            block_off[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023)
+            s_carry = before + v;
+        __syncthreads();
+    }
+}
+
+/* rows[]: the nodes with a non-empty row in ascending order -- the SpMV walks
+ * this list, so the work is spread evenly over the CTAs however the active
+ * set is scattered over the image */
+__global__ void __launch_bounds__(256)
+cg_list_kernel (int n_nodes, uint16_t const* __restrict__ rowmask,
+    uint32_t const* __restrict__ block_off, uint32_t* __restrict__ rows)
+{
+    __shared__ uint32_t s_warp[8];
+    int const node = blockIdx.x * blockDim.x + threadIdx.x;
+    bool const on = node < n_nodes && rowmask[node] != 0;
+    unsigned int const ballot = __ballot_sync(0xffffffffu, on);
+    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+        s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    uint32_t before = block_off[blockIdx.x];
+    for (int w = 0; w < warp; ++w)
+        before += s_warp[w];
+    before += __popc(ballot & ((1u << lane) - 1u));
+    if (on)
+        rows[before] = node;
 }
 
 __global__ void
@@ -546,15 +636,24 @@ make_args (smvsb_ctx* c)
     a.n_nodes = c->n_nodes; a.npx = c->npx; a.npy = c->npy;
     a.max_iter = 0; a.err_tol = 0; a.q_tol = 0;
     a.H = c->H.p; a.P = c->P.p; a.g = c->g.p;
+    int const nb = (c->n_nodes + 255) / 256;
     c->cg_rowmask.reserve(c->n_nodes);
+    c->cg_row_list.reserve(c->n_nodes);
+    c->cg_block_rows.reserve(2 * static_cast<size_t>(nb));
     c->cg_counts.reserve(2);
     a.rowmask = c->cg_rowmask.p;
+    a.rows = c->cg_row_list.p;
+    a.counts = c->cg_counts.p;
     CUDA_CHECK(cudaMemsetAsync(c->cg_counts.p, 0,
         2 * sizeof(unsigned long long), c->stream));
-    cg_mark_kernel<<<(c->n_nodes + 255) / 256, 256, 0, c->stream>>>(c->npx,
-        c->npy, c->node_valid.p, c->active.p, c->cg_rowmask.p,
+    cg_mark_kernel<<<nb, 256, 0, c->stream>>>(c->npx, c->npy,
+        c->node_valid.p, c->active.p, c->cg_rowmask.p, c->cg_block_rows.p,
         c->cg_counts.p);
-    smvsb::count_launches(c, 1);
+    cg_scan_kernel<<<1, 1024, 0, c->stream>>>(c->cg_block_rows.p,
+        c->cg_block_rows.p + nb, nb);
+    cg_list_kernel<<<nb, 256, 0, c->stream>>>(c->n_nodes, c->cg_rowmask.p,
+        c->cg_block_rows.p + nb, c->cg_row_list.p);
+    smvsb::count_launches(c, 3);
     a.x = c->x.p; a.r = c->r.p; a.d = c->d.p; a.d2 = c->d2.p;
     a.Ad = c->Ad.p; a.z = c->z.p;
     a.partials = c->cg_partials.p; a.sync = c->cg_sync.p;

@@ -149,6 +149,7 @@ struct smvsb_ctx
     smvsb::DevBuf<double> x, r, d, d2, z, Ad;
     smvsb::DevBuf<double> cg_partials;
     smvsb::DevBuf<uint16_t> cg_rowmask; /* existing blocks per stencil row */
+    smvsb::DevBuf<uint32_t> cg_row_list, cg_block_rows;
     smvsb::DevBuf<unsigned long long> cg_counts;
     uint64_t cg_blocks = 0, cg_rows = 0;    /* of the last solve's system */
     smvsb::DevBuf<unsigned int> cg_sync;
