@@ -381,13 +381,13 @@ def run_product(args):
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650",
                     "unit": "GB/s", "frac": achieved / hbm_peak,
                     # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full
-                    # capture (profiles/r1c_cg.txt: 29.45 GB for a 200-iteration launch
-                    # on the full system = 147.3 MB per CG iteration: H only -- P and
-                    # the vectors stay in L2), scaled by the blocks this run's launches
-                    # read
-                    "traffic": 29.45e9 / (200.0 * blocks_full) * cg_blocks / max(newton, 1),
-                    "traffic_source": "profiles/r1c_cg.txt, scaled by system blocks x iterations",
-                    "frac_dram": (29.45e9 / (200.0 * blocks_full) * cg_blocks
+                    # capture (profiles/r1g_cg.txt: 27.15 GB for a 200-iteration launch
+                    # on the full system = 135.8 MB per CG iteration = 127 B per 4x4
+                    # block: H only -- P and the vectors stay in L2), scaled by the
+                    # blocks this run's launches read
+                    "traffic": 27.15e9 / (200.0 * blocks_full) * cg_blocks / max(newton, 1),
+                    "traffic_source": "profiles/r1g_cg.txt, scaled by system blocks x iterations",
+                    "frac_dram": (27.15e9 / (200.0 * blocks_full) * cg_blocks
                                   / max(cg_ms * 1e-3, 1e-12)) / 1e9 / hbm_peak,
                     "algorithmic_bytes_per_launch": algorithmic / max(newton, 1),
                     "system_blocks_full": blocks_full,

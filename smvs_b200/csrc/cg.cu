@@ -79,9 +79,13 @@ grid_barrier (unsigned int* counter, unsigned int& epoch)
         unsigned int const target = epoch * gridDim.x;
         __threadfence();
         atomicAdd(counter, 1u);
+        /* spin with relaxed loads (served by L2), one fence at the end: an
+         * acquire load in the loop invalidates the SM's L1 on every poll
+         * (CCTL.IVALL, ~40 polls per barrier) -- under the other CTA of the
+         * SM, which may still be gathering vector entries through L1 */
         unsigned int v;
         do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];"
                 : "=r"(v) : "l"(counter) : "memory");
         } while (v < target);
         __threadfence();
