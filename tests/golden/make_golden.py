@@ -98,7 +98,49 @@ def sgm_fixture(name, w, h, D, seed_index):
     print(name, "valid", float((r["depth"] > 0).mean()))
 
 
+def vis_fixture(name, w, h, n_sub, scale, seed_index):
+    """create_subview_surfaces (use_sgm) + the cut_boundaries loop + the joint
+    bilateral filter + one set_scale, on a scene with occluders and a depth
+    step (same recipe as tests/test_gpu_visibility.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_visibility import occluded_scene
+    sc, init, sgm = occluded_scene(w, h, n_sub, seed_index)
+    R = oref.RefScene(sc)
+    R.set_scale(scale)
+    R.surface_create(scale, init)
+    R.set_sgm_depth(sgm)
+    info = R.surface_info()
+    nodes, nv, pv = R.surface_get()
+    Mi, ti = R.Mt()
+    d = dict(w=w, h=h, n_sub=n_sub, scale=scale, npx=info["npx"], npy=info["npy"],
+             start_x=info["start_x"], start_y=info["start_y"], flen=R.flen(0),
+             inv_flen=R.inverse_flen(0), main_grad=R.gradients(0), Mi=Mi, ti=ti,
+             nodes=nodes, node_valid=nv, patch_valid=pv, sgm=sgm,
+             inv_calib=R.inverse_calibration(), depth_map=R.surface_depth(),
+             image=R.image(0), scaleimage=R.scaleimage(0))
+    for k in range(n_sub):
+        d[f"sub_grad{k}"] = R.gradients(k + 1)
+        d[f"sub_hess{k}"] = R.hessian(k + 1)
+    d["filtered"] = R.bilateral_filter(sgm)
+    d["vis_left"] = R.create_subview_surfaces(True)
+    _, d["vis_node_valid"], d["vis_patch_valid"] = R.surface_get()
+    d["vis_off"], d["vis_ids"] = R.get_visibility()
+    cuts, states = [], []
+    for _ in range(12):
+        cuts.append(R.cut_boundaries())
+        _, cnv, cpv = R.surface_get()
+        states.append(np.concatenate([cnv, cpv]))
+        if cuts[-1] <= 10:
+            break
+    d["cuts"] = np.array(cuts, dtype=np.int32)
+    d["cut_states"] = np.stack(states)
+    np.savez_compressed(os.path.join(OUT, name), **d)
+    R.close()
+    print(name, "patches", int(pv.sum()), "left", d["vis_left"], "cuts", cuts)
+
+
 if __name__ == "__main__":
     gn_fixture("gn_s2.npz", 128, 96, 2, 2, True, 11)
     gn_fixture("gn_s4.npz", 256, 192, 2, 4, False, 12)
     sgm_fixture("sgm.npz", 96, 72, 64, 13)
+    vis_fixture("vis_s2.npz", 160, 120, 2, 2, 14)
