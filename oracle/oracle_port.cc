@@ -15,6 +15,10 @@
  * Deliberately written in the reference's formulation (16-column Jacobian
  * rows, rank-1 updates, std::map block assembly, O(D^2) SGM minimum), NOT in
  * the restructured form the CUDA kernels use, so it is an independent check.
+ * The same holds for the callers' side of the loop restated here: sequential
+ * z-buffer and per-patch tests of create_subview_surfaces, cut_boundaries with
+ * mse_for_patch, the depth-map render and the joint bilateral filter (libm's
+ * expf) -- all pinned for EQUALITY against oracle/_ref and tests/golden.
  */
 #include <algorithm>
 #include <cmath>
@@ -1023,6 +1027,392 @@ census_filter (uint8_t const* img, int w, int h, int c, uint64_t* out)
 
 } /* namespace */
 
+/* ------------------------------------------------------------------ */
+/* visibility lists, boundary cutting, bilateral filter               */
+/* ------------------------------------------------------------------ */
+
+/* SurfacePatch::fill_values_at_pixels (lib/surface_patch.cc:57-120), all
+ * pixels: depth and first derivatives (already / size) in pid order. */
+void
+patch_pixels (Port const& P, int patch, std::vector<double>* w,
+    std::vector<double>* wx, std::vector<double>* wy)
+{
+    double n16[16], coeffs[4][4];
+    P.patch_nodes16(patch, n16);
+    patch_coefficients(n16, coeffs);
+    int const size = P.ps;
+    w->resize(size * size);
+    if (wx) { wx->resize(size * size); wy->resize(size * size); }
+    for (int pid = 0; pid < size * size; ++pid)
+    {
+        double x = static_cast<double>(pid % size);
+        double y = static_cast<double>(pid / size);
+        x += 0.5; y += 0.5;
+        x /= size; y /= size;
+        double out6[6];
+        patch_evaluate(coeffs, x, y, out6);
+        (*w)[pid] = out6[0];
+        if (wx) { (*wx)[pid] = out6[1] / size; (*wy)[pid] = out6[2] / size; }
+    }
+}
+
+/* Surface::get_depth_map (lib/surface.cc:155-168) */
+void
+depth_map (Port const& P, std::vector<float>* out)
+{
+    out->assign(static_cast<std::size_t>(P.w) * P.h, 0.0f);
+    std::vector<double> w;
+    for (int patch = 0; patch < P.npx * P.npy; ++patch)
+    {
+        if (!P.patch_valid[patch])
+            continue;
+        patch_pixels(P, patch, &w, nullptr, nullptr);
+        int const px0 = P.sx + (patch % P.npx) * P.ps;
+        int const py0 = P.sy + (patch / P.npx) * P.ps;
+        for (int pid = 0; pid < P.ps * P.ps; ++pid)
+            (*out)[static_cast<std::size_t>(py0 + pid / P.ps) * P.w
+                + px0 + pid % P.ps] = static_cast<float>(w[pid]);
+    }
+}
+
+/* Surface::remove_nodes_without_patch (lib/surface.cc:762-867): a node goes
+ * when none of the patches around it that lie inside the grid is left. */
+void
+remove_nodes_without_patch (Port& P)
+{
+    int const ns = P.npx + 1;
+    for (int node = 0; node < P.n_nodes(); ++node)
+    {
+        if (!P.node_valid[node])
+            continue;
+        int const ix = node % ns, iy = node / ns;
+        bool any = false;
+        for (int dy = -1; dy <= 0; ++dy)
+            for (int dx = -1; dx <= 0; ++dx)
+            {
+                int const px = ix + dx, py = iy + dy;
+                if (px < 0 || py < 0 || px >= P.npx || py >= P.npy)
+                    continue;
+                any = any || P.patch_valid[py * P.npx + px];
+            }
+        if (!any)
+            P.node_valid[node] = 0;
+    }
+}
+
+/* DepthOptimizer::create_subview_surfaces, use_sgm mode
+ * (lib/depth_optimizer.cc:433-604). Returns the patches deleted. */
+int
+create_subview_surfaces (Port& P, float const* sgm_depth)
+{
+    int const np = P.npx * P.npy;
+    std::vector<std::vector<uint8_t> > subsurfaces(np);
+
+    /* depth caches, :441-450 */
+    std::vector<std::vector<float> > cache(P.n_sub);
+    for (int s = 0; s < P.n_sub; ++s)
+        cache[s].assign(static_cast<std::size_t>(P.sub_w[s] + 1)
+            * (P.sub_h[s] + 1), 10000.0f);
+
+    /* pixel list, :452-469 (x outer, y inner) */
+    std::vector<float> depth;
+    depth_map(P, &depth);
+    std::vector<double> px, py, pd;
+    for (int x = 0; x < P.w; ++x)
+        for (int y = 0; y < P.h; ++y)
+        {
+            std::size_t const i = static_cast<std::size_t>(y) * P.w + x;
+            if (depth[i] != 0)
+            { px.push_back(x); py.push_back(y); pd.push_back(depth[i]); }
+            if (sgm_depth[i] != 0)
+            { px.push_back(x); py.push_back(y); pd.push_back(sgm_depth[i]); }
+        }
+
+    /* first pass: minimal depth, :471-500 */
+    Corr C;
+    for (int s = 0; s < P.n_sub; ++s)
+    {
+        double const sw = P.sub_w[s], sh = P.sub_h[s];
+        int const cw = P.sub_w[s] + 1;
+        for (std::size_t i = 0; i < px.size(); ++i)
+        {
+            C.update(&P.Mi[9 * s], &P.ti[3 * s], px[i] + 0.5, py[i] + 0.5,
+                pd[i], 0.0, 0.0);
+            double proj[2];
+            C.fill(proj);
+            proj[0] -= 0.5; proj[1] -= 0.5;
+            double const cutoffset = 3.0;
+            if (proj[0] < cutoffset || proj[0] >= sw - cutoffset
+                || proj[1] < cutoffset || proj[1] >= sh - cutoffset)
+                continue;
+            int const cx = static_cast<int>(proj[0]);
+            int const cy = static_cast<int>(proj[1]);
+            for (int x = -1; x < 2; ++x)
+                for (int y = -1; y < 2; ++y)
+                    if (C.d < cache[s][(cy + y) * cw + cx + x])
+                        cache[s][(cy + y) * cw + cx + x]
+                            = static_cast<float>(C.d);
+        }
+    }
+
+    /* second pass, :502-583 */
+    std::vector<double> w, wx, wy;
+    for (int patch = 0; patch < np; ++patch)
+    {
+        if (!P.patch_valid[patch])
+            continue;
+        patch_pixels(P, patch, &w, &wx, &wy);
+        int const px0 = P.sx + (patch % P.npx) * P.ps;
+        int const py0 = P.sy + (patch / P.npx) * P.ps;
+        for (int s = 0; s < P.n_sub; ++s)
+        {
+            double const sw = P.sub_w[s], sh = P.sub_h[s];
+            int const cw = P.sub_w[s] + 1;
+            bool success = true;
+            for (int i = 0; i < P.ps * P.ps && success; ++i)
+            {
+                Corr c;
+                c.update(&P.Mi[9 * s], &P.ti[3 * s], px0 + i % P.ps + 0.5,
+                    py0 + i / P.ps + 0.5, w[i], 0.0, 0.0);
+                double proj[2];
+                c.fill(proj);
+                proj[0] -= 0.5; proj[1] -= 0.5;
+                double const cutoffset = 0.03 * std::max(sw, sh);
+                if (proj[0] < cutoffset || proj[0] >= sw - cutoffset
+                    || proj[1] < cutoffset || proj[1] >= sh - cutoffset)
+                {
+                    success = false;
+                    break;
+                }
+                int const cx = static_cast<int>(proj[0]);
+                int const cy = static_cast<int>(proj[1]);
+                for (int x = -1; x < 2; ++x)
+                    for (int y = -1; y < 2; ++y)
+                        if (c.d * 0.95 > cache[s][(cy + y) * cw + cx + x])
+                            success = false;
+            }
+            if (!success)
+                continue;
+
+            double max = 0.0;
+            for (int i = 0; i < P.ps * P.ps; ++i)
+            {
+                Corr c;
+                c.update(&P.Mi[9 * s], &P.ti[3 * s], px0 + i % P.ps + 0.5,
+                    py0 + i / P.ps + 0.5, w[i], wx[i], wy[i]);
+                double jac[4];
+                c.fill_jacobian(jac);
+                double S[2];
+                S[0] = (std::sqrt((jac[0] - jac[3]) * (jac[0] - jac[3])
+                    + (jac[1] + jac[2]) * (jac[1] + jac[2]))
+                    + std::sqrt((jac[0] + jac[3]) * (jac[0] + jac[3])
+                    + (jac[1] - jac[2]) * (jac[1] - jac[2]))) / 2.0;
+                S[1] = std::fabs(S[0] - std::sqrt((jac[0] - jac[3])
+                    * (jac[0] - jac[3]) + (jac[1] + jac[2]) * (jac[1] + jac[2])));
+                double const hi = std::max(S[0], S[1]), lo = std::min(S[0], S[1]);
+                double const sigma0 = hi * hi, sigma1 = lo * lo;
+                max = std::max(max, sigma0 / sigma1);
+            }
+            if (max > 8.0)
+                continue;
+            subsurfaces[patch].push_back(static_cast<uint8_t>(s));
+        }
+    }
+
+    /* :585-600 */
+    int removed = 0;
+    for (int patch = 0; patch < np; ++patch)
+        if (P.patch_valid[patch] && subsurfaces[patch].empty())
+        {
+            P.patch_valid[patch] = 0;
+            removed += 1;
+        }
+    if (removed > 0)
+        remove_nodes_without_patch(P);
+    P.vis_off.assign(np + 1, 0);
+    P.vis_ids.clear();
+    for (int patch = 0; patch < np; ++patch)
+    {
+        P.vis_off[patch] = static_cast<uint32_t>(P.vis_ids.size());
+        P.vis_ids.insert(P.vis_ids.end(), subsurfaces[patch].begin(),
+            subsurfaces[patch].end());
+    }
+    P.vis_off[np] = static_cast<uint32_t>(P.vis_ids.size());
+    return removed;
+}
+
+/* DepthOptimizer::mse_for_patch, lib/depth_optimizer.cc:747-793 */
+double
+mse_for_patch (Port const& P, int patch)
+{
+    std::vector<double> w, wx, wy;
+    patch_pixels(P, patch, &w, &wx, &wy);
+    int const px0 = P.sx + (patch % P.npx) * P.ps;
+    int const py0 = P.sy + (patch / P.npx) * P.ps;
+    double error = 0.0, counter = 0.0;
+    for (int i = 0; i < P.ps * P.ps; ++i)
+    {
+        int const x = px0 + i % P.ps, y = py0 + i / P.ps;
+        double const gm0 = P.main_grad[(static_cast<std::size_t>(y) * P.w + x) * 2];
+        double const gm1 = P.main_grad[(static_cast<std::size_t>(y) * P.w + x) * 2 + 1];
+        for (uint32_t k = P.vis_off[patch]; k < P.vis_off[patch + 1]; ++k)
+        {
+            int const s = P.vis_ids[k];
+            Corr c;
+            c.update(&P.Mi[9 * s], &P.ti[3 * s], x + 0.5, y + 0.5, w[i],
+                wx[i], wy[i]);
+            double proj[2], jac[4];
+            c.fill(proj);
+            c.fill_jacobian(jac);
+            proj[0] -= 0.5; proj[1] -= 0.5;
+            double const gs0 = linear_at_f(P.sub_grad[s].data(), P.sub_w[s],
+                P.sub_h[s], 2, static_cast<float>(proj[0]),
+                static_cast<float>(proj[1]), 0);
+            double const gs1 = linear_at_f(P.sub_grad[s].data(), P.sub_w[s],
+                P.sub_h[s], 2, static_cast<float>(proj[0]),
+                static_cast<float>(proj[1]), 1);
+            double const d0 = gm0 - (0.0 + jac[0] * gs0 + jac[1] * gs1);
+            double const d1 = gm1 - (0.0 + jac[2] * gs0 + jac[3] * gs1);
+            error += std::sqrt(0.0 + d0 * d0 + d1 * d1);
+            counter += 1.0;
+        }
+    }
+    if (counter == 0.0)
+        return 1.0;
+    return error / counter;
+}
+
+/* DepthOptimizer::cut_boundaries, lib/depth_optimizer.cc:360-431.
+ * inv: the main camera's inverse calibration (3x3, fp32). */
+int
+cut_boundaries (Port& P, float const* inv)
+{
+    int deleted = 0;
+    int const np = P.npx * P.npy, ns = P.npx + 1;
+    for (int patch = 0; patch < np; ++patch)
+    {
+        if (!P.patch_valid[patch])
+            continue;
+        int ids[4];
+        P.node_ids(patch, ids);
+        double depths[4];
+        for (int i = 0; i < 4; ++i)
+            depths[i] = P.nodes[ids[i] * 4];
+        /* std::multimap<double, size_t>: first of the minima, last of the maxima */
+        int lo = 0, hi = 0;
+        for (int i = 1; i < 4; ++i)
+        {
+            if (depths[i] < depths[lo]) lo = i;
+            if (!(depths[i] < depths[hi])) hi = i;
+        }
+        double dd_factor = 5.0;
+        if (lo + hi == 3)
+            dd_factor *= 1.41421356237309504880168872420969808;
+        float const fx = static_cast<float>(static_cast<double>(
+            P.sx + (patch % P.npx) * P.ps)) + 0.5f;
+        float const fy = static_cast<float>(static_cast<double>(
+            P.sy + (patch / P.npx) * P.ps)) + 0.5f;
+        float v[3];
+        for (int r = 0; r < 3; ++r)
+        {
+            float sum = 0.0f;
+            sum += inv[r * 3 + 0] * fx;
+            sum += inv[r * 3 + 1] * fy;
+            sum += inv[r * 3 + 2] * 1.0f;
+            v[r] = sum;
+        }
+        float sq = 0.0f;
+        for (int r = 0; r < 3; ++r)
+            sq += v[r] * v[r];
+        float const norm = std::sqrt(sq);
+        double const threshold = dd_factor * depths[lo] * inv[0] * P.ps / norm;
+        double const dist = depths[hi] - depths[lo];
+        if (dist > threshold)
+        {
+            P.patch_valid[patch] = 0;
+            deleted += 1;
+        }
+    }
+    for (int patch = 0; patch < np; ++patch)
+    {
+        if (!P.patch_valid[patch])
+            continue;
+        int ids[4];
+        P.node_ids(patch, ids);
+        double const error = mse_for_patch(P, patch);
+        for (int n = 0; n < 4; ++n)
+        {
+            /* Surface::fill_node_neighbors: the eight grid neighbours,
+             * missing when outside the grid or not valid */
+            int const ix = ids[n] % ns, iy = ids[n] / ns;
+            int num_invalid = 0;
+            for (int dy = -1; dy < 2; ++dy)
+                for (int dx = -1; dx < 2; ++dx)
+                {
+                    if (dx == 0 && dy == 0)
+                        continue;
+                    int const qx = ix + dx, qy = iy + dy;
+                    if (qx < 0 || qy < 0 || qx > P.npx || qy > P.npy
+                        || !P.node_valid[qy * ns + qx])
+                        num_invalid += 1;
+                }
+            if (num_invalid > 1 && error > 0.05)
+            {
+                P.patch_valid[patch] = 0;
+                deleted += 1;
+                break;
+            }
+        }
+    }
+    remove_nodes_without_patch(P);
+    return deleted;
+}
+
+/* DepthOptimizer::depthmap_bilateral_filter, lib/depth_optimizer.cc:957-1004 */
+void
+bilateral_filter (int w, int h, int channels, float const* ci, int dm_w,
+    int dm_h, float const* dm, float sigma, int kernel_size, float* out)
+{
+    float const scale_x = static_cast<float>(dm_w) / static_cast<float>(w);
+    float const scale_y = static_cast<float>(dm_h) / static_cast<float>(h);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+        {
+            float acc_v = 0.0f, acc_w = 0.0f;
+            for (int ky = -kernel_size; ky <= kernel_size; ++ky)
+                for (int kx = -kernel_size; kx <= kernel_size; ++kx)
+                {
+                    int const ci_x = std::min(std::max(x + kx, 0), w - 1);
+                    int const ci_y = std::min(std::max(y + ky, 0), h - 1);
+                    float fx = scale_x * ci_x, fy = scale_y * ci_y;
+                    float const mx = static_cast<float>(dm_w) - 1.f;
+                    float const my = static_cast<float>(dm_h) - 1.f;
+                    fx = fx < 0.f ? 0.f : (fx > mx ? mx : fx);
+                    fy = fy < 0.f ? 0.f : (fy > my ? my : fy);
+                    int const dm_x = static_cast<int>(fx);
+                    int const dm_y = static_cast<int>(fy);
+                    float const d = dm[dm_y * dm_w + dm_x];
+                    if (d == 0.0f)
+                        continue;
+                    float weight = 1.0f;
+                    float const gx = static_cast<float>(kx);
+                    float const gy = static_cast<float>(ky);
+                    weight *= std::exp(-(gx * gx) / (2.0f * sigma * sigma)
+                        - (gy * gy) / (2.0f * sigma * sigma));
+                    for (int c = 0; c < channels; ++c)
+                    {
+                        float const diff = ci[(ci_y * w + ci_x) * channels + c]
+                            - ci[(y * w + x) * channels + c];
+                        weight *= std::exp(-((diff * diff)
+                            / (2.0f * 0.1f * 0.1f)));
+                    }
+                    acc_v += d * weight;
+                    acc_w += weight;
+                }
+            out[y * w + x] = (acc_w > 0) ? acc_v / acc_w : 0.0f;
+        }
+}
+
 extern "C" {
 
 /* ---- unit-level entry points (same signatures as oracle/ref_driver.cc) -- */
@@ -1238,6 +1628,48 @@ port_newton_loop (void* p, double const* light16, double regularization,
 /* SGMStereo::run_sgm, lib/sgm_stereo.cc:98-124 with create_cost_volume
  * (:192-244), aggregate_sgm_costs (:429-667, SSE semantics) and
  * depth_from_sgm_volume (:274-306). cost_out / sgm_out: w*h*D uint16. */
+
+/* create_subview_surfaces (use_sgm) on the port's surface; sgm_depth: w*h. */
+int
+port_visibility (void* p, float const* sgm_depth)
+{
+    return create_subview_surfaces(*static_cast<Port*>(p), sgm_depth);
+}
+
+int
+port_cut_boundaries (void* p, float const* inv_calib9)
+{
+    return cut_boundaries(*static_cast<Port*>(p), inv_calib9);
+}
+
+void
+port_get_surface_state (void* p, uint8_t* node_valid, uint8_t* patch_valid,
+    uint32_t* vis_off, uint8_t* vis_ids)
+{
+    Port* P = static_cast<Port*>(p);
+    std::copy(P->node_valid.begin(), P->node_valid.end(), node_valid);
+    std::copy(P->patch_valid.begin(), P->patch_valid.end(), patch_valid);
+    std::copy(P->vis_off.begin(), P->vis_off.end(), vis_off);
+    std::copy(P->vis_ids.begin(), P->vis_ids.end(), vis_ids);
+}
+
+void
+port_depth_map (void* p, float* out)
+{
+    std::vector<float> d;
+    depth_map(*static_cast<Port*>(p), &d);
+    std::copy(d.begin(), d.end(), out);
+}
+
+void
+port_bilateral_filter (int w, int h, int channels, float const* guide,
+    int dm_w, int dm_h, float const* depth, float sigma, int kernel_size,
+    float* out)
+{
+    bilateral_filter(w, h, channels, guide, dm_w, dm_h, depth, sigma,
+        kernel_size, out);
+}
+
 int
 port_sgm (int w, int h, uint8_t const* main_img, int nw, int nh,
     uint8_t const* neigh, float const* M, float const* t, float min_depth,

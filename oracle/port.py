@@ -70,10 +70,14 @@ class PortScene:
         nodes = np.ascontiguousarray(nodes, np.float64)
         nv = np.ascontiguousarray(node_valid, np.uint8)
         pv = np.ascontiguousarray(patch_valid, np.uint8)
+        if vis_off is None:          # no lists yet: visibility() makes them
+            vis_off, vis_ids = np.zeros(npx * npy + 1, np.uint32), np.zeros(1, np.uint8)
         vo = np.ascontiguousarray(vis_off, np.uint32)
         vi = np.ascontiguousarray(vis_ids, np.uint8)
         if vi.size == 0:
             vi = np.zeros(1, np.uint8)
+        self.n_patches = npx * npy
+        self._wh = None
         lib().port_set_surface(self.h_, int(scale), int(npx), int(npy), int(sx), int(sy),
                                _p(nodes), _p(nv), _p(pv), _p(vo), _p(vi))
         self.n_nodes = (npx + 1) * (npy + 1)
@@ -109,6 +113,29 @@ class PortScene:
         lib().port_update_nodes(self.h_, _p(d), C.c_double(reproj_thresh), int(full_opt),
                                 _p(act), C.byref(n_active), C.byref(shift))
         return act, int(n_active.value), float(shift.value)
+
+    # -- visibility / cutting (the callers' side of the loop) ----------------
+    def visibility(self, sgm_depth):
+        d = np.ascontiguousarray(sgm_depth, np.float32)
+        self._hw = d.shape
+        return int(lib().port_visibility(self.h_, _p(d)))
+
+    def cut_boundaries(self, inv_calib9):
+        k = np.ascontiguousarray(inv_calib9, np.float32).reshape(9)
+        return int(lib().port_cut_boundaries(self.h_, _p(k)))
+
+    def surface_state(self):
+        nv = np.empty(self.n_nodes, np.uint8)
+        pv = np.empty(self.n_patches, np.uint8)
+        vo = np.empty(self.n_patches + 1, np.uint32)
+        vi = np.empty(self.n_patches * 32 + 1, np.uint8)
+        lib().port_get_surface_state(self.h_, _p(nv), _p(pv), _p(vo), _p(vi))
+        return nv, pv, vo, vi[:vo[-1]].copy()
+
+    def get_depth(self, h, w):
+        out = np.empty((h, w), np.float32)
+        lib().port_depth_map(self.h_, _p(out))
+        return out
 
     def get_nodes(self):
         out = np.empty((self.n_nodes, 4))
@@ -193,3 +220,15 @@ class Units:
         A = np.array(A, dtype=np.float64, copy=True)
         lib().port_ldl_inverse(_p(A), A.shape[0])
         return A
+
+
+def bilateral_filter(guide, depth, sigma=5.0, kernel_size=5):
+    """DepthOptimizer::depthmap_bilateral_filter, restated."""
+    g = np.ascontiguousarray(guide, np.float32)
+    d = np.ascontiguousarray(depth, np.float32)
+    h, w = g.shape[:2]
+    ch = 1 if g.ndim == 2 else g.shape[2]
+    out = np.empty((h, w), np.float32)
+    lib().port_bilateral_filter(w, h, ch, _p(g), d.shape[1], d.shape[0], _p(d),
+                                C.c_float(sigma), int(kernel_size), _p(out))
+    return out

@@ -91,3 +91,73 @@ def test_port_sgm_live_dark_regions():
     assert np.array_equal(p["sgm"], r["sgm"])
     assert np.array_equal(p["depth"], r["depth"])
     R.close()
+
+
+# ---------------------------------------------------------------------------
+# visibility lists, boundary cutting, bilateral filter: the restatement in
+# oracle_port.cc against the committed fixture (always) and the compiled
+# reference (when built)
+# ---------------------------------------------------------------------------
+
+def _port_from_vis_fixture(G):
+    n = int(G["n_sub"])
+    P = oport.PortScene(G["main_grad"], [G[f"sub_grad{k}"] for k in range(n)],
+                        [G[f"sub_hess{k}"] for k in range(n)], G["Mi"], G["ti"],
+                        float(G["flen"]), float(G["inv_flen"]))
+    P.set_surface(int(G["scale"]), int(G["npx"]), int(G["npy"]), int(G["start_x"]),
+                  int(G["start_y"]), G["nodes"], G["node_valid"], G["patch_valid"],
+                  None, None)
+    return P
+
+
+def test_port_visibility_and_cutting_match_the_fixture():
+    G = np.load(os.path.join(GOLD, "vis_s2.npz"))
+    P = _port_from_vis_fixture(G)
+    assert np.array_equal(P.get_depth(int(G["h"]), int(G["w"])), G["depth_map"])
+    removed = P.visibility(G["sgm"])
+    nv, pv, off, ids = P.surface_state()
+    assert int(G["patch_valid"].sum()) - removed == int(G["vis_left"])
+    assert np.array_equal(pv, G["vis_patch_valid"]) and np.array_equal(nv, G["vis_node_valid"])
+    assert np.array_equal(off, G["vis_off"]) and np.array_equal(ids, G["vis_ids"])
+    for k, want in enumerate(G["cuts"]):
+        assert P.cut_boundaries(G["inv_calib"]) == int(want)
+        nv, pv, _, _ = P.surface_state()
+        assert np.array_equal(np.concatenate([nv, pv]), G["cut_states"][k])
+    assert np.array_equal(oport.bilateral_filter(G["image"], G["sgm"]), G["filtered"])
+
+
+@pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("scale,seed", [(3, 61), (4, 62)])
+def test_port_visibility_and_cutting_match_the_reference(scale, seed):
+    from test_gpu_visibility import occluded_scene
+    sc, init, sgm = occluded_scene(256, 192, 3, seed)
+    R = oref.RefScene(sc)
+    R.set_scale(scale)
+    R.surface_create(scale, init)
+    R.set_sgm_depth(sgm)
+    info = R.surface_info()
+    nodes, nv, pv = R.surface_get()
+    Mi, ti = R.Mt()
+    P = oport.PortScene(R.gradients(0), [R.gradients(k + 1) for k in range(3)],
+                        [R.hessian(k + 1) for k in range(3)], Mi, ti, R.flen(0),
+                        R.inverse_flen(0))
+    P.set_surface(info["scale"], info["npx"], info["npy"], info["start_x"],
+                  info["start_y"], nodes, nv, pv, None, None)
+    left = R.create_subview_surfaces(True)
+    removed = P.visibility(sgm)
+    assert int(pv.sum()) - removed == left
+    _, nv_r, pv_r = R.surface_get()
+    off_r, ids_r = R.get_visibility()
+    nv_p, pv_p, off_p, ids_p = P.surface_state()
+    assert np.array_equal(pv_p, pv_r) and np.array_equal(nv_p, nv_r)
+    assert np.array_equal(off_p, off_r) and np.array_equal(ids_p, ids_r)
+    K = R.inverse_calibration()
+    for _ in range(12):
+        d = R.cut_boundaries()
+        assert P.cut_boundaries(K) == d
+        _, nv_r, pv_r = R.surface_get()
+        nv_p, pv_p, _, _ = P.surface_state()
+        assert np.array_equal(pv_p, pv_r) and np.array_equal(nv_p, nv_r)
+        if d <= 10:
+            break
+    R.close()
