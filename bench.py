@@ -394,8 +394,8 @@ def run_product(args):
                     "system_block_iterations_per_launch": cg_blocks / max(newton, 1),
                     "launches_timed": newton}
 
-        cpu_base = None
-        if not args.no_cpu_baseline:
+        cpu_base = None          # timed on rank 0 at N = 1 only
+        if not args.no_cpu_baseline and world == 1:
             try:
                 workers = ReferenceWorkers(wl, 1, 2)
                 p, s = workers.run(repeats=1)
