@@ -501,6 +501,10 @@ struct Port
     std::vector<int> sub_w, sub_h;
     std::vector<std::vector<float> > sub_grad, sub_hess;
     std::vector<double> Mi, ti;
+    /* StereoView::get_image(): unblurred float images, 3 channels (only the
+     * use_sgm = false mode of create_subview_surfaces reads them) */
+    std::vector<float> main_image;
+    std::vector<std::vector<float> > sub_image;
 
     int scale, ps, npx, npy, sx, sy;
     std::vector<double> nodes;
@@ -1100,8 +1104,118 @@ remove_nodes_without_patch (Port& P)
     }
 }
 
-/* DepthOptimizer::create_subview_surfaces, use_sgm mode
- * (lib/depth_optimizer.cc:433-604). Returns the patches deleted. */
+/* DepthOptimizer::ncc_for_patch, lib/depth_optimizer.cc:795-912: NCC of the
+ * patch (plus a two-pixel rim, where it fits) between the main colour image
+ * and one neighbour's, -1 when a pixel warps outside the neighbour. */
+double
+ncc_for_patch (Port const& P, int patch, int sub, std::vector<double>* px_io,
+    std::vector<double>* py_io, std::vector<double>* pd_io)
+{
+    /* The reference works on the optimizer's member vectors `pixels` and
+     * `depths`: the rim pixels appended here stay in them after the return
+     * (px_io / py_io / pd_io), and the caller's next neighbour tests them. */
+    std::vector<double>& px = *px_io;
+    std::vector<double>& py = *py_io;
+    std::vector<double>& pd = *pd_io;
+    int const ps = P.ps;
+    int const px0 = P.sx + (patch % P.npx) * ps;
+    int const py0 = P.sy + (patch / P.npx) * ps;
+    int ids[4];
+    P.node_ids(patch, ids);
+    /* fill_values_at_nodes: corners and their depths */
+    double const cx[4] = { double(px0), double(px0 + ps), double(px0),
+        double(px0 + ps) };
+    double const cy[4] = { double(py0), double(py0), double(py0 + ps),
+        double(py0 + ps) };
+    double cd[4];
+    for (int i = 0; i < 4; ++i)
+        cd[i] = P.nodes[ids[i] * 4];
+    double const min0 = cx[0], min1 = cy[0], max0 = cx[3], max1 = cy[3];
+
+    std::vector<double> w;
+    patch_pixels(P, patch, &w, nullptr, nullptr);
+    px.clear(); py.clear(); pd.clear();
+    for (int i = 0; i < ps * ps; ++i)
+    {
+        px.push_back(px0 + i % ps);
+        py.push_back(py0 + i / ps);
+        pd.push_back(w[i]);
+    }
+    /* boundary, :813-859 (the loop runs over the list while it grows) */
+    if (min0 > 1 && max0 < P.w - 2 && min1 > 1 && max1 < P.h - 2)
+    {
+        px.push_back(cx[0] - 1); py.push_back(cy[0] - 1); pd.push_back(cd[0]);
+        px.push_back(cx[1] + 1); py.push_back(cy[1] - 1); pd.push_back(cd[1]);
+        px.push_back(cx[2] - 1); py.push_back(cy[2] + 1); pd.push_back(cd[2]);
+        px.push_back(cx[3] + 1); py.push_back(cy[3] + 1); pd.push_back(cd[3]);
+    }
+    for (std::size_t i = 0; i < px.size(); ++i)
+    {
+        if (min1 > 2 && py[i] == min1)
+        {
+            px.push_back(px[i]); py.push_back(py[i] - 2); pd.push_back(pd[i]);
+            px.push_back(px[i]); py.push_back(py[i] - 1); pd.push_back(pd[i]);
+        }
+        if (max1 < P.h - 3 && py[i] == max1)
+        {
+            px.push_back(px[i]); py.push_back(py[i] + 2); pd.push_back(pd[i]);
+            px.push_back(px[i]); py.push_back(py[i] + 1); pd.push_back(pd[i]);
+        }
+        if (min0 > 2 && px[i] == min0)
+        {
+            px.push_back(px[i] - 2); py.push_back(py[i]); pd.push_back(pd[i]);
+            px.push_back(px[i] - 1); py.push_back(py[i]); pd.push_back(pd[i]);
+        }
+        if (max0 < P.w - 3 && px[i] == max0)
+        {
+            px.push_back(px[i] + 2); py.push_back(py[i]); pd.push_back(pd[i]);
+            px.push_back(px[i] + 1); py.push_back(py[i]); pd.push_back(pd[i]);
+        }
+    }
+
+    std::size_t const n = px.size();
+    std::vector<double> v0(n * 3), v1(n * 3);
+    double means0[3] = {0, 0, 0}, means1[3] = {0, 0, 0}, counter[3] = {0, 0, 0};
+    int const sw = P.sub_w[sub], sh = P.sub_h[sub];
+    for (std::size_t i = 0; i < n; ++i)
+    {
+        Corr c;
+        c.update(&P.Mi[9 * sub], &P.ti[3 * sub], px[i] + 0.5, py[i] + 0.5,
+            pd[i], 0.0, 0.0);
+        double proj[2];
+        c.fill(proj);
+        proj[0] -= 0.5; proj[1] -= 0.5;
+        if (proj[0] < 1 || proj[0] > sw - 2 || proj[1] < 1 || proj[1] > sh - 2)
+            return -1;
+        for (int ch = 0; ch < 3; ++ch)
+        {
+            double const cm = P.main_image[(static_cast<std::size_t>(
+                static_cast<int>(py[i])) * P.w + static_cast<int>(px[i])) * 3 + ch];
+            double const cs = linear_at_f(P.sub_image[sub].data(), sw, sh, 3,
+                static_cast<float>(proj[0]), static_cast<float>(proj[1]), ch);
+            counter[ch] += 1.0;
+            means0[ch] += (cm - means0[ch]) / counter[ch];
+            means1[ch] += (cs - means1[ch]) / counter[ch];
+            v0[i * 3 + ch] = cm;
+            v1[i * 3 + ch] = cs;
+        }
+    }
+    for (std::size_t i = 0; i < n; ++i)
+        for (int ch = 0; ch < 3; ++ch)
+        {
+            v0[i * 3 + ch] -= means0[ch];
+            v1[i * 3 + ch] -= means1[ch];
+        }
+    double const norm0 = std::sqrt(dot(v0, v0)), norm1 = std::sqrt(dot(v1, v1));
+    if (norm0 + norm1 < 0.001 * n)
+        return 1;
+    return dot(v0, v1) / (norm0 * norm1);
+}
+
+/* DepthOptimizer::create_subview_surfaces (lib/depth_optimizer.cc:433-604).
+ * sgm_depth != NULL: the use_sgm mode; NULL: use_sgm = false, with the NCC
+ * occlusion filter of :579-581 (needs the colour images). Returns the
+ * patches deleted. */
 int
 create_subview_surfaces (Port& P, float const* sgm_depth)
 {
@@ -1124,7 +1238,7 @@ create_subview_surfaces (Port& P, float const* sgm_depth)
             std::size_t const i = static_cast<std::size_t>(y) * P.w + x;
             if (depth[i] != 0)
             { px.push_back(x); py.push_back(y); pd.push_back(depth[i]); }
-            if (sgm_depth[i] != 0)
+            if (sgm_depth != nullptr && sgm_depth[i] != 0)
             { px.push_back(x); py.push_back(y); pd.push_back(sgm_depth[i]); }
         }
 
@@ -1155,8 +1269,11 @@ create_subview_surfaces (Port& P, float const* sgm_depth)
         }
     }
 
-    /* second pass, :502-583 */
-    std::vector<double> w, wx, wy;
+    /* second pass, :502-583. `lx, ly, ld` are the optimizer's member vectors
+     * pixels / depths: filled once per patch (:508), refilled after a
+     * neighbour passes the first test (:551), and -- in the use_sgm = false
+     * mode -- left extended by ncc_for_patch for the next neighbour. */
+    std::vector<double> w, wx, wy, lx, ly, ld;
     for (int patch = 0; patch < np; ++patch)
     {
         if (!P.patch_valid[patch])
@@ -1164,16 +1281,23 @@ create_subview_surfaces (Port& P, float const* sgm_depth)
         patch_pixels(P, patch, &w, &wx, &wy);
         int const px0 = P.sx + (patch % P.npx) * P.ps;
         int const py0 = P.sy + (patch / P.npx) * P.ps;
+        lx.clear(); ly.clear(); ld.clear();
+        for (int i = 0; i < P.ps * P.ps; ++i)
+        {
+            lx.push_back(px0 + i % P.ps);
+            ly.push_back(py0 + i / P.ps);
+            ld.push_back(w[i]);
+        }
         for (int s = 0; s < P.n_sub; ++s)
         {
             double const sw = P.sub_w[s], sh = P.sub_h[s];
             int const cw = P.sub_w[s] + 1;
             bool success = true;
-            for (int i = 0; i < P.ps * P.ps && success; ++i)
+            for (std::size_t i = 0; i < lx.size() && success; ++i)
             {
                 Corr c;
-                c.update(&P.Mi[9 * s], &P.ti[3 * s], px0 + i % P.ps + 0.5,
-                    py0 + i / P.ps + 0.5, w[i], 0.0, 0.0);
+                c.update(&P.Mi[9 * s], &P.ti[3 * s], lx[i] + 0.5, ly[i] + 0.5,
+                    ld[i], 0.0, 0.0);
                 double proj[2];
                 c.fill(proj);
                 proj[0] -= 0.5; proj[1] -= 0.5;
@@ -1194,6 +1318,13 @@ create_subview_surfaces (Port& P, float const* sgm_depth)
             if (!success)
                 continue;
 
+            /* :551: the member vectors are the patch's own pixels again */
+            lx.resize(P.ps * P.ps); ly.resize(P.ps * P.ps);
+            ld.resize(P.ps * P.ps);
+            for (int i = 0; i < P.ps * P.ps; ++i)
+            {
+                lx[i] = px0 + i % P.ps; ly[i] = py0 + i / P.ps; ld[i] = w[i];
+            }
             double max = 0.0;
             for (int i = 0; i < P.ps * P.ps; ++i)
             {
@@ -1214,6 +1345,10 @@ create_subview_surfaces (Port& P, float const* sgm_depth)
                 max = std::max(max, sigma0 / sigma1);
             }
             if (max > 8.0)
+                continue;
+            /* filter possible occlusions from unreconstructed geometry */
+            if (sgm_depth == nullptr
+                && ncc_for_patch(P, patch, s, &lx, &ly, &ld) < 0)
                 continue;
             subsurfaces[patch].push_back(static_cast<uint8_t>(s));
         }
@@ -1629,7 +1764,22 @@ port_newton_loop (void* p, double const* light16, double regularization,
  * (:192-244), aggregate_sgm_costs (:429-667, SSE semantics) and
  * depth_from_sgm_volume (:274-306). cost_out / sgm_out: w*h*D uint16. */
 
-/* create_subview_surfaces (use_sgm) on the port's surface; sgm_depth: w*h. */
+/* The views' unblurred float images, 3 channels each (StereoView::get_image). */
+void
+port_set_images (void* p, float const* main_image,
+    float const* const* sub_images)
+{
+    Port* P = static_cast<Port*>(p);
+    P->main_image.assign(main_image, main_image
+        + static_cast<std::size_t>(P->w) * P->h * 3);
+    P->sub_image.clear();
+    for (int k = 0; k < P->n_sub; ++k)
+        P->sub_image.emplace_back(sub_images[k], sub_images[k]
+            + static_cast<std::size_t>(P->sub_w[k]) * P->sub_h[k] * 3);
+}
+
+/* create_subview_surfaces on the port's surface; sgm_depth: w*h, or NULL for
+ * the use_sgm = false mode (port_set_images first). */
 int
 port_visibility (void* p, float const* sgm_depth)
 {

@@ -115,9 +115,18 @@ class PortScene:
         return act, int(n_active.value), float(shift.value)
 
     # -- visibility / cutting (the callers' side of the loop) ----------------
+    def set_images(self, main_image, sub_images):
+        """Unblurred float images (h, w, 3) of the main view and the neighbours:
+        what the use_sgm = false mode's NCC filter reads."""
+        m = np.ascontiguousarray(main_image, np.float32)
+        subs = [np.ascontiguousarray(a, np.float32) for a in sub_images]
+        self._keep_images = [m, subs]
+        ptrs = (C.c_void_p * max(len(subs), 1))(*[a.ctypes.data for a in subs])
+        lib().port_set_images(self.h_, _p(m), ptrs)
+
     def visibility(self, sgm_depth):
-        d = np.ascontiguousarray(sgm_depth, np.float32)
-        self._hw = d.shape
+        """create_subview_surfaces; sgm_depth None = the use_sgm = false mode."""
+        d = None if sgm_depth is None else np.ascontiguousarray(sgm_depth, np.float32)
         return int(lib().port_visibility(self.h_, _p(d)))
 
     def cut_boundaries(self, inv_calib9):

@@ -161,3 +161,37 @@ def test_port_visibility_and_cutting_match_the_reference(scale, seed):
         if d <= 10:
             break
     R.close()
+
+
+@pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")
+def test_port_visibility_without_sgm_matches_the_reference():
+    """use_sgm = false: depth-map pixels only in the z-buffer, NCC occlusion
+    filter on the colour images (ncc_for_patch)."""
+    import copy
+    sc = synth.make_scene(256, 192, 3, seed_index=63)
+    col = copy.copy(sc)
+    col.images = [np.repeat(im[:, :, None], 3, axis=2) for im in sc.images]
+    init = sc.init_depth.copy()
+    init[60:100, 80:140] *= 0.8
+    R = oref.RefScene(col)
+    R.set_scale(3)
+    R.surface_create(3, init)
+    info = R.surface_info()
+    nodes, nv, pv = R.surface_get()
+    Mi, ti = R.Mt()
+    P = oport.PortScene(R.gradients(0), [R.gradients(k + 1) for k in range(3)],
+                        [R.hessian(k + 1) for k in range(3)], Mi, ti, R.flen(0),
+                        R.inverse_flen(0))
+    P.set_surface(info["scale"], info["npx"], info["npy"], info["start_x"],
+                  info["start_y"], nodes, nv, pv, None, None)
+    P.set_images(R.image(0), [R.image(k + 1) for k in range(3)])
+    left = R.create_subview_surfaces(False)
+    removed = P.visibility(None)
+    assert int(pv.sum()) - removed == left
+    _, nv_r, pv_r = R.surface_get()
+    off_r, ids_r = R.get_visibility()
+    nv_p, pv_p, off_p, ids_p = P.surface_state()
+    assert np.array_equal(pv_p, pv_r) and np.array_equal(nv_p, nv_r)
+    assert np.array_equal(off_p, off_r) and np.array_equal(ids_p, ids_r)
+    assert 0 < left < int(pv.sum())
+    R.close()
