@@ -505,6 +505,8 @@ struct Port
      * use_sgm = false mode of create_subview_surfaces reads them) */
     std::vector<float> main_image;
     std::vector<std::vector<float> > sub_image;
+    /* Surface::depth: the initialisation depth the nodes are made from */
+    std::vector<float> init_depth;
 
     int scale, ps, npx, npy, sx, sy;
     std::vector<double> nodes;
@@ -1030,6 +1032,246 @@ census_filter (uint8_t const* img, int w, int h, int c, uint64_t* out)
 }
 
 } /* namespace */
+
+/* ------------------------------------------------------------------ */
+/* surface topology: creation from a depth map, subdivision, clean-up  */
+/* ------------------------------------------------------------------ */
+
+void remove_nodes_without_patch (Port& P);
+
+/* Surface::fill_holes, lib/surface.cc:628-649: a patch wherever its four
+ * nodes exist. */
+int
+fill_holes (Port& P)
+{
+    int filled = 0;
+    for (int patch = 0; patch < P.npx * P.npy; ++patch)
+    {
+        if (P.patch_valid[patch])
+            continue;
+        int ids[4];
+        P.node_ids(patch, ids);
+        if (P.node_valid[ids[0]] && P.node_valid[ids[1]]
+            && P.node_valid[ids[2]] && P.node_valid[ids[3]])
+        {
+            P.patch_valid[patch] = 1;
+            filled += 1;
+        }
+    }
+    return filled;
+}
+
+/* Surface::initialize_node_from_depth, lib/surface.cc:665-760 */
+void
+initialize_node_from_depth (Port& P, int idx, int idy)
+{
+    int const ns = P.npx + 1;
+    int const x = idx * P.ps + P.sx, y = idy * P.ps + P.sy;
+    if (P.node_valid[idy * ns + idx])
+        return;
+    int const win = P.ps / 2;
+    std::vector<double> d[4];
+    int const lo_i[4] = { -win, 0, -win, 0 }, hi_i[4] = { 0, win, 0, win };
+    int const lo_j[4] = { -win, -win, 0, 0 }, hi_j[4] = { 0, 0, win, win };
+    for (int q = 0; q < 4; ++q)
+        for (int i = lo_i[q]; i < hi_i[q]; ++i)
+            for (int j = lo_j[q]; j < hi_j[q]; ++j)
+                if (x + i >= 0 && x + i < P.w && y + j >= 0 && y + j < P.h
+                    && P.init_depth[static_cast<std::size_t>(y + j) * P.w
+                        + x + i] > 0.0)
+                    d[q].push_back(P.init_depth[static_cast<std::size_t>(
+                        y + j) * P.w + x + i]);
+
+    int num_non_zeros = 4;
+    double avg[4];
+    std::vector<double> all;
+    for (int i = 0; i < 4; ++i)
+    {
+        all.insert(all.end(), d[i].begin(), d[i].end());
+        if (d[i].empty())
+        {
+            avg[i] = 0.0;
+            num_non_zeros -= 1;
+            continue;
+        }
+        avg[i] = *std::min_element(d[i].begin(), d[i].end());
+    }
+    if (num_non_zeros == 0)
+        return;
+    if (all.size() < 2)
+        return;
+    std::nth_element(all.begin(), all.begin() + all.size() / 2, all.end());
+
+    double f = all[all.size() / 2], dx = 0.0, dy = 0.0, dxy = 0.0;
+    if (num_non_zeros == 4)
+    {
+        dx = ((avg[1] + avg[3]) - (avg[0] + avg[2])) / 2.0;
+        dy = ((avg[2] + avg[3]) - (avg[0] + avg[1])) / 2.0;
+        dxy = ((avg[3] - avg[2]) - (avg[1] - avg[0]));
+    }
+    else
+    {
+        if ((avg[1] == 0 || avg[0] == 0) && avg[3] != 0 && avg[2] != 0)
+            dx = (avg[3] - avg[2]);
+        else if ((avg[2] == 0 || avg[3] == 0) && avg[1] != 0 && avg[0] != 0)
+            dx = (avg[1] - avg[0]);
+        if ((avg[0] == 0 || avg[2] == 0) && avg[3] != 0 && avg[1] != 0)
+            dy = (avg[3] - avg[1]);
+        else if ((avg[1] == 0 || avg[2] == 0) && avg[0] != 0 && avg[2] != 0)
+            dy = (avg[2] - avg[0]);
+    }
+    int const node = idy * ns + idx;
+    P.node_valid[node] = 1;
+    P.nodes[node * 4 + 0] = f; P.nodes[node * 4 + 1] = dx;
+    P.nodes[node * 4 + 2] = dy; P.nodes[node * 4 + 3] = dxy;
+}
+
+/* Surface::fill_patches_from_depth, lib/surface.cc:141-152 */
+void
+fill_patches_from_depth (Port& P)
+{
+    for (int i = 0; i < P.npx + 1; ++i)
+        for (int j = 0; j < P.npy + 1; ++j)
+            initialize_node_from_depth(P, i, j);
+    fill_holes(P);
+    remove_nodes_without_patch(P);
+}
+
+/* Surface::Surface(bundle, view, scale, init_depth), lib/surface.cc:19-53 */
+void
+surface_create (Port& P, int scale, float const* init_depth)
+{
+    P.scale = scale;
+    P.ps = 1 << scale;
+    P.npx = (P.w - 2) / P.ps - 1;
+    P.npy = (P.h - 2) / P.ps - 1;
+    P.sx = (P.w - P.npx * P.ps) / 2;
+    P.sy = (P.h - P.npy * P.ps) / 2;
+    P.nodes.assign(static_cast<std::size_t>(P.n_nodes()) * 4, 0.0);
+    P.node_valid.assign(P.n_nodes(), 0);
+    P.patch_valid.assign(P.npx * P.npy, 0);
+    P.vis_off.assign(P.npx * P.npy + 1, 0);
+    P.vis_ids.clear();
+    P.init_depth.assign(static_cast<std::size_t>(P.w) * P.h, 0.0f);
+    for (std::size_t p = 0; p < P.init_depth.size(); ++p)
+        if (init_depth[p] > 0.0)
+            P.init_depth[p] = init_depth[p];
+    fill_patches_from_depth(P);
+}
+
+/* Surface::subdivide_patches, lib/surface.cc:983-1107 */
+void
+subdivide_patches (Port& P)
+{
+    P.scale -= 1;
+    P.ps = 1 << P.scale;
+    int new_npx = (P.w - 2) / P.ps, new_npy = (P.h - 2) / P.ps;
+    int offset_x = new_npx - P.npx * 2, offset_y = new_npy - P.npy * 2;
+    if (offset_x >= 2)
+    {
+        new_npx = P.npx * 2 + 2;
+        P.sx = (P.w - new_npx * P.ps) / 2;
+        offset_x = 1;
+    }
+    else
+    {
+        offset_x = 0;
+        new_npx = P.npx * 2;
+    }
+    if (offset_y >= 2)
+    {
+        new_npy = P.npy * 2 + 2;
+        P.sy = (P.h - new_npy * P.ps) / 2;
+        offset_y = 1;
+    }
+    else
+    {
+        offset_y = 0;
+        new_npy = P.npy * 2;
+    }
+    int const new_ns = new_npx + 1;
+    std::vector<double> new_nodes(static_cast<std::size_t>(new_ns)
+        * (new_npy + 1) * 4, 0.0);
+    std::vector<uint8_t> new_valid(static_cast<std::size_t>(new_ns)
+        * (new_npy + 1), 0);
+
+    /* five new nodes per patch; later patches overwrite shared edge nodes */
+    double const at[5][2] = { {0.5, 0.0}, {0.0, 0.5}, {0.5, 0.5}, {1.0, 0.5},
+        {0.5, 1.0} };
+    int const off[5][2] = { {1, 0}, {0, 1}, {1, 1}, {2, 1}, {1, 2} };
+    for (int patch = 0; patch < P.npx * P.npy; ++patch)
+    {
+        if (!P.patch_valid[patch])
+            continue;
+        int const new_idx = 2 * (patch % P.npx) + offset_x;
+        int const new_idy = 2 * (patch / P.npx) + offset_y;
+        double n16[16], coeffs[4][4];
+        P.patch_nodes16(patch, n16);
+        patch_coefficients(n16, coeffs);
+        for (int k = 0; k < 5; ++k)
+        {
+            double out6[6];
+            patch_evaluate(coeffs, at[k][0], at[k][1], out6);
+            int const node = new_idx + off[k][0]
+                + new_ns * (new_idy + off[k][1]);
+            new_valid[node] = 1;
+            new_nodes[node * 4 + 0] = out6[0];
+            new_nodes[node * 4 + 1] = out6[1] / 2;
+            new_nodes[node * 4 + 2] = out6[2] / 2;
+            new_nodes[node * 4 + 3] = out6[3] / 4;
+        }
+    }
+    /* old nodes, derivatives rescaled to the new patch size */
+    int const ns = P.npx + 1;
+    for (int node = 0; node < P.n_nodes(); ++node)
+    {
+        if (!P.node_valid[node])
+            continue;
+        int const new_node = 2 * (node % ns) + offset_x
+            + new_ns * (2 * (node / ns) + offset_y);
+        new_valid[new_node] = 1;
+        new_nodes[new_node * 4 + 0] = P.nodes[node * 4 + 0];
+        new_nodes[new_node * 4 + 1] = P.nodes[node * 4 + 1] / 2;
+        new_nodes[new_node * 4 + 2] = P.nodes[node * 4 + 2] / 2;
+        new_nodes[new_node * 4 + 3] = P.nodes[node * 4 + 3] / 4;
+    }
+    P.npx = new_npx;
+    P.npy = new_npy;
+    P.nodes.swap(new_nodes);
+    P.node_valid.swap(new_valid);
+    P.patch_valid.assign(P.npx * P.npy, 0);
+    P.vis_off.assign(P.npx * P.npy + 1, 0);
+    P.vis_ids.clear();
+    fill_holes(P);
+    remove_nodes_without_patch(P);
+}
+
+/* Surface::remove_isolated_patches, lib/surface.cc:887-927: sequential, x
+ * outer / y inner, deletions feed the counts of the patches visited later. */
+void
+remove_isolated_patches (Port& P)
+{
+    for (int x = 0; x < P.npx; ++x)
+        for (int y = 0; y < P.npy; ++y)
+        {
+            if (!P.patch_valid[y * P.npx + x])
+                continue;
+            int valid_neighbors = 0;
+            for (int dx = -1; dx < 2; ++dx)
+                for (int dy = -1; dy < 2; ++dy)
+                {
+                    if (dx == 0 && dy == 0)
+                        continue;
+                    int const qx = x + dx, qy = y + dy;
+                    if (qx < 0 || qy < 0 || qx > P.npx - 1 || qy > P.npy - 1)
+                        continue;
+                    valid_neighbors += P.patch_valid[qy * P.npx + qx] ? 1 : 0;
+                }
+            if (valid_neighbors < 3)
+                P.patch_valid[y * P.npx + x] = 0;
+        }
+    remove_nodes_without_patch(P);
+}
 
 /* ------------------------------------------------------------------ */
 /* visibility lists, boundary cutting, bilateral filter               */
@@ -1763,6 +2005,39 @@ port_newton_loop (void* p, double const* light16, double regularization,
 /* SGMStereo::run_sgm, lib/sgm_stereo.cc:98-124 with create_cost_volume
  * (:192-244), aggregate_sgm_costs (:429-667, SSE semantics) and
  * depth_from_sgm_volume (:274-306). cost_out / sgm_out: w*h*D uint16. */
+
+/* Surface::create from an initial depth map (w*h); info[6] as ref_surface_info. */
+void
+port_surface_create (void* p, int scale, float const* init_depth)
+{
+    surface_create(*static_cast<Port*>(p), scale, init_depth);
+}
+
+void
+port_surface_subdivide (void* p)
+{
+    subdivide_patches(*static_cast<Port*>(p));
+}
+
+void
+port_surface_fill_from_depth (void* p)
+{
+    fill_patches_from_depth(*static_cast<Port*>(p));
+}
+
+void
+port_surface_remove_isolated (void* p)
+{
+    remove_isolated_patches(*static_cast<Port*>(p));
+}
+
+void
+port_surface_info (void* p, int* info)
+{
+    Port* P = static_cast<Port*>(p);
+    info[0] = P->scale; info[1] = P->npx; info[2] = P->npy;
+    info[3] = P->sx; info[4] = P->sy; info[5] = P->ps;
+}
 
 /* The views' unblurred float images, 3 channels each (StereoView::get_image). */
 void

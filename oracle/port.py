@@ -114,6 +114,30 @@ class PortScene:
                                 _p(act), C.byref(n_active), C.byref(shift))
         return act, int(n_active.value), float(shift.value)
 
+    # -- surface topology -----------------------------------------------------
+    def _after_topology(self):
+        info = (C.c_int * 6)()
+        lib().port_surface_info(self.h_, info)
+        self.info = dict(scale=info[0], npx=info[1], npy=info[2], start_x=info[3],
+                         start_y=info[4], patchsize=info[5])
+        self.n_nodes = (info[1] + 1) * (info[2] + 1)
+        self.n_patches = info[1] * info[2]
+
+    def surface_create(self, scale, init_depth):
+        d = np.ascontiguousarray(init_depth, np.float32)
+        lib().port_surface_create(self.h_, int(scale), _p(d))
+        self._after_topology()
+
+    def surface_subdivide(self):
+        lib().port_surface_subdivide(self.h_)
+        self._after_topology()
+
+    def surface_fill_from_depth(self):
+        lib().port_surface_fill_from_depth(self.h_)
+
+    def surface_remove_isolated(self):
+        lib().port_surface_remove_isolated(self.h_)
+
     # -- visibility / cutting (the callers' side of the loop) ----------------
     def set_images(self, main_image, sub_images):
         """Unblurred float images (h, w, 3) of the main view and the neighbours:

@@ -161,6 +161,12 @@ class RefScene:
     def surface_subdivide(self):
         self.L.ref_surface_subdivide(self.h_)
 
+    def surface_fill_from_depth(self):
+        self.L.ref_surface_fill_from_depth(self.h_)
+
+    def surface_remove_isolated(self):
+        self.L.ref_surface_remove_isolated(self.h_)
+
     def surface_depth(self):
         out = np.empty((self.h, self.w), dtype=np.float32)
         self.L.ref_surface_get_depth(self.h_, _p(out))

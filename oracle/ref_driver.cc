@@ -341,6 +341,20 @@ ref_surface_subdivide (void* scene)
     static_cast<RefScene*>(scene)->optimizer->surface->subdivide_patches();
 }
 
+void
+ref_surface_fill_from_depth (void* scene)
+{
+    static_cast<RefScene*>(scene)->optimizer->surface
+        ->fill_patches_from_depth();
+}
+
+void
+ref_surface_remove_isolated (void* scene)
+{
+    static_cast<RefScene*>(scene)->optimizer->surface
+        ->remove_isolated_patches();
+}
+
 /* Surface::get_depth_map, lib/surface.cc:155-168. */
 void
 ref_surface_get_depth (void* scene, float* depth)

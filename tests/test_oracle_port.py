@@ -195,3 +195,50 @@ def test_port_visibility_without_sgm_matches_the_reference():
     assert np.array_equal(off_p, off_r) and np.array_equal(ids_p, ids_r)
     assert 0 < left < int(pv.sum())
     R.close()
+
+
+@pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("w,h,scale", [(256, 192, 4), (333, 207, 3), (160, 120, 2)])
+def test_port_surface_topology_matches_the_reference(w, h, scale):
+    """Surface::create from a depth map with holes, subdivide_patches,
+    fill_patches_from_depth, remove_isolated_patches: same grids, nodes and
+    flags as the reference after every operation."""
+    sc = synth.make_scene(w, h, 1, seed_index=64)
+    init = sc.init_depth.astype(np.float32).copy()
+    yy, xx = np.mgrid[0:h, 0:w]
+    init[(xx - 0.3 * w) ** 2 + (yy - 0.4 * h) ** 2 < (0.15 * h) ** 2] = 0.0
+    init[:, int(0.7 * w):int(0.7 * w) + 3 * (1 << scale)] = 0.0
+    R = oref.RefScene(sc)
+    R.set_scale(scale)
+    Mi, ti = R.Mt()
+    P = oport.PortScene(R.gradients(0), [R.gradients(1)], [R.hessian(1)], Mi, ti,
+                        R.flen(0), R.inverse_flen(0))
+
+    def same():
+        info = R.surface_info()
+        assert {k: info[k] for k in P.info} == P.info
+        nodes_r, nv_r, pv_r = R.surface_get()
+        nv_p, pv_p, _, _ = P.surface_state()
+        assert np.array_equal(pv_p, pv_r) and np.array_equal(nv_p, nv_r)
+        m = np.repeat(nv_r.astype(bool), 4)
+        assert np.array_equal(P.get_nodes().reshape(-1)[m], nodes_r.reshape(-1)[m])
+        return int(pv_r.sum())
+
+    R.surface_create(scale, init)
+    P.surface_create(scale, init)
+    n0 = same()
+    assert 0 < n0 < P.n_patches
+    R.surface_remove_isolated()
+    P.surface_remove_isolated()
+    same()
+    for _ in range(2 if scale > 2 else 1):
+        R.surface_subdivide()
+        P.surface_subdivide()
+        same()
+        R.surface_fill_from_depth()
+        P.surface_fill_from_depth()
+        same()
+        R.surface_remove_isolated()
+        P.surface_remove_isolated()
+        same()
+    R.close()
