@@ -165,3 +165,24 @@ def test_expf_twin_matches_libm():
                          np.float32([-0.0, -1e-7, -1.0, -50.0, -86.9])])
     for x in xs:
         assert L.smvsb_debug_expf(float(x)) == libm.expf(float(x))
+
+
+@pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference needs no GPU: one short step must end with one
+    JSON line carrying the contract's keys (metric, value, unit, impl,
+    cpu_baseline, e2e with zero transfer bytes)."""
+    import json
+    import subprocess
+    env = dict(os.environ, SMVSB_REF_THREADS="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl",
+                          "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"].startswith("Gauss-Newton")
+    assert line["value"] > 0 and line["unit"] == "Mpix-iters/s"
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == 2
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["higher_is_better"] is True and line["scaling"] == "weak"
