@@ -1246,6 +1246,88 @@ subdivide_patches (Port& P)
     remove_nodes_without_patch(P);
 }
 
+/* Surface::expand, lib/surface.cc:482-628: two rounds of new nodes at the rim
+ * (largest of up to eight extrapolations from neighbour triples, with the 0.9
+ * hysteresis of check_swap_nodes :472-480), then fill_holes. Returns the
+ * patches created. */
+int
+expand (Port& P)
+{
+    int const ns = P.npx + 1, nn = P.n_nodes();
+    std::vector<uint8_t> has_new(nn, 0);
+    std::vector<double> new_f(nn, 0.0);
+    for (int iter = 0; iter < 2; ++iter)
+    {
+        for (int node = 0; node < nn; ++node)
+        {
+            if (P.node_valid[node] && !has_new[node])
+                continue;
+            int const ix = node % ns, iy = node / ns;
+            /* fill_node_neighbors: 0..7 = NW N NE W E SW S SE, absent when
+             * outside the grid or not valid */
+            bool ok[8];
+            double f[8], dx[8], dy[8];
+            int k = 0;
+            for (int oy = -1; oy < 2; ++oy)
+                for (int ox = -1; ox < 2; ++ox)
+                {
+                    if (ox == 0 && oy == 0)
+                        continue;
+                    int const qx = ix + ox, qy = iy + oy;
+                    ok[k] = qx >= 0 && qy >= 0 && qx <= P.npx && qy <= P.npy
+                        && P.node_valid[qy * ns + qx];
+                    if (ok[k])
+                    {
+                        double const* n = &P.nodes[(qy * ns + qx) * 4];
+                        f[k] = n[0]; dx[k] = n[1]; dy[k] = n[2];
+                    }
+                    k += 1;
+                }
+            auto offer = [&] (double value)
+            {
+                /* check_swap_nodes */
+                if (!has_new[node] || value * 0.9 > new_f[node])
+                {
+                    has_new[node] = 1;
+                    new_f[node] = value;
+                }
+            };
+            if (ok[0] && ok[1] && ok[3])
+                offer(((f[3] + dx[3] / 2.0) + (f[1] + dy[1] / 2.0)) / 2.0);
+            if (ok[1] && ok[2] && ok[4])
+                offer(((f[4] - dx[4] / 2.0) + (f[1] + dy[1] / 2.0)) / 2.0);
+            if (ok[3] && ok[5] && ok[6])
+                offer(((f[3] + dx[3] / 2.0) + (f[6] - dy[6] / 2.0)) / 2.0);
+            if (ok[4] && ok[6] && ok[7])
+                offer(((f[4] - dx[4] / 2.0) + (f[6] - dy[6] / 2.0)) / 2.0);
+            if (ok[0] && ok[1] && ok[2])
+                offer(((f[0] + dy[0] / 2.0) + (f[1] + dy[1] / 2.0)
+                    + (f[2] + dy[2] / 2.0)) / 3.0);
+            if (ok[0] && ok[3] && ok[5])
+                offer(((f[0] + dx[0] / 2.0) + (f[3] + dx[3] / 2.0)
+                    + (f[5] + dx[5] / 2.0)) / 3.0);
+            if (ok[5] && ok[6] && ok[7])
+                offer(((f[5] - dy[5] / 2.0) + (f[6] - dy[6] / 2.0)
+                    + (f[7] - dy[7] / 2.0)) / 3.0);
+            if (ok[2] && ok[4] && ok[7])
+                offer(((f[2] - dx[2] / 2.0) + (f[4] - dx[4] / 2.0)
+                    + (f[7] - dx[7] / 2.0)) / 3.0);
+        }
+        for (int node = 0; node < nn; ++node)
+            if (has_new[node])
+            {
+                P.node_valid[node] = 1;
+                P.nodes[node * 4 + 0] = new_f[node];
+                P.nodes[node * 4 + 1] = 0.0;
+                P.nodes[node * 4 + 2] = 0.0;
+                P.nodes[node * 4 + 3] = 0.0;
+            }
+    }
+    int const filled = fill_holes(P);
+    remove_nodes_without_patch(P);
+    return filled;
+}
+
 /* Surface::remove_isolated_patches, lib/surface.cc:887-927: sequential, x
  * outer / y inner, deletions feed the counts of the patches visited later. */
 void
@@ -2023,6 +2105,12 @@ void
 port_surface_fill_from_depth (void* p)
 {
     fill_patches_from_depth(*static_cast<Port*>(p));
+}
+
+int
+port_surface_expand (void* p)
+{
+    return expand(*static_cast<Port*>(p));
 }
 
 void

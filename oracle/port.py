@@ -138,6 +138,9 @@ class PortScene:
     def surface_remove_isolated(self):
         lib().port_surface_remove_isolated(self.h_)
 
+    def surface_expand(self):
+        return int(lib().port_surface_expand(self.h_))
+
     # -- visibility / cutting (the callers' side of the loop) ----------------
     def set_images(self, main_image, sub_images):
         """Unblurred float images (h, w, 3) of the main view and the neighbours:

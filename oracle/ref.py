@@ -167,6 +167,9 @@ class RefScene:
     def surface_remove_isolated(self):
         self.L.ref_surface_remove_isolated(self.h_)
 
+    def surface_expand(self):
+        return int(self.L.ref_surface_expand(self.h_))
+
     def surface_depth(self):
         out = np.empty((self.h, self.w), dtype=np.float32)
         self.L.ref_surface_get_depth(self.h_, _p(out))

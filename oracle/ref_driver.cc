@@ -348,6 +348,12 @@ ref_surface_fill_from_depth (void* scene)
         ->fill_patches_from_depth();
 }
 
+int
+ref_surface_expand (void* scene)
+{
+    return static_cast<RefScene*>(scene)->optimizer->surface->expand();
+}
+
 void
 ref_surface_remove_isolated (void* scene)
 {

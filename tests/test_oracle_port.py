@@ -231,6 +231,8 @@ def test_port_surface_topology_matches_the_reference(w, h, scale):
     R.surface_remove_isolated()
     P.surface_remove_isolated()
     same()
+    assert R.surface_expand() == P.surface_expand() > 0
+    same()
     for _ in range(2 if scale > 2 else 1):
         R.surface_subdivide()
         P.surface_subdivide()
