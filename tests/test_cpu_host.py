@@ -29,6 +29,10 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), name
     assert b"sm_100a" in L.smvsb_version()
+    # the documents quote the number of entry points
+    for doc in ("README.md", "DESIGN.md"):
+        text = open(os.path.join(ROOT, doc)).read()
+        assert f"{len(declared)} entry points" in text, doc
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure path")
