@@ -73,6 +73,10 @@ typedef struct smvsb_newton_stats
 
 /* ---- lifetime ------------------------------------------------------- */
 
+/* Number of CUDA devices this process can use (0 without a GPU or driver);
+ * hosts spread their pool threads over them: thread k -> device k mod count,
+ * the reference's one-view-per-thread model of app/smvsrecon.cc:658-733. */
+int smvsb_device_count (void);
 int smvsb_create (int device, smvsb_ctx** out);
 void smvsb_destroy (smvsb_ctx* ctx);
 /* Message of the last failed call on ctx (or, with ctx == NULL, of the last
@@ -85,6 +89,8 @@ uint64_t smvsb_launch_count (const smvsb_ctx* ctx);
 /* Kernel launches issued by this library in this process (all contexts and
  * smvsb_sgm calls); lets a host prove that the GPU path did the work. */
 uint64_t smvsb_global_launch_count (void);
+/* The same per device: shows which GPUs a multi-threaded host really used. */
+uint64_t smvsb_device_launch_count (int device);
 
 /* ---- inputs --------------------------------------------------------- */
 

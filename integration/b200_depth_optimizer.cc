@@ -55,6 +55,7 @@ namespace
         void const* owner = nullptr;
         void const* gradients = nullptr;
         int scale = -1;
+        std::uint64_t generation = 0;   /* b200_context.h: views_generation */
     };
     ViewsKey&
     views_key (void)
@@ -95,6 +96,7 @@ namespace
         views_key().owner = owner;
         views_key().gradients = main_view->get_image_gradients().get();
         views_key().scale = scale;
+        views_key().generation = smvs_b200_integration::views_generation();
     }
 
     bool
@@ -102,6 +104,7 @@ namespace
     {
         ViewsKey const& k = views_key();
         return k.owner == owner && k.scale == scale
+            && k.generation == smvs_b200_integration::views_generation()
             && k.gradients == main_view->get_image_gradients().get();
     }
 

@@ -10,7 +10,7 @@
 
 #include "sgm_stereo.h"
 
-#include "smvs_b200.h"
+#include "b200_context.h"
 
 SMVS_NAMESPACE_BEGIN
 
@@ -27,7 +27,8 @@ SGMStereo::run_sgm (float min_depth, float max_depth)
 
     mve::FloatImage::Ptr depth = mve::FloatImage::create(
         this->main_image->width(), this->main_image->height(), 1);
-    int const rc = smvsb_sgm(0, this->main_image->width(),
+    int const rc = smvsb_sgm(smvs_b200_integration::thread_device(),
+        this->main_image->width(),
         this->main_image->height(), this->main_image->begin(),
         this->neighbor_image->width(), this->neighbor_image->height(),
         this->neighbor_image->begin(), *M, *t, min_depth, max_depth,

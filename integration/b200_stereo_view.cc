@@ -23,6 +23,8 @@ extern "C" void smvs_ref_stereo_view_set_scale (StereoView* self, int scale,
 void
 StereoView::set_scale (int scale, bool debug)
 {
+    /* whatever a context of this thread holds of older images is stale now */
+    smvs_b200_integration::views_generation() += 1;
     if (debug || this->image->channels() != 1)
     {
         smvs_ref_stereo_view_set_scale(this, scale, debug);

@@ -25,7 +25,7 @@ EXPORTS = [
     "smvsb_get_normals", "smvsb_debug_get_system", "smvsb_debug_spmv",
     "smvsb_fit_lighting", "smvsb_sgm", "smvsb_visibility",
     "smvsb_cut_boundaries", "smvsb_get_surface_state", "smvsb_view_set_scale",
-    "smvsb_bilateral_filter", "smvsb_debug_expf",
+    "smvsb_bilateral_filter", "smvsb_debug_expf", "smvsb_device_count", "smvsb_device_launch_count",
 ]
 
 
@@ -61,6 +61,8 @@ def lib():
         L.smvsb_launch_count.restype = C.c_uint64
         L.smvsb_launch_count.argtypes = [C.c_void_p]
         L.smvsb_global_launch_count.restype = C.c_uint64
+        L.smvsb_device_launch_count.restype = C.c_uint64
+        L.smvsb_device_launch_count.argtypes = [C.c_int]
         L.smvsb_destroy.argtypes = [C.c_void_p]
         L.smvsb_destroy.restype = None
         _lib = L

@@ -37,6 +37,7 @@ int sgm_run (int device, int w, int h, uint8_t const* main_lum, int nw, int nh,
 
 namespace smvsb {
 std::atomic<uint64_t> g_launches(0);
+std::atomic<uint64_t> g_device_launches[SMVSB_MAX_DEVICES];
 }
 
 namespace {
@@ -245,6 +246,23 @@ smvsb_global_launch_count (void)
     return smvsb::g_launches.load();
 }
 
+uint64_t
+smvsb_device_launch_count (int device)
+{
+    if (device < 0 || device >= SMVSB_MAX_DEVICES)
+        return 0;
+    return smvsb::g_device_launches[device].load();
+}
+
+int
+smvsb_device_count (void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess)
+        return 0;
+    return count;
+}
+
 int
 smvsb_create (int device, smvsb_ctx** out)
 {
@@ -266,7 +284,7 @@ smvsb_create (int device, smvsb_ctx** out)
         {
             CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream,
                 cudaStreamNonBlocking));
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < SMVSB_NUM_EVENTS; ++i)
                 CUDA_CHECK(cudaEventCreate(&c->ev[i]));
             CUDA_CHECK(cudaDeviceGetAttribute(&c->num_sms,
                 cudaDevAttrMultiProcessorCount, device));
@@ -287,7 +305,7 @@ smvsb_destroy (smvsb_ctx* ctx)
         return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < SMVSB_NUM_EVENTS; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -311,6 +329,10 @@ smvsb_set_views (smvsb_ctx* ctx, int w, int h, double flen_px,
         require(n_sub == 0 || (sub_w && sub_h && sub_grad && sub_hess && Mi
             && ti), SMVSB_ERR_INVALID, "neighbour arrays missing");
         smvsb_ctx* c = ctx;
+        /* the stored grid and visibility ids were checked against the old
+         * image size and neighbour count */
+        if (c->w != w || c->h != h || c->n_sub != n_sub)
+            c->have_surface = false;
         c->w = w; c->h = h; c->flen = flen_px; c->inv_flen = inv_flen;
         size_t const npix = static_cast<size_t>(w) * h;
         upload(c, c->main_grad, main_grad, npix * 2);
@@ -369,6 +391,8 @@ smvsb_set_views_u8 (smvsb_ctx* ctx, int scale, int w, int h, double flen_px,
         require(n_sub == 0 || (sub_w && sub_h && sub_img && Mi && ti),
             SMVSB_ERR_INVALID, "neighbour arrays missing");
         smvsb_ctx* c = ctx;
+        if (c->w != w || c->h != h || c->n_sub != n_sub)
+            c->have_surface = false;
         c->w = w; c->h = h; c->flen = flen_px; c->inv_flen = inv_flen;
         size_t max_pix = static_cast<size_t>(w) * h;
         for (int k = 0; k < n_sub; ++k)
@@ -560,10 +584,28 @@ smvsb_set_surface (smvsb_ctx* ctx, int scale, int npx, int npy, int start_x,
             vis_off = no_off.data();
             vis_ids = &no_id;
         }
+        /* the kernels fill a fixed array of SMVSB_MAX_SUBS rows per patch
+         * from these lists: offsets must start at 0 and be monotone, a list
+         * holds each neighbour at most once */
+        require(vis_off[0] == 0, SMVSB_ERR_INVALID, "vis_off[0] must be 0");
+        for (int p = 0; p < npx * npy; ++p)
+        {
+            require(vis_off[p] <= vis_off[p + 1], SMVSB_ERR_INVALID,
+                "vis_off must be monotone");
+            require(vis_off[p + 1] - vis_off[p] <= static_cast<uint32_t>(
+                c->n_sub), SMVSB_ERR_INVALID,
+                "visibility list longer than the number of neighbours");
+            uint32_t seen = 0;
+            for (uint32_t i = vis_off[p]; i < vis_off[p + 1]; ++i)
+            {
+                require(vis_ids[i] < c->n_sub, SMVSB_ERR_INVALID,
+                    "visibility id out of range");
+                require(!((seen >> vis_ids[i]) & 1u), SMVSB_ERR_INVALID,
+                    "duplicate neighbour in a visibility list");
+                seen |= 1u << vis_ids[i];
+            }
+        }
         size_t const total_vis = vis_off[c->n_patches];
-        for (size_t i = 0; i < total_vis; ++i)
-            require(vis_ids[i] < c->n_sub, SMVSB_ERR_INVALID,
-                "visibility id out of range");
         upload(c, c->nodes, nodes, static_cast<size_t>(c->n_nodes) * 4);
         upload(c, c->node_valid, node_valid, c->n_nodes);
         upload(c, c->patch_valid, patch_valid, c->n_patches);
@@ -581,6 +623,7 @@ smvsb_set_surface (smvsb_ctx* ctx, int scale, int npx, int npy, int start_x,
         set_active(c, nullptr);
         c->have_surface = true;
         c->have_system = false;
+        c->x_count = 0;
     });
 }
 
@@ -621,6 +664,7 @@ smvsb_cg_solve (smvsb_ctx* ctx, int max_iter, double err_tol, double q_tol,
         require(ctx->have_system, SMVSB_ERR_STATE,
             "smvsb_gn_construct must precede smvsb_cg_solve");
         smvsb::run_cg(ctx, max_iter, err_tol, q_tol, iters, info, nullptr);
+        ctx->x_count = static_cast<size_t>(ctx->n_nodes) * 4;
     });
 }
 
@@ -642,6 +686,7 @@ smvsb_set_delta (smvsb_ctx* ctx, const double* delta)
         require(ctx->have_surface && delta, SMVSB_ERR_STATE, "no surface");
         upload(ctx, ctx->x, delta, static_cast<size_t>(ctx->n_nodes) * 4);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        ctx->x_count = static_cast<size_t>(ctx->n_nodes) * 4;
     });
 }
 
@@ -651,8 +696,10 @@ smvsb_update_nodes (smvsb_ctx* ctx, double reproj_thresh, int full_opt,
 {
     if (ctx == nullptr) return SMVSB_ERR_INVALID;
     return guarded(ctx, [&]() {
-        require(ctx->have_surface && ctx->x.p != nullptr, SMVSB_ERR_STATE,
-            "no delta to apply");
+        require(ctx->have_surface && ctx->x.p != nullptr
+            && ctx->x_count == static_cast<size_t>(ctx->n_nodes) * 4,
+            SMVSB_ERR_STATE, "no delta for this surface (solve or "
+            "smvsb_set_delta after the last smvsb_set_surface)");
         smvsb::launch_update(ctx, reproj_thresh, full_opt != 0, n_active,
             mean_shift);
         if (active_out)
@@ -682,9 +729,7 @@ smvsb_newton_loop (smvsb_ctx* ctx, const double* light16,
         double const samples = double(c->npos) * c->npos;
 
         float ms = 0.f;
-        cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-        CUDA_CHECK(cudaEventCreate(&ev_begin));
-        CUDA_CHECK(cudaEventCreate(&ev_end));
+        cudaEvent_t const ev_begin = c->ev[4], ev_end = c->ev[5];
         CUDA_CHECK(cudaEventRecord(ev_begin, c->stream));
         for (; st.newton_steps < max_steps && num_active > num_initial / 20;)
         {
@@ -700,6 +745,7 @@ smvsb_newton_loop (smvsb_ctx* ctx, const double* light16,
             int iters = 0, info = 0;
             bool x0_nan = false;
             smvsb::run_cg(c, 200, -1.0, 1e-3, &iters, &info, &x0_nan);
+            c->x_count = static_cast<size_t>(c->n_nodes) * 4;
             CUDA_CHECK(cudaEventRecord(c->ev[2], c->stream));
             st.cg_iterations += iters;
             st.cg_block_iterations += double(c->cg_blocks) * iters;
@@ -737,8 +783,6 @@ smvsb_newton_loop (smvsb_ctx* ctx, const double* light16,
         CUDA_CHECK(cudaEventSynchronize(ev_end));
         CUDA_CHECK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
         st.ms_total = ms;
-        cudaEventDestroy(ev_begin);
-        cudaEventDestroy(ev_end);
         st.n_active = num_active;
         c->have_system = false;
         if (stats) *stats = st;
@@ -1017,7 +1061,8 @@ smvsb_sgm (int device, int w, int h, const uint8_t* main_lum, int nw, int nh,
     if (rc != SMVSB_OK)
         g_last_error = smvsb::sgm_last_error();
     else
-        smvsb::g_launches += 3;     /* cost volume, 8-path aggregation, sum + WTA */
+        smvsb::count_device_launches(device, 3);   /* cost volume, 8-path
+                                           aggregation, sum + WTA */
     return rc;
 }
 

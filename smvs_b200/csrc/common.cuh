@@ -17,6 +17,7 @@
 
 #define SMVSB_MAX_SUBS 32          /* neighbours per reference view */
 #define SMVSB_NB_STRIDE 8          /* floats per packed neighbour texel */
+#define SMVSB_NUM_EVENTS 6
 
 /* Throws smvsb::Error (caught at the ABI boundary). */
 #define CUDA_CHECK(call)                                                     \
@@ -104,7 +105,7 @@ struct smvsb_ctx
 {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[SMVSB_NUM_EVENTS] = {};
     std::string last_error;
     uint64_t launches = 0;
     int num_sms = 0;
@@ -147,6 +148,8 @@ struct smvsb_ctx
 
     /* CG */
     smvsb::DevBuf<double> x, r, d, d2, z, Ad;
+    size_t x_count = 0;                 /* entries of x that belong to the
+                                           current surface (0 = none) */
     smvsb::DevBuf<double> cg_partials;
     smvsb::DevBuf<uint16_t> cg_rowmask; /* existing blocks per stencil row */
     smvsb::DevBuf<uint32_t> cg_row_list, cg_block_rows;
@@ -174,14 +177,25 @@ struct smvsb_ctx
 
 namespace smvsb {
 
-/* process-wide launch counter (smvsb_global_launch_count) */
+/* process-wide launch counters (smvsb_global_launch_count,
+ * smvsb_device_launch_count) */
+#define SMVSB_MAX_DEVICES 64
 extern std::atomic<uint64_t> g_launches;
+extern std::atomic<uint64_t> g_device_launches[SMVSB_MAX_DEVICES];
+
+inline void
+count_device_launches (int device, int n)
+{
+    g_launches += n;
+    if (device >= 0 && device < SMVSB_MAX_DEVICES)
+        g_device_launches[device] += n;
+}
 
 inline void
 count_launches (smvsb_ctx* c, int n)
 {
     c->launches += n;
-    g_launches += n;
+    count_device_launches(c->device, n);
 }
 
 inline SurfaceDev

@@ -271,8 +271,10 @@ render_kernel (SurfaceDev const sf, float* __restrict__ out, int normals)
     double const x = px + 0.5 - static_cast<double>(sf.w) / 2.0;
     double const y = py + 0.5 - static_cast<double>(sf.h) / 2.0;
     double nrm[3];
-    /* get_normal_map takes a float inv_flen, lib/surface.cc:170 */
-    fill_normal(x, y, sf.inv_flen, w, wx, wy, nrm);
+    /* get_normal_map takes a FLOAT inv_flen (lib/surface.cc:170-171): the
+     * caller's value is narrowed before it reaches fill_normal */
+    fill_normal(x, y, static_cast<double>(static_cast<float>(sf.inv_flen)),
+        w, wx, wy, nrm);
     out[pix * 3 + 0] = static_cast<float>(nrm[0]);
     out[pix * 3 + 1] = static_cast<float>(nrm[1]);
     out[pix * 3 + 2] = static_cast<float>(nrm[2]);
