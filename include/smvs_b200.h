@@ -35,6 +35,9 @@ extern "C" {
 
 typedef struct smvsb_ctx smvsb_ctx;
 
+/* Views (contexts) one smvsb_newton_loop_batch call can advance together. */
+#define SMVSB_MAX_BATCH 8
+
 typedef enum smvsb_status
 {
     SMVSB_OK = 0,
@@ -199,6 +202,25 @@ int smvsb_update_nodes (smvsb_ctx* ctx, double reproj_thresh, int full_opt,
 int smvsb_newton_loop (smvsb_ctx* ctx, const double* light16,
     double regularization, double light_surf_regularization, int max_steps,
     int full_opt, smvsb_newton_stats* stats);
+
+/*
+ * The inner Newton loops of `n` views (contexts of the SAME device, each with
+ * its own views and surface set) advanced in lock-step: per step the systems
+ * of all views that are still iterating are constructed, solved by ONE
+ * persistent PCG launch (every view with its own dot products and stopping
+ * decisions) and updated. A view leaves the batch when its own loop ends
+ * (lib/depth_optimizer.cc:219,267,284). The reference runs one view per pool
+ * thread (app/smvsrecon.cc:658-733); this is the same work for the views a
+ * GPU holds, with the per-iteration synchronisation cost of the PCG shared.
+ * Results per view are bitwise those of smvsb_newton_loop on that view.
+ *   light16   n pointers (each 16 doubles or NULL), or NULL for no lighting
+ *   stats     n entries; the ms_* fields hold the batch's device times
+ * n <= SMVSB_MAX_BATCH. All work runs on the stream of ctxs[0].
+ */
+int smvsb_newton_loop_batch (smvsb_ctx* const* ctxs, int n,
+    const double* const* light16, double regularization,
+    double light_surf_regularization, int max_steps, int full_opt,
+    smvsb_newton_stats* stats);
 
 /*
  * StereoView::set_scale (lib/stereo_view.cc:24-46, 97-188) for ONE view whose

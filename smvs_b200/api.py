@@ -25,7 +25,7 @@ EXPORTS = [
     "smvsb_get_normals", "smvsb_debug_get_system", "smvsb_debug_spmv",
     "smvsb_fit_lighting", "smvsb_sgm", "smvsb_visibility",
     "smvsb_cut_boundaries", "smvsb_get_surface_state", "smvsb_view_set_scale",
-    "smvsb_bilateral_filter", "smvsb_debug_expf", "smvsb_device_count", "smvsb_device_launch_count",
+    "smvsb_bilateral_filter", "smvsb_debug_expf", "smvsb_device_count", "smvsb_newton_loop_batch", "smvsb_device_launch_count",
 ]
 
 
@@ -336,6 +336,36 @@ class Context:
         comm = C.c_void_p(nccl_comm) if nccl_comm else None
         self._check(lib().smvsb_fit_lighting(self._h, _p(out), comm))
         return out
+
+
+def _stats_dict(st):
+    return dict(newton_steps=st.newton_steps, cg_iterations=st.cg_iterations,
+                nan=bool(st.nan_break), n_active=int(st.n_active),
+                pixel_iterations=float(st.pixel_iterations),
+                ms_construct=st.ms_construct, ms_solve=st.ms_solve,
+                ms_update=st.ms_update, ms_total=st.ms_total,
+                cg_block_iterations=st.cg_block_iterations,
+                cg_row_iterations=st.cg_row_iterations)
+
+
+def newton_loop_batch(ctxs, lights=None, regularization=0.01,
+                      light_surf_regularization=0.0, max_steps=200, full_opt=False):
+    """smvsb_newton_loop_batch: the inner Newton loops of several contexts of
+    one device in lock-step (one PCG launch per step for all of them).
+    Returns one stats dict per context; the ms_* fields are the batch's."""
+    n = len(ctxs)
+    handles = (C.c_void_p * n)(*[c._h for c in ctxs])
+    keep, lp = [], None
+    if lights is not None and any(l is not None for l in lights):
+        keep = [None if l is None else _f64(l) for l in lights]
+        lp = (C.c_void_p * n)(*[None if l is None else l.ctypes.data for l in keep])
+    st = (NewtonStats * n)()
+    rc = lib().smvsb_newton_loop_batch(handles, n, lp, C.c_double(regularization),
+                                       C.c_double(light_surf_regularization),
+                                       int(max_steps), int(full_opt), st)
+    if rc != 0:
+        raise SmvsbError(rc, lib().smvsb_last_error(ctxs[0]._h).decode())
+    return [_stats_dict(s) for s in st]
 
 
 def sgm(main_lum, neigh_lum, M, t, min_depth, max_depth, num_steps=128,

@@ -288,9 +288,11 @@ smvsb_create (int device, smvsb_ctx** out)
                 CUDA_CHECK(cudaEventCreate(&c->ev[i]));
             CUDA_CHECK(cudaDeviceGetAttribute(&c->num_sms,
                 cudaDevAttrMultiProcessorCount, device));
+            CUDA_CHECK(cudaMallocHost(&c->h_scalars, 32 * sizeof(double)));
         }
         catch (...)
         {
+            if (c->h_scalars) cudaFreeHost(c->h_scalars);
             delete c;
             throw;
         }
@@ -308,6 +310,7 @@ smvsb_destroy (smvsb_ctx* ctx)
     for (int i = 0; i < SMVSB_NUM_EVENTS; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     delete ctx;
 }
 
@@ -708,6 +711,148 @@ smvsb_update_nodes (smvsb_ctx* ctx, double reproj_thresh, int full_opt,
     });
 }
 
+/*
+ * The inner loop of DepthOptimizer::run_newton_iterations
+ * (lib/depth_optimizer.cc:204-304) for n views in lock-step; n = 1 is
+ * smvsb_newton_loop. All launches go to the lead context's stream.
+ */
+static void
+newton_loop_batch (smvsb_ctx* const* cs, int n, double const* const* light16,
+    double regularization, double light_surf_regularization, int max_steps,
+    int full_opt, smvsb_newton_stats* stats)
+{
+    smvsb_ctx* lead = cs[0];
+    /* every context of the batch works on the lead's stream for the duration
+     * of the call (its own stream is idle: all entry points synchronise) */
+    struct StreamSwap
+    {
+        smvsb_ctx* const* cs; int n; cudaStream_t saved[SMVSB_MAX_BATCH];
+        StreamSwap (smvsb_ctx* const* c, int k) : cs(c), n(k)
+        {
+            for (int i = 0; i < n; ++i)
+            {
+                saved[i] = cs[i]->stream;
+                cs[i]->stream = cs[0]->stream;
+            }
+        }
+        ~StreamSwap (void)
+        {
+            for (int i = n - 1; i >= 0; --i)
+                cs[i]->stream = saved[i];
+        }
+    } swap(cs, n);
+
+    smvsb_newton_stats st[SMVSB_MAX_BATCH];
+    uint64_t num_initial[SMVSB_MAX_BATCH], num_active[SMVSB_MAX_BATCH];
+    bool running[SMVSB_MAX_BATCH];
+    for (int k = 0; k < n; ++k)
+    {
+        smvsb_ctx* c = cs[k];
+        std::memset(&st[k], 0, sizeof(st[k]));
+        /* lib/depth_optimizer.cc:203-213 */
+        set_active(c, nullptr);
+        num_initial[k] = 0;
+        for (uint8_t v : c->h_node_valid) num_initial[k] += (v != 0);
+        num_active[k] = num_initial[k];
+        running[k] = true;
+    }
+
+    float ms = 0.f;
+    double ms_construct = 0, ms_solve = 0, ms_update = 0;
+    cudaEvent_t const ev_begin = lead->ev[4], ev_end = lead->ev[5];
+    CUDA_CHECK(cudaEventRecord(ev_begin, lead->stream));
+    for (;;)
+    {
+        /* lib/depth_optimizer.cc:219: the views whose loop goes on */
+        smvsb_ctx* act[SMVSB_MAX_BATCH];
+        int idx[SMVSB_MAX_BATCH];
+        int m = 0;
+        for (int k = 0; k < n; ++k)
+        {
+            running[k] = running[k] && st[k].newton_steps < max_steps
+                && num_active[k] > num_initial[k] / 20;
+            if (running[k])
+            {
+                act[m] = cs[k];
+                idx[m] = k;
+                m += 1;
+            }
+        }
+        if (m == 0)
+            break;
+
+        CUDA_CHECK(cudaEventRecord(lead->ev[0], lead->stream));
+        for (int j = 0; j < m; ++j)
+        {
+            st[idx[j]].newton_steps += 1;
+            smvsb::count_processed_enqueue(act[j]);
+            construct(act[j], light16 ? light16[idx[j]] : nullptr,
+                regularization, light_surf_regularization);
+        }
+        CUDA_CHECK(cudaEventRecord(lead->ev[1], lead->stream));
+        smvsb::cg_enqueue(act, m, 200, -1.0, 1e-3);
+        CUDA_CHECK(cudaEventRecord(lead->ev[2], lead->stream));
+        CUDA_CHECK(cudaStreamSynchronize(lead->stream));
+
+        int n_update = 0;
+        for (int j = 0; j < m; ++j)
+        {
+            smvsb_ctx* c = act[j];
+            smvsb_newton_stats& s = st[idx[j]];
+            double const samples = double(c->npos) * c->npos;
+            s.pixel_iterations += samples
+                * double(smvsb::count_processed_collect(c));
+            int iters = 0, info = 0;
+            bool x0_nan = false;
+            smvsb::cg_collect(c, &iters, &info, &x0_nan);
+            c->x_count = static_cast<size_t>(c->n_nodes) * 4;
+            s.cg_iterations += iters;
+            s.cg_block_iterations += double(c->cg_blocks) * iters;
+            s.cg_row_iterations += double(c->cg_rows) * iters;
+            if (x0_nan)     /* lib/depth_optimizer.cc:267 */
+            {
+                s.nan_break = 1;
+                running[idx[j]] = false;
+                continue;
+            }
+            smvsb::update_enqueue(c, 0.15, full_opt != 0);
+            n_update += 1;
+        }
+        CUDA_CHECK(cudaEventRecord(lead->ev[3], lead->stream));
+        CUDA_CHECK(cudaEventSynchronize(lead->ev[3]));
+        CUDA_CHECK(cudaEventElapsedTime(&ms, lead->ev[0], lead->ev[1]));
+        ms_construct += ms;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, lead->ev[1], lead->ev[2]));
+        ms_solve += ms;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, lead->ev[2], lead->ev[3]));
+        ms_update += ms;
+        for (int j = 0; j < m; ++j)
+        {
+            int const k = idx[j];
+            if (!running[k])
+                continue;
+            double mean_shift = 0.0;
+            smvsb::update_collect(act[j], &num_active[k], &mean_shift);
+            /* lib/depth_optimizer.cc:275-289 */
+            if (full_opt && mean_shift < 0.01)
+                running[k] = false;
+        }
+    }
+    CUDA_CHECK(cudaEventRecord(ev_end, lead->stream));
+    CUDA_CHECK(cudaEventSynchronize(ev_end));
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+    for (int k = 0; k < n; ++k)
+    {
+        st[k].ms_construct = ms_construct;
+        st[k].ms_solve = ms_solve;
+        st[k].ms_update = ms_update;
+        st[k].ms_total = ms;
+        st[k].n_active = num_active[k];
+        cs[k]->have_system = false;
+        if (stats) stats[k] = st[k];
+    }
+}
+
 int
 smvsb_newton_loop (smvsb_ctx* ctx, const double* light16,
     double regularization, double light_surf_regularization, int max_steps,
@@ -715,77 +860,44 @@ smvsb_newton_loop (smvsb_ctx* ctx, const double* light16,
 {
     if (ctx == nullptr) return SMVSB_ERR_INVALID;
     return guarded(ctx, [&]() {
-        smvsb_ctx* c = ctx;
-        require(c->have_views && c->have_surface, SMVSB_ERR_STATE,
+        require(ctx->have_views && ctx->have_surface, SMVSB_ERR_STATE,
             "views / surface not set");
-        smvsb_newton_stats st;
-        std::memset(&st, 0, sizeof(st));
+        smvsb_ctx* cs[1] = { ctx };
+        double const* lights[1] = { light16 };
+        newton_loop_batch(cs, 1, lights, regularization,
+            light_surf_regularization, max_steps, full_opt, stats);
+    });
+}
 
-        /* lib/depth_optimizer.cc:203-213 */
-        set_active(c, nullptr);
-        uint64_t num_initial = 0;
-        for (uint8_t v : c->h_node_valid) num_initial += (v != 0);
-        uint64_t num_active = num_initial;
-        double const samples = double(c->npos) * c->npos;
-
-        float ms = 0.f;
-        cudaEvent_t const ev_begin = c->ev[4], ev_end = c->ev[5];
-        CUDA_CHECK(cudaEventRecord(ev_begin, c->stream));
-        for (; st.newton_steps < max_steps && num_active > num_initial / 20;)
+int
+smvsb_newton_loop_batch (smvsb_ctx* const* ctxs, int n,
+    const double* const* light16, double regularization,
+    double light_surf_regularization, int max_steps, int full_opt,
+    smvsb_newton_stats* stats)
+{
+    if (ctxs == nullptr || n < 1 || ctxs[0] == nullptr)
+        return SMVSB_ERR_INVALID;
+    return guarded(ctxs[0], [&]() {
+        require(n <= SMVSB_MAX_BATCH, SMVSB_ERR_INVALID,
+            "batch larger than SMVSB_MAX_BATCH");
+        for (int k = 0; k < n; ++k)
         {
-            st.newton_steps += 1;
-            unsigned long long n_proc = 0;
-            smvsb::launch_count_processed(c, &n_proc);
-            st.pixel_iterations += samples * double(n_proc);
-
-            CUDA_CHECK(cudaEventRecord(c->ev[0], c->stream));
-            construct(c, light16, regularization, light_surf_regularization);
-            CUDA_CHECK(cudaEventRecord(c->ev[1], c->stream));
-
-            int iters = 0, info = 0;
-            bool x0_nan = false;
-            smvsb::run_cg(c, 200, -1.0, 1e-3, &iters, &info, &x0_nan);
-            c->x_count = static_cast<size_t>(c->n_nodes) * 4;
-            CUDA_CHECK(cudaEventRecord(c->ev[2], c->stream));
-            st.cg_iterations += iters;
-            st.cg_block_iterations += double(c->cg_blocks) * iters;
-            st.cg_row_iterations += double(c->cg_rows) * iters;
-            if (x0_nan)     /* lib/depth_optimizer.cc:267 */
-            {
-                st.nan_break = 1;
-                CUDA_CHECK(cudaEventSynchronize(c->ev[2]));
-                CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
-                st.ms_construct += ms;
-                CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]));
-                st.ms_solve += ms;
-                break;
-            }
-            double mean_shift = 0.0;
-            smvsb::launch_update(c, 0.15, full_opt != 0, &num_active,
-                &mean_shift);
-            CUDA_CHECK(cudaEventRecord(c->ev[3], c->stream));
-            CUDA_CHECK(cudaEventSynchronize(c->ev[3]));
-            CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
-            st.ms_construct += ms;
-            CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]));
-            st.ms_solve += ms;
-            CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
-            st.ms_update += ms;
-            if (full_opt)
-            {
-                /* lib/depth_optimizer.cc:275-289 */
-                if (mean_shift < 0.01)
-                    break;
-                continue;
-            }
+            require(ctxs[k] != nullptr, SMVSB_ERR_INVALID, "NULL context");
+            require(ctxs[k]->device == ctxs[0]->device, SMVSB_ERR_INVALID,
+                "the contexts of a batch must live on one device");
+            for (int j = 0; j < k; ++j)
+                require(ctxs[j] != ctxs[k], SMVSB_ERR_INVALID,
+                    "a context appears twice in the batch");
+            require(ctxs[k]->have_views && ctxs[k]->have_surface,
+                SMVSB_ERR_STATE, "views / surface not set");
+            if (light16 != nullptr && light16[k] != nullptr)
+                require(ctxs[k]->have_shading, SMVSB_ERR_STATE,
+                    "lighting given but the main view has no shading image");
+            /* pending work of the context's own stream */
+            CUDA_CHECK(cudaStreamSynchronize(ctxs[k]->stream));
         }
-        CUDA_CHECK(cudaEventRecord(ev_end, c->stream));
-        CUDA_CHECK(cudaEventSynchronize(ev_end));
-        CUDA_CHECK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
-        st.ms_total = ms;
-        st.n_active = num_active;
-        c->have_system = false;
-        if (stats) *stats = st;
+        newton_loop_batch(ctxs, n, light16, regularization,
+            light_surf_regularization, max_steps, full_opt, stats);
     });
 }
 

@@ -1,7 +1,9 @@
 /*
  * cg.cu -- ConjugateGradient::solve (lib/conjugate_gradient.h:72-202) with
  * BlockSparseMatrix<4>::multiply (lib/block_sparse_matrix.h:276-298) and the
- * SSEVector updates (lib/sse_vector.cc) as ONE persistent kernel.
+ * SSEVector updates (lib/sse_vector.cc) as ONE persistent kernel -- for one
+ * view, or for several independent views (one system each) in the same
+ * launch.
  *
  * The Hessian lives in a fixed 3x3-stencil block row format
  * H[node][9][4][4] (a node couples only to its 8 grid neighbours), the
@@ -20,6 +22,23 @@
  * neighbours), the block-diagonal preconditioner into the residual update
  * (quad shuffles).
  *
+ * All three phases (initialisation, SpMV, vector update) walk the compacted
+ * list of the system's block rows (the nodes that are valid and active,
+ * lib/gauss_newton_step.cc:91-105), so a system that has shrunk to 10 % of
+ * the grid costs 10 % of the vector traffic as well.
+ *
+ * Several views per launch (smvsb_newton_loop_batch; the reference runs one
+ * view per pool thread, app/smvsrecon.cc:658-733): what an iteration costs
+ * besides the Hessian stream is two grid-wide synchronisations, a fixed
+ * ~6 us whatever the system size. With V views in one launch every CTA
+ * works through "its" rows of view 0, then of view 1, ... between two
+ * barriers, so the fixed cost is paid once per V views. CTA b handles of
+ * every view exactly the rows it would handle in a launch of its own, the
+ * per-view partial sums are kept apart and re-summed in the same order, and
+ * every view takes its stopping decisions for itself: the result of a view
+ * is bitwise the one of a single-view launch. Views that have converged are
+ * skipped.
+ *
  * Measured and NOT kept (1920x1080 scale 2, B200): parking what only the
  * owning thread touches (x, r, A d, its row of P) in shared memory for the
  * whole solve. It shortens the vector-update phase (5.1 -> 3.9 us) but every
@@ -34,7 +53,9 @@
  * issued while HBM idles in the vector-update phase: the SpMV gains 1.3 us,
  * the update phase and the barriers lose more.
  */
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -43,30 +64,52 @@ namespace smvsb {
 namespace {
 
 constexpr int CG_THREADS = 256;
+constexpr int CG_WARPS = CG_THREADS / 32;
+constexpr int CG_QUADS = CG_THREADS / 4;     /* block rows per CTA and pass */
 constexpr int CG_MAX_BLOCKS = 1024;
-constexpr int CG_UF = 4;          /* entries per thread in flight, update phase */
+constexpr int CG_UF = 4;          /* rows per thread in flight, update phase */
+constexpr int CG_SLOTS = 10;      /* partial-sum slots per view */
 
-struct CgArgs
+/* One view's system and vectors. */
+struct CgView
 {
-    int n_nodes, npx, npy;
-    int max_iter;
+    int n_nodes, npx;
+    int grid;                /* CTAs that work on this view: min(launch grid,
+                                ceil(4 n_nodes / 256)) -- what a launch of its
+                                own would use */
+    int pad;
     double err_tol;          /* < 0: 0.01 * ||g|| (lib/depth_optimizer.cc:247) */
-    double q_tol;
     double const* H;
     double const* P;
     double const* g;         /* b = -g (lib/depth_optimizer.cc:251) */
     uint16_t const* rowmask; /* bit k: block k of the node's row exists */
     uint32_t const* rows;    /* nodes with a non-empty row, ascending */
     unsigned long long const* counts;   /* [0] blocks, [1] rows of the system */
-    double* x;
+    double* x;               /* zeroed by the host before the launch */
     double* r;
     double* d;               /* search direction, double buffered */
     double* d2;
     double* Ad;
     double* z;
-    double* partials;        /* [slot][CG_MAX_BLOCKS] */
+    double* partials;        /* [CG_SLOTS][CG_MAX_BLOCKS] */
+    double* result;          /* [0] iterations, [1] info, [2] isnan(x[0]),
+                                [4..7] phase times in ns (timing build) */
+};
+
+struct CgArgs
+{
+    int n_views;
+    int max_iter;
+    double q_tol;
     unsigned int* sync;      /* barrier counter */
-    double* result;          /* [0] iterations, [1] info, [2] isnan(x[0]) */
+    CgView v[SMVSB_MAX_BATCH];
+};
+
+/* Per-view scalars of the iteration, identical in every CTA. */
+struct CgState
+{
+    double r_dot_r, Q0, beta, alpha, tol;
+    int n_rows, passes, done, iters, info;
 };
 
 __device__ __forceinline__ void
@@ -93,9 +136,12 @@ grid_barrier (unsigned int* counter, unsigned int& epoch)
     __syncthreads();
 }
 
+template <bool TIMING>
 __device__ __forceinline__ unsigned long long
 now_ns (void)
 {
+    if (!TIMING)
+        return 0;
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
@@ -142,52 +188,72 @@ policy_evict_last (void)
     return pol;
 }
 
-/* Sums of NV values over the block, each in a fixed order (warp shuffle
- * tree, then the warps' results left to right); valid in thread 0. */
+/*
+ * Block-wide sums in two stages, each in a fixed order. Stage 1 (flush, once
+ * per view and phase): shuffle tree inside every warp, lane 0 parks the
+ * warp's value in shared memory. Stage 2 (publish, once per phase): after a
+ * __syncthreads one thread per (view, value) adds the warps' results left to
+ * right and writes the CTA's partial sum for that view.
+ */
 template <int NV>
 __device__ __forceinline__ void
-block_sums (double (&v)[NV], double* s_red)
+warp_flush (double (&v)[NV], double* s_red, int view)
 {
 #pragma unroll
     for (int j = 0; j < NV; ++j)
         for (int off = 16; off > 0; off >>= 1)
             v[j] += __shfl_down_sync(0xffffffffu, v[j], off);
-    int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0)
+    if ((threadIdx.x & 31) == 0)
     {
 #pragma unroll
         for (int j = 0; j < NV; ++j)
-            s_red[j * (CG_THREADS / 32) + warp] = v[j];
+            s_red[(view * 3 + j) * CG_WARPS + (threadIdx.x >> 5)] = v[j];
     }
+}
+
+template <int NV>
+__device__ __forceinline__ void
+publish (CgArgs const& a, CgState const* s_state, double const* s_red,
+    int first_slot, bool init)
+{
     __syncthreads();
-    if (threadIdx.x == 0)
+    int const t = threadIdx.x;
+    if (t < a.n_views * NV)
     {
-#pragma unroll
-        for (int j = 0; j < NV; ++j)
+        int const view = t / NV, j = t % NV;
+        CgView const& V = a.v[view];
+        if (static_cast<int>(blockIdx.x) < V.grid
+            && (init || !s_state[view].done))
         {
+            /* a view without rows was never flushed */
             double total = 0.0;
-            for (int i = 0; i < CG_THREADS / 32; ++i)
-                total += s_red[j * (CG_THREADS / 32) + i];
-            v[j] = total;
+            if (s_state[view].passes > 0)
+                for (int i = 0; i < CG_WARPS; ++i)
+                    total += s_red[(view * 3 + j) * CG_WARPS + i];
+            V.partials[(first_slot + j) * CG_MAX_BLOCKS + blockIdx.x] = total;
         }
     }
 }
 
-/* Every block sums all per-block partials of slots first .. first+NV-1 in
- * the same order: warp j takes slot first+j, lane l adds partials l, l+32,
- * ... in sequence (loads issued in batches ahead of the adds), then the
- * shuffle tree. Results in s_bcast[0..NV-1], valid for all threads. */
+/* Every CTA sums, per view, the partials of slots first .. first+NV-1 of all
+ * the view's CTAs in the same order: one warp per (view, slot), lane l adds
+ * partials l, l+32, ... in sequence (loads issued in batches ahead of the
+ * adds), then the shuffle tree. Results in s_bcast[view * 3 + j]. */
 template <int NV>
 __device__ __forceinline__ void
-all_sums (double const* partials, int first, double* s_bcast)
+all_sums (CgArgs const& a, CgState const* s_state, int first_slot,
+    double* s_bcast, bool init)
 {
     __syncthreads();
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp < NV)
+    for (int pair = warp; pair < a.n_views * NV; pair += CG_WARPS)
     {
-        double const* p = partials + (first + warp) * CG_MAX_BLOCKS;
-        int const nb = gridDim.x;
+        int const view = pair / NV, j = pair % NV;
+        if (!init && s_state[view].done)
+            continue;
+        CgView const& V = a.v[view];
+        double const* p = V.partials + (first_slot + j) * CG_MAX_BLOCKS;
+        int const nb = V.grid;
         double v = 0.0;
         for (int base = lane; base < nb; base += 32 * 8)
         {
@@ -203,7 +269,7 @@ all_sums (double const* partials, int first, double* s_bcast)
         for (int off = 16; off > 0; off >>= 1)
             v += __shfl_down_sync(0xffffffffu, v, off);
         if (lane == 0)
-            s_bcast[warp] = v;
+            s_bcast[view * 3 + j] = v;
     }
     __syncthreads();
 }
@@ -211,7 +277,7 @@ all_sums (double const* partials, int first, double* s_bcast)
 /*
  * Plain (weak, L1-cached) loads are correct for the vectors other CTAs wrote
  * in the previous phase: the grid barrier is a release (fence + atomic) /
- * acquire (ld.acquire.gpu + fence) pair extended to the CTA by bar.sync, so
+ * acquire (relaxed polls + fence) pair extended to the CTA by bar.sync, so
  * causality order covers them, and the gpu-scope fence after the spin drops
  * the SM's L1 lines. Each vector entry is used by up to nine rows, most of
  * them in the same CTA pass: L1 serves the re-use instead of L2.
@@ -255,12 +321,11 @@ struct DirVec
  * lib/block_sparse_matrix.h:283-296). own[] receives v[node]. */
 template <typename VecOp>
 __device__ __forceinline__ double
-spmv_row (CgArgs const& a, VecOp const& vec, int node, int rp,
-    unsigned int mask, double* own)
+spmv_row (double const* __restrict__ H, int ns, VecOp const& vec, int node,
+    int rp, unsigned int mask, double* own)
 {
-    int const ns = a.npx + 1;
     int const ix = node % ns, iy = node / ns;
-    double const* hrow = a.H + static_cast<size_t>(node) * 144 + rp * 4;
+    double const* hrow = H + static_cast<size_t>(node) * 144 + rp * 4;
     double acc = 0.0;
     own[0] = 0.0; own[1] = 0.0; own[2] = 0.0; own[3] = 0.0;
     /* The reference drops the rows and columns of inactive nodes
@@ -294,215 +359,329 @@ spmv_row (CgArgs const& a, VecOp const& vec, int node, int rp,
     return acc;
 }
 
+/* The passes a CTA makes between two barriers, over all views: (view, pass)
+ * pairs in ascending order, skipping the views this CTA has no share in and
+ * the ones that have converged. view == n_views: end. */
+struct PassIter
+{
+    int view, pass;
+};
+
+__device__ __forceinline__ void
+pass_next (CgArgs const& a, CgState const* s_state, bool init, int step,
+    PassIter& it)
+{
+    if (it.view >= 0 && it.view < a.n_views)
+    {
+        it.pass += step;
+        if (it.pass < s_state[it.view].passes)
+            return;
+    }
+    it.pass = 0;
+    for (it.view += 1; it.view < a.n_views; ++it.view)
+    {
+        if (static_cast<int>(blockIdx.x) >= a.v[it.view].grid)
+            continue;
+        if (!init && s_state[it.view].done)
+            continue;
+        if (s_state[it.view].passes > 0)
+            return;
+    }
+}
+
+/* The row this thread's quad handles in pass `it`: node index or -1. */
+__device__ __forceinline__ int
+pass_row (CgArgs const& a, CgState const* s_state, PassIter const& it,
+    int pass_offset)
+{
+    if (it.view >= a.n_views)
+        return -1;
+    CgView const& V = a.v[it.view];
+    int const q = (it.pass + pass_offset) * (V.grid * CG_QUADS)
+        + blockIdx.x * CG_QUADS + (threadIdx.x >> 2);
+    if (q >= s_state[it.view].n_rows)
+        return -1;
+    return static_cast<int>(V.rows[q]);
+}
+
 /* 2 CTAs / SM: measured faster than 3 at 80 registers (fewer loads hoisted,
  * more barrier participants). */
+template <bool TIMING>
 __global__ void __launch_bounds__(CG_THREADS, 2)
 cg_kernel (CgArgs const a)
 {
     unsigned long long const keep = policy_evict_last();
-    __shared__ double s_red[3 * CG_THREADS / 32];
-    __shared__ double s_bcast[3];
+    __shared__ double s_red[SMVSB_MAX_BATCH * 3 * CG_WARPS];
+    __shared__ double s_bcast[SMVSB_MAX_BATCH * 3];
+    __shared__ CgState s_state[SMVSB_MAX_BATCH];
     unsigned int epoch = 0;
-    int const n = a.n_nodes * 4;
-    int const stride = gridDim.x * CG_THREADS;
-    int const t0 = blockIdx.x * CG_THREADS + threadIdx.x;
     int const quad = threadIdx.x & 28;      /* first lane of the node's quad */
     int const rp = threadIdx.x & 3;
-    /* bound rounded up: whole warps iterate together (shuffles below) */
-    int const n_round = ((n + CG_UF * stride - 1) / (CG_UF * stride))
-        * (CG_UF * stride);
 
-    /* r = b = -g; x = 0; z = P r; r_dot_r = z.r; ||g||^2
+    if (threadIdx.x < a.n_views)
+    {
+        CgView const& V = a.v[threadIdx.x];
+        CgState& S = s_state[threadIdx.x];
+        S.n_rows = static_cast<int>(V.counts[1]);
+        int const per_pass = V.grid * CG_QUADS;
+        int const passes = (S.n_rows + per_pass - 1) / per_pass;
+        S.passes = ((passes + CG_UF - 1) / CG_UF) * CG_UF;
+        S.done = 0; S.iters = 0; S.info = SMVSB_CG_MAX_ITERATIONS;
+        S.r_dot_r = 0.0; S.Q0 = 0.0; S.beta = 0.0; S.alpha = 0.0; S.tol = 0.0;
+    }
+    __syncthreads();
+
+    /* r = b = -g; x = 0 (host memset); z = P r; r_dot_r = z.r; ||g||^2
      * (lib/conjugate_gradient.h:85-117). d_old = 0 with beta = 0 makes the
      * first direction d = z. P is block diagonal: the four threads of a node
      * exchange their r entries by shuffle. */
-    double p_zr = 0.0, p_gg = 0.0;
-    for (int i = t0; i < n_round; i += stride)
     {
-        bool const ok = i < n;
-        double const gi = ok ? a.g[i] : 0.0;
-        double const ri = -gi;
-        double const r0 = __shfl_sync(0xffffffffu, ri, quad);
-        double const r1 = __shfl_sync(0xffffffffu, ri, quad + 1);
-        double const r2 = __shfl_sync(0xffffffffu, ri, quad + 2);
-        double const r3 = __shfl_sync(0xffffffffu, ri, quad + 3);
-        if (!ok)
-            continue;
-        double const* prow = a.P + static_cast<size_t>(i >> 2) * 16 + rp * 4;
-        double2 const p01 = *reinterpret_cast<double2 const*>(prow);
-        double2 const p23 = *reinterpret_cast<double2 const*>(prow + 2);
-        double const zi = p01.x * r0 + p01.y * r1 + p23.x * r2 + p23.y * r3;
-        a.r[i] = ri;
-        a.x[i] = 0.0;
-        a.z[i] = zi;
-        a.d[i] = 0.0;
-        a.d2[i] = 0.0;      /* rows outside the system are never written again */
-        a.Ad[i] = 0.0;
-        p_gg += gi * gi;
-        p_zr += zi * ri;
-    }
-    {
-        double v[2] = { p_zr, p_gg };
-        block_sums<2>(v, s_red);
-        if (threadIdx.x == 0)
+        PassIter it; it.view = -1; it.pass = 0;
+        pass_next(a, s_state, true, 1, it);
+        double acc[2] = { 0.0, 0.0 };       /* z.r, g.g */
+        while (it.view < a.n_views)
         {
-            a.partials[0 * CG_MAX_BLOCKS + blockIdx.x] = v[0];
-            a.partials[1 * CG_MAX_BLOCKS + blockIdx.x] = v[1];
+            CgView const& V = a.v[it.view];
+            int const node = pass_row(a, s_state, it, 0);
+            bool const ok = node >= 0;
+            size_t const i = static_cast<size_t>(ok ? node : 0) * 4 + rp;
+            double const gi = ok ? V.g[i] : 0.0;
+            double const ri = -gi;
+            double const r0 = __shfl_sync(0xffffffffu, ri, quad);
+            double const r1 = __shfl_sync(0xffffffffu, ri, quad + 1);
+            double const r2 = __shfl_sync(0xffffffffu, ri, quad + 2);
+            double const r3 = __shfl_sync(0xffffffffu, ri, quad + 3);
+            if (ok)
+            {
+                double const* prow = V.P + static_cast<size_t>(node) * 16
+                    + rp * 4;
+                double2 const p01 = *reinterpret_cast<double2 const*>(prow);
+                double2 const p23 = *reinterpret_cast<double2 const*>(prow + 2);
+                double const zi = p01.x * r0 + p01.y * r1 + p23.x * r2
+                    + p23.y * r3;
+                V.r[i] = ri;
+                V.z[i] = zi;
+                V.d[i] = 0.0;
+                V.d2[i] = 0.0;
+                V.Ad[i] = 0.0;
+                acc[1] += gi * gi;
+                acc[0] += zi * ri;
+            }
+            int const view = it.view;
+            pass_next(a, s_state, true, 1, it);
+            if (it.view != view)
+            {
+                warp_flush<2>(acc, s_red, view);
+                acc[0] = 0.0; acc[1] = 0.0;
+            }
         }
+        publish<2>(a, s_state, s_red, 0, true);
     }
     grid_barrier(a.sync, epoch);
-    all_sums<2>(a.partials, 0, s_bcast);
-    double r_dot_r = s_bcast[0];
-    double const gg = s_bcast[1];
-    double const tol = (a.err_tol < 0.0) ? sqrt(gg) * 0.01 : a.err_tol;
-    double Q0 = 0.0;     /* -x.(b + r) with x = 0 */
-    double beta = 0.0;
-    double* d_old = a.d;
-    double* d_new = a.d2;
+    all_sums<2>(a, s_state, 0, s_bcast, true);
+    if (threadIdx.x < a.n_views)
+    {
+        CgState& S = s_state[threadIdx.x];
+        S.r_dot_r = s_bcast[threadIdx.x * 3 + 0];
+        double const gg = s_bcast[threadIdx.x * 3 + 1];
+        double const et = a.v[threadIdx.x].err_tol;
+        S.tol = (et < 0.0) ? sqrt(gg) * 0.01 : et;
+    }
+    __syncthreads();
 
-    /* the masks do not change during a solve: the first pass's is fetched
-     * once, the others one pass ahead */
-    int const n_rows = static_cast<int>(a.counts[1]);
-    int const quad0 = t0 >> 2, quads = stride >> 2;
-    int const node_first = (quad0 < n_rows) ? static_cast<int>(a.rows[quad0])
-        : 0;
-    unsigned int const mask_first = (quad0 < n_rows) ? a.rowmask[node_first]
-        : 0u;
     int iter = 1;
-    int info = SMVSB_CG_MAX_ITERATIONS;
     unsigned long long tm[4] = {0, 0, 0, 0};
     for (; iter < a.max_iter; ++iter)
     {
-        unsigned long long const t_a = now_ns();
+        unsigned long long const t_a = now_ns<TIMING>();
+        /* the direction is double buffered; all views swap in lock-step */
+        bool const odd = (iter & 1) != 0;
+        int const slot = 2 + 4 * (iter & 1);
+
         /* d = z + beta d_old (:192-198 of the previous iteration);
          * Ad = A d; alpha = r_dot_r / d.Ad (:126-127) */
-        DirVec dir;
-        dir.z = a.z; dir.d_old = d_old; dir.beta = beta;
-        double p_dAd = 0.0;
-        unsigned int mask = mask_first;
-        int node = node_first;
-        for (int q = quad0; q < n_rows; q += quads)
         {
-            /* next pass's row and mask travel while this pass streams */
-            int const qn = q + quads;
-            int const node_next = (qn < n_rows) ? static_cast<int>(a.rows[qn])
-                : 0;
-            unsigned int const mask_next = (qn < n_rows)
-                ? a.rowmask[node_next] : 0u;
-            double own[4];
-            int const i = node * 4 + rp;
-            double const v = spmv_row(a, dir, node, rp, mask, own);
-            node = node_next;
-            mask = mask_next;
-            double const di = (rp == 0) ? own[0] : (rp == 1) ? own[1]
-                : (rp == 2) ? own[2] : own[3];
-            a.Ad[i] = v;
-            d_new[i] = di;
-            p_dAd += v * di;
+            PassIter it; it.view = -1; it.pass = 0;
+            pass_next(a, s_state, false, 1, it);
+            /* the row and its mask travel one pass ahead of the stream */
+            int node = pass_row(a, s_state, it, 0);
+            unsigned int mask = (node >= 0)
+                ? a.v[it.view].rowmask[node] : 0u;
+            double acc[1] = { 0.0 };
+            while (it.view < a.n_views)
+            {
+                PassIter nx = it;
+                pass_next(a, s_state, false, 1, nx);
+                int const node_next = pass_row(a, s_state, nx, 0);
+                unsigned int const mask_next = (node_next >= 0)
+                    ? a.v[nx.view].rowmask[node_next] : 0u;
+                if (node >= 0)
+                {
+                    CgView const& V = a.v[it.view];
+                    DirVec dir;
+                    dir.z = V.z;
+                    dir.d_old = odd ? V.d : V.d2;
+                    dir.beta = s_state[it.view].beta;
+                    double own[4];
+                    double const v = spmv_row(V.H, V.npx + 1, dir, node, rp,
+                        mask, own);
+                    double const di = (rp == 0) ? own[0] : (rp == 1) ? own[1]
+                        : (rp == 2) ? own[2] : own[3];
+                    size_t const i = static_cast<size_t>(node) * 4 + rp;
+                    V.Ad[i] = v;
+                    (odd ? V.d2 : V.d)[i] = di;
+                    acc[0] += v * di;
+                }
+                if (nx.view != it.view)
+                {
+                    warp_flush<1>(acc, s_red, it.view);
+                    acc[0] = 0.0;
+                }
+                it = nx; node = node_next; mask = mask_next;
+            }
+            publish<1>(a, s_state, s_red, slot, false);
         }
-        int const slot = 2 + 4 * (iter & 1);
-        {
-            double v[1] = { p_dAd };
-            block_sums<1>(v, s_red);
-            if (threadIdx.x == 0)
-                a.partials[slot * CG_MAX_BLOCKS + blockIdx.x] = v[0];
-        }
-        unsigned long long const t_b = now_ns();
+        unsigned long long const t_b = now_ns<TIMING>();
         grid_barrier(a.sync, epoch);
-        unsigned long long const t_c = now_ns();
-        tm[0] += t_b - t_a; tm[1] += t_c - t_b;
-        all_sums<1>(a.partials, slot, s_bcast);
-        double const dAd = s_bcast[0];
-        double const alpha = r_dot_r / dAd;
+        unsigned long long const t_c = now_ns<TIMING>();
+        all_sums<1>(a, s_state, slot, s_bcast, false);
+        if (threadIdx.x < a.n_views && !s_state[threadIdx.x].done)
+            s_state[threadIdx.x].alpha = s_state[threadIdx.x].r_dot_r
+                / s_bcast[threadIdx.x * 3];
+        __syncthreads();
 
         /* x += alpha d; r -= alpha Ad; r.r; Q1 = -x.(b + r); z = P r; z.r
          * (:130-181) */
-        double p_rr = 0.0, p_q = 0.0, p_zr2 = 0.0;
-        /* CG_UF entries per thread in flight: the pass is latency bound */
-        for (int i0 = t0; i0 < n_round; i0 += CG_UF * stride)
         {
-            double xv[CG_UF], rv[CG_UF], gv[CG_UF];
-            double2 p01[CG_UF], p23[CG_UF];
+            PassIter it; it.view = -1; it.pass = 0;
+            pass_next(a, s_state, false, CG_UF, it);
+            double acc[3] = { 0.0, 0.0, 0.0 };    /* r.r, x.(r - g), z.r */
+            int nodes[CG_UF];
 #pragma unroll
             for (int u = 0; u < CG_UF; ++u)
+                nodes[u] = pass_row(a, s_state, it, u);
+            /* CG_UF rows per thread in flight: the pass is latency bound */
+            while (it.view < a.n_views)
             {
-                int const i = i0 + u * stride;
-                xv[u] = 0.0; rv[u] = 0.0; gv[u] = 0.0;
-                p01[u] = make_double2(0, 0); p23[u] = p01[u];
-                if (i < n)
-                {
-                    double const dn = d_new[i], ad = a.Ad[i];
-                    gv[u] = a.g[i];
-                    xv[u] = a.x[i]; rv[u] = a.r[i];
-                    double const* prow = a.P + static_cast<size_t>(i >> 2) * 16
-                        + rp * 4;
-                    p01[u] = ld_hint(prow, keep);
-                    p23[u] = ld_hint(prow + 2, keep);
-                    xv[u] += dn * alpha; rv[u] -= ad * alpha;
-                }
-            }
+                CgView const& V = a.v[it.view];
+                double const alpha = s_state[it.view].alpha;
+                double const* d_new = odd ? V.d2 : V.d;
+                PassIter nx = it;
+                pass_next(a, s_state, false, CG_UF, nx);
+                int nodes_next[CG_UF];
 #pragma unroll
-            for (int u = 0; u < CG_UF; ++u)
-            {
-                int const i = i0 + u * stride;
-                double const q0 = __shfl_sync(0xffffffffu, rv[u], quad);
-                double const q1 = __shfl_sync(0xffffffffu, rv[u], quad + 1);
-                double const q2 = __shfl_sync(0xffffffffu, rv[u], quad + 2);
-                double const q3 = __shfl_sync(0xffffffffu, rv[u], quad + 3);
-                if (i < n)
-                {
-                    double const zi = p01[u].x * q0 + p01[u].y * q1
-                        + p23[u].x * q2 + p23[u].y * q3;
-                    a.x[i] = xv[u]; a.r[i] = rv[u];
-                    a.z[i] = zi;
-                    p_rr += rv[u] * rv[u];
-                    p_q += xv[u] * (rv[u] - gv[u]);
-                    p_zr2 += zi * rv[u];
-                }
-            }
-        }
-        {
-            double v[3] = { p_rr, p_q, p_zr2 };
-            block_sums<3>(v, s_red);
-            if (threadIdx.x == 0)
-            {
-                a.partials[(slot + 1) * CG_MAX_BLOCKS + blockIdx.x] = v[0];
-                a.partials[(slot + 2) * CG_MAX_BLOCKS + blockIdx.x] = v[1];
-                a.partials[(slot + 3) * CG_MAX_BLOCKS + blockIdx.x] = v[2];
-            }
-        }
-        unsigned long long const t_d = now_ns();
-        grid_barrier(a.sync, epoch);
-        all_sums<3>(a.partials, slot + 1, s_bcast);
-        tm[2] += t_d - t_c; tm[3] += now_ns() - t_d;
-        double const new_rr = s_bcast[0];
-        double const xbr = s_bcast[1];
-        double const new_zr = s_bcast[2];
+                for (int u = 0; u < CG_UF; ++u)
+                    nodes_next[u] = pass_row(a, s_state, nx, u);
 
-        if (new_rr < tol)
-        {
-            info = SMVSB_CG_CONVERGENCE;
-            break;
+                double xv[CG_UF], rv[CG_UF], gv[CG_UF];
+                double2 p01[CG_UF], p23[CG_UF];
+#pragma unroll
+                for (int u = 0; u < CG_UF; ++u)
+                {
+                    xv[u] = 0.0; rv[u] = 0.0; gv[u] = 0.0;
+                    p01[u] = make_double2(0, 0); p23[u] = p01[u];
+                    if (nodes[u] >= 0)
+                    {
+                        size_t const i = static_cast<size_t>(nodes[u]) * 4 + rp;
+                        double const dn = d_new[i], ad = V.Ad[i];
+                        gv[u] = V.g[i];
+                        xv[u] = V.x[i]; rv[u] = V.r[i];
+                        double const* prow = V.P
+                            + static_cast<size_t>(nodes[u]) * 16 + rp * 4;
+                        p01[u] = ld_hint(prow, keep);
+                        p23[u] = ld_hint(prow + 2, keep);
+                        xv[u] += dn * alpha; rv[u] -= ad * alpha;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < CG_UF; ++u)
+                {
+                    double const q0 = __shfl_sync(0xffffffffu, rv[u], quad);
+                    double const q1 = __shfl_sync(0xffffffffu, rv[u], quad + 1);
+                    double const q2 = __shfl_sync(0xffffffffu, rv[u], quad + 2);
+                    double const q3 = __shfl_sync(0xffffffffu, rv[u], quad + 3);
+                    if (nodes[u] >= 0)
+                    {
+                        size_t const i = static_cast<size_t>(nodes[u]) * 4 + rp;
+                        double const zi = p01[u].x * q0 + p01[u].y * q1
+                            + p23[u].x * q2 + p23[u].y * q3;
+                        V.x[i] = xv[u]; V.r[i] = rv[u];
+                        V.z[i] = zi;
+                        acc[0] += rv[u] * rv[u];
+                        acc[1] += xv[u] * (rv[u] - gv[u]);
+                        acc[2] += zi * rv[u];
+                    }
+                }
+                if (nx.view != it.view)
+                {
+                    warp_flush<3>(acc, s_red, it.view);
+                    acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0;
+                }
+                it = nx;
+#pragma unroll
+                for (int u = 0; u < CG_UF; ++u)
+                    nodes[u] = nodes_next[u];
+            }
+            publish<3>(a, s_state, s_red, slot + 1, false);
         }
-        double const Q1 = -1.0 * xbr;
-        double const zeta = iter * (Q1 - Q0) / Q1;
-        if (zeta < a.q_tol)
+        unsigned long long const t_d = now_ns<TIMING>();
+        grid_barrier(a.sync, epoch);
+        all_sums<3>(a, s_state, slot + 1, s_bcast, false);
+        if (TIMING)
         {
-            info = SMVSB_CG_CONVERGENCE;
-            break;
+            tm[0] += t_b - t_a; tm[1] += t_c - t_b;
+            tm[2] += t_d - t_c; tm[3] += now_ns<TIMING>() - t_d;
         }
-        Q0 = Q1;
-        beta = new_zr / r_dot_r;
-        r_dot_r = new_zr;
-        double* const tmp = d_old; d_old = d_new; d_new = tmp;
+
+        /* the reference's two stopping tests, per view (:139, :170-176) */
+        if (threadIdx.x < a.n_views && !s_state[threadIdx.x].done)
+        {
+            CgState& S = s_state[threadIdx.x];
+            double const new_rr = s_bcast[threadIdx.x * 3 + 0];
+            double const xbr = s_bcast[threadIdx.x * 3 + 1];
+            double const new_zr = s_bcast[threadIdx.x * 3 + 2];
+            bool stop = false;
+            if (new_rr < S.tol)
+                stop = true;
+            else
+            {
+                double const Q1 = -1.0 * xbr;
+                double const zeta = iter * (Q1 - S.Q0) / Q1;
+                if (zeta < a.q_tol)
+                    stop = true;
+                else
+                {
+                    S.Q0 = Q1;
+                    S.beta = new_zr / S.r_dot_r;
+                    S.r_dot_r = new_zr;
+                }
+            }
+            if (stop)
+            {
+                S.done = 1;
+                S.iters = iter;
+                S.info = SMVSB_CG_CONVERGENCE;
+            }
+        }
+        __syncthreads();
+        bool all_done = true;
+        for (int v = 0; v < a.n_views; ++v)
+            all_done = all_done && (s_state[v].done != 0);
+        if (all_done)
+            break;
     }
 
-    if (blockIdx.x == 0 && threadIdx.x == 0)
+    if (blockIdx.x == 0 && threadIdx.x < a.n_views)
     {
-        a.result[0] = iter;
-        a.result[1] = info;
+        CgState const& S = s_state[threadIdx.x];
+        double* res = a.v[threadIdx.x].result;
+        res[0] = S.done ? S.iters : iter;
+        res[1] = S.info;
+        /* lib/depth_optimizer.cc:267 looks at the first entry of the solution;
+         * the final barrier has made every CTA's x visible */
+        res[2] = isnan(__ldcg(a.v[threadIdx.x].x)) ? 1.0 : 0.0;
         for (int i = 0; i < 4; ++i)
-            a.result[4 + i] = static_cast<double>(tm[i]);
+            res[4 + i] = static_cast<double>(tm[i]);
     }
 }
 
@@ -591,9 +770,9 @@ cg_scan_kernel (uint32_t const* __restrict__ block_rows,
     }
 }
 
-/* rows[]: the nodes with a non-empty row in ascending order -- the SpMV walks
- * this list, so the work is spread evenly over the CTAs however the active
- * set is scattered over the image */
+/* rows[]: the nodes with a non-empty row in ascending order -- the solver
+ * walks this list, so the work is spread evenly over the CTAs however the
+ * active set is scattered over the image */
 __global__ void __launch_bounds__(256)
 cg_list_kernel (int n_nodes, uint16_t const* __restrict__ rowmask,
     uint32_t const* __restrict__ block_off, uint32_t* __restrict__ rows)
@@ -615,39 +794,29 @@ cg_list_kernel (int n_nodes, uint16_t const* __restrict__ rowmask,
 }
 
 __global__ void
-cg_finish_kernel (double const* x, double* result)
-{
-    result[2] = isnan(x[0]) ? 1.0 : 0.0;
-}
-
-__global__ void
-spmv_kernel (CgArgs const a, double const* __restrict__ x,
+spmv_kernel (int n_nodes, int npx, double const* __restrict__ H,
+    uint16_t const* __restrict__ rowmask, double const* __restrict__ x,
     double* __restrict__ y)
 {
     int const i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_nodes * 4)
+    if (i >= n_nodes * 4)
         return;
     PlainVec vec;
     vec.v = x;
     double own[4];
-    y[i] = spmv_row(a, vec, i >> 2, i & 3, a.rowmask[i >> 2], own);
+    y[i] = spmv_row(H, npx + 1, vec, i >> 2, i & 3, rowmask[i >> 2], own);
 }
 
-CgArgs
-make_args (smvsb_ctx* c)
+/* The system's row masks, counts and compacted row list (three small kernels
+ * per solve). */
+void
+mark_system (smvsb_ctx* c)
 {
-    CgArgs a;
-    a.n_nodes = c->n_nodes; a.npx = c->npx; a.npy = c->npy;
-    a.max_iter = 0; a.err_tol = 0; a.q_tol = 0;
-    a.H = c->H.p; a.P = c->P.p; a.g = c->g.p;
     int const nb = (c->n_nodes + 255) / 256;
     c->cg_rowmask.reserve(c->n_nodes);
     c->cg_row_list.reserve(c->n_nodes);
     c->cg_block_rows.reserve(2 * static_cast<size_t>(nb));
     c->cg_counts.reserve(2);
-    a.rowmask = c->cg_rowmask.p;
-    a.rows = c->cg_row_list.p;
-    a.counts = c->cg_counts.p;
     CUDA_CHECK(cudaMemsetAsync(c->cg_counts.p, 0,
         2 * sizeof(unsigned long long), c->stream));
     cg_mark_kernel<<<nb, 256, 0, c->stream>>>(c->npx, c->npy,
@@ -658,11 +827,7 @@ make_args (smvsb_ctx* c)
     cg_list_kernel<<<nb, 256, 0, c->stream>>>(c->n_nodes, c->cg_rowmask.p,
         c->cg_block_rows.p + nb, c->cg_row_list.p);
     smvsb::count_launches(c, 3);
-    a.x = c->x.p; a.r = c->r.p; a.d = c->d.p; a.d2 = c->d2.p;
-    a.Ad = c->Ad.p; a.z = c->z.p;
-    a.partials = c->cg_partials.p; a.sync = c->cg_sync.p;
-    a.result = c->cg_result.p;
-    return a;
+    CUDA_CHECK(cudaGetLastError());
 }
 
 } /* namespace */
@@ -670,55 +835,96 @@ make_args (smvsb_ctx* c)
 void
 launch_spmv (smvsb_ctx* c, double const* x, double* y)
 {
-    CgArgs a = make_args(c);
+    mark_system(c);
     int const n = c->n_nodes * 4;
-    spmv_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(a, x, y);
+    spmv_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->n_nodes, c->npx,
+        c->H.p, c->cg_rowmask.p, x, y);
     smvsb::count_launches(c, 1);
     CUDA_CHECK(cudaGetLastError());
 }
 
+/*
+ * Enqueues one PCG launch for the systems of `n` contexts (same device; all
+ * work goes to the stream of cs[0], which the caller has made the stream of
+ * every context of the batch) and the copies of the results into the
+ * contexts' pinned scalars. cg_collect() reads them after the caller has
+ * synchronised the stream.
+ */
 void
-run_cg (smvsb_ctx* c, int max_iter, double err_tol, double q_tol, int* iters,
-    int* info, bool* x0_nan)
+cg_enqueue (smvsb_ctx* const* cs, int n, int max_iter, double err_tol,
+    double q_tol)
 {
-    size_t const n = static_cast<size_t>(c->n_nodes) * 4;
-    c->x.reserve(n); c->r.reserve(n); c->d.reserve(n); c->d2.reserve(n);
-    c->Ad.reserve(n); c->z.reserve(n);
-    c->cg_partials.reserve(10 * CG_MAX_BLOCKS);
-    c->cg_sync.reserve(1);
-    c->cg_result.reserve(16);
-
-    CgArgs a = make_args(c);
-    a.max_iter = max_iter; a.err_tol = err_tol; a.q_tol = q_tol;
+    if (n < 1 || n > SMVSB_MAX_BATCH)
+        throw Error(SMVSB_ERR_INVALID, "batch size out of range");
+    smvsb_ctx* lead = cs[0];
+    bool const timing = getenv("SMVSB_CG_TIMING") != nullptr;
+    void const* kernel = timing ? (void const*)cg_kernel<true>
+        : (void const*)cg_kernel<false>;
 
     int per_sm = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm,
-        cg_kernel, CG_THREADS, 0));
+        kernel, CG_THREADS, 0));
     if (per_sm < 1)
         throw Error(SMVSB_ERR_CUDA, "cg_kernel does not fit on an SM");
-    int grid = c->num_sms * std::min(per_sm, 2);
-    int const need = static_cast<int>((n + CG_THREADS - 1) / CG_THREADS);
-    grid = std::max(1, std::min(std::min(grid, need), CG_MAX_BLOCKS));
+    int const grid_max = std::min(lead->num_sms * std::min(per_sm, 2),
+        CG_MAX_BLOCKS);
 
-    CUDA_CHECK(cudaMemsetAsync(c->cg_sync.p, 0, sizeof(unsigned int),
-        c->stream));
+    CgArgs a;
+    a.n_views = n; a.max_iter = max_iter; a.q_tol = q_tol;
+    lead->cg_sync.reserve(1);
+    a.sync = lead->cg_sync.p;
+    int grid = 1;
+    for (int k = 0; k < n; ++k)
+    {
+        smvsb_ctx* c = cs[k];
+        size_t const nn = static_cast<size_t>(c->n_nodes) * 4;
+        c->x.reserve(nn); c->r.reserve(nn); c->d.reserve(nn);
+        c->d2.reserve(nn); c->Ad.reserve(nn); c->z.reserve(nn);
+        c->cg_partials.reserve(static_cast<size_t>(CG_SLOTS) * CG_MAX_BLOCKS);
+        c->cg_result.reserve(16);
+        mark_system(c);
+        CUDA_CHECK(cudaMemsetAsync(c->x.p, 0, nn * sizeof(double),
+            c->stream));
+        CgView& V = a.v[k];
+        V.n_nodes = c->n_nodes; V.npx = c->npx; V.pad = 0;
+        int const need = static_cast<int>((nn + CG_THREADS - 1) / CG_THREADS);
+        V.grid = std::max(1, std::min(grid_max, need));
+        grid = std::max(grid, V.grid);
+        V.err_tol = err_tol;
+        V.H = c->H.p; V.P = c->P.p; V.g = c->g.p;
+        V.rowmask = c->cg_rowmask.p; V.rows = c->cg_row_list.p;
+        V.counts = c->cg_counts.p;
+        V.x = c->x.p; V.r = c->r.p; V.d = c->d.p; V.d2 = c->d2.p;
+        V.Ad = c->Ad.p; V.z = c->z.p;
+        V.partials = c->cg_partials.p; V.result = c->cg_result.p;
+    }
+    CUDA_CHECK(cudaMemsetAsync(a.sync, 0, sizeof(unsigned int), lead->stream));
     void* params[] = { &a };
-    CUDA_CHECK(cudaLaunchCooperativeKernel((void const*)cg_kernel, dim3(grid),
-        dim3(CG_THREADS), params, 0, c->stream));
-    cg_finish_kernel<<<1, 1, 0, c->stream>>>(c->x.p, c->cg_result.p);
-    smvsb::count_launches(c, 2);
+    CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid),
+        dim3(CG_THREADS), params, 0, lead->stream));
+    smvsb::count_launches(lead, 1);
     CUDA_CHECK(cudaGetLastError());
+    for (int k = 0; k < n; ++k)
+    {
+        smvsb_ctx* c = cs[k];
+        c->cg_grid = grid;
+        CUDA_CHECK(cudaMemcpyAsync(c->h_scalars, c->cg_result.p,
+            8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 8, c->cg_counts.p,
+            2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+            c->stream));
+    }
+}
 
-    double res[10];
-    CUDA_CHECK(cudaMemcpyAsync(res, c->cg_result.p, sizeof(res),
-        cudaMemcpyDeviceToHost, c->stream));
-    unsigned long long counts[2] = {0, 0};
-    CUDA_CHECK(cudaMemcpyAsync(counts, c->cg_counts.p, sizeof(counts),
-        cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+void
+cg_collect (smvsb_ctx* c, int* iters, int* info, bool* x0_nan)
+{
+    double const* res = c->h_scalars;
+    unsigned long long counts[2];
+    std::memcpy(counts, c->h_scalars + 8, sizeof(counts));
     if (getenv("SMVSB_CG_TIMING"))
         fprintf(stderr, "cg: iters %d grid %d | us/iter: spmv %.1f wait %.1f | "
-            "update %.1f wait %.1f\n", (int)res[0], grid,
+            "update %.1f wait %.1f\n", (int)res[0], c->cg_grid,
             res[4] / 1e3 / res[0], res[5] / 1e3 / res[0], res[6] / 1e3 / res[0],
             res[7] / 1e3 / res[0]);
     c->cg_blocks = counts[0];
@@ -726,6 +932,16 @@ run_cg (smvsb_ctx* c, int max_iter, double err_tol, double q_tol, int* iters,
     if (iters) *iters = static_cast<int>(res[0]);
     if (info) *info = static_cast<int>(res[1]);
     if (x0_nan) *x0_nan = (res[2] != 0.0);
+}
+
+void
+run_cg (smvsb_ctx* c, int max_iter, double err_tol, double q_tol, int* iters,
+    int* info, bool* x0_nan)
+{
+    smvsb_ctx* cs[1] = { c };
+    cg_enqueue(cs, 1, max_iter, err_tol, q_tol);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    cg_collect(c, iters, info, x0_nan);
 }
 
 } /* namespace smvsb */

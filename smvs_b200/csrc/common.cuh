@@ -155,11 +155,15 @@ struct smvsb_ctx
     smvsb::DevBuf<uint32_t> cg_row_list, cg_block_rows;
     smvsb::DevBuf<unsigned long long> cg_counts;
     uint64_t cg_blocks = 0, cg_rows = 0;    /* of the last solve's system */
+    int cg_grid = 0;
+    double* h_scalars = nullptr;        /* pinned, 32 doubles: results of the
+                                           asynchronous read-backs */
     smvsb::DevBuf<unsigned int> cg_sync;
     smvsb::DevBuf<double> cg_result;    /* iters, info, ... */
 
     /* update */
     smvsb::DevBuf<double> patch_shift;  /* n_patches * 2: sum, count */
+    smvsb::DevBuf<double> upd_partials, upd_result;
     smvsb::DevBuf<unsigned long long> counters;
 
     /* visibility / cutting */
@@ -230,8 +234,15 @@ void launch_construct (smvsb_ctx* c, bool use_light, double reg,
 void launch_spmv (smvsb_ctx* c, double const* x, double* y);
 void run_cg (smvsb_ctx* c, int max_iter, double err_tol, double q_tol,
     int* iters, int* info, bool* x0_nan);
+void cg_enqueue (smvsb_ctx* const* cs, int n, int max_iter, double err_tol,
+    double q_tol);
+void cg_collect (smvsb_ctx* c, int* iters, int* info, bool* x0_nan);
 void launch_update (smvsb_ctx* c, double thresh, bool full_opt,
     uint64_t* n_active, double* mean_shift);
+void update_enqueue (smvsb_ctx* c, double thresh, bool full_opt);
+void update_collect (smvsb_ctx* c, uint64_t* n_active, double* mean_shift);
+void count_processed_enqueue (smvsb_ctx* c);
+unsigned long long count_processed_collect (smvsb_ctx* c);
 void launch_render_depth (smvsb_ctx* c, float* out_dev);
 void launch_render_normals (smvsb_ctx* c, float* out_dev);
 void run_fit_lighting (smvsb_ctx* c, double* A_b_host /*272*/);

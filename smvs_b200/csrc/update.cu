@@ -15,6 +15,8 @@
  *   K5  light_partials_kernel  LightOptimizer::fit_lighting_to_image sums
  *                        (lib/light_optimizer.cc:22-55)
  */
+#include <cstring>
+
 #include "gn_math.cuh"
 #include "patch_eval.cuh"
 
@@ -340,13 +342,12 @@ light_partials_kernel (int npix, float const* __restrict__ normals,
 } /* namespace */
 
 void
-launch_update (smvsb_ctx* c, double thresh, bool full_opt,
-    uint64_t* n_active, double* mean_shift)
+update_enqueue (smvsb_ctx* c, double thresh, bool full_opt)
 {
     SurfaceDev const sf = surface_args(c);
     c->patch_shift.reserve(static_cast<size_t>(c->n_patches) * 2);
     c->active_new.reserve(c->n_nodes);
-    c->cg_result.reserve(16);
+    c->upd_result.reserve(4);
     CUDA_CHECK(cudaMemsetAsync(c->active_new.p, 0, c->n_nodes, c->stream));
     int const npix_patch = c->ps * c->ps;
     auto grid_for = [&](int g) { int const ppb = UPD_THREADS / g;
@@ -374,24 +375,38 @@ launch_update (smvsb_ctx* c, double thresh, bool full_opt,
         CUDA_CHECK(cudaMemcpyAsync(c->active.p, c->active_new.p, c->n_nodes,
             cudaMemcpyDeviceToDevice, c->stream));
     }
-    c->light_partials.reserve(3 * RED_BLOCKS);
+    c->upd_partials.reserve(3 * RED_BLOCKS);
     update_reduce_kernel<<<RED_BLOCKS, 256, 0, c->stream>>>(c->n_patches,
-        c->patch_shift.p, c->n_nodes, c->active.p, c->light_partials.p);
+        c->patch_shift.p, c->n_nodes, c->active.p, c->upd_partials.p);
     CUDA_CHECK(cudaGetLastError());
     update_reduce_final_kernel<<<1, 32, 0, c->stream>>>(RED_BLOCKS,
-        c->light_partials.p, c->cg_result.p);
+        c->upd_partials.p, c->upd_result.p);
     CUDA_CHECK(cudaGetLastError());
     smvsb::count_launches(c, 4);
-    double res[3];
-    CUDA_CHECK(cudaMemcpyAsync(res, c->cg_result.p, sizeof(res),
-        cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 12, c->upd_result.p,
+        3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+}
+
+/* after the stream has been synchronised */
+void
+update_collect (smvsb_ctx* c, uint64_t* n_active, double* mean_shift)
+{
+    double const* res = c->h_scalars + 12;
     if (n_active) *n_active = static_cast<uint64_t>(res[2]);
     if (mean_shift) *mean_shift = res[0] / res[1];
 }
 
 void
-launch_count_processed (smvsb_ctx* c, unsigned long long* n_proc_host)
+launch_update (smvsb_ctx* c, double thresh, bool full_opt,
+    uint64_t* n_active, double* mean_shift)
+{
+    update_enqueue(c, thresh, full_opt);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    update_collect(c, n_active, mean_shift);
+}
+
+void
+count_processed_enqueue (smvsb_ctx* c)
 {
     SurfaceDev const sf = surface_args(c);
     c->counters.reserve(4);
@@ -401,9 +416,24 @@ launch_count_processed (smvsb_ctx* c, unsigned long long* n_proc_host)
         c->stream>>>(sf, c->counters.p);
     smvsb::count_launches(c, 1);
     CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaMemcpyAsync(n_proc_host, c->counters.p,
+    CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 16, c->counters.p,
         sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+}
+
+unsigned long long
+count_processed_collect (smvsb_ctx* c)
+{
+    unsigned long long n;
+    memcpy(&n, c->h_scalars + 16, sizeof(n));
+    return n;
+}
+
+void
+launch_count_processed (smvsb_ctx* c, unsigned long long* n_proc_host)
+{
+    count_processed_enqueue(c);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    *n_proc_host = count_processed_collect(c);
 }
 
 static void

@@ -491,3 +491,54 @@ def test_full_size_live_parity(shading):
         valid = wl.node_valid.astype(bool)      # the reference reports 0 for null nodes
         assert np.array_equal(ctx.get_nodes()[valid], R.surface_get()[0][valid])
     R.close()
+
+
+# ---------------------------------------------------------------------------
+# several views per launch (smvsb_newton_loop_batch)
+# ---------------------------------------------------------------------------
+
+def test_batch_is_bitwise_the_single_view_loop():
+    """Views of different sizes, with and without lighting, advanced in
+    lock-step with one PCG launch per step: every view's nodes, step and
+    iteration counts are EXACTLY those of its own smvsb_newton_loop (the
+    reference runs the views independently, app/smvsrecon.cc:658-733)."""
+    from smvs_b200 import workload
+    specs = [(640, 480, 3, 2, False, 11), (400, 300, 2, 2, True, 12),
+             (640, 480, 2, 3, False, 13), (333, 207, 2, 2, True, 14),
+             (96, 72, 2, 2, False, 15)]
+    wls = [workload.build_workload(w, h, n, scale=s, shading=sh, seed_index=seed)
+           for (w, h, n, s, sh, seed) in specs]
+    ctxs = [api.Context(0) for _ in wls]
+    try:
+        lights, single, nodes_single = [], [], []
+        for wl, ctx in zip(wls, ctxs):
+            wl.push_views_u8(ctx)
+            wl.push_surface(ctx)
+            lights.append(ctx.fit_lighting() if wl.shading is not None else None)
+        for wl, ctx, light in zip(wls, ctxs, lights):
+            single.append(ctx.newton_loop(light, 0.01, 0.0))
+            nodes_single.append(ctx.get_nodes())
+            ctx.set_nodes(wl.nodes)
+        before = sum(c.launches for c in ctxs)
+        batch = api.newton_loop_batch(ctxs, lights, 0.01, 0.0)
+        assert sum(c.launches for c in ctxs) > before
+        for k, (ctx, s, b) in enumerate(zip(ctxs, single, batch)):
+            for key in ("newton_steps", "cg_iterations", "n_active", "pixel_iterations",
+                        "nan", "cg_block_iterations", "cg_row_iterations"):
+                assert b[key] == s[key], (k, key, b[key], s[key])
+            assert np.array_equal(ctx.get_nodes(), nodes_single[k]), k
+        # a batch of one is the plain loop
+        ctxs[0].set_nodes(wls[0].nodes)
+        one = api.newton_loop_batch(ctxs[:1], None, 0.01, 0.0)[0]
+        assert one["cg_iterations"] == single[0]["cg_iterations"]
+        assert np.array_equal(ctxs[0].get_nodes(), nodes_single[0])
+        # error paths: the same context twice, too many contexts
+        with pytest.raises(api.SmvsbError) as e:
+            api.newton_loop_batch([ctxs[0], ctxs[0]], None, 0.01, 0.0)
+        assert e.value.code == -1
+        with pytest.raises(api.SmvsbError) as e:
+            api.newton_loop_batch([ctxs[k % 5] for k in range(9)], None, 0.01, 0.0)
+        assert e.value.code == -1
+    finally:
+        for c in ctxs:
+            c.close()
