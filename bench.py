@@ -309,6 +309,14 @@ def _system_blocks_full(wl):
     return blocks
 
 
+# fp64 operations (DADD + DMUL + 2 DFMA, as executed) of gn_patch_kernel<16> per
+# pixel-iteration at 6 visible neighbours, no shading term: from the ncu capture
+# named below (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on.sum of
+# one launch / its samples). This is the basis-space formulation's work -- the
+# reference's 16-wide rank-1 formulation would be ~20 kFLOP.
+K1_FLOP_PER_PIXEL_ITER = 5600.0
+K1_FLOP_SOURCE = "profiles/r2_k1.txt"
+
 # DRAM bytes per 4x4 block and CG iteration of cg_kernel, from the ncu --set
 # full capture named below (dram__bytes_read.sum + dram__bytes_write.sum of a
 # 200-iteration launch on the full system / (200 x its blocks)): H only, the
@@ -486,6 +494,20 @@ def run_product(args):
         roofline = cg_roofline((cg_blocks, cg_rows), float(t_split[1]), newton, hbm_peak,
                                peak_source)
         roofline["system_blocks_full"] = _system_blocks_full(pool[0])
+        # second roofline: the construct stage is fp64-ALU bound, not HBM bound
+        roofline_k1 = None
+        try:
+            fp64_peak = api.measure_fp64_peak(local)
+            k1_tflops = K1_FLOP_PER_PIXEL_ITER * pix / max(float(t_split[0]) * 1e-3, 1e-12) / 1e12
+            roofline_k1 = {"bound": "fp64", "kernel": "gn_patch_kernel<16> (timed with the "
+                           "assemble and preconditioner kernels of the construct stage)",
+                           "achieved": k1_tflops, "peak": fp64_peak,
+                           "peak_source": "smvsb_measure_fp64_peak (DFMA micro-benchmark, this run)",
+                           "unit": "TFLOP/s", "frac": k1_tflops / fp64_peak,
+                           "flop_per_pixel_iteration": K1_FLOP_PER_PIXEL_ITER,
+                           "flop_source": K1_FLOP_SOURCE}
+        except Exception as exc:      # noqa: BLE001
+            roofline_k1 = {"error": str(exc)}
 
         cpu_base = None          # timed on rank 0 at N = 1 only
         if not args.no_cpu_baseline and world == 1:
@@ -523,6 +545,7 @@ def run_product(args):
                         [1e3 * float(x) / max(args.steps, 1) for x in e2e_parts]},
             "gpu_launches": int(launches_all),
             "roofline": roofline,
+            "roofline_construct": roofline_k1,
             "cpu_baseline": cpu_base,
             "configs": configs,
             "wall_s_resident": wall_resident,

@@ -26,7 +26,7 @@ from smvs_b200.workload import build_workload  # noqa: E402
 
 CACHE = os.path.join(ROOT, "benchmarks", "_cache")
 JOBS = ("loop_n", "loop_S", "opt_n", "opt_S", "sgm")
-VERSION = 2           # bump when inputs change: old caches are then ignored
+VERSION = 3           # bump when inputs change: old caches are then ignored
 
 
 def cache_path(job):
@@ -56,6 +56,17 @@ def sgm_inputs():
     return sc, dmin, dmax, M, t
 
 
+def lighting_condition_number(wl, normals_i16):
+    """cond_2 of the 16x16 normal matrix of LightOptimizer::fit_lighting_to_image
+    (lib/light_optimizer.cc:22-55), from the reference's normal map."""
+    from smvs_b200.synth import sh_basis
+    n = normals_i16.astype(np.float64).reshape(-1, 3) / 32767.0
+    keep = (np.abs(np.linalg.norm(n, axis=1) - 1.0) < 1e-3) \
+        & (wl.shading.reshape(-1) >= 0.05)
+    sh = sh_basis(n[keep])
+    return float(np.linalg.cond(sh.T @ sh))
+
+
 def volume_digest(vol):
     """(crc32 of the bytes, sum of the entries) of a uint16 volume."""
     v = np.ascontiguousarray(vol, dtype=np.uint16)
@@ -73,8 +84,11 @@ def run(job):
         wl = loop_workload(shading)
         R = _ref_scene_for(wl)
         light = R.fit_lighting() if shading else None
+        # the normal map the lighting was fitted to, as int16 (for cond(A))
+        normals0 = np.round(R.surface_normals() * 32767.0).astype(np.int16) \
+            if shading else np.zeros(1, np.int16)
         st = R.newton_loop(light, 0.01, 0.0)
-        out = dict(depth=R.surface_depth(), nodes=R.surface_get()[0],
+        out = dict(depth=R.surface_depth(), nodes=R.surface_get()[0], normals0=normals0,
                    light=np.zeros(16) if light is None else light,
                    newton_steps=st["newton_steps"], cg_iterations=st["cg_iterations"],
                    pixel_iterations=st["pixel_iterations"], n_active=st["n_active"])

@@ -80,6 +80,10 @@ typedef struct smvsb_newton_stats
  * hosts spread their pool threads over them: thread k -> device k mod count,
  * the reference's one-view-per-thread model of app/smvsrecon.cc:658-733. */
 int smvsb_device_count (void);
+/* Dense fp64 FMA throughput of the device in TFLOP/s, measured on the spot
+ * (8 independent DFMA chains per thread, CUDA events, best of 5): the roof the
+ * Gauss-Newton construct kernel is reported against. */
+int smvsb_measure_fp64_peak (int device, double* tflops_out);
 int smvsb_create (int device, smvsb_ctx** out);
 void smvsb_destroy (smvsb_ctx* ctx);
 /* Message of the last failed call on ctx (or, with ctx == NULL, of the last
@@ -333,6 +337,29 @@ int smvsb_sgm (int device, int w, int h, const uint8_t* main_lum,
     float min_depth, float max_depth, int num_steps, uint16_t penalty1,
     uint16_t penalty2, float* depth_out, uint16_t* cost_out,
     uint16_t* sgm_out, double* ms_out);
+
+/*
+ * SGMStereo::reconstruct (lib/sgm_stereo.cc:45-96) for one main / neighbour
+ * luminance pair at SGM working resolution: run_sgm main -> neighbour and
+ * neighbour -> main (both on the device, volumes never leave it), then the
+ * consistency check of :64-91 -- a main depth survives if its reprojection
+ * lands inside the neighbour's 3 % border on a pixel with depth and the two
+ * depths agree within 20 % -- and, if merge_with != NULL, the merge of
+ * app/smvsrecon.cc:362-377 with an earlier result for the same main view
+ * (mean where both have depth). One depth image leaves the GPU.
+ *   M_mn, t_mn   fp32 reprojection main -> neighbour (fill_reprojection at the
+ *                working sizes; also used by the consistency check, :66-69)
+ *   M_nm, t_nm   the same, neighbour -> main
+ *   depth_range_main / _neigh   {min, max} depth of the two runs (:50-61)
+ *   merge_with   w*h floats or NULL
+ *   ms_out       optional double[2]: device ms of the two run_sgm
+ */
+int smvsb_sgm_reconstruct (int device, int w, int h, const uint8_t* main_lum,
+    int nw, int nh, const uint8_t* neigh_lum, const float* M_mn,
+    const float* t_mn, const float* M_nm, const float* t_nm,
+    const float* depth_range_main, const float* depth_range_neigh,
+    int num_steps, uint16_t penalty1, uint16_t penalty2,
+    const float* merge_with, float* depth_out, double* ms_out);
 
 #ifdef __cplusplus
 }

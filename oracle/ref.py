@@ -404,3 +404,33 @@ class Units:
         n = A.shape[0]
         lib().ref_ldl_inverse(_p(A), n)
         return A
+
+
+    # -- tests/gtest_matrix_vector.cc:33-356 ---------------------------------
+    has_linear_algebra = True
+
+    @staticmethod
+    def ssevector(op, a, b=None, factor=0.0):
+        ops = dict(dot=0, add=1, subtract=2, multiply=3, multiply_add=4, multiply_sub=5)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        out = np.empty(1 if op == "dot" else len(a), dtype=np.float64)
+        lib().ref_ssevector_op(ops[op], len(a), _p(a), _p(bb), C.c_double(factor), _p(out))
+        return float(out[0]) if op == "dot" else out
+
+    @staticmethod
+    def bsm2(dim, blocks=None, triplets=None, invert=False, x=None):
+        """BlockSparseMatrix<2>: (num_non_zero, A x)."""
+        blocks = blocks or []
+        triplets = triplets or []
+        brc = np.array([[r, c] for r, c, _ in blocks], dtype=np.int32).reshape(-1)
+        bv = np.array([v for _, _, v in blocks], dtype=np.float64).reshape(-1)
+        trc = np.array([[r, c] for r, c, _ in triplets], dtype=np.int32).reshape(-1)
+        tv = np.array([v for _, _, v in triplets], dtype=np.float64)
+        xv = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+        y = None if x is None else np.empty(dim, dtype=np.float64)
+        nnz = lib().ref_bsm2(dim, len(blocks), _p(brc) if len(brc) else None,
+                             _p(bv) if len(bv) else None, len(triplets),
+                             _p(trc) if len(trc) else None, _p(tv) if len(tv) else None,
+                             int(invert), _p(xv), _p(y))
+        return int(nnz), y

@@ -49,6 +49,8 @@
 #include "surface_derivative.h"
 #include "spherical_harmonics.h"
 #include "ldl_decomposition.h"
+#include "sse_vector.h"
+#include "block_sparse_matrix.h"
 #undef private
 #undef protected
 
@@ -992,6 +994,79 @@ void
 ref_ldl_inverse (double* A, int n)
 {
     smvs::ldl_inverse(A, n);
+}
+
+/* SSEVector operations (lib/sse_vector.cc:19-205), for the reference's own
+ * known answers (tests/gtest_matrix_vector.cc:33-195).
+ * op: 0 dot (out[0]), 1 add, 2 subtract, 3 multiply (a * factor),
+ *     4 multiply_add (a + b * factor), 5 multiply_sub (a - b * factor). */
+void
+ref_ssevector_op (int op, int n, double const* a, double const* b,
+    double factor, double* out)
+{
+    smvs::SSEVector va(n), vb(n);
+    for (int i = 0; i < n; ++i)
+    {
+        va[i] = a[i];
+        vb[i] = b ? b[i] : 0.0;
+    }
+    if (op == 0)
+    {
+        out[0] = va.dot(vb);
+        return;
+    }
+    smvs::SSEVector c;
+    switch (op)
+    {
+    case 1: c = va.add(vb); break;
+    case 2: c = va.subtract(vb); break;
+    case 3: c = va.multiply(factor); break;
+    case 4: c = va.multiply_add(vb, factor); break;
+    default: c = va.multiply_sub(vb, factor); break;
+    }
+    for (int i = 0; i < n; ++i)
+        out[i] = c[i];
+}
+
+/* BlockSparseMatrix<2> (lib/block_sparse_matrix.h) from blocks (row, col,
+ * 4 row-major values each) or from scalar triplets; optionally
+ * invert_blocks_inplace(); y = A x; returns num_non_zero()
+ * (tests/gtest_matrix_vector.cc:197-356). */
+int
+ref_bsm2 (int dim, int n_blocks, int const* block_rc, double const* block_vals,
+    int n_triplets, int const* trip_rc, double const* trip_vals, int invert,
+    double const* x, double* y)
+{
+    typedef smvs::BlockSparseMatrix<2> BSMatrix;
+    BSMatrix m(dim, dim);
+    if (n_triplets > 0)
+    {
+        BSMatrix::Triplets trips;
+        for (int i = 0; i < n_triplets; ++i)
+            trips.emplace_back(trip_rc[2 * i], trip_rc[2 * i + 1],
+                trip_vals[i]);
+        m.set_from_triplets(trips);
+    }
+    else
+    {
+        BSMatrix::Blocks blocks;
+        for (int i = 0; i < n_blocks; ++i)
+            blocks.emplace_back(block_rc[2 * i], block_rc[2 * i + 1],
+                block_vals + 4 * i);
+        m.set_from_blocks(blocks);
+    }
+    if (invert)
+        m.invert_blocks_inplace();
+    if (x != nullptr && y != nullptr)
+    {
+        smvs::SSEVector vx(dim);
+        for (int i = 0; i < dim; ++i)
+            vx[i] = x[i];
+        smvs::SSEVector r = m.multiply(vx);
+        for (int i = 0; i < dim; ++i)
+            y[i] = r[i];
+    }
+    return static_cast<int>(m.num_non_zero());
 }
 
 } /* extern "C" */

@@ -25,7 +25,7 @@ EXPORTS = [
     "smvsb_get_normals", "smvsb_debug_get_system", "smvsb_debug_spmv",
     "smvsb_fit_lighting", "smvsb_sgm", "smvsb_visibility",
     "smvsb_cut_boundaries", "smvsb_get_surface_state", "smvsb_view_set_scale",
-    "smvsb_bilateral_filter", "smvsb_debug_expf", "smvsb_device_count", "smvsb_newton_loop_batch", "smvsb_device_launch_count",
+    "smvsb_bilateral_filter", "smvsb_debug_expf", "smvsb_device_count", "smvsb_measure_fp64_peak", "smvsb_sgm_reconstruct", "smvsb_newton_loop_batch", "smvsb_device_launch_count",
 ]
 
 
@@ -386,3 +386,31 @@ def sgm(main_lum, neigh_lum, M, t, min_depth, max_depth, num_steps=128,
     if rc != 0:
         raise SmvsbError(rc, lib().smvsb_last_error(None).decode())
     return dict(depth=depth, cost=cost, sgm=S, ms=ms)
+
+
+def sgm_reconstruct(main_lum, neigh_lum, M_mn, t_mn, M_nm, t_nm, range_main, range_neigh,
+                    num_steps=128, penalty1=6, penalty2=96, merge_with=None, device=0):
+    """SGMStereo::reconstruct for one luminance pair (smvsb_sgm_reconstruct):
+    both directions, consistency check and optional merge on the device."""
+    main_lum, neigh_lum = _u8(main_lum), _u8(neigh_lum)
+    h, w = main_lum.shape
+    nh, nw = neigh_lum.shape
+    arrs = [_f32(a) for a in (M_mn, t_mn, M_nm, t_nm, range_main, range_neigh)]
+    prev = _f32(merge_with)
+    depth = np.empty((h, w), dtype=np.float32)
+    ms = np.zeros(2, dtype=np.float64)
+    rc = lib().smvsb_sgm_reconstruct(
+        int(device), w, h, _p(main_lum), nw, nh, _p(neigh_lum), *[_p(a) for a in arrs],
+        int(num_steps), C.c_uint16(penalty1), C.c_uint16(penalty2), _p(prev), _p(depth), _p(ms))
+    if rc != 0:
+        raise SmvsbError(rc, lib().smvsb_last_error(None).decode())
+    return dict(depth=depth, ms=ms)
+
+
+def measure_fp64_peak(device=0):
+    """Measured dense fp64 FMA throughput in TFLOP/s (smvsb_measure_fp64_peak)."""
+    out = C.c_double(0)
+    rc = lib().smvsb_measure_fp64_peak(int(device), C.byref(out))
+    if rc != 0:
+        raise SmvsbError(rc, lib().smvsb_last_error(None).decode())
+    return float(out.value)

@@ -33,6 +33,13 @@ int sgm_run (int device, int w, int h, uint8_t const* main_lum, int nw, int nh,
     float min_depth, float max_depth, int num_steps, uint16_t penalty1,
     uint16_t penalty2, float* depth_out, uint16_t* cost_out,
     uint16_t* sgm_out, double* ms_out);
+double measure_fp64_peak (int device);
+int sgm_reconstruct (int device, int w, int h, uint8_t const* main_lum, int nw,
+    int nh, uint8_t const* neigh_lum, float const* M_mn, float const* t_mn,
+    float const* M_nm, float const* t_nm, float const* depth_range_main,
+    float const* depth_range_neigh, int num_steps, uint16_t penalty1,
+    uint16_t penalty2, float const* merge_with, float* depth_out,
+    double* ms_out);
 }
 
 namespace smvsb {
@@ -261,6 +268,21 @@ smvsb_device_count (void)
     if (cudaGetDeviceCount(&count) != cudaSuccess)
         return 0;
     return count;
+}
+
+int
+smvsb_measure_fp64_peak (int device, double* tflops_out)
+{
+    return guarded(nullptr, [&]() {
+        require(tflops_out != nullptr, SMVSB_ERR_INVALID, "NULL output");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+            throw smvsb::Error(SMVSB_ERR_CUDA,
+                "no CUDA device (smvs_b200 has no CPU fallback)");
+        require(device >= 0 && device < count, SMVSB_ERR_INVALID,
+            "device index out of range");
+        *tflops_out = smvsb::measure_fp64_peak(device);
+    });
 }
 
 int
@@ -1175,6 +1197,25 @@ smvsb_sgm (int device, int w, int h, const uint8_t* main_lum, int nw, int nh,
     else
         smvsb::count_device_launches(device, 3);   /* cost volume, 8-path
                                            aggregation, sum + WTA */
+    return rc;
+}
+
+int
+smvsb_sgm_reconstruct (int device, int w, int h, const uint8_t* main_lum,
+    int nw, int nh, const uint8_t* neigh_lum, const float* M_mn,
+    const float* t_mn, const float* M_nm, const float* t_nm,
+    const float* depth_range_main, const float* depth_range_neigh,
+    int num_steps, uint16_t penalty1, uint16_t penalty2,
+    const float* merge_with, float* depth_out, double* ms_out)
+{
+    int const rc = smvsb::sgm_reconstruct(device, w, h, main_lum, nw, nh,
+        neigh_lum, M_mn, t_mn, M_nm, t_nm, depth_range_main,
+        depth_range_neigh, num_steps, penalty1, penalty2, merge_with,
+        depth_out, ms_out);
+    if (rc != SMVSB_OK)
+        g_last_error = smvsb::sgm_last_error();
+    else    /* 2 x (cost, paths, WTA) + consistency (+ merge) */
+        smvsb::count_device_launches(device, merge_with ? 8 : 7);
     return rc;
 }
 

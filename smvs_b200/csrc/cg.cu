@@ -389,19 +389,22 @@ pass_next (CgArgs const& a, CgState const* s_state, bool init, int step,
     }
 }
 
-/* The row this thread's quad handles in pass `it`: node index or -1. */
-__device__ __forceinline__ int
+/* The row this thread's quad handles in pass `it` (+ pass_offset): whether
+ * there is one is decided from the position alone, so that nothing branches
+ * on the loaded index and the load can travel while other work is issued. */
+__device__ __forceinline__ bool
 pass_row (CgArgs const& a, CgState const* s_state, PassIter const& it,
-    int pass_offset)
+    int pass_offset, int& node)
 {
+    node = 0;
     if (it.view >= a.n_views)
-        return -1;
+        return false;
     CgView const& V = a.v[it.view];
     int const q = (it.pass + pass_offset) * (V.grid * CG_QUADS)
         + blockIdx.x * CG_QUADS + (threadIdx.x >> 2);
-    if (q >= s_state[it.view].n_rows)
-        return -1;
-    return static_cast<int>(V.rows[q]);
+    bool const ok = q < s_state[it.view].n_rows;
+    node = ok ? static_cast<int>(V.rows[q]) : 0;
+    return ok;
 }
 
 /* 2 CTAs / SM: measured faster than 3 at 80 registers (fewer loads hoisted,
@@ -442,9 +445,9 @@ cg_kernel (CgArgs const a)
         while (it.view < a.n_views)
         {
             CgView const& V = a.v[it.view];
-            int const node = pass_row(a, s_state, it, 0);
-            bool const ok = node >= 0;
-            size_t const i = static_cast<size_t>(ok ? node : 0) * 4 + rp;
+            int node;
+            bool const ok = pass_row(a, s_state, it, 0, node);
+            size_t const i = static_cast<size_t>(node) * 4 + rp;
             double const gi = ok ? V.g[i] : 0.0;
             double const ri = -gi;
             double const r0 = __shfl_sync(0xffffffffu, ri, quad);
@@ -491,6 +494,10 @@ cg_kernel (CgArgs const a)
 
     int iter = 1;
     unsigned long long tm[4] = {0, 0, 0, 0};
+    /* first two passes of the SpMV walk, kept across iterations */
+    int pa_view = -2, pa_node0 = 0, pa_node1 = 0;
+    bool pa_ok0 = false, pa_ok1 = false;
+    unsigned int pa_mask0 = 0;
     for (; iter < a.max_iter; ++iter)
     {
         unsigned long long const t_a = now_ns<TIMING>();
@@ -501,43 +508,60 @@ cg_kernel (CgArgs const a)
         /* d = z + beta d_old (:192-198 of the previous iteration);
          * Ad = A d; alpha = r_dot_r / d.Ad (:126-127) */
         {
-            PassIter it; it.view = -1; it.pass = 0;
-            pass_next(a, s_state, false, 1, it);
-            /* the row and its mask travel one pass ahead of the stream */
-            int node = pass_row(a, s_state, it, 0);
-            unsigned int mask = (node >= 0)
-                ? a.v[it.view].rowmask[node] : 0u;
-            double acc[1] = { 0.0 };
-            while (it.view < a.n_views)
+            /* Software pipeline over the passes: the row index travels two
+             * passes ahead of the stream, its mask one pass ahead, so no load
+             * of a pass waits for another one. The rows and masks do not
+             * change during a solve: what the first two passes need is kept
+             * in registers from one iteration to the next (reloaded when the
+             * first view of the walk changes because a view has converged). */
+            PassIter it0; it0.view = -1; it0.pass = 0;
+            pass_next(a, s_state, false, 1, it0);
+            PassIter it1 = it0;
+            pass_next(a, s_state, false, 1, it1);
+            if (it0.view != pa_view)
             {
-                PassIter nx = it;
-                pass_next(a, s_state, false, 1, nx);
-                int const node_next = pass_row(a, s_state, nx, 0);
-                unsigned int const mask_next = (node_next >= 0)
-                    ? a.v[nx.view].rowmask[node_next] : 0u;
-                if (node >= 0)
+                pa_view = it0.view;
+                pa_ok0 = pass_row(a, s_state, it0, 0, pa_node0);
+                pa_mask0 = (pa_ok0 && it0.view < a.n_views)
+                    ? a.v[it0.view].rowmask[pa_node0] : 0u;
+                pa_ok1 = pass_row(a, s_state, it1, 0, pa_node1);
+            }
+            int node0 = pa_node0, node1 = pa_node1;
+            bool ok0 = pa_ok0, ok1 = pa_ok1;
+            unsigned int mask0 = pa_mask0;
+            double acc[1] = { 0.0 };
+            while (it0.view < a.n_views)
+            {
+                PassIter it2 = it1;
+                pass_next(a, s_state, false, 1, it2);
+                int node2;
+                bool const ok2 = pass_row(a, s_state, it2, 0, node2);
+                unsigned int const mask1 = (ok1 && it1.view < a.n_views)
+                    ? a.v[it1.view].rowmask[node1] : 0u;
+                if (ok0)
                 {
-                    CgView const& V = a.v[it.view];
+                    CgView const& V = a.v[it0.view];
                     DirVec dir;
                     dir.z = V.z;
                     dir.d_old = odd ? V.d : V.d2;
-                    dir.beta = s_state[it.view].beta;
+                    dir.beta = s_state[it0.view].beta;
                     double own[4];
-                    double const v = spmv_row(V.H, V.npx + 1, dir, node, rp,
-                        mask, own);
+                    double const v = spmv_row(V.H, V.npx + 1, dir, node0, rp,
+                        mask0, own);
                     double const di = (rp == 0) ? own[0] : (rp == 1) ? own[1]
                         : (rp == 2) ? own[2] : own[3];
-                    size_t const i = static_cast<size_t>(node) * 4 + rp;
+                    size_t const i = static_cast<size_t>(node0) * 4 + rp;
                     V.Ad[i] = v;
                     (odd ? V.d2 : V.d)[i] = di;
                     acc[0] += v * di;
                 }
-                if (nx.view != it.view)
+                if (it1.view != it0.view)
                 {
-                    warp_flush<1>(acc, s_red, it.view);
+                    warp_flush<1>(acc, s_red, it0.view);
                     acc[0] = 0.0;
                 }
-                it = nx; node = node_next; mask = mask_next;
+                it0 = it1; node0 = node1; ok0 = ok1; mask0 = mask1;
+                it1 = it2; node1 = node2; ok1 = ok2;
             }
             publish<1>(a, s_state, s_red, slot, false);
         }
@@ -557,9 +581,10 @@ cg_kernel (CgArgs const a)
             pass_next(a, s_state, false, CG_UF, it);
             double acc[3] = { 0.0, 0.0, 0.0 };    /* r.r, x.(r - g), z.r */
             int nodes[CG_UF];
+            bool oks[CG_UF];
 #pragma unroll
             for (int u = 0; u < CG_UF; ++u)
-                nodes[u] = pass_row(a, s_state, it, u);
+                oks[u] = pass_row(a, s_state, it, u, nodes[u]);
             /* CG_UF rows per thread in flight: the pass is latency bound */
             while (it.view < a.n_views)
             {
@@ -569,9 +594,10 @@ cg_kernel (CgArgs const a)
                 PassIter nx = it;
                 pass_next(a, s_state, false, CG_UF, nx);
                 int nodes_next[CG_UF];
+                bool oks_next[CG_UF];
 #pragma unroll
                 for (int u = 0; u < CG_UF; ++u)
-                    nodes_next[u] = pass_row(a, s_state, nx, u);
+                    oks_next[u] = pass_row(a, s_state, nx, u, nodes_next[u]);
 
                 double xv[CG_UF], rv[CG_UF], gv[CG_UF];
                 double2 p01[CG_UF], p23[CG_UF];
@@ -580,7 +606,7 @@ cg_kernel (CgArgs const a)
                 {
                     xv[u] = 0.0; rv[u] = 0.0; gv[u] = 0.0;
                     p01[u] = make_double2(0, 0); p23[u] = p01[u];
-                    if (nodes[u] >= 0)
+                    if (oks[u])
                     {
                         size_t const i = static_cast<size_t>(nodes[u]) * 4 + rp;
                         double const dn = d_new[i], ad = V.Ad[i];
@@ -600,7 +626,7 @@ cg_kernel (CgArgs const a)
                     double const q1 = __shfl_sync(0xffffffffu, rv[u], quad + 1);
                     double const q2 = __shfl_sync(0xffffffffu, rv[u], quad + 2);
                     double const q3 = __shfl_sync(0xffffffffu, rv[u], quad + 3);
-                    if (nodes[u] >= 0)
+                    if (oks[u])
                     {
                         size_t const i = static_cast<size_t>(nodes[u]) * 4 + rp;
                         double const zi = p01[u].x * q0 + p01[u].y * q1
@@ -620,7 +646,10 @@ cg_kernel (CgArgs const a)
                 it = nx;
 #pragma unroll
                 for (int u = 0; u < CG_UF; ++u)
+                {
                     nodes[u] = nodes_next[u];
+                    oks[u] = oks_next[u];
+                }
             }
             publish<3>(a, s_state, s_red, slot + 1, false);
         }
@@ -850,6 +879,8 @@ launch_spmv (smvsb_ctx* c, double const* x, double* y)
  * contexts' pinned scalars. cg_collect() reads them after the caller has
  * synchronised the stream.
  */
+void cg_v1_launch (smvsb_ctx* c, int max_iter, double err_tol, double q_tol);
+
 void
 cg_enqueue (smvsb_ctx* const* cs, int n, int max_iter, double err_tol,
     double q_tol)
@@ -900,6 +931,10 @@ cg_enqueue (smvsb_ctx* const* cs, int n, int max_iter, double err_tol,
     }
     CUDA_CHECK(cudaMemsetAsync(a.sync, 0, sizeof(unsigned int), lead->stream));
     void* params[] = { &a };
+    char const* variant = getenv("SMVSB_CG_VARIANT");
+    if (variant != nullptr && variant[0] == 'v' && n == 1)
+        cg_v1_launch(lead, max_iter, err_tol, q_tol);
+    else
     CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid),
         dim3(CG_THREADS), params, 0, lead->stream));
     smvsb::count_launches(lead, 1);

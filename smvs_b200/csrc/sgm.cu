@@ -34,6 +34,9 @@
  */
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
+
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -49,24 +52,30 @@ struct SgmParams
 };
 
 /*
- * Cost volume, SWAR formulation. A thread owns two horizontally adjacent
- * pixels and works on four depth planes at a time.
+ * Cost volume. A thread owns two horizontally adjacent pixels and works on
+ * four depth planes at a time.
  *
- *  - Pixels are kept as 16-bit fields, two per register. For centre pair A
- *    and neighbour pair B, R = B + 0x00FF00FF - A has bit 8 of each field
- *    set iff A < B (field value B - A + 255 in [0, 510], no borrow between
- *    the fields): ONE integer add per two census comparisons.
+ *  - The 63 census comparisons per pixel run on the half-precision pipe, two
+ *    pixels per instruction: pixels (0..255, exact in fp16) are kept as
+ *    half2 pairs; for centre pair A and neighbour pair B, HSET2.LT gives
+ *    c = (A < B) as 1.0 / 0.0 per half.
  *  - The Hamming distance of two census words does not depend on the bit
- *    order, so no 63-bit word is ever assembled: per offset the comparison
- *    bits of the warped slice are XORed with the main image's bits for the
- *    same offset (precomputed once per block into shared memory, reused for
- *    all planes) and accumulated in the fields: 3 instructions per 2
- *    comparisons instead of ~8.
+ *    order, so no 63-bit word is ever assembled, and it is linear in the
+ *    warped slice's bits once the main image's bits are known:
+ *        distance = sum_o [c_w(o) != c_m(o)] = K + sum_o s(o) c_w(o),
+ *    s(o) = +1 where c_m(o) = 0, -1 where it is 1, K = popcount(c_m). The
+ *    signs of a block's main pixels are computed once into shared memory
+ *    (63 KB) and reused for all planes; per offset and plane a pixel pair
+ *    costs one HSET2 and one HFMA2 (|sum| <= 63 is exact in fp16) -- on the
+ *    FMA pipe, which the integer formulation (three ALU-pipe instructions)
+ *    left idle.
  *  - The warped slice of a 32 x 16 pixel tile with its 9x7 halo is computed
  *    once per plane into shared memory by the whole block (fp32 steps
  *    restated with explicit round-to-nearest ops, so bit-identical to the
  *    CPU); M * (x, y, 1) does not depend on the plane and is kept in
- *    registers.
+ *    registers. Integer <-> float conversions run on the quarter-rate XU
+ *    pipe: the neighbour image is read from a float copy, floor() is taken
+ *    with the 1.5 * 2^23 trick.
  * Semantics restated from census_filter / create_cost_volume
  * (lib/sgm_stereo.cc:126-148, 192-244): census only for pixels with
  * 4 <= x < w-5, 3 <= y < h-4 and a non-zero centre; cost 255 where the
@@ -79,37 +88,65 @@ constexpr int HALO_N = HALO_W * HALO_H;          /* 880 */
 constexpr int HALO_PER_THREAD = (HALO_N + CT_THREADS - 1) / CT_THREADS;
 constexpr int PLANES = 4;                        /* planes per iteration */
 
-__device__ __forceinline__ uint8_t
-warp_from_tp (SgmParams const& p, uint8_t const* __restrict__ neigh,
-    float const* tp, float depth)
+/* floor of 0 <= x < 2^22 as a float and as an int, without F2I / I2F */
+__device__ __forceinline__ void
+floor_pos (float x, float& fl, int& n)
+{
+    float const magic = 12582912.0f;              /* 1.5 * 2^23 */
+    float const t = __fadd_rn(x, magic);          /* nearest integer */
+    fl = __fsub_rn(t, magic);
+    n = __float_as_int(t) - 0x4B400000;
+    if (fl > x)
+    {
+        fl = __fsub_rn(fl, 1.0f);
+        n -= 1;
+    }
+}
+
+/* warped_neighbors_for_depth (lib/sgm_stereo.cc:150-190) for one pixel and
+ * plane: the neighbour's luminance as the byte value the reference stores,
+ * returned as a float (0 = no sample). neigh: float copy of the byte image. */
+__device__ __forceinline__ float
+warp_from_tp (SgmParams const& p, float const* __restrict__ neigh,
+    float const* tp, float depth, float nw1, float nh1)
 {
     float q0 = __fadd_rn(__fmul_rn(tp[0], depth), p.t[0]);
     float q1 = __fadd_rn(__fmul_rn(tp[1], depth), p.t[1]);
     float const q2 = __fadd_rn(__fmul_rn(tp[2], depth), p.t[2]);
     if (q2 < 0)
-        return 0;
+        return 0.0f;
     q0 = __fsub_rn(__fdiv_rn(q0, q2), 0.5f);
     q1 = __fsub_rn(__fdiv_rn(q1, q2), 0.5f);
-    if (q0 < 0 || q1 < 0 || q0 > static_cast<float>(p.nw - 1)
-        || q1 > static_cast<float>(p.nh - 1))
-        return 0;
+    /* written so that NaN coordinates pass like in the reference's test
+     * (all comparisons false) and are then clamped by fmaxf / fminf */
+    if (q0 < 0 || q1 < 0 || q0 > nw1 || q1 > nh1)
+        return 0.0f;
     /* mve::Image<uint8_t>::linear_at */
-    float const xx = fmaxf(0.0f, fminf(static_cast<float>(p.nw - 1), q0));
-    float const yy = fmaxf(0.0f, fminf(static_cast<float>(p.nh - 1), q1));
-    int const fx = static_cast<int>(xx), fy = static_cast<int>(yy);
+    float const xx = fmaxf(0.0f, fminf(nw1, q0));
+    float const yy = fmaxf(0.0f, fminf(nh1, q1));
+    float fxf, fyf;
+    int fx, fy;
+    floor_pos(xx, fxf, fx);
+    floor_pos(yy, fyf, fy);
     int const fx1 = min(fx + 1, p.nw - 1), fy1 = min(fy + 1, p.nh - 1);
-    float const w1 = __fsub_rn(xx, static_cast<float>(fx));
+    float const w1 = __fsub_rn(xx, fxf);
     float const w0 = __fsub_rn(1.0f, w1);
-    float const w3 = __fsub_rn(yy, static_cast<float>(fy));
+    float const w3 = __fsub_rn(yy, fyf);
     float const w2 = __fsub_rn(1.0f, w3);
-    float const v00 = neigh[fy * p.nw + fx], v10 = neigh[fy * p.nw + fx1];
-    float const v01 = neigh[fy1 * p.nw + fx], v11 = neigh[fy1 * p.nw + fx1];
+    float const v00 = __ldg(neigh + fy * p.nw + fx);
+    float const v10 = __ldg(neigh + fy * p.nw + fx1);
+    float const v01 = __ldg(neigh + fy1 * p.nw + fx);
+    float const v11 = __ldg(neigh + fy1 * p.nw + fx1);
     float s = __fmul_rn(v00, __fmul_rn(w0, w2));
     s = __fadd_rn(s, __fmul_rn(v10, __fmul_rn(w1, w2)));
     s = __fadd_rn(s, __fmul_rn(v01, __fmul_rn(w0, w3)));
     s = __fadd_rn(s, __fmul_rn(v11, __fmul_rn(w1, w3)));
     s = __fadd_rn(s, 0.5f);
-    return static_cast<uint8_t>(s);
+    /* static_cast<uint8_t>(s): truncation, 0 <= s < 256 */
+    float fl;
+    int n;
+    floor_pos(s, fl, n);
+    return fl;
 }
 
 /* Pair of 16-bit fields at element offset e (0..8) of the five words
@@ -117,14 +154,37 @@ warp_from_tp (SgmParams const& p, uint8_t const* __restrict__ neigh,
 #define SMVSB_WINDOW(wd, e) (((e) & 1) ? __funnelshift_r((wd)[(e) >> 1],   \
     (wd)[((e) >> 1) + 1], 16) : (wd)[(e) >> 1])
 
-__global__ void __launch_bounds__(CT_THREADS)
+__device__ __forceinline__ __half2
+as_half2 (unsigned v)
+{
+    return *reinterpret_cast<__half2*>(&v);
+}
+
+__device__ __forceinline__ unsigned
+as_word (__half2 v)
+{
+    return *reinterpret_cast<unsigned*>(&v);
+}
+
+__global__ void
+u8_to_float_kernel (size_t n, uint8_t const* __restrict__ in,
+    float* __restrict__ out)
+{
+    size_t const i = static_cast<size_t>(blockIdx.x) * blockDim.x
+        + threadIdx.x;
+    if (i < n)
+        out[i] = static_cast<float>(in[i]);
+}
+
+__global__ void __launch_bounds__(CT_THREADS, 2)
 sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
-    uint8_t const* __restrict__ neigh, float const* __restrict__ depths,
+    float const* __restrict__ neigh, float const* __restrict__ depths,
     uint8_t* __restrict__ cost)
 {
-    /* tile of 16-bit pixels, HALO_W even; as words: HALO_W / 2 per row */
+    /* tile of fp16 pixels, HALO_W even; as words: HALO_W / 2 per row */
     __shared__ unsigned s_tile[PLANES][HALO_H][HALO_W / 2];
-    /* main comparison bits, [63][CT_THREADS] words = 63 KB: dynamic */
+    /* signs of the main comparison bits, [63][CT_THREADS] half2 = 63 KB:
+     * dynamic; then [CT_THREADS] half2 of the bit counts K */
     extern __shared__ unsigned s_mask_dyn[];
     unsigned (*s_mask)[CT_THREADS] =
         reinterpret_cast<unsigned (*)[CT_THREADS]>(s_mask_dyn);
@@ -134,6 +194,8 @@ sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
     int const tx = tid % (CT_W / 2), ty = tid / (CT_W / 2);
     int const x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
     int const px = x0 + 2 * tx, py = y0 + ty;        /* left pixel of the pair */
+    float const nw1 = static_cast<float>(p.nw - 1);
+    float const nh1 = static_cast<float>(p.nh - 1);
 
     for (int i = tid; i < p.D; i += CT_THREADS)
         s_depths[i] = depths[i];
@@ -158,8 +220,8 @@ sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
         }
     }
 
-    /* main image tile -> comparison bits per offset */
-    unsigned short* tile16 = reinterpret_cast<unsigned short*>(&s_tile[0][0][0]);
+    /* main image tile -> signs of its comparison bits per offset */
+    __half* tile16 = reinterpret_cast<__half*>(&s_tile[0][0][0]);
 #pragma unroll
     for (int k = 0; k < HALO_PER_THREAD; ++k)
     {
@@ -167,7 +229,8 @@ sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
         if (i < HALO_N)
         {
             int const gx = x0 - 4 + i % HALO_W, gy = y0 - 3 + i / HALO_W;
-            tile16[i] = in_img[k] ? main_img[gy * p.w + gx] : 0;
+            tile16[i] = __ushort2half_rn(in_img[k]
+                ? main_img[gy * p.w + gx] : 0);
         }
     }
     __syncthreads();
@@ -175,12 +238,15 @@ sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
     bool const int0 = in0 && px >= 4 && px < p.w - 5 && py >= 3 && py < p.h - 4;
     bool const int1 = in1 && px + 1 >= 4 && px + 1 < p.w - 5 && py >= 3
         && py < p.h - 4;
+    __half2 K2 = __float2half2_rn(0.0f);
     {
-        unsigned const A = s_tile[0][ty + 3][tx + 2];
-        /* fields of pixels without a census (border, zero centre) stay 0 */
-        unsigned keep = 0;
-        if (int0 && (A & 0xffffu) != 0) keep |= 0x00000100u;
-        if (int1 && (A >> 16) != 0) keep |= 0x01000000u;
+        __half2 const A = as_half2(s_tile[0][ty + 3][tx + 2]);
+        /* pixels without a census (border, zero centre): all bits 0 */
+        __half2 const keep = __floats2half2_rn(
+            (int0 && __low2float(A) != 0.0f) ? 1.0f : 0.0f,
+            (int1 && __high2float(A) != 0.0f) ? 1.0f : 0.0f);
+        __half2 const one = __float2half2_rn(1.0f);
+        __half2 const mtwo = __float2half2_rn(-2.0f);
 #pragma unroll
         for (int j = 0; j < 7; ++j)
         {
@@ -190,8 +256,10 @@ sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
 #pragma unroll
             for (int e = 0; e < 9; ++e)
             {
-                unsigned const B = SMVSB_WINDOW(wd, e);
-                s_mask[j * 9 + e][tid] = (B + 0x00FF00FFu - A) & keep;
+                __half2 const B = as_half2(SMVSB_WINDOW(wd, e));
+                __half2 const cm = __hmul2(__hlt2(A, B), keep);
+                K2 = __hadd2(K2, cm);
+                s_mask[j * 9 + e][tid] = as_word(__hfma2(cm, mtwo, one));
             }
         }
     }
@@ -208,22 +276,23 @@ sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
 #pragma unroll
                 for (int pl = 0; pl < PLANES; ++pl)
                 {
-                    unsigned short v = 0;
+                    float v = 0.0f;
                     if (in_img[k])
-                        v = warp_from_tp(p, neigh, tp[k], s_depths[d0 + pl]);
-                    reinterpret_cast<unsigned short*>(
-                        &s_tile[pl][0][0])[i] = v;
+                        v = warp_from_tp(p, neigh, tp[k], s_depths[d0 + pl],
+                            nw1, nh1);
+                    reinterpret_cast<__half*>(&s_tile[pl][0][0])[i]
+                        = __float2half_rn(v);
                 }
             }
         }
         __syncthreads();
 
-        unsigned A[PLANES], acc[PLANES];
+        __half2 A[PLANES], acc[PLANES];
 #pragma unroll
         for (int pl = 0; pl < PLANES; ++pl)
         {
-            A[pl] = s_tile[pl][ty + 3][tx + 2];
-            acc[pl] = 0;
+            A[pl] = as_half2(s_tile[pl][ty + 3][tx + 2]);
+            acc[pl] = K2;
         }
 #pragma unroll
         for (int j = 0; j < 7; ++j)
@@ -237,12 +306,12 @@ sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
 #pragma unroll
             for (int e = 0; e < 9; ++e)
             {
-                unsigned const mm = s_mask[j * 9 + e][tid];
+                __half2 const sg = as_half2(s_mask[j * 9 + e][tid]);
 #pragma unroll
                 for (int pl = 0; pl < PLANES; ++pl)
                 {
-                    unsigned const B = SMVSB_WINDOW(wd[pl], e);
-                    acc[pl] += ((B + 0x00FF00FFu - A[pl]) ^ mm) & 0x01000100u;
+                    __half2 const B = as_half2(SMVSB_WINDOW(wd[pl], e));
+                    acc[pl] = __hfma2(__hlt2(A[pl], B), sg, acc[pl]);
                 }
             }
         }
@@ -251,12 +320,13 @@ sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
 #pragma unroll
         for (int pl = 0; pl < PLANES; ++pl)
         {
-            unsigned const w0v = A[pl] & 0xffffu, w1v = A[pl] >> 16;
             /* border pixels have no census on either side: distance 0 */
-            unsigned c0 = int0 ? ((acc[pl] >> 8) & 0xffu) : 0u;
-            unsigned c1 = int1 ? (acc[pl] >> 24) : 0u;
-            if (w0v == 0) c0 = 255u;
-            if (w1v == 0) c1 = 255u;
+            unsigned c0 = int0 ? static_cast<unsigned>(
+                __half2int_rn(__low2half(acc[pl]))) : 0u;
+            unsigned c1 = int1 ? static_cast<unsigned>(
+                __half2int_rn(__high2half(acc[pl]))) : 0u;
+            if ((as_word(A[pl]) & 0x7fffu) == 0) c0 = 255u;
+            if ((as_word(A[pl]) & 0x7fff0000u) == 0) c1 = 255u;
             out0 |= c0 << (8 * pl);
             out1 |= c1 << (8 * pl);
         }
@@ -357,57 +427,84 @@ sgm_paths_kernel (int w, int h, unsigned P1, unsigned P2,
         unsigned const P1x2 = P1 | (P1 << 16), P2x2 = P2 | (P2 << 16);
         unsigned const BIG = 0x7000u;      /* "no neighbour" sentinel */
         unsigned P01 = 0, P23 = 0;
-        size_t base = (static_cast<size_t>(y) * w + x) * D + lane * 4;
-        unsigned c4 = *reinterpret_cast<unsigned const*>(cost + base);
-        bool start = true;
-        for (int s = 0; s < steps; ++s)
+        /* the cost words travel PF steps ahead of the recurrence: a step is a
+         * short dependent chain (shuffle reduction), so a warp has few loads
+         * in flight unless it fetches ahead */
+        constexpr int PF = 4;
+        unsigned cq[PF];
+        int xp = x, yp = y;
+        auto advance = [&](int& ax, int& ay)
         {
-            int xn = x + dx, yn = y + dy;
-            if (xn < 0) xn = w - 1;
-            if (xn >= w) xn = 0;
-            bool const startn = diagonal && (xn == restart_x);
-            size_t const basen = (static_cast<size_t>(yn) * w + xn) * D
-                + lane * 4;
-            unsigned c4n = 0;
-            if (s + 1 < steps)
-                c4n = *reinterpret_cast<unsigned const*>(cost + basen);
-
-            unsigned const C01 = __byte_perm(c4, 0, 0x4140);
-            unsigned const C23 = __byte_perm(c4, 0, 0x4342);
-            unsigned D01 = 0, D23 = 0;
-            if (start)
+            ax += dx; ay += dy;
+            if (ax < 0) ax = w - 1;
+            if (ax >= w) ax = 0;
+        };
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+        {
+            cq[u] = 0;
+            if (u < steps)
             {
-                P01 = C01; P23 = C23;
+                cq[u] = *reinterpret_cast<unsigned const*>(cost
+                    + (static_cast<size_t>(yp) * w + xp) * D + lane * 4);
+                advance(xp, yp);
             }
-            else
+        }
+        bool start = true;
+        for (int s0 = 0; s0 < steps; s0 += PF)
+        {
+#pragma unroll
+            for (int u = 0; u < PF; ++u)
             {
-                unsigned const m2 = __vminu2(P01, P23);
-                unsigned mn = min(m2 & 0xffffu, m2 >> 16);
-                for (int off = 16; off > 0; off >>= 1)
-                    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-                unsigned below = __shfl_up_sync(0xffffffffu, P23, 1) >> 16;
-                unsigned above = __shfl_down_sync(0xffffffffu, P01, 1)
-                    & 0xffffu;
-                if (lane == 0) below = BIG;
-                if (lane == 31) above = BIG;
-                unsigned const mid = (P01 >> 16) | (P23 << 16);   /* L1, L2 */
-                unsigned const lo01 = below | (P01 << 16);        /* -, L0 */
-                unsigned const hi23 = (P23 >> 16) | (above << 16);/* L3, - */
-                unsigned const mn2 = mn * 0x10001u;
-                unsigned const far2 = mn2 + P2x2;
-                unsigned const b01 = __vimin3_u16x2(P01, far2,
-                    __viaddmin_u16x2(mid, P1x2, lo01 + P1x2));
-                unsigned const b23 = __vimin3_u16x2(P23, far2,
-                    __viaddmin_u16x2(hi23, P1x2, mid + P1x2));
-                D01 = b01 - mn2;          /* = L - C, in [0, P2] per half */
-                D23 = b23 - mn2;
-                P01 = C01 + D01;
-                P23 = C23 + D23;
+                int const s = s0 + u;
+                if (s >= steps)
+                    break;
+                unsigned const c4 = cq[u];
+                if (s + PF < steps)
+                {
+                    cq[u] = *reinterpret_cast<unsigned const*>(cost
+                        + (static_cast<size_t>(yp) * w + xp) * D + lane * 4);
+                    advance(xp, yp);
+                }
+                size_t const base = (static_cast<size_t>(y) * w + x) * D
+                    + lane * 4;
+                unsigned const C01 = __byte_perm(c4, 0, 0x4140);
+                unsigned const C23 = __byte_perm(c4, 0, 0x4342);
+                unsigned D01 = 0, D23 = 0;
+                if (start)
+                {
+                    P01 = C01; P23 = C23;
+                }
+                else
+                {
+                    unsigned const m2 = __vminu2(P01, P23);
+                    unsigned mn = min(m2 & 0xffffu, m2 >> 16);
+                    for (int off = 16; off > 0; off >>= 1)
+                        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+                    unsigned below = __shfl_up_sync(0xffffffffu, P23, 1) >> 16;
+                    unsigned above = __shfl_down_sync(0xffffffffu, P01, 1)
+                        & 0xffffu;
+                    if (lane == 0) below = BIG;
+                    if (lane == 31) above = BIG;
+                    unsigned const mid = (P01 >> 16) | (P23 << 16);  /* L1, L2 */
+                    unsigned const lo01 = below | (P01 << 16);       /* -, L0 */
+                    unsigned const hi23 = (P23 >> 16) | (above << 16);/* L3, - */
+                    unsigned const mn2 = mn * 0x10001u;
+                    unsigned const far2 = mn2 + P2x2;
+                    unsigned const b01 = __vimin3_u16x2(P01, far2,
+                        __viaddmin_u16x2(mid, P1x2, lo01 + P1x2));
+                    unsigned const b23 = __vimin3_u16x2(P23, far2,
+                        __viaddmin_u16x2(hi23, P1x2, mid + P1x2));
+                    D01 = b01 - mn2;      /* = L - C, in [0, P2] per half */
+                    D23 = b23 - mn2;
+                    P01 = C01 + D01;
+                    P23 = C23 + D23;
+                }
+                *reinterpret_cast<unsigned*>(Dr + base) =
+                    __byte_perm(D01, D23, 0x6420);
+                advance(x, y);
+                start = diagonal && (x == restart_x);
             }
-            *reinterpret_cast<unsigned*>(Dr + base) =
-                __byte_perm(D01, D23, 0x6420);
-            c4 = c4n;
-            x = xn; y = yn; base = basen; start = startn;
         }
         return;
     }
@@ -582,6 +679,220 @@ run_wta (int w, int h, uint8_t const* cost, uint8_t const* Dvol,
 
 thread_local std::string g_sgm_error;
 
+/*
+ * SGMStereo::reconstruct's consistency check (lib/sgm_stereo.cc:64-91): every
+ * main-view depth is reprojected into the neighbour (Correspondence::update /
+ * fill, lib/correspondence.cc:20-51, in double with the fp32 reprojection
+ * widened, pixel coordinates WITHOUT the half-pixel offset) and dropped when
+ * it lands inside the 3 % border, on a neighbour pixel without depth, or when
+ * the two depths differ by more than 20 %. Arithmetic in the reference's
+ * order, no contraction: decisions are the CPU's.
+ */
+struct ConsistencyParams
+{
+    int w, h, nw, nh, cut;
+    double M[9], t[3];
+};
+
+__global__ void
+sgm_consistency_kernel (ConsistencyParams const p,
+    float* __restrict__ d_main, float const* __restrict__ d_neig)
+{
+    int const x = blockIdx.x * blockDim.x + threadIdx.x;
+    int const y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= p.w || y >= p.h)
+        return;
+    size_t const i = static_cast<size_t>(y) * p.w + x;
+    float const dm = d_main[i];
+    if (dm == 0.0f)
+        return;
+    double const u = x, v = y, wd = dm;
+    double const pp = __dadd_rn(__dadd_rn(__dmul_rn(p.M[0], u),
+        __dmul_rn(p.M[1], v)), p.M[2]);
+    double const qq = __dadd_rn(__dadd_rn(__dmul_rn(p.M[3], u),
+        __dmul_rn(p.M[4], v)), p.M[5]);
+    double const rr = __dadd_rn(__dadd_rn(__dmul_rn(p.M[6], u),
+        __dmul_rn(p.M[7], v)), p.M[8]);
+    double const a = __dadd_rn(__dmul_rn(wd, pp), p.t[0]);
+    double const b = __dadd_rn(__dmul_rn(wd, qq), p.t[1]);
+    double const d = __dadd_rn(__dmul_rn(wd, rr), p.t[2]);
+    double const cx = __ddiv_rn(a, d), cy = __ddiv_rn(b, d);
+    /* written as the negation of "inside" so that NaN coordinates (d == 0)
+     * behave like the reference's comparisons: all false -> not rejected
+     * here, then indexed with whatever (int)NaN is -- not reproduced: the
+     * reference's behaviour is undefined there; such a pixel is dropped */
+    if (!(cx == cx) || !(cy == cy))
+    {
+        d_main[i] = 0.0f;
+        return;
+    }
+    if (cx < p.cut || cx >= p.nw - p.cut || cy < p.cut || cy >= p.nh - p.cut)
+    {
+        d_main[i] = 0.0f;
+        return;
+    }
+    float const cdepth = static_cast<float>(d);
+    float const ndepth = d_neig[static_cast<size_t>(static_cast<int>(cy))
+        * p.nw + static_cast<int>(cx)];
+    float const ratio = __fdiv_rn(fminf(cdepth, ndepth),
+        fmaxf(cdepth, ndepth));
+    if (ndepth == 0.0f || ratio < 0.8f)
+        d_main[i] = 0.0f;
+}
+
+/* app/smvsrecon.cc:362-377: the mean of two SGM results where both have a
+ * depth, otherwise the one that has. */
+__global__ void
+sgm_merge_kernel (size_t n, float const* __restrict__ first,
+    float* __restrict__ second_inout)
+{
+    size_t const i = static_cast<size_t>(blockIdx.x) * blockDim.x
+        + threadIdx.x;
+    if (i >= n)
+        return;
+    float const d1 = first[i], d2 = second_inout[i];
+    float out = d1;
+    if (d2 != 0.0f)
+        out = (d1 == 0.0f) ? d2 : __fmul_rn(__fadd_rn(d1, d2), 0.5f);
+    second_inout[i] = out;
+}
+
+/* One workspace per device, shared by all host threads (calls on a device
+ * serialise: the volumes of one 2 MP x 128 run take 2.4 GB). */
+struct SgmWorkspace
+{
+    std::mutex lock;
+    bool ready = false;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[8] = {};
+    DevBuf<uint8_t> d_main, d_neigh, d_cost, d_D;
+    DevBuf<uint16_t> d_S;
+    DevBuf<float> d_depths, d_out, d_out2, d_prev, d_neigh_f;
+};
+
+SgmWorkspace g_sgm_ws[SMVSB_MAX_DEVICES];
+
+void
+check_sgm_args (int w, int h, int nw, int nh, void const* a, void const* b,
+    void const* M, void const* t, void const* out, int num_steps,
+    uint16_t penalty1, uint16_t penalty2)
+{
+    if (!(w > 9 && h > 7 && nw > 1 && nh > 1 && a && b && M && t && out))
+        throw Error(SMVSB_ERR_INVALID, "smvsb_sgm: bad image arguments");
+    if (num_steps < 32 || num_steps > 256 || num_steps % 32 != 0
+        || (num_steps / 32 != 1 && num_steps / 32 != 2
+            && num_steps / 32 != 4 && num_steps / 32 != 8))
+        throw Error(SMVSB_ERR_INVALID,
+            "smvsb_sgm: num_steps must be 32, 64, 128 or 256");
+    /* the O(D) recurrence equals the reference's O(D^2) minimum only
+     * for P1 <= P2 and without uint16 wrap-around */
+    if (penalty1 > penalty2 || penalty2 > 255)
+        throw Error(SMVSB_ERR_INVALID,
+            "smvsb_sgm: need penalty1 <= penalty2 <= 255");
+}
+
+SgmWorkspace&
+workspace_for (int device)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        throw Error(SMVSB_ERR_CUDA, "no CUDA device (no CPU fallback)");
+    if (device < 0 || device >= count || device >= SMVSB_MAX_DEVICES)
+        throw Error(SMVSB_ERR_INVALID, "device index out of range");
+    return g_sgm_ws[device];
+}
+
+void
+prepare_workspace (SgmWorkspace& ws, int device)
+{
+    CUDA_CHECK(cudaSetDevice(device));
+    if (!ws.ready)
+    {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&ws.st, cudaStreamNonBlocking));
+        for (int i = 0; i < 8; ++i)
+            CUDA_CHECK(cudaEventCreate(&ws.ev[i]));
+        ws.ready = true;
+    }
+}
+
+/* create_cost_volume + aggregate_sgm_costs + depth_from_sgm_volume for the
+ * image pair already on the device; ev[e0 .. e0+3] bracket the three stages. */
+void
+sgm_pair (SgmWorkspace& ws, int w, int h, uint8_t const* main_dev, int nw,
+    int nh, uint8_t const* neigh_dev, float const* M, float const* t,
+    float min_depth, float max_depth, int num_steps, unsigned P1, unsigned P2,
+    bool want_S, float* out_dev, int e0)
+{
+    cudaStream_t st = ws.st;
+    /* plane depths, lib/sgm_stereo.cc:195-203 (fp32 recurrence) */
+    std::vector<float> depths(num_steps);
+    {
+        float inv_depth = 1.0f / max_depth;
+        float const increment = (1.0f / min_depth - inv_depth)
+            / (num_steps - 1);
+        for (int i = 0; i < num_steps; ++i)
+        {
+            depths[i] = 1.0f / inv_depth;
+            inv_depth += increment;
+        }
+    }
+    size_t const npix = static_cast<size_t>(w) * h;
+    size_t const nvox = npix * num_steps;
+    ws.d_cost.reserve(nvox);
+    ws.d_D.reserve(nvox * 8);                 /* L - C per direction */
+    if (want_S)
+        ws.d_S.reserve(nvox);
+    /* two slots: the first pair of a reconstruct call may still be reading
+     * its depths when the second pair's are copied */
+    ws.d_depths.reserve(512);
+    float* const depths_dev = ws.d_depths.p + (e0 != 0 ? 256 : 0);
+    CUDA_CHECK(cudaMemcpyAsync(depths_dev, depths.data(),
+        num_steps * sizeof(float), cudaMemcpyHostToDevice, st));
+    /* pageable source: staged before the call returns */
+
+    SgmParams p;
+    p.w = w; p.h = h; p.nw = nw; p.nh = nh; p.D = num_steps;
+    std::copy(M, M + 9, p.M);
+    std::copy(t, t + 3, p.t);
+
+    CUDA_CHECK(cudaEventRecord(ws.ev[e0], st));
+    /* float copy of the neighbour's byte image (part of the cost stage) */
+    size_t const nnpix = static_cast<size_t>(nw) * nh;
+    ws.d_neigh_f.reserve(nnpix);
+    u8_to_float_kernel<<<static_cast<unsigned>((nnpix + 255) / 256), 256, 0,
+        st>>>(nnpix, neigh_dev, ws.d_neigh_f.p);
+    CUDA_CHECK(cudaGetLastError());
+    dim3 const cb(CT_THREADS);
+    dim3 const cg((w + CT_W - 1) / CT_W, (h + CT_H - 1) / CT_H);
+    size_t const mask_bytes = 63 * CT_THREADS * sizeof(unsigned);
+    CUDA_CHECK(cudaFuncSetAttribute(sgm_cost_kernel,
+        cudaFuncAttributeMaxDynamicSharedMemorySize,
+        static_cast<int>(mask_bytes)));
+    sgm_cost_kernel<<<cg, cb, mask_bytes, st>>>(p, main_dev, ws.d_neigh_f.p,
+        depths_dev, ws.d_cost.p);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaEventRecord(ws.ev[e0 + 1], st));
+
+    int const dpl = num_steps / 32;
+    switch (dpl)
+    {
+    case 1: run_paths<1>(w, h, P1, P2, ws.d_cost.p, ws.d_D.p, st); break;
+    case 2: run_paths<2>(w, h, P1, P2, ws.d_cost.p, ws.d_D.p, st); break;
+    case 4: run_paths<4>(w, h, P1, P2, ws.d_cost.p, ws.d_D.p, st); break;
+    default: run_paths<8>(w, h, P1, P2, ws.d_cost.p, ws.d_D.p, st); break;
+    }
+    CUDA_CHECK(cudaEventRecord(ws.ev[e0 + 2], st));
+    uint16_t* const S_dev = want_S ? ws.d_S.p : nullptr;
+    switch (dpl)
+    {
+    case 1: run_wta<1>(w, h, ws.d_cost.p, ws.d_D.p, main_dev, depths_dev, S_dev, out_dev, st); break;
+    case 2: run_wta<2>(w, h, ws.d_cost.p, ws.d_D.p, main_dev, depths_dev, S_dev, out_dev, st); break;
+    case 4: run_wta<4>(w, h, ws.d_cost.p, ws.d_D.p, main_dev, depths_dev, S_dev, out_dev, st); break;
+    default: run_wta<8>(w, h, ws.d_cost.p, ws.d_D.p, main_dev, depths_dev, S_dev, out_dev, st); break;
+    }
+    CUDA_CHECK(cudaEventRecord(ws.ev[e0 + 3], st));
+}
+
 } /* namespace */
 
 std::string const&
@@ -597,116 +908,42 @@ sgm_run (int device, int w, int h, uint8_t const* main_lum, int nw, int nh,
     uint16_t penalty2, float* depth_out, uint16_t* cost_out,
     uint16_t* sgm_out, double* ms_out)
 {
-    cudaStream_t st = nullptr;
-    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     int rc = SMVSB_OK;
     try
     {
-        if (!(w > 9 && h > 7 && nw > 1 && nh > 1 && main_lum && neigh_lum
-            && M && t && depth_out))
-            throw Error(SMVSB_ERR_INVALID, "smvsb_sgm: bad image arguments");
-        if (num_steps < 32 || num_steps > 256 || num_steps % 32 != 0
-            || (num_steps / 32 != 1 && num_steps / 32 != 2
-                && num_steps / 32 != 4 && num_steps / 32 != 8))
-            throw Error(SMVSB_ERR_INVALID,
-                "smvsb_sgm: num_steps must be 32, 64, 128 or 256");
-        /* the O(D) recurrence equals the reference's O(D^2) minimum only
-         * for P1 <= P2 and without uint16 wrap-around */
-        if (penalty1 > penalty2 || penalty2 > 255)
-            throw Error(SMVSB_ERR_INVALID,
-                "smvsb_sgm: need penalty1 <= penalty2 <= 255");
-        int count = 0;
-        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
-            throw Error(SMVSB_ERR_CUDA, "no CUDA device (no CPU fallback)");
-        if (device < 0 || device >= count)
-            throw Error(SMVSB_ERR_INVALID, "device index out of range");
-        CUDA_CHECK(cudaSetDevice(device));
-        CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        for (int i = 0; i < 4; ++i)
-            CUDA_CHECK(cudaEventCreate(&ev[i]));
-
-        /* plane depths, lib/sgm_stereo.cc:195-203 (fp32 recurrence) */
-        std::vector<float> depths(num_steps);
-        {
-            float inv_depth = 1.0f / max_depth;
-            float const increment = (1.0f / min_depth - inv_depth)
-                / (num_steps - 1);
-            for (int i = 0; i < num_steps; ++i)
-            {
-                depths[i] = 1.0f / inv_depth;
-                inv_depth += increment;
-            }
-        }
-
+        check_sgm_args(w, h, nw, nh, main_lum, neigh_lum, M, t, depth_out,
+            num_steps, penalty1, penalty2);
+        SgmWorkspace& ws = workspace_for(device);
+        std::lock_guard<std::mutex> guard(ws.lock);
+        prepare_workspace(ws, device);
+        cudaStream_t st = ws.st;
         size_t const npix = static_cast<size_t>(w) * h;
         size_t const nvox = npix * num_steps;
-        DevBuf<uint8_t> d_main, d_neigh, d_cost, d_D;
-        DevBuf<uint16_t> d_S;
-        DevBuf<float> d_depths, d_out;
-        d_main.reserve(npix);
-        d_neigh.reserve(static_cast<size_t>(nw) * nh);
-        d_cost.reserve(nvox);
-        d_D.reserve(nvox * 8);                 /* L - C per direction */
-        if (sgm_out || cost_out)
-            d_S.reserve(nvox);
-        d_depths.reserve(num_steps);
-        d_out.reserve(npix);
-        CUDA_CHECK(cudaMemcpyAsync(d_main.p, main_lum, npix,
+        ws.d_main.reserve(npix);
+        ws.d_neigh.reserve(static_cast<size_t>(nw) * nh);
+        ws.d_out.reserve(npix);
+        if (cost_out)
+            ws.d_S.reserve(nvox);
+        CUDA_CHECK(cudaMemcpyAsync(ws.d_main.p, main_lum, npix,
             cudaMemcpyHostToDevice, st));
-        CUDA_CHECK(cudaMemcpyAsync(d_neigh.p, neigh_lum,
+        CUDA_CHECK(cudaMemcpyAsync(ws.d_neigh.p, neigh_lum,
             static_cast<size_t>(nw) * nh, cudaMemcpyHostToDevice, st));
-        CUDA_CHECK(cudaMemcpyAsync(d_depths.p, depths.data(),
-            num_steps * sizeof(float), cudaMemcpyHostToDevice, st));
-
-        SgmParams p;
-        p.w = w; p.h = h; p.nw = nw; p.nh = nh; p.D = num_steps;
-        std::copy(M, M + 9, p.M);
-        std::copy(t, t + 3, p.t);
-
-        CUDA_CHECK(cudaEventRecord(ev[0], st));
-        dim3 const cb(CT_THREADS);
-        dim3 const cg((w + CT_W - 1) / CT_W, (h + CT_H - 1) / CT_H);
-        size_t const mask_bytes = 63 * CT_THREADS * sizeof(unsigned);
-        CUDA_CHECK(cudaFuncSetAttribute(sgm_cost_kernel,
-            cudaFuncAttributeMaxDynamicSharedMemorySize,
-            static_cast<int>(mask_bytes)));
-        sgm_cost_kernel<<<cg, cb, mask_bytes, st>>>(p, d_main.p, d_neigh.p, d_depths.p,
-            d_cost.p);
-        CUDA_CHECK(cudaGetLastError());
-        CUDA_CHECK(cudaEventRecord(ev[1], st));
-
-        int const dpl = num_steps / 32;
-        switch (dpl)
-        {
-        case 1: run_paths<1>(w, h, penalty1, penalty2, d_cost.p, d_D.p, st); break;
-        case 2: run_paths<2>(w, h, penalty1, penalty2, d_cost.p, d_D.p, st); break;
-        case 4: run_paths<4>(w, h, penalty1, penalty2, d_cost.p, d_D.p, st); break;
-        default: run_paths<8>(w, h, penalty1, penalty2, d_cost.p, d_D.p, st); break;
-        }
-        CUDA_CHECK(cudaEventRecord(ev[2], st));
-        uint16_t* const S_dev = sgm_out ? d_S.p : nullptr;
-        switch (dpl)
-        {
-        case 1: run_wta<1>(w, h, d_cost.p, d_D.p, d_main.p, d_depths.p, S_dev, d_out.p, st); break;
-        case 2: run_wta<2>(w, h, d_cost.p, d_D.p, d_main.p, d_depths.p, S_dev, d_out.p, st); break;
-        case 4: run_wta<4>(w, h, d_cost.p, d_D.p, d_main.p, d_depths.p, S_dev, d_out.p, st); break;
-        default: run_wta<8>(w, h, d_cost.p, d_D.p, d_main.p, d_depths.p, S_dev, d_out.p, st); break;
-        }
-        CUDA_CHECK(cudaEventRecord(ev[3], st));
-
-        CUDA_CHECK(cudaMemcpyAsync(depth_out, d_out.p, npix * sizeof(float),
+        sgm_pair(ws, w, h, ws.d_main.p, nw, nh, ws.d_neigh.p, M, t, min_depth,
+            max_depth, num_steps, penalty1, penalty2, sgm_out != nullptr,
+            ws.d_out.p, 0);
+        CUDA_CHECK(cudaMemcpyAsync(depth_out, ws.d_out.p, npix * sizeof(float),
             cudaMemcpyDeviceToHost, st));
         if (sgm_out)
-            CUDA_CHECK(cudaMemcpyAsync(sgm_out, d_S.p,
+            CUDA_CHECK(cudaMemcpyAsync(sgm_out, ws.d_S.p,
                 nvox * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         if (cost_out)
         {
             /* widen through the (now free) S buffer */
             u8_to_u16_kernel<<<static_cast<unsigned>((nvox + 255) / 256), 256,
-                0, st>>>(nvox, d_cost.p, d_S.p);
+                0, st>>>(nvox, ws.d_cost.p, ws.d_S.p);
             CUDA_CHECK(cudaGetLastError());
-            CUDA_CHECK(cudaMemcpyAsync(cost_out, d_S.p,
+            CUDA_CHECK(cudaMemcpyAsync(cost_out, ws.d_S.p,
                 nvox * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
             CUDA_CHECK(cudaStreamSynchronize(st));
         }
@@ -715,7 +952,7 @@ sgm_run (int device, int w, int h, uint8_t const* main_lum, int nw, int nh,
             float ms;
             for (int i = 0; i < 3; ++i)
             {
-                CUDA_CHECK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+                CUDA_CHECK(cudaEventElapsedTime(&ms, ws.ev[i], ws.ev[i + 1]));
                 ms_out[i] = ms;
             }
         }
@@ -725,9 +962,90 @@ sgm_run (int device, int w, int h, uint8_t const* main_lum, int nw, int nh,
         g_sgm_error = e.msg;
         rc = e.code;
     }
-    for (int i = 0; i < 4; ++i)
-        if (ev[i]) cudaEventDestroy(ev[i]);
-    if (st) cudaStreamDestroy(st);
+    return rc;
+}
+
+/* SGMStereo::reconstruct (lib/sgm_stereo.cc:45-96) for an image pair at SGM
+ * working resolution, optionally followed by the merge of
+ * app/smvsrecon.cc:362-377 with an earlier result. */
+int
+sgm_reconstruct (int device, int w, int h, uint8_t const* main_lum, int nw,
+    int nh, uint8_t const* neigh_lum, float const* M_mn, float const* t_mn,
+    float const* M_nm, float const* t_nm, float const* depth_range_main,
+    float const* depth_range_neigh, int num_steps, uint16_t penalty1,
+    uint16_t penalty2, float const* merge_with, float* depth_out,
+    double* ms_out)
+{
+    int rc = SMVSB_OK;
+    try
+    {
+        check_sgm_args(w, h, nw, nh, main_lum, neigh_lum, M_mn, t_mn,
+            depth_out, num_steps, penalty1, penalty2);
+        if (!(nw > 9 && nh > 7 && M_nm && t_nm && depth_range_main
+            && depth_range_neigh))
+            throw Error(SMVSB_ERR_INVALID,
+                "smvsb_sgm_reconstruct: bad arguments");
+        SgmWorkspace& ws = workspace_for(device);
+        std::lock_guard<std::mutex> guard(ws.lock);
+        prepare_workspace(ws, device);
+        cudaStream_t st = ws.st;
+        size_t const npix = static_cast<size_t>(w) * h;
+        size_t const nnpix = static_cast<size_t>(nw) * nh;
+        ws.d_main.reserve(npix);
+        ws.d_neigh.reserve(nnpix);
+        ws.d_out.reserve(npix);
+        ws.d_out2.reserve(nnpix);
+        CUDA_CHECK(cudaMemcpyAsync(ws.d_main.p, main_lum, npix,
+            cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(ws.d_neigh.p, neigh_lum, nnpix,
+            cudaMemcpyHostToDevice, st));
+        if (merge_with != nullptr)
+        {
+            ws.d_prev.reserve(npix);
+            CUDA_CHECK(cudaMemcpyAsync(ws.d_prev.p, merge_with,
+                npix * sizeof(float), cudaMemcpyHostToDevice, st));
+        }
+        /* sgm1: main against neighbour; sgm2: the roles swapped (:56-62) */
+        sgm_pair(ws, w, h, ws.d_main.p, nw, nh, ws.d_neigh.p, M_mn, t_mn,
+            depth_range_main[0], depth_range_main[1], num_steps, penalty1,
+            penalty2, false, ws.d_out.p, 0);
+        sgm_pair(ws, nw, nh, ws.d_neigh.p, w, h, ws.d_main.p, M_nm, t_nm,
+            depth_range_neigh[0], depth_range_neigh[1], num_steps, penalty1,
+            penalty2, false, ws.d_out2.p, 4);
+
+        ConsistencyParams cp;
+        cp.w = w; cp.h = h; cp.nw = nw; cp.nh = nh;
+        cp.cut = static_cast<int>(0.03 * std::max(nw, nh));
+        for (int i = 0; i < 9; ++i) cp.M[i] = M_mn[i];
+        for (int i = 0; i < 3; ++i) cp.t[i] = t_mn[i];
+        dim3 const block(32, 8);
+        dim3 const grid((w + 31) / 32, (h + 7) / 8);
+        sgm_consistency_kernel<<<grid, block, 0, st>>>(cp, ws.d_out.p,
+            ws.d_out2.p);
+        CUDA_CHECK(cudaGetLastError());
+        if (merge_with != nullptr)
+        {
+            sgm_merge_kernel<<<static_cast<unsigned>((npix + 255) / 256), 256,
+                0, st>>>(npix, ws.d_prev.p, ws.d_out.p);
+            CUDA_CHECK(cudaGetLastError());
+        }
+        CUDA_CHECK(cudaMemcpyAsync(depth_out, ws.d_out.p, npix * sizeof(float),
+            cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (ms_out)
+        {
+            float ms;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[3]));
+            ms_out[0] = ms;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, ws.ev[4], ws.ev[7]));
+            ms_out[1] = ms;
+        }
+    }
+    catch (Error const& e)
+    {
+        g_sgm_error = e.msg;
+        rc = e.code;
+    }
     return rc;
 }
 

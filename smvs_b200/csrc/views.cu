@@ -13,7 +13,11 @@
  * 6x9 matrix applied term by term.
  */
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+
+#include <cuda.h>               /* CUtensorMap types only; the driver entry
+                                   point is fetched through the runtime */
 
 #include "common.cuh"
 
@@ -169,6 +173,250 @@ unpack_texels_kernel (float const* __restrict__ texels, int n,
     hess[3 * i] = a.z; hess[3 * i + 1] = a.w; hess[3 * i + 2] = b.x;
 }
 
+/* ------------------------------------------------------------------ */
+/*
+ * The same three steps as ONE kernel with the image tile staged by TMA
+ * (north star: "image pyramids staged to shared memory via TMA"). A block
+ * owns a TW x TH output tile; one elected thread issues a single
+ * cp.async.bulk.tensor.2d for the tile plus its halo of R = ks + 1 pixels
+ * (blur radius + the 3x3 stencil) and the block waits on an mbarrier. The
+ * hardware fills what lies outside the image with zeros; the reference clamps
+ * indices (edge replication, mve::image::blur_gaussian), so the blocks on the
+ * image border overwrite those cells with the edge pixels before use. Then
+ * blur along x, blur along y (both with the CPU's operation order) and the
+ * 6x9 stencil run out of shared memory: the two float images the three-kernel
+ * version writes and reads back (16 B per pixel of DRAM traffic) never exist.
+ * Needs a row pitch that is a multiple of 16 bytes (TMA global strides);
+ * other widths keep the three kernels.
+ */
+constexpr int FT_W = 64, FT_H = 32, FT_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(FT_THREADS)
+set_scale_tma_kernel (const __grid_constant__ CUtensorMap tmap, int w, int h,
+    int R, int box_w, BlurKernel const k, int mode, float* __restrict__ out,
+    float* __restrict__ blur_out)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    int const rows_in = FT_H + 2 * R;
+    size_t const in_bytes = (static_cast<size_t>(box_w) * rows_in * sizeof(T)
+        + 127) / 128 * 128;
+    T* s_in = reinterpret_cast<T*>(smem);
+    float* s_bx = reinterpret_cast<float*>(smem + in_bytes);
+    int const bw = FT_W + 2;                     /* blurred columns kept */
+    float* s_by = s_bx + static_cast<size_t>(rows_in) * bw;
+
+    int const tid = threadIdx.x;
+    int const x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H;
+    unsigned const bar_addr = static_cast<unsigned>(
+        __cvta_generic_to_shared(&bar));
+    unsigned const in_addr = static_cast<unsigned>(
+        __cvta_generic_to_shared(s_in));
+    if (tid == 0)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;"
+            :: "r"(bar_addr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        unsigned const bytes = static_cast<unsigned>(box_w * rows_in
+            * sizeof(T));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+            :: "r"(bar_addr), "r"(bytes) : "memory");
+        int const cx = x0 - R, cy = y0 - R;
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global"
+            ".mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            :: "r"(in_addr), "l"(reinterpret_cast<unsigned long long>(&tmap)),
+               "r"(bar_addr), "r"(cx), "r"(cy) : "memory");
+    }
+    {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n.reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                "selp.u32 %0, 1, 0, p;\n}"
+                : "=r"(done) : "r"(bar_addr) : "memory");
+    }
+
+    /* edge replication where the tile leaves the image */
+    if (x0 - R < 0 || y0 - R < 0 || x0 + FT_W + R > w || y0 + FT_H + R > h)
+    {
+        int const cols = FT_W + 2 * R;
+        for (int i = tid; i < cols * rows_in; i += FT_THREADS)
+        {
+            int const r = i / cols, c = i % cols;
+            int const gx = x0 - R + c, gy = y0 - R + r;
+            if (gx < 0 || gx >= w || gy < 0 || gy >= h)
+            {
+                int const sx = min(max(gx, 0), w - 1) - (x0 - R);
+                int const sy = min(max(gy, 0), h - 1) - (y0 - R);
+                s_in[r * box_w + c] = s_in[sy * box_w + sx];
+            }
+        }
+        __syncthreads();
+    }
+
+    /* blur along x: rows of the tile with halo, columns x0 - 1 .. x0 + TW */
+    for (int i = tid; i < rows_in * bw; i += FT_THREADS)
+    {
+        int const r = i / bw, c = i % bw;
+        T const* row = s_in + r * box_w + (c - 1 + R);
+        float acc = 0.0f;
+        for (int j = -k.ks; j <= k.ks; ++j)
+            acc = __fadd_rn(acc, __fmul_rn(pixel_value(row[j]),
+                k.w[abs(j)]));
+        s_bx[i] = __fdiv_rn(acc, k.wsum);
+    }
+    __syncthreads();
+    /* blur along y: rows y0 - 1 .. y0 + TH */
+    for (int i = tid; i < (FT_H + 2) * bw; i += FT_THREADS)
+    {
+        int const r = i / bw, c = i % bw;
+        float const* col = s_bx + (r - 1 + R) * bw + c;
+        float acc = 0.0f;
+        for (int j = -k.ks; j <= k.ks; ++j)
+            acc = __fadd_rn(acc, __fmul_rn(col[j * bw], k.w[abs(j)]));
+        s_by[i] = __fdiv_rn(acc, k.wsum);
+    }
+    __syncthreads();
+
+    /* compute_gradients_and_hessian on the blurred tile */
+    for (int i = tid; i < FT_W * FT_H; i += FT_THREADS)
+    {
+        int const ly = i / FT_W, lx = i % FT_W;
+        int const x = x0 + lx, y = y0 + ly;
+        if (x >= w || y >= h)
+            continue;
+        size_t const pix = static_cast<size_t>(y) * w + x;
+        if (blur_out != nullptr)
+            blur_out[pix] = s_by[(ly + 1) * bw + lx + 1];
+        double r[6] = {0, 0, 0, 0, 0, 0};
+        if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1)
+        {
+            double const s6 = 1.0 / 6.0, s3 = -1.0 / 3.0, s4 = 1.0 / 4.0;
+            double const M[6][9] = {
+                { s6, s6, s6, s3, s3, s3, s6, s6, s6 },
+                { s6, s3, s6, s6, s3, s6, s6, s3, s6 },
+                { s4, 0.0, -s4, 0.0, 0.0, 0.0, -s4, 0.0, s4 },
+                { -s6, -s6, -s6, 0.0, 0.0, 0.0, s6, s6, s6 },
+                { -s6, 0.0, s6, -s6, 0.0, s6, -s6, 0.0, s6 },
+                { -1.0 / 9.0, 2.0 / 9.0, -1.0 / 9.0, 2.0 / 9.0, 5.0 / 9.0,
+                  2.0 / 9.0, -1.0 / 9.0, 2.0 / 9.0, -1.0 / 9.0 } };
+            double v[9];
+            int cc = 0;
+#pragma unroll
+            for (int a = -1; a < 2; ++a)
+#pragma unroll
+                for (int b = -1; b < 2; ++b)
+                    v[cc++] = s_by[(ly + 1 + b) * bw + (lx + 1 + a)];
+#pragma unroll
+            for (int row = 0; row < 5; ++row)
+            {
+                double sacc = 0.0;
+#pragma unroll
+                for (int q = 0; q < 9; ++q)
+                    sacc = __dadd_rn(sacc, __dmul_rn(M[row][q], v[q]));
+                r[row] = sacc;
+            }
+        }
+        if (mode == 0)
+        {
+            reinterpret_cast<float2*>(out)[pix] = make_float2(
+                static_cast<float>(r[3]), static_cast<float>(r[4]));
+        }
+        else
+        {
+            float4 a, b;
+            a.x = static_cast<float>(r[3]);
+            a.y = static_cast<float>(r[4]);
+            a.z = static_cast<float>(__dmul_rn(2.0, r[0]));
+            a.w = static_cast<float>(r[2]);
+            b.x = static_cast<float>(__dmul_rn(2.0, r[1]));
+            b.y = b.z = b.w = 0.0f;
+            reinterpret_cast<float4*>(out)[2 * pix] = a;
+            reinterpret_cast<float4*>(out)[2 * pix + 1] = b;
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType,
+    cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+/* cuTensorMapEncodeTiled through the runtime (the library does not link
+ * libcuda); nullptr if this driver has none. */
+EncodeTiledFn
+encode_tiled_fn (void)
+{
+    static EncodeTiledFn fn = [] () -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p,
+            cudaEnableDefault, &q) != cudaSuccess
+            || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+/* Launches the fused kernel if the image qualifies; false = use the three
+ * kernels (pitch not a multiple of 16 bytes, very large blur radius, or
+ * SMVSB_NO_TMA set -- the A/B switch of benchmarks/members_bench.py). */
+template <typename T>
+bool
+try_set_scale_tma (smvsb_ctx* c, T const* img_dev, int w, int h,
+    BlurKernel const& k, int mode, float* out_dev, float* blur_out)
+{
+    if (getenv("SMVSB_NO_TMA") != nullptr)
+        return false;
+    if ((static_cast<size_t>(w) * sizeof(T)) % 16 != 0
+        || reinterpret_cast<uintptr_t>(img_dev) % 16 != 0)
+        return false;
+    int const R = k.ks + 1;
+    int const per16 = 16 / static_cast<int>(sizeof(T));
+    int const box_w = (FT_W + 2 * R + per16 - 1) / per16 * per16;
+    int const rows_in = FT_H + 2 * R;
+    if (box_w > 256 || rows_in > 256)
+        return false;
+    EncodeTiledFn const encode = encode_tiled_fn();
+    if (encode == nullptr)
+        return false;
+    CUtensorMap tmap;
+    cuuint64_t const gdim[2] = { static_cast<cuuint64_t>(w),
+        static_cast<cuuint64_t>(h) };
+    cuuint64_t const gstride[1] = { static_cast<cuuint64_t>(w) * sizeof(T) };
+    cuuint32_t const box[2] = { static_cast<cuuint32_t>(box_w),
+        static_cast<cuuint32_t>(rows_in) };
+    cuuint32_t const estride[2] = { 1, 1 };
+    CUresult const rc = encode(&tmap, sizeof(T) == 1
+        ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+        const_cast<T*>(img_dev), gdim, gstride, box, estride,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS)
+        return false;
+    size_t const in_bytes = (static_cast<size_t>(box_w) * rows_in * sizeof(T)
+        + 127) / 128 * 128;
+    size_t const smem = in_bytes + (static_cast<size_t>(rows_in)
+        + FT_H + 2) * (FT_W + 2) * sizeof(float);
+    if (smem > 200 * 1024)
+        return false;
+    CUDA_CHECK(cudaFuncSetAttribute(set_scale_tma_kernel<T>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    dim3 const grid((w + FT_W - 1) / FT_W, (h + FT_H - 1) / FT_H);
+    set_scale_tma_kernel<T><<<grid, FT_THREADS, smem, c->stream>>>(tmap, w,
+        h, R, box_w, k, mode, out_dev, blur_out);
+    CUDA_CHECK(cudaGetLastError());
+    count_launches(c, 1);
+    return true;
+}
+
 } /* namespace */
 
 /* sigma = 0.12 * 2^scale + 0.2 (lib/stereo_view.cc:28), narrowed to float
@@ -201,6 +449,9 @@ device_set_scale (smvsb_ctx* c, uint8_t const* img_dev, int w, int h,
     int scale, float* tmp_a, float* tmp_b, int mode, float* out_dev)
 {
     BlurKernel const k = make_blur_kernel(scale);
+    if (try_set_scale_tma<uint8_t>(c, img_dev, w, h, k, mode, out_dev,
+        nullptr))
+        return;
     dim3 const block(128, 1), grid((w + 127) / 128, h);
     blur_x_kernel<uint8_t><<<grid, block, 0, c->stream>>>(img_dev, w, h, k,
         tmp_a);
@@ -220,6 +471,8 @@ device_set_scale_float (smvsb_ctx* c, float const* img_dev, int w, int h,
     int scale, float* tmp_a, float* tmp_b, float* out_dev)
 {
     BlurKernel const k = make_blur_kernel(scale);
+    if (try_set_scale_tma<float>(c, img_dev, w, h, k, 1, out_dev, tmp_b))
+        return;
     dim3 const block(128, 1), grid((w + 127) / 128, h);
     blur_x_kernel<float><<<grid, block, 0, c->stream>>>(img_dev, w, h, k,
         tmp_a);

@@ -123,21 +123,25 @@ def test_golden_sgm_bit_exact():
     assert np.array_equal(r["depth"], G["depth"])
 
 
-def test_device_set_scale_bitwise():
+@pytest.mark.parametrize("w,h", [(333, 207), (352, 207)])
+def test_device_set_scale_bitwise(w, h):
     """smvsb_set_views_u8 (StereoView::set_scale on the device) against the
-    numpy mirror, which tests/test_cpu_host.py pins bitwise to the reference."""
+    numpy mirror, which tests/test_cpu_host.py pins bitwise to the reference.
+    Row pitches that are a multiple of 16 bytes take the TMA-staged fused
+    kernel, the others the three separate kernels: both must give the same
+    bits, at blur radii from 2 (scale 2) to 12 (scale 5)."""
     from smvs_b200 import stereo_view, workload
-    sc = synth.make_scene(333, 207, 2, seed_index=4, shading=True)
+    sc = synth.make_scene(w, h, 2, seed_index=4, shading=True)
     for scale in (2, 3, 5):
-        wl = workload.build_workload(333, 207, 2, scale=scale, scene=sc, shading=True)
+        wl = workload.build_workload(w, h, 2, scale=scale, scene=sc, shading=True)
         with api.Context(0) as ctx:
             wl.push_views_u8(ctx)
             g, _ = ctx.debug_get_view(0)
             assert np.array_equal(g, wl.main_grad)
             for k in range(2):
-                g, h = ctx.debug_get_view(k + 1)
+                g, hs = ctx.debug_get_view(k + 1)
                 assert np.array_equal(g, wl.sub_grads[k])
-                assert np.array_equal(h, wl.sub_hess[k])
+                assert np.array_equal(hs, wl.sub_hess[k])
             # the Gauss-Newton system built from device-made inputs is the one
             # built from host-made inputs, bit for bit (shading path included)
             wl.push_surface(ctx)
@@ -155,15 +159,16 @@ def test_view_set_scale_bitwise():
     """smvsb_view_set_scale (one StereoView::set_scale, host image in, host
     images out -- what the drop-in member calls) against the numpy mirror."""
     from smvs_b200 import stereo_view
-    sc = synth.make_scene(333, 207, 1, seed_index=5)
-    img = sc.images[1]
-    with api.Context(0) as ctx:
-        for scale in (0, 2, 4, 6):
-            f = stereo_view.byte_to_float(img)
-            blur, grad, hess = ctx.view_set_scale(f, scale)
-            rb, rg, rh = stereo_view.set_scale(img, scale)
-            assert np.array_equal(blur, rb)
-            assert np.array_equal(grad, rg) and np.array_equal(hess, rh)
+    for w in (333, 336):          # 336 * 4 bytes: the TMA-staged fused kernel
+        sc = synth.make_scene(w, 207, 1, seed_index=5)
+        img = sc.images[1]
+        with api.Context(0) as ctx:
+            for scale in (0, 2, 4, 6):
+                f = stereo_view.byte_to_float(img)
+                blur, grad, hess = ctx.view_set_scale(f, scale)
+                rb, rg, rh = stereo_view.set_scale(img, scale)
+                assert np.array_equal(blur, rb)
+                assert np.array_equal(grad, rg) and np.array_equal(hess, rh)
 
 
 @pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")
@@ -542,3 +547,36 @@ def test_batch_is_bitwise_the_single_view_loop():
     finally:
         for c in ctxs:
             c.close()
+
+
+@needs_ref
+def test_sgm_reconstruct_and_merge_bit_exact():
+    """smvsb_sgm_reconstruct: run_sgm in both directions, the consistency check
+    (lib/sgm_stereo.cc:64-91) and the two-neighbour merge
+    (app/smvsrecon.cc:362-377) on the device, against SGMStereo::reconstruct of
+    the compiled reference: the depth image that leaves the GPU is bit-exact."""
+    w, h = 352, 264
+    sc = synth.make_scene(w, h, 2, seed_index=23)
+    dmin, dmax = float(sc.true_depth.min() * 0.7), float(sc.true_depth.max() * 1.3)
+    R = oref.RefScene(sc)
+    ref = [R.sgm_reconstruct(0, k, 0, 64, dmin, dmax) for k in (1, 2)]
+    out, prev = [], None
+    for k in (1, 2):
+        M_mn, t_mn = R.reprojection(0, k, w, h, w, h)
+        M_nm, t_nm = R.reprojection(k, 0, w, h, w, h)
+        single = api.sgm_reconstruct(sc.images[0], sc.images[k], M_mn, t_mn, M_nm, t_nm,
+                                     (dmin, dmax), (dmin, dmax), 64)["depth"]
+        assert np.array_equal(single, ref[k - 1])
+        assert 0.2 < (single > 0).mean() < 1.0      # the check rejects something
+        prev = api.sgm_reconstruct(sc.images[0], sc.images[k], M_mn, t_mn, M_nm, t_nm,
+                                   (dmin, dmax), (dmin, dmax), 64, merge_with=prev)["depth"]
+        out.append(prev)
+    R.close()
+    # app/smvsrecon.cc:362-377 on the two reference results
+    d1, d2 = ref[0].copy(), ref[1]
+    both = (d1 != 0) & (d2 != 0)
+    only2 = (d1 == 0) & (d2 != 0)
+    d1[both] = (d1[both] + d2[both]) * np.float32(0.5)
+    d1[only2] = d2[only2]
+    assert np.array_equal(out[0], ref[0])
+    assert np.array_equal(out[1], d1)

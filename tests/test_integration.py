@@ -113,3 +113,35 @@ def test_visibility_without_sgm_keeps_reference_body():
         r.close()
     assert out[0][0] == out[1][0] > 0
     assert np.array_equal(out[0][2], out[1][2]) and out[0][3] == out[1][3]
+
+
+def test_pool_threads_spread_over_devices():
+    """The drop-in build maps host (pool) thread k to device k mod device count
+    (integration/b200_context.h; the reference runs one view per pool thread,
+    app/smvsrecon.cc:558,658-733). Two threads run the reference's optimize()
+    concurrently: with >= 2 GPUs both devices launch kernels, and either way
+    every result equals the single-threaded CPU result."""
+    import threading
+    L = api.lib()
+    ndev = L.smvsb_device_count()
+    scenes = [synth.make_scene(320, 240, 2, seed_index=60 + k) for k in range(2)]
+    cpu = [_run(sc, None, False) for sc in scenes]
+    before = [L.smvsb_device_launch_count(d) for d in range(max(ndev, 1))]
+    out = [None, None]
+
+    def work(k):
+        out[k] = _run(scenes[k], oref.INTEGRATION_LIB_PATH, False)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    after = [L.smvsb_device_launch_count(d) for d in range(max(ndev, 1))]
+    used = [d for d in range(max(ndev, 1)) if after[d] > before[d]]
+    assert len(used) == min(ndev, 2), (ndev, before, after)
+    for k in range(2):
+        d_cpu, d_gpu = cpu[k][0], out[k][0]
+        assert np.array_equal(d_cpu > 0, d_gpu > 0)
+        m = d_cpu > 0
+        assert (np.abs(d_gpu[m] - d_cpu[m]) / d_cpu[m]).max() < 1e-4

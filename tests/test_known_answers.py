@@ -237,3 +237,93 @@ def test_ldl_inverse_zero_pivot_leaves_input(U):
     """lib/ldl_decomposition.h:60-61: early return on an exactly-zero pivot."""
     A0 = np.array([[0.0, 1], [1, 0]])
     np.testing.assert_array_equal(U.ldl_inverse(A0), A0)
+
+
+# --- gtest_matrix_vector.cc:33-195: SSEVector ----------------------------------
+
+def _la(U):
+    if not getattr(U, "has_linear_algebra", False):
+        pytest.skip("SSEVector / BlockSparseMatrix are the reference's own classes: "
+                    "only the compiled reference has them")
+    return U
+
+
+def test_ssevector_dot(U):
+    U = _la(U)
+    a = [1.0, 2.0, 3.0, 1.0, 2.0]
+    assert U.ssevector("dot", a, a) == 19.0
+
+
+@pytest.mark.parametrize("op,a,b,factor", [
+    ("add", [4.0, 2, 3, 1, 2], [1.0, 7, 3, 8, 2], 0.0),
+    ("subtract", [1.0, 2, 3, 10, 2], [11.0, 2, 30, 1, 29], 0.0),
+    ("multiply", [12.0, 2, 3, 10, 2], None, 4.3),
+    ("multiply_add", [12.0, 2, 3, 10, 2], [11.0, 2, 30, 1, 29], 4.3),
+    ("multiply_sub", [12.0, 2, 3, 10, 2], [11.0, 2, 30, 1, 29], 4.3)])
+def test_ssevector_elementwise(U, op, a, b, factor):
+    U = _la(U)
+    a = np.array(a)
+    bb = None if b is None else np.array(b)
+    want = {"add": lambda: a + bb, "subtract": lambda: a - bb,
+            "multiply": lambda: a * factor, "multiply_add": lambda: a + bb * factor,
+            "multiply_sub": lambda: a - bb * factor}[op]()
+    np.testing.assert_array_equal(U.ssevector(op, a, bb, factor), want)   # EXPECT_DOUBLE_EQ
+
+
+@pytest.mark.parametrize("op,ma,mb", [("multiply_add", 3, 7), ("multiply_sub", 7, 3)])
+def test_ssevector_large(U, op, ma, mb):
+    """multiply_add_large / multiply_sub_large: 1e6 entries, odd tail included."""
+    U = _la(U)
+    i = np.arange(1000000)
+    a, b = (i % ma).astype(np.float64), (i % mb).astype(np.float64)
+    want = a + b * 0.3 if op == "multiply_add" else a - b * 0.3
+    np.testing.assert_array_equal(U.ssevector(op, a, b, 0.3), want)
+
+
+# --- gtest_matrix_vector.cc:197-356: BlockSparseMatrix<2> ---------------------------
+
+V1, V2 = [1.0, 2, 3, 4], [4.0, 3, 2, 1]
+
+
+def test_bsm_set_from_blocks(U):
+    U = _la(U)
+    assert U.bsm2(4, blocks=[(0, 0, V1), (2, 2, V2)])[0] == 2
+    assert U.bsm2(4, blocks=[(2, 2, V2), (0, 0, V1)])[0] == 2
+
+
+def test_bsm_set_from_triplets(U):
+    U = _la(U)
+    trips = [(0, 0, 11), (0, 1, 12), (0, 2, 13), (0, 3, 14), (1, 1, 22), (1, 2, 23),
+             (2, 2, 33), (2, 3, 34), (2, 4, 35), (2, 5, 36), (3, 3, 44), (3, 4, 45),
+             (4, 5, 56), (5, 5, 66)]
+    assert U.bsm2(6, triplets=trips)[0] == 5
+
+
+def test_bsm_multiply(U):
+    U = _la(U)
+    v2 = [5.0, 3, 2, 0]
+    ones = np.ones(4)
+    for blocks in ([(0, 0, V1), (2, 2, v2)], [(2, 2, v2), (0, 0, V1)]):
+        np.testing.assert_array_equal(U.bsm2(4, blocks=blocks, x=ones)[1], [3, 7, 8, 2])
+    y = U.bsm2(4, blocks=[(2, 2, v2), (0, 2, V1), (0, 0, V1)], x=ones)[1]
+    np.testing.assert_array_equal(y, [6, 14, 8, 2])
+
+
+def test_bsm_set_from_triplets_multiply(U):
+    U = _la(U)
+    trips = [(0, 0, 1), (0, 1, 2), (1, 0, 3), (1, 1, 4), (2, 2, 5), (2, 3, 3),
+             (3, 2, 2), (3, 3, 0)]
+    ones = np.ones(4)
+    np.testing.assert_array_equal(U.bsm2(4, triplets=trips, x=ones)[1], [3, 7, 8, 2])
+    trips += [(2, 0, 2), (2, 1, 7), (3, 0, 4), (3, 1, 1)]
+    y1 = U.bsm2(4, triplets=trips, x=ones)[1]
+    y2 = U.bsm2(4, triplets=trips, x=ones)[1]
+    np.testing.assert_array_equal(y1, y2)
+    np.testing.assert_array_equal(y1, [3, 7, 17, 7])      # rows 2, 3 gained 2+7, 4+1
+
+
+def test_bsm_block_invert(U):
+    U = _la(U)
+    two = [2.0, 0, 0, 2]
+    y = U.bsm2(4, blocks=[(0, 0, two), (2, 2, two)], invert=True, x=np.ones(4))[1]
+    np.testing.assert_allclose(y, 0.5, atol=1e-10)
