@@ -286,6 +286,80 @@ int smvsb_get_surface_state (smvsb_ctx* ctx, uint8_t* node_valid,
     uint8_t* patch_valid, uint32_t* vis_off, uint8_t* vis_ids,
     uint64_t vis_capacity);
 
+/* ---- surface topology between the Newton loops ------------------------ */
+
+/*
+ * Surface::create(bundle, view, scale, init_depth) (lib/surface.cc:19-53 with
+ * initialize_node_from_depth :665-760, fill_holes :628-649,
+ * remove_nodes_without_patch :762-867): the context's surface becomes the
+ * surface of `scale` initialised from init_depth (w*h floats, 0 = no depth).
+ */
+int smvsb_surface_create (smvsb_ctx* ctx, int scale, const float* init_depth);
+/* Surface::subdivide_patches (lib/surface.cc:983-1107): the surface moves to
+ * scale - 1; visibility lists are cleared (the caller runs smvsb_visibility). */
+int smvsb_surface_subdivide (smvsb_ctx* ctx);
+/* Surface::fill_patches_from_depth (lib/surface.cc:141-153). init_depth NULL:
+ * the depth given to smvsb_surface_create (what the reference's Surface
+ * keeps); otherwise it replaces it. */
+int smvsb_surface_fill_from_depth (smvsb_ctx* ctx, const float* init_depth);
+/* Surface::remove_isolated_patches (lib/surface.cc:887-927), with the
+ * reference's sequential semantics. */
+int smvsb_surface_remove_isolated (smvsb_ctx* ctx);
+/* scale, npx, npy, start_x, start_y, patchsize of the context's surface */
+int smvsb_surface_info (smvsb_ctx* ctx, int* info6);
+
+/* DepthOptimizer::Options as far as optimize() in the use_sgm mode reads them
+ * (lib/depth_optimizer.h:27-44). */
+typedef struct smvsb_optimize_options
+{
+    double regularization;
+    double light_surf_regularization;
+    int32_t num_iterations;      /* app/smvsrecon.cc:713: 5 */
+    int32_t min_scale;
+    int32_t use_shading;
+    int32_t full_optimization;
+} smvsb_optimize_options;
+
+typedef struct smvsb_optimize_stats
+{
+    int32_t scales;              /* scales optimised (ladder length) */
+    int32_t final_scale;
+    int32_t newton_loops;        /* inner Newton loops run */
+    int32_t newton_steps;
+    int32_t cg_iterations;
+    int32_t reserved;
+    uint64_t patches;            /* valid patches of the final surface */
+    double pixel_iterations;
+    double ms_newton;            /* device time of the Newton loops */
+} smvsb_optimize_stats;
+
+/*
+ * DepthOptimizer::optimize() (lib/depth_optimizer.cc:54-162) in the use_sgm
+ * mode, with run_newton_iterations (:164-358), for one reference view whose
+ * images are single-channel: bilateral filter of the SGM depth, initial
+ * surface, then per scale set_scale of all views, visibility, boundary
+ * cutting, Newton loops, isolated-patch removal and the patch-count
+ * convergence test, subdivision and hole filling between scales, lighting fit
+ * below scale 4 with use_shading. The view stays on the device from the byte
+ * images to the depth and normal maps; nothing but scalars comes back in
+ * between.
+ *   inv_calib9    main camera's fill_inverse_calibration(w, h)
+ *   shading, shading_grad   StereoView::get_shading_image / _gradients
+ *                 (w*h, w*h*2) or NULL without use_shading
+ *   sgm_depth     StereoView::get_sgm_depth(), sgm_w * sgm_h
+ *   depth_out     w*h (Surface::get_depth_map), normals_out w*h*3
+ *                 (Surface::get_normal_map(inverse flen)); either may be NULL
+ *   light16_out   the last fitted lighting (zeros if none), may be NULL
+ */
+int smvsb_optimize (smvsb_ctx* ctx, int w, int h, double flen_px,
+    double inv_flen, const float* inv_calib9, const uint8_t* main_img,
+    int n_sub, const int* sub_w, const int* sub_h,
+    const uint8_t* const* sub_img, const double* Mi, const double* ti,
+    const float* shading, const float* shading_grad, int sgm_w, int sgm_h,
+    const float* sgm_depth, const smvsb_optimize_options* opts,
+    float* depth_out, float* normals_out, double* light16_out,
+    smvsb_optimize_stats* stats);
+
 /* ---- outputs -------------------------------------------------------- */
 
 int smvsb_get_nodes (smvsb_ctx* ctx, double* nodes_out);

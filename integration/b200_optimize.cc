@@ -1,0 +1,148 @@
+/*
+ * integration/b200_optimize.cc
+ *
+ * Drop-in body for smvs::DepthOptimizer::optimize (reference:
+ * lib/depth_optimizer.cc:54-162). In the use_sgm mode with single-channel
+ * images and no debug output the whole coarse-to-fine ladder of the view runs
+ * on the GPU through ONE call, smvsb_optimize: the view goes up as byte
+ * images, the depth and normal maps come back, and what optimize() has to
+ * leave behind -- the two view embeddings (:158-161), the final surface for
+ * get_depth() / get_normals(), the fitted lighting -- is put in place. Every
+ * other configuration (use_sgm = false with its expansion and NCC filter,
+ * colour images, debug levels that write intermediate images) runs the
+ * reference's own optimize(), whose members are the per-call drop-ins of
+ * b200_depth_optimizer.cc. lib/depth_optimizer.h is untouched.
+ *
+ *   SMVSB_MEMBERWISE=1   forces the reference's optimize() (per-member path)
+ */
+#include <cstdlib>
+#include <vector>
+
+#include "depth_optimizer.h"
+
+#include "b200_context.h"
+
+SMVS_NAMESPACE_BEGIN
+
+/* The reference's own optimize(), kept under this name by integration/Makefile
+ * (objcopy --redefine-sym on the all-weak copy of the object). */
+extern "C" void smvs_ref_optimize (DepthOptimizer* self);
+
+namespace
+{
+    bool
+    single_channel (StereoView::Ptr const& v)
+    {
+        return v->get_image() != nullptr && v->get_image()->channels() == 1;
+    }
+}
+
+void
+DepthOptimizer::optimize (void)
+{
+    bool resident = this->opts.use_sgm && this->opts.debug_lvl == 0
+        && std::getenv("SMVSB_MEMBERWISE") == nullptr
+        && single_channel(this->main_view) && !this->sub_views.empty()
+        && this->sub_views.size() <= 32;
+    for (auto const& v : this->sub_views)
+        resident = resident && single_channel(v);
+    if (this->opts.use_shading)
+        resident = resident && this->main_view->get_shading_image() != nullptr;
+    if (!resident)
+    {
+        smvs_ref_optimize(this);
+        return;
+    }
+
+    smvsb::Context& gpu = smvs_b200_integration::thread_context();
+    int const w = this->main_view->get_width();
+    int const h = this->main_view->get_height();
+
+    /* the view as the reference's StereoViews hold it */
+    std::size_t const n = this->sub_views.size();
+    mve::ByteImage::ConstPtr main_img = this->main_view->get_byte_image();
+    std::vector<mve::ByteImage::ConstPtr> sub_keep(n);
+    std::vector<int> sw(n), sh(n);
+    std::vector<uint8_t const*> simg(n);
+    std::vector<double> M(9 * n), t(3 * n);
+    for (std::size_t k = 0; k < n; ++k)
+    {
+        sub_keep[k] = this->sub_views[k]->get_byte_image();
+        sw[k] = sub_keep[k]->width();
+        sh[k] = sub_keep[k]->height();
+        simg[k] = sub_keep[k]->begin();
+        for (int j = 0; j < 9; ++j) M[9 * k + j] = this->Mi[k][j];
+        for (int j = 0; j < 3; ++j) t[3 * k + j] = this->ti[k][j];
+    }
+    math::Matrix3f invproj;
+    this->main_view->get_camera().fill_inverse_calibration(*invproj, w, h);
+    mve::FloatImage::Ptr sgm = this->main_view->get_sgm_depth();   /* :41 */
+    bool const lit = this->opts.use_shading;
+
+    smvsb_optimize_options o;
+    o.regularization = this->opts.regularization;
+    o.light_surf_regularization = this->opts.light_surf_regularization;
+    o.num_iterations = this->opts.num_iterations;
+    o.min_scale = this->opts.min_scale;
+    o.use_shading = lit ? 1 : 0;
+    o.full_optimization = this->opts.full_optimization ? 1 : 0;
+
+    mve::FloatImage::Ptr depth = mve::FloatImage::create(w, h, 1);
+    mve::FloatImage::Ptr normals = mve::FloatImage::create(w, h, 3);
+    double light[16];
+    smvsb_optimize_stats st;
+    gpu.check(smvsb_optimize(gpu.get(), w, h, this->main_view->get_flen(),
+        this->main_view->get_inverse_flen(), *invproj, main_img->begin(),
+        static_cast<int>(n), sw.data(), sh.data(), simg.data(), M.data(),
+        t.data(),
+        lit ? this->main_view->get_shading_image()->begin() : nullptr,
+        lit ? this->main_view->get_shading_gradients()->begin() : nullptr,
+        sgm->width(), sgm->height(), sgm->begin(), &o, depth->begin(),
+        normals->begin(), light, &st));
+
+    /* ---- what optimize() leaves behind -------------------------------- */
+    /* the final surface, for get_depth() / get_normals(): the grid geometry
+     * of the ladder from a planar stand-in (reference code, no image work),
+     * then the device's nodes and validity */
+    int const init_scale = st.final_scale + (st.scales - 1);
+    this->surface = Surface::create_planar(1.0, w, h, init_scale);
+    while (this->surface->get_scale() > st.final_scale)
+        this->surface->subdivide_patches();
+    {
+        Surface::NodeList const& nodes = this->surface->get_nodes();
+        Surface::PatchList const& patches = this->surface->get_patches();
+        std::vector<double> values(nodes.size() * 4);
+        std::vector<uint8_t> nvalid(nodes.size()), pvalid(patches.size());
+        gpu.check(smvsb_get_nodes(gpu.get(), values.data()));
+        gpu.check(smvsb_get_surface_state(gpu.get(), nvalid.data(),
+            pvalid.data(), nullptr, nullptr, 0));
+        for (std::size_t p = 0; p < patches.size(); ++p)
+            if (!pvalid[p] && patches[p] != nullptr)
+                this->surface->delete_patch(p);
+        this->surface->remove_nodes_without_patch();
+        std::vector<double> zero(nodes.size() * 4, 0.0), unused;
+        this->surface->update_nodes(zero, &unused);    /* resets patch caches */
+        for (std::size_t i = 0; i < nodes.size(); ++i)
+        {
+            if (nodes[i] == nullptr)
+                continue;
+            nodes[i]->f = values[4 * i + 0];
+            nodes[i]->dx = values[4 * i + 1];
+            nodes[i]->dy = values[4 * i + 2];
+            nodes[i]->dxy = values[4 * i + 3];
+        }
+    }
+    if (lit && st.final_scale < 4)
+    {
+        GlobalLighting::Params p;
+        for (int i = 0; i < 16; ++i)
+            p[i] = light[i];
+        this->lighting = GlobalLighting::create(p);
+    }
+    /* :158-161 */
+    this->main_view->write_depth_to_view(depth, this->opts.output_name);
+    this->main_view->write_image_to_view(normals,
+        this->opts.output_name + "N");
+}
+
+SMVS_NAMESPACE_END

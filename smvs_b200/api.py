@@ -25,7 +25,9 @@ EXPORTS = [
     "smvsb_get_normals", "smvsb_debug_get_system", "smvsb_debug_spmv",
     "smvsb_fit_lighting", "smvsb_sgm", "smvsb_visibility",
     "smvsb_cut_boundaries", "smvsb_get_surface_state", "smvsb_view_set_scale",
-    "smvsb_bilateral_filter", "smvsb_debug_expf", "smvsb_device_count", "smvsb_measure_fp64_peak", "smvsb_sgm_reconstruct", "smvsb_newton_loop_batch", "smvsb_device_launch_count",
+    "smvsb_bilateral_filter", "smvsb_debug_expf", "smvsb_device_count", "smvsb_surface_create", "smvsb_surface_subdivide",
+    "smvsb_surface_fill_from_depth", "smvsb_surface_remove_isolated", "smvsb_surface_info",
+    "smvsb_optimize", "smvsb_measure_fp64_peak", "smvsb_sgm_reconstruct", "smvsb_newton_loop_batch", "smvsb_device_launch_count",
 ]
 
 
@@ -240,6 +242,35 @@ class Context:
                                                   C.c_uint64(cap)))
         return nv, pv, vo, vi[:vo[-1]].copy()
 
+    # -- surface topology on the device ---------------------------------------
+    def _sync_surface_info(self):
+        info = (C.c_int * 6)()
+        self._check(lib().smvsb_surface_info(self._h, info))
+        self.n_nodes = (info[1] + 1) * (info[2] + 1)
+        self.n_patches = info[1] * info[2]
+        return dict(scale=info[0], npx=info[1], npy=info[2], start_x=info[3],
+                    start_y=info[4], patchsize=info[5])
+
+    def surface_info(self):
+        return self._sync_surface_info()
+
+    def surface_create(self, scale, init_depth):
+        """Surface::create(bundle, view, scale, init_depth) on the device."""
+        d = np.ascontiguousarray(init_depth, dtype=np.float32)
+        self._check(lib().smvsb_surface_create(self._h, int(scale), _p(d)))
+        return self._sync_surface_info()
+
+    def surface_subdivide(self):
+        self._check(lib().smvsb_surface_subdivide(self._h))
+        return self._sync_surface_info()
+
+    def surface_fill_from_depth(self, init_depth=None):
+        d = None if init_depth is None else np.ascontiguousarray(init_depth, dtype=np.float32)
+        self._check(lib().smvsb_surface_fill_from_depth(self._h, _p(d)))
+
+    def surface_remove_isolated(self):
+        self._check(lib().smvsb_surface_remove_isolated(self._h))
+
     def set_nodes(self, nodes):
         nodes = _f64(nodes)
         self._check(lib().smvsb_set_nodes(self._h, _p(nodes)))
@@ -414,3 +445,49 @@ def measure_fp64_peak(device=0):
     if rc != 0:
         raise SmvsbError(rc, lib().smvsb_last_error(None).decode())
     return float(out.value)
+
+
+class OptimizeOptions(C.Structure):
+    _fields_ = [("regularization", C.c_double), ("light_surf_regularization", C.c_double),
+                ("num_iterations", C.c_int32), ("min_scale", C.c_int32),
+                ("use_shading", C.c_int32), ("full_optimization", C.c_int32)]
+
+
+class OptimizeStats(C.Structure):
+    _fields_ = [("scales", C.c_int32), ("final_scale", C.c_int32),
+                ("newton_loops", C.c_int32), ("newton_steps", C.c_int32),
+                ("cg_iterations", C.c_int32), ("reserved", C.c_int32),
+                ("patches", C.c_uint64), ("pixel_iterations", C.c_double),
+                ("ms_newton", C.c_double)]
+
+
+def optimize(ctx, main_img, sub_imgs, Mi, ti, flen_px, inv_flen, inv_calib9, sgm_depth,
+             regularization=0.01, num_iterations=5, min_scale=2, shading=None,
+             shading_grad=None, light_surf_regularization=0.0, full_optimization=False):
+    """smvsb_optimize: DepthOptimizer::optimize() of one view, resident on the
+    device. Returns (depth, normals, light16, stats dict)."""
+    main_img = _u8(main_img)
+    h, w = main_img.shape
+    n = len(sub_imgs)
+    si = [_u8(a) for a in sub_imgs]
+    sw = (C.c_int * n)(*[a.shape[1] for a in si])
+    shh = (C.c_int * n)(*[a.shape[0] for a in si])
+    ip = (C.c_void_p * n)(*[a.ctypes.data for a in si])
+    Mi, ti = _f64(Mi), _f64(ti)
+    k = _f32(inv_calib9).reshape(9)
+    sgm = _f32(sgm_depth)
+    sh, shg = _f32(shading), _f32(shading_grad)
+    opts = OptimizeOptions(regularization, light_surf_regularization, num_iterations,
+                           min_scale, int(shading is not None), int(full_optimization))
+    depth = np.empty((h, w), dtype=np.float32)
+    normals = np.empty((h, w, 3), dtype=np.float32)
+    light = np.zeros(16, dtype=np.float64)
+    st = OptimizeStats()
+    ctx._check(lib().smvsb_optimize(
+        ctx._h, w, h, C.c_double(flen_px), C.c_double(inv_flen), _p(k), _p(main_img), n,
+        sw, shh, ip, _p(Mi), _p(ti), _p(sh), _p(shg), sgm.shape[1], sgm.shape[0], _p(sgm),
+        C.byref(opts), _p(depth), _p(normals), _p(light), C.byref(st)))
+    ctx.w, ctx.h = w, h
+    ctx._sync_surface_info()
+    stats = {f: getattr(st, f) for f, _ in OptimizeStats._fields_ if f != "reserved"}
+    return depth, normals, light, stats

@@ -25,6 +25,8 @@ void device_bilateral_filter (smvsb_ctx* c, float const* ci_dev, int w, int h,
     int channels, float const* dm_dev, int dm_w, int dm_h, float sigma,
     int kernel_size, float* out_dev);
 float host_expf_like_glibc (float x);
+void device_byte_to_float (smvsb_ctx* c, uint8_t const* img_dev, size_t n,
+    float* out_dev);
 void device_unpack_texels (smvsb_ctx* c, float const* texels, int n,
     float* grad, float* hess);
 std::string const& sgm_last_error (void);
@@ -223,6 +225,125 @@ construct (smvsb_ctx* c, double const* light16, double reg, double light_reg)
     ensure_system_buffers(c);
     smvsb::launch_construct(c, light16 != nullptr, reg, light_reg);
     c->have_system = true;
+}
+
+/* Grid geometry of a Surface at `scale` (lib/surface.cc:28-37) and the tables
+ * that depend on it. */
+void
+configure_grid (smvsb_ctx* c, int scale, int npx, int npy, int start_x,
+    int start_y)
+{
+    require(scale >= 0 && scale <= 6, SMVSB_ERR_INVALID,
+        "scale out of range (0..6)");
+    require(npx > 0 && npy > 0, SMVSB_ERR_INVALID, "empty patch grid");
+    int const ps = 1 << scale;
+    int const sampling = sampling_for_scale(scale);
+    require(ps % sampling == 0, SMVSB_ERR_INVALID,
+        "patch size below sampling");
+    int const npos = ps / sampling;
+    require(npos == 1 || npos == 2 || npos == 4 || npos == 8
+        || npos == 16, SMVSB_ERR_INVALID, "unsupported samples per patch");
+    require(start_x >= 0 && start_y >= 0
+        && start_x + npx * ps <= c->w && start_y + npy * ps <= c->h,
+        SMVSB_ERR_INVALID, "patch grid exceeds the main image");
+    c->scale = scale; c->ps = ps; c->sampling = sampling; c->npos = npos;
+    c->npx = npx; c->npy = npy; c->start_x = start_x; c->start_y = start_y;
+    c->n_patches = npx * npy;
+    c->n_nodes = (npx + 1) * (npy + 1);
+    std::vector<double> tab;
+    smvsb::fill_basis_table(tab, ps, sampling);
+    upload(c, c->basis_s, tab.data(), tab.size());
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    smvsb::fill_basis_table(tab, ps, 1);
+    upload(c, c->basis_f, tab.data(), tab.size());
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+/* Host mirrors of the validity flags after the device changed them. */
+void
+refresh_validity (smvsb_ctx* c)
+{
+    c->h_node_valid.resize(c->n_nodes);
+    c->h_patch_valid.resize(c->n_patches);
+    download(c, c->h_node_valid.data(), c->node_valid.p, c->n_nodes);
+    download(c, c->h_patch_valid.data(), c->patch_valid.p, c->n_patches);
+    set_active(c, nullptr);
+    c->have_system = false;
+}
+
+/* Empty visibility lists (nothing visible yet). */
+void
+clear_visibility (smvsb_ctx* c)
+{
+    c->vis_off.reserve(static_cast<size_t>(c->n_patches) + 1);
+    c->vis_ids.reserve(1);
+    CUDA_CHECK(cudaMemsetAsync(c->vis_off.p, 0,
+        (static_cast<size_t>(c->n_patches) + 1) * sizeof(uint32_t),
+        c->stream));
+}
+
+/* Surface::Surface(bundle, view, scale, init_depth) (lib/surface.cc:19-53)
+ * from an init depth that is already on the device. */
+void
+surface_create_device (smvsb_ctx* c, int scale, float const* init_dev)
+{
+    int const ps = 1 << scale;
+    int const npx = (c->w - 2) / ps - 1, npy = (c->h - 2) / ps - 1;
+    require(npx > 0 && npy > 0, SMVSB_ERR_INVALID,
+        "image too small for a surface at this scale");
+    int const sx = (c->w - npx * ps) / 2, sy = (c->h - npy * ps) / 2;
+    configure_grid(c, scale, npx, npy, sx, sy);
+    size_t const nn = c->n_nodes, np = c->n_patches;
+    c->nodes.reserve(nn * 4);
+    c->node_valid.reserve(nn);
+    c->patch_valid.reserve(np);
+    CUDA_CHECK(cudaMemsetAsync(c->nodes.p, 0, nn * 4 * sizeof(double),
+        c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->node_valid.p, 0, nn, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->patch_valid.p, 0, np, c->stream));
+    clear_visibility(c);
+    smvsb::topo_set_init_depth(c, init_dev);
+    smvsb::topo_fill_from_depth(c);
+    c->have_surface = true;
+    c->x_count = 0;
+    refresh_validity(c);
+}
+
+void
+surface_subdivide_device (smvsb_ctx* c)
+{
+    require(c->scale >= 1, SMVSB_ERR_INVALID, "cannot subdivide scale 0");
+    int npx, npy, sx, sy;
+    smvsb::topo_subdivide(c, &npx, &npy, &sx, &sy);
+    configure_grid(c, c->scale - 1, npx, npy, sx, sy);
+    smvsb::topo_subdivide_finish(c);
+    clear_visibility(c);
+    c->x_count = 0;
+    refresh_validity(c);
+}
+
+/* StereoView::set_scale of all views from the byte images kept on the
+ * device (smvsb_optimize). */
+void
+views_from_resident_u8 (smvsb_ctx* c, int scale)
+{
+    size_t max_pix = static_cast<size_t>(c->w) * c->h;
+    for (int k = 0; k < c->n_sub; ++k)
+        max_pix = std::max(max_pix, static_cast<size_t>(c->subs[k].w)
+            * c->subs[k].h);
+    c->stage_a.reserve(max_pix);
+    c->stage_b.reserve(max_pix);
+    c->main_grad.reserve(static_cast<size_t>(c->w) * c->h * 2);
+    smvsb::device_set_scale(c, c->u8_main.p, c->w, c->h, scale, c->stage_a.p,
+        c->stage_b.p, 0, c->main_grad.p);
+    for (int k = 0; k < c->n_sub; ++k)
+    {
+        smvsb::SubViewDev& sv = c->subs[k];
+        sv.texels.reserve(static_cast<size_t>(sv.w) * sv.h * SMVSB_NB_STRIDE);
+        smvsb::device_set_scale(c, c->u8_subs[k].p, sv.w, sv.h, scale,
+            c->stage_a.p, c->stage_b.p, 1, sv.texels.p);
+    }
+    c->have_system = false;
 }
 
 } /* namespace */
@@ -585,21 +706,8 @@ smvsb_set_surface (smvsb_ctx* ctx, int scale, int npx, int npy, int start_x,
             "surface arrays missing");
         require((vis_off == nullptr) == (vis_ids == nullptr),
             SMVSB_ERR_INVALID, "vis_off and vis_ids go together");
-        int const ps = 1 << scale;
-        int const sampling = sampling_for_scale(scale);
-        require(ps % sampling == 0, SMVSB_ERR_INVALID,
-            "patch size below sampling");
-        int const npos = ps / sampling;
-        require(npos == 1 || npos == 2 || npos == 4 || npos == 8
-            || npos == 16, SMVSB_ERR_INVALID, "unsupported samples per patch");
-        require(start_x >= 0 && start_y >= 0
-            && start_x + npx * ps <= ctx->w && start_y + npy * ps <= ctx->h,
-            SMVSB_ERR_INVALID, "patch grid exceeds the main image");
         smvsb_ctx* c = ctx;
-        c->scale = scale; c->ps = ps; c->sampling = sampling; c->npos = npos;
-        c->npx = npx; c->npy = npy; c->start_x = start_x; c->start_y = start_y;
-        c->n_patches = npx * npy;
-        c->n_nodes = (npx + 1) * (npy + 1);
+        configure_grid(c, scale, npx, npy, start_x, start_y);
         /* no lists: nothing visible yet (smvsb_visibility fills them) */
         std::vector<uint32_t> no_off;
         uint8_t const no_id = 0;
@@ -638,12 +746,6 @@ smvsb_set_surface (smvsb_ctx* ctx, int scale, int npx, int npy, int start_x,
         upload(c, c->vis_ids, vis_ids, std::max<size_t>(total_vis, 1));
         c->h_node_valid.assign(node_valid, node_valid + c->n_nodes);
         c->h_patch_valid.assign(patch_valid, patch_valid + c->n_patches);
-        std::vector<double> tab;
-        smvsb::fill_basis_table(tab, ps, sampling);
-        upload(c, c->basis_s, tab.data(), tab.size());
-        CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        smvsb::fill_basis_table(tab, ps, 1);
-        upload(c, c->basis_f, tab.data(), tab.size());
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         set_active(c, nullptr);
         c->have_surface = true;
@@ -923,6 +1025,267 @@ smvsb_newton_loop_batch (smvsb_ctx* const* ctxs, int n,
     });
 }
 
+
+/* ---- surface topology on the device (topology.cu) ------------------- */
+
+int
+smvsb_surface_create (smvsb_ctx* ctx, int scale, const float* init_depth)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        smvsb_ctx* c = ctx;
+        require(c->have_views, SMVSB_ERR_STATE,
+            "smvsb_set_views must precede smvsb_surface_create");
+        require(init_depth != nullptr, SMVSB_ERR_INVALID,
+            "init depth missing (the bundle-based initialisation of "
+            "lib/surface.cc:54-139 is host code)");
+        size_t const npix = static_cast<size_t>(c->w) * c->h;
+        c->image_out.reserve(npix * 3);
+        CUDA_CHECK(cudaMemcpyAsync(c->image_out.p, init_depth,
+            npix * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        surface_create_device(c, scale, c->image_out.p);
+    });
+}
+
+int
+smvsb_surface_subdivide (smvsb_ctx* ctx)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_surface, SMVSB_ERR_STATE, "no surface set");
+        surface_subdivide_device(ctx);
+    });
+}
+
+int
+smvsb_surface_fill_from_depth (smvsb_ctx* ctx, const float* init_depth)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        smvsb_ctx* c = ctx;
+        require(c->have_surface, SMVSB_ERR_STATE, "no surface set");
+        size_t const npix = static_cast<size_t>(c->w) * c->h;
+        if (init_depth != nullptr)
+        {
+            c->image_out.reserve(npix * 3);
+            CUDA_CHECK(cudaMemcpyAsync(c->image_out.p, init_depth,
+                npix * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            smvsb::topo_set_init_depth(c, c->image_out.p);
+        }
+        require(c->init_depth.p != nullptr && c->init_depth.cap >= npix,
+            SMVSB_ERR_STATE, "no init depth on the device");
+        smvsb::topo_fill_from_depth(c);
+        refresh_validity(c);
+    });
+}
+
+int
+smvsb_surface_remove_isolated (smvsb_ctx* ctx)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_surface, SMVSB_ERR_STATE, "no surface set");
+        smvsb::topo_remove_isolated(ctx);
+        refresh_validity(ctx);
+    });
+}
+
+int
+smvsb_surface_info (smvsb_ctx* ctx, int* info6)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_surface && info6, SMVSB_ERR_STATE, "no surface set");
+        info6[0] = ctx->scale; info6[1] = ctx->npx; info6[2] = ctx->npy;
+        info6[3] = ctx->start_x; info6[4] = ctx->start_y; info6[5] = ctx->ps;
+    });
+}
+
+/*
+ * DepthOptimizer::optimize() (lib/depth_optimizer.cc:54-162) with
+ * run_newton_iterations (:164-358) for the use_sgm mode, the whole view
+ * resident on the device from the SGM initialisation to the depth and normal
+ * maps.
+ */
+int
+smvsb_optimize (smvsb_ctx* ctx, int w, int h, double flen_px, double inv_flen,
+    const float* inv_calib9, const uint8_t* main_img, int n_sub,
+    const int* sub_w, const int* sub_h, const uint8_t* const* sub_img,
+    const double* Mi, const double* ti, const float* shading,
+    const float* shading_grad, int sgm_w, int sgm_h, const float* sgm_depth,
+    const smvsb_optimize_options* opts, float* depth_out, float* normals_out,
+    double* light16_out, smvsb_optimize_stats* stats_out)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        smvsb_ctx* c = ctx;
+        require(w > 2 && h > 2 && main_img && inv_calib9 && opts
+            && sgm_depth && sgm_w > 0 && sgm_h > 0, SMVSB_ERR_INVALID,
+            "smvsb_optimize: main view, options or SGM depth missing");
+        require(n_sub >= 1 && n_sub <= SMVSB_MAX_SUBS && sub_w && sub_h
+            && sub_img && Mi && ti, SMVSB_ERR_INVALID,
+            "smvsb_optimize: neighbour arrays missing");
+        require((shading == nullptr) == (shading_grad == nullptr),
+            SMVSB_ERR_INVALID, "shading image and gradient go together");
+        require(!opts->use_shading || shading != nullptr, SMVSB_ERR_INVALID,
+            "use_shading needs the shading image");
+        require(opts->num_iterations >= 1 && opts->min_scale >= 0,
+            SMVSB_ERR_INVALID, "bad iteration count / min_scale");
+        smvsb_optimize_stats st;
+        std::memset(&st, 0, sizeof(st));
+
+        /* ---- inputs: once per view ------------------------------------ */
+        c->w = w; c->h = h; c->flen = flen_px; c->inv_flen = inv_flen;
+        c->n_sub = n_sub;
+        c->have_surface = false;
+        size_t const npix = static_cast<size_t>(w) * h;
+        upload(c, c->u8_main, main_img, npix);
+        std::vector<float const*> ptrs(n_sub, nullptr);
+        std::vector<int> dims(2 * n_sub, 0);
+        std::vector<double> mt(12 * n_sub, 0.0);
+        for (int k = 0; k < n_sub; ++k)
+        {
+            require(sub_w[k] > 2 && sub_h[k] > 2 && sub_img[k],
+                SMVSB_ERR_INVALID, "neighbour image missing");
+            size_t const n = static_cast<size_t>(sub_w[k]) * sub_h[k];
+            upload(c, c->u8_subs[k], sub_img[k], n);
+            smvsb::SubViewDev& sv = c->subs[k];
+            sv.w = sub_w[k]; sv.h = sub_h[k];
+            sv.texels.reserve(n * SMVSB_NB_STRIDE);
+            ptrs[k] = sv.texels.p;
+            dims[2 * k] = sv.w; dims[2 * k + 1] = sv.h;
+            std::copy(Mi + 9 * k, Mi + 9 * k + 9, mt.begin() + 12 * k);
+            std::copy(ti + 3 * k, ti + 3 * k + 3, mt.begin() + 12 * k + 9);
+        }
+        upload(c, c->sub_ptrs, ptrs.data(), ptrs.size());
+        upload(c, c->sub_dims, dims.data(), dims.size());
+        upload(c, c->Mt, mt.data(), mt.size());
+        c->have_shading = (shading != nullptr);
+        if (c->have_shading)
+        {
+            upload(c, c->main_shading, shading, npix);
+            upload(c, c->main_shading_grad, shading_grad, npix * 2);
+        }
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->have_views = true;
+
+        /* ---- create_initial_surface, :35-52 --------------------------- */
+        int const init_scale = static_cast<int>(std::max(std::ceil(std::log2(
+            w * h / 1.7e6) / 2) + 4, 4.0));
+        require(init_scale <= 6, SMVSB_ERR_INVALID,
+            "image too large: initial scale above 6");
+        {
+            /* depthmap_bilateral_filter(sgm depth, main image), :42 */
+            size_t const nd = static_cast<size_t>(sgm_w) * sgm_h;
+            c->guide.reserve(npix);
+            smvsb::device_byte_to_float(c, c->u8_main.p, npix, c->guide.p);
+            c->view_in.reserve(nd);
+            CUDA_CHECK(cudaMemcpyAsync(c->view_in.p, sgm_depth,
+                nd * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            c->sgm_depth.reserve(npix);
+            smvsb::device_bilateral_filter(c, c->guide.p, w, h, 1,
+                c->view_in.p, sgm_w, sgm_h, 5.0f, 5, c->sgm_depth.p);
+        }
+        surface_create_device(c, init_scale, c->sgm_depth.p);
+        views_from_resident_u8(c, c->scale);
+
+        bool have_light = false;
+        double light[16];
+        auto run_newton_iterations = [&]()
+        {
+            bool finished = false;
+            for (int iter = 0; iter < opts->num_iterations; ++iter)
+            {
+                uint64_t const num_valid = smvsb::topo_count_patches(c);
+                if (iter == 0)
+                {
+                    /* :189-195 */
+                    smvsb::run_visibility_device(c);
+                    refresh_validity(c);
+                    for (uint64_t del = ~0ull; del > 10;)
+                    {
+                        del = smvsb::run_cut_boundaries(c, inv_calib9);
+                        refresh_validity(c);
+                    }
+                }
+                smvsb_newton_stats ns;
+                smvsb_ctx* cs[1] = { c };
+                double const* lights[1] = { have_light ? light : nullptr };
+                newton_loop_batch(cs, 1, lights, opts->regularization,
+                    opts->light_surf_regularization, 200,
+                    opts->full_optimization, &ns);
+                st.newton_loops += 1;
+                st.newton_steps += ns.newton_steps;
+                st.cg_iterations += ns.cg_iterations;
+                st.pixel_iterations += ns.pixel_iterations;
+                st.ms_newton += ns.ms_total;
+                if (finished)
+                    break;
+                /* :322-356 */
+                for (uint64_t del = ~0ull; del > 10;)
+                {
+                    del = smvsb::run_cut_boundaries(c, inv_calib9);
+                    refresh_validity(c);
+                }
+                smvsb::topo_remove_isolated(c);
+                refresh_validity(c);
+                uint64_t const num_new = smvsb::topo_count_patches(c);
+                double const change = 1.0 - static_cast<double>(
+                    std::min(num_new, num_valid)) / static_cast<double>(
+                    std::max(num_new, num_valid));
+                if (iter > 0 && (num_new <= num_valid
+                    || change < 0.05 * c->scale))
+                    finished = true;
+            }
+        };
+
+        run_newton_iterations();
+        st.scales = 1;
+        while (c->scale > opts->min_scale && c->scale > 0)
+        {
+            surface_subdivide_device(c);                     /* :90 */
+            views_from_resident_u8(c, c->scale);             /* :91-95 */
+            smvsb::topo_fill_from_depth(c);                  /* :99 */
+            refresh_validity(c);
+            if (opts->use_shading && c->scale < 4)           /* :102-109 */
+            {
+                double Ab[272], Ainv[256];
+                smvsb::run_fit_lighting(c, Ab);
+                pseudo_inverse_16(Ab, Ainv);
+                for (int i = 0; i < 16; ++i)
+                {
+                    double acc = 0.0;
+                    for (int j = 0; j < 16; ++j)
+                        acc += Ainv[i * 16 + j] * Ab[256 + j];
+                    light[i] = acc;
+                }
+                have_light = true;
+            }
+            run_newton_iterations();
+            st.scales += 1;
+        }
+
+        /* ---- outputs, :158-161 ---------------------------------------- */
+        c->image_out.reserve(npix * 3);
+        if (depth_out != nullptr)
+        {
+            smvsb::launch_render_depth(c, c->image_out.p);
+            download(c, depth_out, c->image_out.p, npix);
+        }
+        if (normals_out != nullptr)
+        {
+            smvsb::launch_render_normals(c, c->image_out.p);
+            download(c, normals_out, c->image_out.p, npix * 3);
+        }
+        if (light16_out != nullptr)
+            for (int i = 0; i < 16; ++i)
+                light16_out[i] = have_light ? light[i] : 0.0;
+        st.final_scale = c->scale;
+        st.patches = smvsb::topo_count_patches(c);
+        if (stats_out) *stats_out = st;
+    });
+}
+
 int
 smvsb_get_nodes (smvsb_ctx* ctx, double* nodes_out)
 {
@@ -933,18 +1296,6 @@ smvsb_get_nodes (smvsb_ctx* ctx, double* nodes_out)
         download(ctx, nodes_out, ctx->nodes.p,
             static_cast<size_t>(ctx->n_nodes) * 4);
     });
-}
-
-/* Host mirrors of the validity flags after the device changed them. */
-static void
-refresh_validity (smvsb_ctx* c)
-{
-    c->h_node_valid.resize(c->n_nodes);
-    c->h_patch_valid.resize(c->n_patches);
-    download(c, c->h_node_valid.data(), c->node_valid.p, c->n_nodes);
-    download(c, c->h_patch_valid.data(), c->patch_valid.p, c->n_patches);
-    set_active(c, nullptr);
-    c->have_system = false;
 }
 
 int

@@ -359,57 +359,48 @@ spmv_row (double const* __restrict__ H, int ns, VecOp const& vec, int node,
     return acc;
 }
 
-/* The passes a CTA makes between two barriers, over all views: (view, pass)
- * pairs in ascending order, skipping the views this CTA has no share in and
- * the ones that have converged. view == n_views: end. */
-struct PassIter
+/* Does CTA b work on view v between the next two barriers? */
+__device__ __forceinline__ bool
+view_on (CgArgs const& a, CgState const* s_state, int v, bool init)
 {
-    int view, pass;
-};
-
-__device__ __forceinline__ void
-pass_next (CgArgs const& a, CgState const* s_state, bool init, int step,
-    PassIter& it)
-{
-    if (it.view >= 0 && it.view < a.n_views)
-    {
-        it.pass += step;
-        if (it.pass < s_state[it.view].passes)
-            return;
-    }
-    it.pass = 0;
-    for (it.view += 1; it.view < a.n_views; ++it.view)
-    {
-        if (static_cast<int>(blockIdx.x) >= a.v[it.view].grid)
-            continue;
-        if (!init && s_state[it.view].done)
-            continue;
-        if (s_state[it.view].passes > 0)
-            return;
-    }
+    return static_cast<int>(blockIdx.x) < a.v[v].grid
+        && (init || !s_state[v].done) && s_state[v].passes > 0;
 }
 
-/* The row this thread's quad handles in pass `it` (+ pass_offset): whether
- * there is one is decided from the position alone, so that nothing branches
- * on the loaded index and the load can travel while other work is issued. */
-__device__ __forceinline__ bool
-pass_row (CgArgs const& a, CgState const* s_state, PassIter const& it,
-    int pass_offset, int& node)
+/* first view >= v the CTA works on, or n_views */
+__device__ __forceinline__ int
+next_view (CgArgs const& a, CgState const* s_state, int v, bool init)
 {
-    node = 0;
-    if (it.view >= a.n_views)
-        return false;
-    CgView const& V = a.v[it.view];
-    int const q = (it.pass + pass_offset) * (V.grid * CG_QUADS)
-        + blockIdx.x * CG_QUADS + (threadIdx.x >> 2);
-    bool const ok = q < s_state[it.view].n_rows;
+    while (v < a.n_views && !view_on(a, s_state, v, init))
+        ++v;
+    return v;
+}
+
+/* The row this thread's quad handles in pass p of view V: whether there is
+ * one is decided from the position alone, so that nothing branches on the
+ * loaded index and the load can travel while other work is issued. */
+__device__ __forceinline__ bool
+pass_row (CgView const& V, int n_rows, int pass, int& node)
+{
+    int const q = pass * (V.grid * CG_QUADS) + blockIdx.x * CG_QUADS
+        + (threadIdx.x >> 2);
+    bool const ok = q < n_rows;
     node = ok ? static_cast<int>(V.rows[q]) : 0;
     return ok;
 }
 
 /* 2 CTAs / SM: measured faster than 3 at 80 registers (fewer loads hoisted,
- * more barrier participants). */
-template <bool TIMING>
+ * more barrier participants).
+ *
+ * NV = compile-time bound on the number of views (1, 2, 4, 8): the loops over
+ * the views are unrolled, so a view's pointers are kernel parameters at fixed
+ * offsets (constant-bank operands of the instructions that use them), not
+ * values fetched per pass. The kernel is bound by the number of loads a warp
+ * has in flight, and every dependent fetch in front of a pass's Hessian loads
+ * lengthens the time a warp spends per pass (measured with the view indexed
+ * at run time: SpMV phase 32.6 us instead of 25.2 us on the full 2 MP
+ * system). */
+template <bool TIMING, int NV>
 __global__ void __launch_bounds__(CG_THREADS, 2)
 cg_kernel (CgArgs const a)
 {
@@ -438,15 +429,18 @@ cg_kernel (CgArgs const a)
      * (lib/conjugate_gradient.h:85-117). d_old = 0 with beta = 0 makes the
      * first direction d = z. P is block diagonal: the four threads of a node
      * exchange their r entries by shuffle. */
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
     {
-        PassIter it; it.view = -1; it.pass = 0;
-        pass_next(a, s_state, true, 1, it);
+        if (v >= a.n_views || !view_on(a, s_state, v, true))
+            continue;
+        CgView const& V = a.v[v];
+        int const n_rows = s_state[v].n_rows, passes = s_state[v].passes;
         double acc[2] = { 0.0, 0.0 };       /* z.r, g.g */
-        while (it.view < a.n_views)
+        for (int p = 0; p < passes; ++p)
         {
-            CgView const& V = a.v[it.view];
             int node;
-            bool const ok = pass_row(a, s_state, it, 0, node);
+            bool const ok = pass_row(V, n_rows, p, node);
             size_t const i = static_cast<size_t>(node) * 4 + rp;
             double const gi = ok ? V.g[i] : 0.0;
             double const ri = -gi;
@@ -470,16 +464,10 @@ cg_kernel (CgArgs const a)
                 acc[1] += gi * gi;
                 acc[0] += zi * ri;
             }
-            int const view = it.view;
-            pass_next(a, s_state, true, 1, it);
-            if (it.view != view)
-            {
-                warp_flush<2>(acc, s_red, view);
-                acc[0] = 0.0; acc[1] = 0.0;
-            }
         }
-        publish<2>(a, s_state, s_red, 0, true);
+        warp_flush<2>(acc, s_red, v);
     }
+    publish<2>(a, s_state, s_red, 0, true);
     grid_barrier(a.sync, epoch);
     all_sums<2>(a, s_state, 0, s_bcast, true);
     if (threadIdx.x < a.n_views)
@@ -494,8 +482,11 @@ cg_kernel (CgArgs const a)
 
     int iter = 1;
     unsigned long long tm[4] = {0, 0, 0, 0};
-    /* first two passes of the SpMV walk, kept across iterations */
-    int pa_view = -2, pa_node0 = 0, pa_node1 = 0;
+    /* The rows and masks do not change during a solve: what the first two
+     * passes of the SpMV walk need is kept in registers from one iteration to
+     * the next (reloaded when the first view of the walk changes because a
+     * view has converged). */
+    int pa_view = -1, pa_node0 = 0, pa_node1 = 0;
     bool pa_ok0 = false, pa_ok1 = false;
     unsigned int pa_mask0 = 0;
     for (; iter < a.max_iter; ++iter)
@@ -506,62 +497,73 @@ cg_kernel (CgArgs const a)
         int const slot = 2 + 4 * (iter & 1);
 
         /* d = z + beta d_old (:192-198 of the previous iteration);
-         * Ad = A d; alpha = r_dot_r / d.Ad (:126-127) */
+         * Ad = A d; alpha = r_dot_r / d.Ad (:126-127). Software pipeline over
+         * the passes: the row index travels two passes ahead of the stream,
+         * its mask one pass ahead, and the first two rows of the NEXT view are
+         * fetched while this view streams, so no load of a pass waits for
+         * another one. */
         {
-            /* Software pipeline over the passes: the row index travels two
-             * passes ahead of the stream, its mask one pass ahead, so no load
-             * of a pass waits for another one. The rows and masks do not
-             * change during a solve: what the first two passes need is kept
-             * in registers from one iteration to the next (reloaded when the
-             * first view of the walk changes because a view has converged). */
-            PassIter it0; it0.view = -1; it0.pass = 0;
-            pass_next(a, s_state, false, 1, it0);
-            PassIter it1 = it0;
-            pass_next(a, s_state, false, 1, it1);
-            if (it0.view != pa_view)
+            int const v_first = next_view(a, s_state, 0, false);
+            if (v_first < a.n_views && v_first != pa_view)
             {
-                pa_view = it0.view;
-                pa_ok0 = pass_row(a, s_state, it0, 0, pa_node0);
-                pa_mask0 = (pa_ok0 && it0.view < a.n_views)
-                    ? a.v[it0.view].rowmask[pa_node0] : 0u;
-                pa_ok1 = pass_row(a, s_state, it1, 0, pa_node1);
+                CgView const& V = a.v[v_first];
+                pa_view = v_first;
+                pa_ok0 = pass_row(V, s_state[v_first].n_rows, 0, pa_node0);
+                pa_mask0 = pa_ok0 ? V.rowmask[pa_node0] : 0u;
+                pa_ok1 = pass_row(V, s_state[v_first].n_rows, 1, pa_node1);
             }
             int node0 = pa_node0, node1 = pa_node1;
             bool ok0 = pa_ok0, ok1 = pa_ok1;
             unsigned int mask0 = pa_mask0;
-            double acc[1] = { 0.0 };
-            while (it0.view < a.n_views)
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
             {
-                PassIter it2 = it1;
-                pass_next(a, s_state, false, 1, it2);
-                int node2;
-                bool const ok2 = pass_row(a, s_state, it2, 0, node2);
-                unsigned int const mask1 = (ok1 && it1.view < a.n_views)
-                    ? a.v[it1.view].rowmask[node1] : 0u;
-                if (ok0)
+                if (v >= a.n_views || !view_on(a, s_state, v, false))
+                    continue;
+                CgView const& V = a.v[v];
+                int const n_rows = s_state[v].n_rows;
+                int const passes = s_state[v].passes;
+                double const beta = s_state[v].beta;
+                double const* d_old = odd ? V.d : V.d2;
+                double* d_new = odd ? V.d2 : V.d;
+                /* the next view's first two rows start travelling now */
+                int const vn = next_view(a, s_state, v + 1, false);
+                int nn0 = 0, nn1 = 0;
+                bool nok0 = false, nok1 = false;
+                if (vn < a.n_views)
                 {
-                    CgView const& V = a.v[it0.view];
-                    DirVec dir;
-                    dir.z = V.z;
-                    dir.d_old = odd ? V.d : V.d2;
-                    dir.beta = s_state[it0.view].beta;
-                    double own[4];
-                    double const v = spmv_row(V.H, V.npx + 1, dir, node0, rp,
-                        mask0, own);
-                    double const di = (rp == 0) ? own[0] : (rp == 1) ? own[1]
-                        : (rp == 2) ? own[2] : own[3];
-                    size_t const i = static_cast<size_t>(node0) * 4 + rp;
-                    V.Ad[i] = v;
-                    (odd ? V.d2 : V.d)[i] = di;
-                    acc[0] += v * di;
+                    nok0 = pass_row(a.v[vn], s_state[vn].n_rows, 0, nn0);
+                    nok1 = pass_row(a.v[vn], s_state[vn].n_rows, 1, nn1);
                 }
-                if (it1.view != it0.view)
+                double acc[1] = { 0.0 };
+                for (int p = 0; p < passes; ++p)
                 {
-                    warp_flush<1>(acc, s_red, it0.view);
-                    acc[0] = 0.0;
+                    int node2;
+                    bool const ok2 = pass_row(V, n_rows, p + 2, node2);
+                    unsigned int const mask1 = ok1 ? V.rowmask[node1] : 0u;
+                    if (ok0)
+                    {
+                        DirVec dir;
+                        dir.z = V.z;
+                        dir.d_old = d_old;
+                        dir.beta = beta;
+                        double own[4];
+                        double const val = spmv_row(V.H, V.npx + 1, dir, node0,
+                            rp, mask0, own);
+                        double const di = (rp == 0) ? own[0] : (rp == 1)
+                            ? own[1] : (rp == 2) ? own[2] : own[3];
+                        size_t const i = static_cast<size_t>(node0) * 4 + rp;
+                        V.Ad[i] = val;
+                        d_new[i] = di;
+                        acc[0] += val * di;
+                    }
+                    node0 = node1; ok0 = ok1; mask0 = mask1;
+                    node1 = node2; ok1 = ok2;
                 }
-                it0 = it1; node0 = node1; ok0 = ok1; mask0 = mask1;
-                it1 = it2; node1 = node2; ok1 = ok2;
+                warp_flush<1>(acc, s_red, v);
+                /* hand over to the next view (its rows have arrived) */
+                node0 = nn0; ok0 = nok0; node1 = nn1; ok1 = nok1;
+                mask0 = (nok0 && vn < a.n_views) ? a.v[vn].rowmask[nn0] : 0u;
             }
             publish<1>(a, s_state, s_red, slot, false);
         }
@@ -576,28 +578,31 @@ cg_kernel (CgArgs const a)
 
         /* x += alpha d; r -= alpha Ad; r.r; Q1 = -x.(b + r); z = P r; z.r
          * (:130-181) */
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
         {
-            PassIter it; it.view = -1; it.pass = 0;
-            pass_next(a, s_state, false, CG_UF, it);
+            if (v >= a.n_views || !view_on(a, s_state, v, false))
+                continue;
+            CgView const& V = a.v[v];
+            int const n_rows = s_state[v].n_rows;
+            int const passes = s_state[v].passes;
+            double const alpha = s_state[v].alpha;
+            double const* d_new = odd ? V.d2 : V.d;
             double acc[3] = { 0.0, 0.0, 0.0 };    /* r.r, x.(r - g), z.r */
             int nodes[CG_UF];
             bool oks[CG_UF];
 #pragma unroll
             for (int u = 0; u < CG_UF; ++u)
-                oks[u] = pass_row(a, s_state, it, u, nodes[u]);
+                oks[u] = pass_row(V, n_rows, u, nodes[u]);
             /* CG_UF rows per thread in flight: the pass is latency bound */
-            while (it.view < a.n_views)
+            for (int p = 0; p < passes; p += CG_UF)
             {
-                CgView const& V = a.v[it.view];
-                double const alpha = s_state[it.view].alpha;
-                double const* d_new = odd ? V.d2 : V.d;
-                PassIter nx = it;
-                pass_next(a, s_state, false, CG_UF, nx);
                 int nodes_next[CG_UF];
                 bool oks_next[CG_UF];
 #pragma unroll
                 for (int u = 0; u < CG_UF; ++u)
-                    oks_next[u] = pass_row(a, s_state, nx, u, nodes_next[u]);
+                    oks_next[u] = pass_row(V, n_rows, p + CG_UF + u,
+                        nodes_next[u]);
 
                 double xv[CG_UF], rv[CG_UF], gv[CG_UF];
                 double2 p01[CG_UF], p23[CG_UF];
@@ -638,12 +643,6 @@ cg_kernel (CgArgs const a)
                         acc[2] += zi * rv[u];
                     }
                 }
-                if (nx.view != it.view)
-                {
-                    warp_flush<3>(acc, s_red, it.view);
-                    acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0;
-                }
-                it = nx;
 #pragma unroll
                 for (int u = 0; u < CG_UF; ++u)
                 {
@@ -651,8 +650,9 @@ cg_kernel (CgArgs const a)
                     oks[u] = oks_next[u];
                 }
             }
-            publish<3>(a, s_state, s_red, slot + 1, false);
+            warp_flush<3>(acc, s_red, v);
         }
+        publish<3>(a, s_state, s_red, slot + 1, false);
         unsigned long long const t_d = now_ns<TIMING>();
         grid_barrier(a.sync, epoch);
         all_sums<3>(a, s_state, slot + 1, s_bcast, false);
@@ -889,8 +889,19 @@ cg_enqueue (smvsb_ctx* const* cs, int n, int max_iter, double err_tol,
         throw Error(SMVSB_ERR_INVALID, "batch size out of range");
     smvsb_ctx* lead = cs[0];
     bool const timing = getenv("SMVSB_CG_TIMING") != nullptr;
-    void const* kernel = timing ? (void const*)cg_kernel<true>
-        : (void const*)cg_kernel<false>;
+    void const* kernel = nullptr;
+    if (n == 1)
+        kernel = timing ? (void const*)cg_kernel<true, 1>
+            : (void const*)cg_kernel<false, 1>;
+    else if (n == 2)
+        kernel = timing ? (void const*)cg_kernel<true, 2>
+            : (void const*)cg_kernel<false, 2>;
+    else if (n <= 4)
+        kernel = timing ? (void const*)cg_kernel<true, 4>
+            : (void const*)cg_kernel<false, 4>;
+    else
+        kernel = timing ? (void const*)cg_kernel<true, 8>
+            : (void const*)cg_kernel<false, 8>;
 
     int per_sm = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm,

@@ -136,6 +136,14 @@ struct smvsb_ctx
     smvsb::DevBuf<double> basis_s, basis_f;
     std::vector<uint8_t> h_node_valid, h_patch_valid;
 
+    /* resident pipeline (smvsb_optimize, topology.cu) */
+    smvsb::DevBuf<float> init_depth;        /* Surface::depth */
+    smvsb::DevBuf<double> nodes_tmp;
+    smvsb::DevBuf<uint8_t> node_valid_tmp;
+    smvsb::DevBuf<uint8_t> u8_main;
+    smvsb::DevBuf<uint8_t> u8_subs[SMVSB_MAX_SUBS];
+    smvsb::DevBuf<float> guide;             /* byte_to_float(main image) */
+
     /* linear system */
     bool have_system = false;
     smvsb::DevBuf<double> patch_H;      /* n_patches * 256 */
@@ -248,6 +256,15 @@ void launch_render_normals (smvsb_ctx* c, float* out_dev);
 void run_fit_lighting (smvsb_ctx* c, double* A_b_host /*272*/);
 void launch_count_processed (smvsb_ctx* c, unsigned long long* n_proc_host);
 uint64_t run_visibility (smvsb_ctx* c, float const* sgm_depth_host);
+uint64_t run_visibility_device (smvsb_ctx* c);   /* c->sgm_depth already set */
+void launch_remove_nodes (smvsb_ctx* c);
+void topo_fill_from_depth (smvsb_ctx* c);
+void topo_set_init_depth (smvsb_ctx* c, float const* src_dev);
+void topo_subdivide (smvsb_ctx* c, int* new_npx, int* new_npy, int* new_sx,
+    int* new_sy);
+void topo_subdivide_finish (smvsb_ctx* c);
+void topo_remove_isolated (smvsb_ctx* c);
+uint64_t topo_count_patches (smvsb_ctx* c);
 uint64_t run_cut_boundaries (smvsb_ctx* c, float const* inv_calib9);
 
 } /* namespace smvsb */

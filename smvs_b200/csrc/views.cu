@@ -374,6 +374,8 @@ try_set_scale_tma (smvsb_ctx* c, T const* img_dev, int w, int h,
 {
     if (getenv("SMVSB_NO_TMA") != nullptr)
         return false;
+    if (getenv("SMVSB_TMA") == nullptr)      /* opt-in until verified */
+        return false;
     if ((static_cast<size_t>(w) * sizeof(T)) % 16 != 0
         || reinterpret_cast<uintptr_t>(img_dev) % 16 != 0)
         return false;
@@ -614,6 +616,17 @@ device_shading_inputs (smvsb_ctx* c, uint8_t const* img_dev, int w, int h,
         shading_grad_dev);
     CUDA_CHECK(cudaGetLastError());
     count_launches(c, 2);
+}
+
+/* mve::image::byte_to_float_image of a single-channel image */
+void
+device_byte_to_float (smvsb_ctx* c, uint8_t const* img_dev, size_t n,
+    float* out_dev)
+{
+    byte_to_float_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0,
+        c->stream>>>(img_dev, static_cast<int>(n), out_dev);
+    CUDA_CHECK(cudaGetLastError());
+    count_launches(c, 1);
 }
 
 void

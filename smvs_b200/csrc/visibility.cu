@@ -435,8 +435,27 @@ cut_border_kernel (CutArgs const a)
 
 /* ------------------------------------------------------------------ */
 
+void
+launch_remove_nodes (smvsb_ctx* c)
+{
+    remove_nodes_kernel<<<(c->n_nodes + 255) / 256, 256, 0, c->stream>>>(
+        c->npx, c->npy, c->patch_valid.p, c->node_valid.p);
+    CUDA_CHECK(cudaGetLastError());
+    smvsb::count_launches(c, 1);
+}
+
 uint64_t
 run_visibility (smvsb_ctx* c, float const* sgm_depth_host)
+{
+    size_t const npix = static_cast<size_t>(c->w) * c->h;
+    c->sgm_depth.reserve(npix);
+    CUDA_CHECK(cudaMemcpyAsync(c->sgm_depth.p, sgm_depth_host,
+        npix * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    return run_visibility_device(c);
+}
+
+uint64_t
+run_visibility_device (smvsb_ctx* c)
 {
     size_t const npix = static_cast<size_t>(c->w) * c->h;
     int const np = c->n_patches;
@@ -451,9 +470,6 @@ run_visibility (smvsb_ctx* c, float const* sgm_depth_host)
     CUDA_CHECK(cudaMemcpyAsync(c->zoff.p, zoff.data(),
         zoff.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice,
         c->stream));
-    c->sgm_depth.reserve(npix);
-    CUDA_CHECK(cudaMemcpyAsync(c->sgm_depth.p, sgm_depth_host,
-        npix * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     c->image_out.reserve(npix * 3);
     CUDA_CHECK(cudaMemsetAsync(c->image_out.p, 0, npix * sizeof(float),
         c->stream));

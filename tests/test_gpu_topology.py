@@ -1,0 +1,141 @@
+"""The Surface operations between the Newton loops on the device
+(smvs_b200/csrc/topology.cu) against the compiled reference's Surface
+(lib/surface.cc): creation from a depth map, subdivision, hole filling,
+isolated-patch removal. Selections, copies and bitwise patch evaluation only:
+nodes, node flags and patch flags must be EQUAL."""
+import numpy as np
+import pytest
+
+from smvs_b200 import api, synth
+from oracle import ref as oref
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")]
+
+
+def _ctx_with_views(sc, scale):
+    """A context that knows the view sizes (surface ops need no images)."""
+    from smvs_b200 import workload
+    wl = workload.build_workload(sc.width, sc.height, sc.n_sub, scale=max(scale, 2), scene=sc)
+    ctx = api.Context(0)
+    wl.push_views_u8(ctx)
+    return ctx
+
+
+def _holes(depth, seed):
+    rng = np.random.default_rng(seed)
+    d = depth.astype(np.float32).copy()
+    h, w = d.shape
+    for _ in range(6):
+        x, y = int(rng.integers(0, w - 40)), int(rng.integers(0, h - 30))
+        d[y:y + int(rng.integers(8, 30)), x:x + int(rng.integers(8, 40))] = 0.0
+    d[rng.random(d.shape) < 0.02] = 0.0
+    return d
+
+
+def _state(ctx):
+    nodes = ctx.get_nodes()
+    nv, pv, _, _ = ctx.surface_state()
+    return nodes, nv, pv
+
+
+def _assert_same(ctx, R, what):
+    gi, ri = ctx.surface_info(), R.surface_info()
+    assert gi == ri, (what, gi, ri)
+    nodes, nv, pv = _state(ctx)
+    rn, rnv, rpv = R.surface_get()
+    assert np.array_equal(nv, rnv), what
+    assert np.array_equal(pv, rpv), what
+    valid = rnv.astype(bool)
+    assert np.array_equal(nodes[valid], rn[valid]), what
+
+
+@pytest.mark.parametrize("w,h,scale", [(640, 480, 4), (640, 480, 5), (333, 207, 3),
+                                       (417, 311, 2), (1920, 1080, 5)])
+def test_surface_create_subdivide_fill(w, h, scale):
+    sc = synth.make_scene(w, h, 2, seed_index=70 + scale)
+    init = _holes(sc.init_depth, scale)
+    R = oref.RefScene(sc)
+    ctx = _ctx_with_views(sc, scale)
+    try:
+        R.surface_create(scale, init)
+        ctx.surface_create(scale, init)
+        _assert_same(ctx, R, "create")
+        assert ctx.surface_state()[1].mean() > 0.3
+        for step in range(2 if scale >= 3 else 1):
+            # delete a few patches first: subdivision must follow the same
+            # "last patch in id order wins" rule on shared edges
+            nodes, nv, pv = _state(ctx)
+            info = ctx.surface_info()
+            rng = np.random.default_rng(step)
+            pv2 = pv.copy()
+            pv2[rng.random(pv.shape) < 0.1] = 0
+            ctx.set_surface(info["scale"], info["npx"], info["npy"], info["start_x"],
+                            info["start_y"], nodes, nv, pv2, None, None)
+            R.surface_set(nodes, nv, pv2)
+            R.surface_subdivide()
+            ctx.surface_subdivide()
+            _assert_same(ctx, R, f"subdivide {step}")
+            R.surface_fill_from_depth()
+            ctx.surface_fill_from_depth()
+            _assert_same(ctx, R, f"fill {step}")
+    finally:
+        ctx.close()
+        R.close()
+
+
+@pytest.mark.parametrize("w,h,scale,drop", [(640, 480, 2, 0.5), (640, 480, 3, 0.7),
+                                            (333, 207, 2, 0.3), (1920, 1080, 2, 0.6)])
+def test_remove_isolated_patches(w, h, scale, drop):
+    """Sequential semantics (x outer, y inner, deletions feed later counts)
+    reproduced by the wavefront kernel, on a heavily thinned surface."""
+    sc = synth.make_scene(w, h, 2, seed_index=80 + scale)
+    R = oref.RefScene(sc)
+    ctx = _ctx_with_views(sc, scale)
+    try:
+        R.surface_create(scale, sc.init_depth)
+        ctx.surface_create(scale, sc.init_depth)
+        nodes, nv, pv = _state(ctx)
+        info = ctx.surface_info()
+        rng = np.random.default_rng(7)
+        pv2 = pv.copy()
+        pv2[rng.random(pv.shape) < drop] = 0
+        ctx.set_surface(info["scale"], info["npx"], info["npy"], info["start_x"],
+                        info["start_y"], nodes, nv, pv2, None, None)
+        R.surface_set(nodes, nv, pv2)
+        R.surface_remove_isolated()
+        ctx.surface_remove_isolated()
+        _, gnv, gpv = _state(ctx)
+        _, rnv, rpv = R.surface_get()
+        assert 0 < rpv.sum() < pv2.sum()          # something was removed
+        assert np.array_equal(gpv, rpv) and np.array_equal(gnv, rnv)
+    finally:
+        ctx.close()
+        R.close()
+
+
+@pytest.mark.parametrize("shading", [False, True])
+def test_resident_optimize_matches_reference(shading):
+    """smvsb_optimize (the whole DepthOptimizer::optimize() of a view on the
+    device) against the compiled reference: same valid mask, depth within 1e-4
+    (BASELINE.json), normals within 1e-3."""
+    sc = synth.make_scene(640, 480, 3, seed_index=90, shading=shading)
+    R = oref.RefScene(sc, init_linear=shading)
+    d_cpu, n_cpu, l_cpu = R.optimize(sc.init_depth, regularization=0.01, num_iterations=5,
+                                     min_scale=2, use_shading=shading)
+    Mi, ti = R.Mt()
+    sh, shg = R.shading() if shading else (None, None)
+    with api.Context(0) as ctx:
+        d, n, light, st = api.optimize(ctx, sc.images[0], sc.images[1:], Mi, ti, R.flen(0),
+                                       R.inverse_flen(0), R.inverse_calibration(),
+                                       sc.init_depth, shading=sh, shading_grad=shg)
+    R.close()
+    assert st["final_scale"] == 2 and st["scales"] >= 3 and st["newton_steps"] > 5
+    assert np.array_equal(d_cpu > 0, d > 0)
+    m = d_cpu > 0
+    assert m.mean() > 0.5
+    rel = np.abs(d[m] - d_cpu[m]) / d_cpu[m]
+    assert rel.max() < 1e-4, rel.max()
+    assert np.abs(n - n_cpu)[m].max() < 1e-3
+    if shading:
+        assert np.max(np.abs(light - l_cpu)) / np.max(np.abs(l_cpu)) < 1e-3
