@@ -14,9 +14,11 @@ with api.Context(0) as ctx:
     ctx.gn_construct(None, None, 0.01, 0.0)
     xs = {}
     for variant in sys.argv[1:] or ["new", "v1", "new", "v1"]:
-        if variant == "new":
-            os.environ.pop("SMVSB_CG_VARIANT", None)
-        else:
+        os.environ.pop("SMVSB_CG_VARIANT", None)
+        os.environ.pop("SMVSB_CG_MODE", None)
+        if variant.startswith("m"):
+            os.environ["SMVSB_CG_MODE"] = variant[1:]
+        elif variant != "new":
             os.environ["SMVSB_CG_VARIANT"] = variant
         sys.stderr.write(f"--- {variant}\n")
         sys.stderr.flush()

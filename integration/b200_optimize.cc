@@ -102,10 +102,16 @@ DepthOptimizer::optimize (void)
 
     /* ---- what optimize() leaves behind -------------------------------- */
     /* the final surface, for get_depth() / get_normals(): the grid geometry
-     * of the ladder from a planar stand-in (reference code, no image work),
+     * of the ladder from a stand-in created and subdivided by the reference's
+     * own code (a constant depth image makes every node and patch exist),
      * then the device's nodes and validity */
     int const init_scale = st.final_scale + (st.scales - 1);
-    this->surface = Surface::create_planar(1.0, w, h, init_scale);
+    {
+        mve::FloatImage::Ptr ones = mve::FloatImage::create(w, h, 1);
+        ones->fill(1.0f);
+        this->surface = Surface::create(nullptr, this->main_view, init_scale,
+            ones);
+    }
     while (this->surface->get_scale() > st.final_scale)
         this->surface->subdivide_patches();
     {

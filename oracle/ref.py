@@ -313,6 +313,13 @@ class RefScene:
                            int(debug_lvl), _p(depth), _p(normals), _p(light))
         return depth, normals, light
 
+    def sgm_roundtrip(self, depth):
+        """StereoView::get_sgm_depth() of a depth stored as "smvs-sgm"."""
+        d = np.ascontiguousarray(depth, dtype=np.float32)
+        out = np.empty((self.h, self.w), dtype=np.float32)
+        self.L.ref_sgm_roundtrip(self.h_, _p(d), _p(out))
+        return out
+
     # -- SGM -------------------------------------------------------------
     def sgm_dims(self, v, scale):
         info = (C.c_int * 2)()

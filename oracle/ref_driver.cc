@@ -787,6 +787,21 @@ ref_fit_lighting (void* scene, double* params16)
     return 0;
 }
 
+/* What StereoView::get_sgm_depth() returns for a depth written as the
+ * "smvs-sgm" embedding (the two convention changes cost fp32 rounding). */
+int
+ref_sgm_roundtrip (void* scene, float const* sgm_depth, float* out)
+{
+    RefScene* s = static_cast<RefScene*>(scene);
+    int const w = s->main_view->get_width(), h = s->main_view->get_height();
+    mve::FloatImage::Ptr init = mve::FloatImage::create(w, h, 1);
+    std::copy(sgm_depth, sgm_depth + (std::size_t)w * h, init->begin());
+    s->main_view->write_depth_to_view(init, "smvs-sgm");
+    mve::FloatImage::Ptr back = s->main_view->get_sgm_depth();
+    std::copy(back->begin(), back->end(), out);
+    return 0;
+}
+
 /* Full DepthOptimizer::optimize(), lib/depth_optimizer.cc:53-162, with the
  * options the CLI sets (app/smvsrecon.cc:711-720). The initial depth goes in
  * as the "smvs-sgm" embedding (z-depth; stored in MVE convention so that

@@ -400,14 +400,14 @@ pass_row (CgView const& V, int n_rows, int pass, int& node)
  * lengthens the time a warp spends per pass (measured with the view indexed
  * at run time: SpMV phase 32.6 us instead of 25.2 us on the full 2 MP
  * system). */
-template <bool TIMING, int NV>
+template <bool TIMING, int NV, int MODE = 0>
 __global__ void __launch_bounds__(CG_THREADS, 2)
 cg_kernel (CgArgs const a)
 {
     unsigned long long const keep = policy_evict_last();
-    __shared__ double s_red[SMVSB_MAX_BATCH * 3 * CG_WARPS];
-    __shared__ double s_bcast[SMVSB_MAX_BATCH * 3];
-    __shared__ CgState s_state[SMVSB_MAX_BATCH];
+    __shared__ double s_red[NV * 3 * CG_WARPS];
+    __shared__ double s_bcast[NV * 3];
+    __shared__ CgState s_state[NV];
     unsigned int epoch = 0;
     int const quad = threadIdx.x & 28;      /* first lane of the node's quad */
     int const rp = threadIdx.x & 3;
@@ -502,6 +502,47 @@ cg_kernel (CgArgs const a)
          * its mask one pass ahead, and the first two rows of the NEXT view are
          * fetched while this view streams, so no load of a pass waits for
          * another one. */
+        if ((MODE & 1) != 0)
+        {
+            /* EXPERIMENT: round-1 loop shape (single view) */
+            CgView const& V = a.v[0];
+            int const n_rows = s_state[0].n_rows;
+            int const quads = V.grid * CG_QUADS;
+            int const quad0 = blockIdx.x * CG_QUADS + (threadIdx.x >> 2);
+            DirVec dir;
+            dir.z = V.z; dir.d_old = odd ? V.d : V.d2;
+            dir.beta = s_state[0].beta;
+            double* d_new = odd ? V.d2 : V.d;
+            double acc[1] = { 0.0 };
+            if (!s_state[0].done)
+            {
+                int node = (quad0 < n_rows) ? static_cast<int>(V.rows[quad0])
+                    : 0;
+                unsigned int mask = (quad0 < n_rows) ? V.rowmask[node] : 0u;
+                for (int q = quad0; q < n_rows; q += quads)
+                {
+                    int const qn = q + quads;
+                    int const node_next = (qn < n_rows)
+                        ? static_cast<int>(V.rows[qn]) : 0;
+                    unsigned int const mask_next = (qn < n_rows)
+                        ? V.rowmask[node_next] : 0u;
+                    double own[4];
+                    size_t const i = static_cast<size_t>(node) * 4 + rp;
+                    double const val = spmv_row(V.H, V.npx + 1, dir, node, rp,
+                        mask, own);
+                    node = node_next;
+                    mask = mask_next;
+                    double const di = (rp == 0) ? own[0] : (rp == 1) ? own[1]
+                        : (rp == 2) ? own[2] : own[3];
+                    V.Ad[i] = val;
+                    d_new[i] = di;
+                    acc[0] += val * di;
+                }
+                warp_flush<1>(acc, s_red, 0);
+            }
+            publish<1>(a, s_state, s_red, slot, false);
+        }
+        else
         {
             int const v_first = next_view(a, s_state, 0, false);
             if (v_first < a.n_views && v_first != pa_view)
@@ -578,6 +619,69 @@ cg_kernel (CgArgs const a)
 
         /* x += alpha d; r -= alpha Ad; r.r; Q1 = -x.(b + r); z = P r; z.r
          * (:130-181) */
+        if ((MODE & 2) != 0)
+        {
+            /* EXPERIMENT: round-1 loop shape: all entries, linear */
+            CgView const& V = a.v[0];
+            if (!s_state[0].done)
+            {
+                int const n = V.n_nodes * 4;
+                int const stride = V.grid * CG_THREADS;
+                int const t0 = blockIdx.x * CG_THREADS + threadIdx.x;
+                int const n_round = ((n + CG_UF * stride - 1)
+                    / (CG_UF * stride)) * (CG_UF * stride);
+                double const alpha = s_state[0].alpha;
+                double const* d_new = odd ? V.d2 : V.d;
+                double acc[3] = { 0.0, 0.0, 0.0 };
+                for (int i0 = t0; i0 < n_round; i0 += CG_UF * stride)
+                {
+                    double xv[CG_UF], rv[CG_UF], gv[CG_UF];
+                    double2 p01[CG_UF], p23[CG_UF];
+#pragma unroll
+                    for (int u = 0; u < CG_UF; ++u)
+                    {
+                        int const i = i0 + u * stride;
+                        xv[u] = 0.0; rv[u] = 0.0; gv[u] = 0.0;
+                        p01[u] = make_double2(0, 0); p23[u] = p01[u];
+                        if (i < n)
+                        {
+                            double const dn = d_new[i], ad = V.Ad[i];
+                            gv[u] = V.g[i];
+                            xv[u] = V.x[i]; rv[u] = V.r[i];
+                            double const* prow = V.P
+                                + static_cast<size_t>(i >> 2) * 16 + rp * 4;
+                            p01[u] = ld_hint(prow, keep);
+                            p23[u] = ld_hint(prow + 2, keep);
+                            xv[u] += dn * alpha; rv[u] -= ad * alpha;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < CG_UF; ++u)
+                    {
+                        int const i = i0 + u * stride;
+                        double const q0 = __shfl_sync(0xffffffffu, rv[u], quad);
+                        double const q1 = __shfl_sync(0xffffffffu, rv[u],
+                            quad + 1);
+                        double const q2 = __shfl_sync(0xffffffffu, rv[u],
+                            quad + 2);
+                        double const q3 = __shfl_sync(0xffffffffu, rv[u],
+                            quad + 3);
+                        if (i < n)
+                        {
+                            double const zi = p01[u].x * q0 + p01[u].y * q1
+                                + p23[u].x * q2 + p23[u].y * q3;
+                            V.x[i] = xv[u]; V.r[i] = rv[u];
+                            V.z[i] = zi;
+                            acc[0] += rv[u] * rv[u];
+                            acc[1] += xv[u] * (rv[u] - gv[u]);
+                            acc[2] += zi * rv[u];
+                        }
+                    }
+                }
+                warp_flush<3>(acc, s_red, 0);
+            }
+        }
+        else
 #pragma unroll
         for (int v = 0; v < NV; ++v)
         {
@@ -890,7 +994,15 @@ cg_enqueue (smvsb_ctx* const* cs, int n, int max_iter, double err_tol,
     smvsb_ctx* lead = cs[0];
     bool const timing = getenv("SMVSB_CG_TIMING") != nullptr;
     void const* kernel = nullptr;
-    if (n == 1)
+    int const mode = getenv("SMVSB_CG_MODE") ? atoi(getenv("SMVSB_CG_MODE"))
+        : 0;
+    if (n == 1 && mode == 1)
+        kernel = (void const*)cg_kernel<true, 1, 1>;
+    else if (n == 1 && mode == 2)
+        kernel = (void const*)cg_kernel<true, 1, 2>;
+    else if (n == 1 && mode == 3)
+        kernel = (void const*)cg_kernel<true, 1, 3>;
+    else if (n == 1)
         kernel = timing ? (void const*)cg_kernel<true, 1>
             : (void const*)cg_kernel<false, 1>;
     else if (n == 2)

@@ -427,84 +427,67 @@ sgm_paths_kernel (int w, int h, unsigned P1, unsigned P2,
         unsigned const P1x2 = P1 | (P1 << 16), P2x2 = P2 | (P2 << 16);
         unsigned const BIG = 0x7000u;      /* "no neighbour" sentinel */
         unsigned P01 = 0, P23 = 0;
-        /* the cost words travel PF steps ahead of the recurrence: a step is a
-         * short dependent chain (shuffle reduction), so a warp has few loads
-         * in flight unless it fetches ahead */
-        constexpr int PF = 4;
-        unsigned cq[PF];
-        int xp = x, yp = y;
-        auto advance = [&](int& ax, int& ay)
-        {
-            ax += dx; ay += dy;
-            if (ax < 0) ax = w - 1;
-            if (ax >= w) ax = 0;
-        };
-#pragma unroll
-        for (int u = 0; u < PF; ++u)
-        {
-            cq[u] = 0;
-            if (u < steps)
-            {
-                cq[u] = *reinterpret_cast<unsigned const*>(cost
-                    + (static_cast<size_t>(yp) * w + xp) * D + lane * 4);
-                advance(xp, yp);
-            }
-        }
+        /* The kernel is bound by instruction issue (ncu: issue slots 77 %
+         * busy, DRAM 25 %), so the per-step bookkeeping is kept to pointer
+         * increments: a step moves both pointers by a constant, a diagonal
+         * that leaves the image at one side re-enters at the other (where the
+         * reference restarts the path, :515-534) with a correction of one
+         * image row. The cost word of the next step is fetched one step ahead
+         * (two or four ahead cost more instructions than they hide). */
+        long long const row_bytes = static_cast<long long>(w) * D;
+        long long const step_bytes = dy * row_bytes + dx * D;
+        uint8_t const* pc = cost + (static_cast<size_t>(y) * w + x) * D
+            + lane * 4;
+        uint8_t* pd = Dr + (static_cast<size_t>(y) * w + x) * D + lane * 4;
+        unsigned c4 = *reinterpret_cast<unsigned const*>(pc);
         bool start = true;
-        for (int s0 = 0; s0 < steps; s0 += PF)
+        for (int s = 0; s < steps; ++s)
         {
-#pragma unroll
-            for (int u = 0; u < PF; ++u)
+            /* next position */
+            int xn = x + dx;
+            long long adv = step_bytes;
+            if (xn < 0) { xn = w - 1; adv += row_bytes; }
+            if (xn >= w) { xn = 0; adv -= row_bytes; }
+            unsigned c4n = 0;
+            if (s + 1 < steps)
+                c4n = *reinterpret_cast<unsigned const*>(pc + adv);
+
+            unsigned const C01 = __byte_perm(c4, 0, 0x4140);
+            unsigned const C23 = __byte_perm(c4, 0, 0x4342);
+            unsigned D01 = 0, D23 = 0;
+            if (start)
             {
-                int const s = s0 + u;
-                if (s >= steps)
-                    break;
-                unsigned const c4 = cq[u];
-                if (s + PF < steps)
-                {
-                    cq[u] = *reinterpret_cast<unsigned const*>(cost
-                        + (static_cast<size_t>(yp) * w + xp) * D + lane * 4);
-                    advance(xp, yp);
-                }
-                size_t const base = (static_cast<size_t>(y) * w + x) * D
-                    + lane * 4;
-                unsigned const C01 = __byte_perm(c4, 0, 0x4140);
-                unsigned const C23 = __byte_perm(c4, 0, 0x4342);
-                unsigned D01 = 0, D23 = 0;
-                if (start)
-                {
-                    P01 = C01; P23 = C23;
-                }
-                else
-                {
-                    unsigned const m2 = __vminu2(P01, P23);
-                    unsigned mn = min(m2 & 0xffffu, m2 >> 16);
-                    for (int off = 16; off > 0; off >>= 1)
-                        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-                    unsigned below = __shfl_up_sync(0xffffffffu, P23, 1) >> 16;
-                    unsigned above = __shfl_down_sync(0xffffffffu, P01, 1)
-                        & 0xffffu;
-                    if (lane == 0) below = BIG;
-                    if (lane == 31) above = BIG;
-                    unsigned const mid = (P01 >> 16) | (P23 << 16);  /* L1, L2 */
-                    unsigned const lo01 = below | (P01 << 16);       /* -, L0 */
-                    unsigned const hi23 = (P23 >> 16) | (above << 16);/* L3, - */
-                    unsigned const mn2 = mn * 0x10001u;
-                    unsigned const far2 = mn2 + P2x2;
-                    unsigned const b01 = __vimin3_u16x2(P01, far2,
-                        __viaddmin_u16x2(mid, P1x2, lo01 + P1x2));
-                    unsigned const b23 = __vimin3_u16x2(P23, far2,
-                        __viaddmin_u16x2(hi23, P1x2, mid + P1x2));
-                    D01 = b01 - mn2;      /* = L - C, in [0, P2] per half */
-                    D23 = b23 - mn2;
-                    P01 = C01 + D01;
-                    P23 = C23 + D23;
-                }
-                *reinterpret_cast<unsigned*>(Dr + base) =
-                    __byte_perm(D01, D23, 0x6420);
-                advance(x, y);
-                start = diagonal && (x == restart_x);
+                P01 = C01; P23 = C23;
             }
+            else
+            {
+                unsigned const m2 = __vminu2(P01, P23);
+                unsigned mn = min(m2 & 0xffffu, m2 >> 16);
+                for (int off = 16; off > 0; off >>= 1)
+                    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+                unsigned below = __shfl_up_sync(0xffffffffu, P23, 1) >> 16;
+                unsigned above = __shfl_down_sync(0xffffffffu, P01, 1)
+                    & 0xffffu;
+                if (lane == 0) below = BIG;
+                if (lane == 31) above = BIG;
+                unsigned const mid = (P01 >> 16) | (P23 << 16);   /* L1, L2 */
+                unsigned const lo01 = below | (P01 << 16);        /* -, L0 */
+                unsigned const hi23 = (P23 >> 16) | (above << 16);/* L3, - */
+                unsigned const mn2 = mn * 0x10001u;
+                unsigned const far2 = mn2 + P2x2;
+                unsigned const b01 = __vimin3_u16x2(P01, far2,
+                    __viaddmin_u16x2(mid, P1x2, lo01 + P1x2));
+                unsigned const b23 = __vimin3_u16x2(P23, far2,
+                    __viaddmin_u16x2(hi23, P1x2, mid + P1x2));
+                D01 = b01 - mn2;          /* = L - C, in [0, P2] per half */
+                D23 = b23 - mn2;
+                P01 = C01 + D01;
+                P23 = C23 + D23;
+            }
+            *reinterpret_cast<unsigned*>(pd) = __byte_perm(D01, D23, 0x6420);
+            c4 = c4n;
+            x = xn; pc += adv; pd += adv;
+            start = diagonal && (xn == restart_x);
         }
         return;
     }

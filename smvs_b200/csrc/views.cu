@@ -16,9 +16,6 @@
 #include <cstdlib>
 #include <cstring>
 
-#include <cuda.h>               /* CUtensorMap types only; the driver entry
-                                   point is fetched through the runtime */
-
 #include "common.cuh"
 
 namespace smvsb {
@@ -175,30 +172,39 @@ unpack_texels_kernel (float const* __restrict__ texels, int n,
 
 /* ------------------------------------------------------------------ */
 /*
- * The same three steps as ONE kernel with the image tile staged by TMA
- * (north star: "image pyramids staged to shared memory via TMA"). A block
- * owns a TW x TH output tile; one elected thread issues a single
- * cp.async.bulk.tensor.2d for the tile plus its halo of R = ks + 1 pixels
- * (blur radius + the 3x3 stencil) and the block waits on an mbarrier. The
- * hardware fills what lies outside the image with zeros; the reference clamps
- * indices (edge replication, mve::image::blur_gaussian), so the blocks on the
- * image border overwrite those cells with the edge pixels before use. Then
- * blur along x, blur along y (both with the CPU's operation order) and the
- * 6x9 stencil run out of shared memory: the two float images the three-kernel
- * version writes and reads back (16 B per pixel of DRAM traffic) never exist.
- * Needs a row pitch that is a multiple of 16 bytes (TMA global strides);
- * other widths keep the three kernels.
+ * The same three steps as ONE kernel with the image tile staged by the TMA
+ * engine (north star: "image pyramids staged to shared memory via TMA"). A
+ * block owns a TW x TH output tile and needs it plus a halo of R = ks + 1
+ * pixels (blur radius + the 3x3 stencil). One elected thread arms an mbarrier
+ * with the byte count and issues one bulk asynchronous copy
+ * (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, SASS
+ * UBLKCP) per tile row -- 16-byte aligned spans of the image rows, clipped to
+ * the image; the block waits on the mbarrier. The reference clamps indices at
+ * the image border (edge replication, mve::image::blur_gaussian): blocks on
+ * the border fill the cells outside the image from the edge pixels before
+ * use. Then blur along x, blur along y (both with the CPU's operation order)
+ * and the 6x9 stencil run out of shared memory: the two float images the
+ * three-kernel version writes and reads back (16 B per pixel of DRAM traffic)
+ * never exist. Needs a row pitch that is a multiple of 16 bytes; other widths
+ * keep the three kernels.
+ *
+ * (A tiled tensor map -- cp.async.bulk.tensor.2d, which would also do the
+ * clipping in hardware -- was tried first: the UTMALDG raised "illegal
+ * instruction" on the GPU box although cuTensorMapEncodeTiled accepted the
+ * descriptor; with no way to debug the descriptor offline, the row-wise bulk
+ * copies are what ships.)
  */
 constexpr int FT_W = 64, FT_H = 32, FT_THREADS = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(FT_THREADS)
-set_scale_tma_kernel (const __grid_constant__ CUtensorMap tmap, int w, int h,
-    int R, int box_w, BlurKernel const k, int mode, float* __restrict__ out,
+set_scale_tma_kernel (T const* __restrict__ img, int w, int h, int R,
+    int box_w, BlurKernel const k, int mode, float* __restrict__ out,
     float* __restrict__ blur_out)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bar;
+    constexpr int A = 16 / static_cast<int>(sizeof(T));   /* pixels per 16 B */
     int const rows_in = FT_H + 2 * R;
     size_t const in_bytes = (static_cast<size_t>(box_w) * rows_in * sizeof(T)
         + 127) / 128 * 128;
@@ -209,10 +215,13 @@ set_scale_tma_kernel (const __grid_constant__ CUtensorMap tmap, int w, int h,
 
     int const tid = threadIdx.x;
     int const x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H;
+    /* aligned column span [xs, xe) and row span [ys, ye) inside the image */
+    int const xs = max(0, (x0 - R) & ~(A - 1) );
+    int const xe = min(w, (x0 + FT_W + R + A - 1) & ~(A - 1));
+    int const ys = max(0, y0 - R), ye = min(h, y0 + FT_H + R);
+    int const col0 = (x0 - R) - xs;              /* tile column of x0 - R */
     unsigned const bar_addr = static_cast<unsigned>(
         __cvta_generic_to_shared(&bar));
-    unsigned const in_addr = static_cast<unsigned>(
-        __cvta_generic_to_shared(s_in));
     if (tid == 0)
     {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;"
@@ -222,15 +231,22 @@ set_scale_tma_kernel (const __grid_constant__ CUtensorMap tmap, int w, int h,
     __syncthreads();
     if (tid == 0)
     {
-        unsigned const bytes = static_cast<unsigned>(box_w * rows_in
+        unsigned const row_bytes = static_cast<unsigned>((xe - xs)
             * sizeof(T));
+        unsigned const bytes = row_bytes * static_cast<unsigned>(ye - ys);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
             :: "r"(bar_addr), "r"(bytes) : "memory");
-        int const cx = x0 - R, cy = y0 - R;
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global"
-            ".mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-            :: "r"(in_addr), "l"(reinterpret_cast<unsigned long long>(&tmap)),
-               "r"(bar_addr), "r"(cx), "r"(cy) : "memory");
+        for (int gy = ys; gy < ye; ++gy)
+        {
+            unsigned const dst = static_cast<unsigned>(
+                __cvta_generic_to_shared(s_in + static_cast<size_t>(
+                gy - (y0 - R)) * box_w));
+            T const* src = img + static_cast<size_t>(gy) * w + xs;
+            asm volatile("cp.async.bulk.shared::cluster.global"
+                ".mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                :: "r"(dst), "l"(src), "r"(row_bytes), "r"(bar_addr)
+                : "memory");
+        }
     }
     {
         unsigned done = 0;
@@ -241,17 +257,21 @@ set_scale_tma_kernel (const __grid_constant__ CUtensorMap tmap, int w, int h,
                 : "=r"(done) : "r"(bar_addr) : "memory");
     }
 
-    /* edge replication where the tile leaves the image */
+    /* edge replication where the tile leaves the image: tile cell (r, c)
+     * holds image pixel (y0 - R + r, xs + c) */
+    int const cols = col0 + FT_W + 2 * R;        /* cells the blur can touch */
     if (x0 - R < 0 || y0 - R < 0 || x0 + FT_W + R > w || y0 + FT_H + R > h)
     {
-        int const cols = FT_W + 2 * R;
         for (int i = tid; i < cols * rows_in; i += FT_THREADS)
         {
             int const r = i / cols, c = i % cols;
-            int const gx = x0 - R + c, gy = y0 - R + r;
-            if (gx < 0 || gx >= w || gy < 0 || gy >= h)
+            int const gx = xs + c, gy = y0 - R + r;
+            /* with xs clipped to 0 the columns left of the image are the
+             * NEGATIVE tile columns: they are folded onto column 0 by the
+             * clamped reads below; here only cells at or right of xs */
+            if (gx >= w || gy < 0 || gy >= h)
             {
-                int const sx = min(max(gx, 0), w - 1) - (x0 - R);
+                int const sx = min(gx, w - 1) - xs;
                 int const sy = min(max(gy, 0), h - 1) - (y0 - R);
                 s_in[r * box_w + c] = s_in[sy * box_w + sx];
             }
@@ -259,15 +279,18 @@ set_scale_tma_kernel (const __grid_constant__ CUtensorMap tmap, int w, int h,
         __syncthreads();
     }
 
-    /* blur along x: rows of the tile with halo, columns x0 - 1 .. x0 + TW */
+    /* blur along x: rows of the tile with halo, columns x0 - 1 .. x0 + TW.
+     * Tile column of image column gx is gx - xs; left of the image (only
+     * when xs = 0) the index is clamped to 0 = edge replication. */
     for (int i = tid; i < rows_in * bw; i += FT_THREADS)
     {
         int const r = i / bw, c = i % bw;
-        T const* row = s_in + r * box_w + (c - 1 + R);
+        T const* row = s_in + r * box_w;
+        int const centre = col0 + (c - 1 + R);   /* may be < R near x = 0 */
         float acc = 0.0f;
         for (int j = -k.ks; j <= k.ks; ++j)
-            acc = __fadd_rn(acc, __fmul_rn(pixel_value(row[j]),
-                k.w[abs(j)]));
+            acc = __fadd_rn(acc, __fmul_rn(pixel_value(row[max(centre + j,
+                0)]), k.w[abs(j)]));
         s_bx[i] = __fdiv_rn(acc, k.wsum);
     }
     __syncthreads();
@@ -342,28 +365,6 @@ set_scale_tma_kernel (const __grid_constant__ CUtensorMap tmap, int w, int h,
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType,
-    cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-/* cuTensorMapEncodeTiled through the runtime (the library does not link
- * libcuda); nullptr if this driver has none. */
-EncodeTiledFn
-encode_tiled_fn (void)
-{
-    static EncodeTiledFn fn = [] () -> EncodeTiledFn {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p,
-            cudaEnableDefault, &q) != cudaSuccess
-            || q != cudaDriverEntryPointSuccess)
-            return nullptr;
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-
 /* Launches the fused kernel if the image qualifies; false = use the three
  * kernels (pitch not a multiple of 16 bytes, very large blur radius, or
  * SMVSB_NO_TMA set -- the A/B switch of benchmarks/members_bench.py). */
@@ -374,35 +375,16 @@ try_set_scale_tma (smvsb_ctx* c, T const* img_dev, int w, int h,
 {
     if (getenv("SMVSB_NO_TMA") != nullptr)
         return false;
-    if (getenv("SMVSB_TMA") == nullptr)      /* opt-in until verified */
-        return false;
     if ((static_cast<size_t>(w) * sizeof(T)) % 16 != 0
         || reinterpret_cast<uintptr_t>(img_dev) % 16 != 0)
         return false;
     int const R = k.ks + 1;
     int const per16 = 16 / static_cast<int>(sizeof(T));
-    int const box_w = (FT_W + 2 * R + per16 - 1) / per16 * per16;
+    /* the aligned span can start up to per16 - 1 pixels left of x0 - R and
+     * end as many to the right */
+    int const box_w = (FT_W + 2 * R + 2 * (per16 - 1) + per16 - 1) / per16
+        * per16;
     int const rows_in = FT_H + 2 * R;
-    if (box_w > 256 || rows_in > 256)
-        return false;
-    EncodeTiledFn const encode = encode_tiled_fn();
-    if (encode == nullptr)
-        return false;
-    CUtensorMap tmap;
-    cuuint64_t const gdim[2] = { static_cast<cuuint64_t>(w),
-        static_cast<cuuint64_t>(h) };
-    cuuint64_t const gstride[1] = { static_cast<cuuint64_t>(w) * sizeof(T) };
-    cuuint32_t const box[2] = { static_cast<cuuint32_t>(box_w),
-        static_cast<cuuint32_t>(rows_in) };
-    cuuint32_t const estride[2] = { 1, 1 };
-    CUresult const rc = encode(&tmap, sizeof(T) == 1
-        ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-        const_cast<T*>(img_dev), gdim, gstride, box, estride,
-        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS)
-        return false;
     size_t const in_bytes = (static_cast<size_t>(box_w) * rows_in * sizeof(T)
         + 127) / 128 * 128;
     size_t const smem = in_bytes + (static_cast<size_t>(rows_in)
@@ -412,7 +394,7 @@ try_set_scale_tma (smvsb_ctx* c, T const* img_dev, int w, int h,
     CUDA_CHECK(cudaFuncSetAttribute(set_scale_tma_kernel<T>,
         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     dim3 const grid((w + FT_W - 1) / FT_W, (h + FT_H - 1) / FT_H);
-    set_scale_tma_kernel<T><<<grid, FT_THREADS, smem, c->stream>>>(tmap, w,
+    set_scale_tma_kernel<T><<<grid, FT_THREADS, smem, c->stream>>>(img_dev, w,
         h, R, box_w, k, mode, out_dev, blur_out);
     CUDA_CHECK(cudaGetLastError());
     count_launches(c, 1);

@@ -125,17 +125,22 @@ def test_resident_optimize_matches_reference(shading):
                                      min_scale=2, use_shading=shading)
     Mi, ti = R.Mt()
     sh, shg = R.shading() if shading else (None, None)
+    # what the reference's optimize() sees as SGM depth: the "smvs-sgm"
+    # embedding after StereoView::get_sgm_depth()'s convention change
+    sgm = R.sgm_roundtrip(sc.init_depth)
     with api.Context(0) as ctx:
         d, n, light, st = api.optimize(ctx, sc.images[0], sc.images[1:], Mi, ti, R.flen(0),
                                        R.inverse_flen(0), R.inverse_calibration(),
-                                       sc.init_depth, shading=sh, shading_grad=shg)
+                                       sgm, shading=sh, shading_grad=shg)
     R.close()
     assert st["final_scale"] == 2 and st["scales"] >= 3 and st["newton_steps"] > 5
     assert np.array_equal(d_cpu > 0, d > 0)
     m = d_cpu > 0
     assert m.mean() > 0.5
     rel = np.abs(d[m] - d_cpu[m]) / d_cpu[m]
-    assert rel.max() < 1e-4, rel.max()
-    assert np.abs(n - n_cpu)[m].max() < 1e-3
+    # no solve of this ladder runs into the iteration limit: every decision is
+    # the reference's, the depth map differs by fp32 output rounding at most
+    assert rel.max() < 1e-6, rel.max()
+    assert np.abs(n - n_cpu)[m].max() < 1e-5
     if shading:
-        assert np.max(np.abs(light - l_cpu)) / np.max(np.abs(l_cpu)) < 1e-3
+        assert np.max(np.abs(light - l_cpu)) / np.max(np.abs(l_cpu)) < 1e-4
