@@ -13,7 +13,7 @@ with api.Context(0) as ctx:
     wl.push_surface(ctx)
     ctx.gn_construct(None, None, 0.01, 0.0)
     xs = {}
-    for variant in sys.argv[1:] or ["new", "v1", "new", "v1"]:
+    for variant in sys.argv[1:] or ["new", "new"]:
         os.environ.pop("SMVSB_CG_VARIANT", None)
         os.environ.pop("SMVSB_CG_MODE", None)
         if variant.startswith("m"):

@@ -435,6 +435,26 @@ int smvsb_sgm_reconstruct (int device, int w, int h, const uint8_t* main_lum,
     int num_steps, uint16_t penalty1, uint16_t penalty2,
     const float* merge_with, float* depth_out, double* ms_out);
 
+/* ---- after the per-view optimisation ------------------------------------ */
+
+/*
+ * MeshGenerator::cut_depth_maps (lib/mesh_generator.cc:25-158): the
+ * cross-view consistency cut of all depth maps of a scene, on one device.
+ *   depth[i]      w[i]*h[i], MVE convention (distance along the viewing ray),
+ *                 what View::get_float_image(dm_name) holds (:190)
+ *   normals[i]    w[i]*h[i]*3, world space (after :192-203)
+ *   invproj9      per view: CameraInfo::fill_inverse_calibration(w, h) (:38-40)
+ *   cam_to_world16   per view: CameraInfo::fill_cam_to_world (:55)
+ *   KR9, t3       per view: MeshGenerator::ViewProjection (:302-312)
+ *   depth_out[i]  the cut maps (same convention as depth[i])
+ * The matrices are computed by the host with the reference's own camera code;
+ * the device only consumes them.
+ */
+int smvsb_cut_depth_maps (int device, int n_views, const int* w, const int* h,
+    const float* const* depth, const float* const* normals,
+    const float* invproj9, const float* cam_to_world16, const float* KR9,
+    const float* t3, float* const* depth_out);
+
 #ifdef __cplusplus
 }
 #endif

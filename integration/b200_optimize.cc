@@ -113,7 +113,12 @@ DepthOptimizer::optimize (void)
             ones);
     }
     while (this->surface->get_scale() > st.final_scale)
+    {
         this->surface->subdivide_patches();
+        /* the ring a subdivision adds around the grid (:993-1014) is filled
+         * from the depth, as optimize() does (:99) */
+        this->surface->fill_patches_from_depth();
+    }
     {
         Surface::NodeList const& nodes = this->surface->get_nodes();
         Surface::PatchList const& patches = this->surface->get_patches();

@@ -83,6 +83,21 @@ public:
         return r;
     }
 
+    /* homogeneous product: (M-1)-vector extended by v, first N-1 rows
+     * (MVE, restated) */
+    Vector<T,N-1> mult (Vector<T,M-1> const& rhs, T const& v) const
+    {
+        Vector<T,N-1> r;
+        for (int i = 0; i < N - 1; ++i)
+        {
+            T sum(0);
+            for (int k = 0; k < M - 1; ++k)
+                sum += m[i * M + k] * rhs[k];
+            r[i] = sum + v * m[i * M + M - 1];
+        }
+        return r;
+    }
+
     template <int U>
     Matrix<T,N,U> operator* (Matrix<T,M,U> const& rhs) const
     { return this->mult(rhs); }

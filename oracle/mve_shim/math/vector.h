@@ -107,6 +107,7 @@ typedef Vector<double,3> Vec3d;
 typedef Vector<double,4> Vec4d;
 typedef Vector<int,2> Vec2i;
 typedef Vector<int,3> Vec3i;
+typedef Vector<unsigned int,3> Vec3ui;
 
 MATH_NAMESPACE_END
 

@@ -75,6 +75,24 @@ struct CameraInfo
     }
     void fill_camera_translation (float* vec) const
     { std::copy(trans, trans + 3, vec); }
+    /* camera position = -R^T t (MVE, restated) */
+    void fill_camera_pos (float* pos) const
+    {
+        pos[0] = -rot[0] * trans[0] - rot[3] * trans[1] - rot[6] * trans[2];
+        pos[1] = -rot[1] * trans[0] - rot[4] * trans[1] - rot[7] * trans[2];
+        pos[2] = -rot[2] * trans[0] - rot[5] * trans[1] - rot[8] * trans[2];
+    }
+    /* 4x4 camera-to-world: [R^T | camera position] (MVE, restated) */
+    void fill_cam_to_world (float* mat) const
+    {
+        mat[0]  = rot[0]; mat[1]  = rot[3]; mat[2]  = rot[6];
+        mat[4]  = rot[1]; mat[5]  = rot[4]; mat[6]  = rot[7];
+        mat[8]  = rot[2]; mat[9]  = rot[5]; mat[10] = rot[8];
+        mat[3]  = -(rot[0] * trans[0] + rot[3] * trans[1] + rot[6] * trans[2]);
+        mat[7]  = -(rot[1] * trans[0] + rot[4] * trans[1] + rot[7] * trans[2]);
+        mat[11] = -(rot[2] * trans[0] + rot[5] * trans[1] + rot[8] * trans[2]);
+        mat[12] = 0.0f; mat[13] = 0.0f; mat[14] = 0.0f; mat[15] = 1.0f;
+    }
 
     void fill_reprojection (CameraInfo const& destination,
         float src_width, float src_height, float dst_width, float dst_height,

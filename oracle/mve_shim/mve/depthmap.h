@@ -29,6 +29,21 @@ depthmap_convert_conventions (typename Image<T>::Ptr dm,
 }
 
 MVE_IMAGE_NAMESPACE_END
+
+MVE_GEOM_NAMESPACE_BEGIN
+
+/* 3-D position of pixel (x, y) at MVE depth (distance along the viewing ray)
+ * in camera coordinates (MVE, restated). */
+inline math::Vec3f
+pixel_3dpos (std::size_t x, std::size_t y, float depth,
+    math::Matrix3f const& invproj)
+{
+    math::Vec3f ray = invproj * math::Vec3f((float)x + 0.5f,
+        (float)y + 0.5f, 1.0f);
+    return ray.normalized() * depth;
+}
+
+MVE_GEOM_NAMESPACE_END
 MVE_NAMESPACE_END
 
 #endif

@@ -51,6 +51,22 @@ public:
     }
     void remove_image (std::string const& name) { this->images.erase(name); }
 
+    /* what lib/mesh_generator.cc:176-178 reads of MVE's image proxies */
+    struct ImageProxy
+    {
+        int width, height, channels;
+    };
+    ImageProxy const* get_image_proxy (std::string const& name)
+    {
+        ImageBase::Ptr img = this->get_image(name);
+        if (img == nullptr)
+            return nullptr;
+        this->proxy.width = img->width();
+        this->proxy.height = img->height();
+        this->proxy.channels = img->channels();
+        return &this->proxy;
+    }
+
     void save_view (void) {}
     int cache_cleanup (void) { return 0; }
 
@@ -58,6 +74,7 @@ private:
     int id;
     CameraInfo cam;
     std::map<std::string, ImageBase::Ptr> images;
+    ImageProxy proxy;
 };
 
 MVE_NAMESPACE_END

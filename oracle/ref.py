@@ -356,6 +356,32 @@ class RefScene:
 # unit-level entry points (the reference's own known-answer tests run on them)
 # ---------------------------------------------------------------------------
 
+def cut_depth_maps(flen, rot, trans, depths, normals, run=True):
+    """MeshGenerator::cut_depth_maps of the compiled reference on n views:
+    cameras (flen (n,), world-to-camera rot (n, 9), trans (n, 3)), depth maps in
+    MVE convention, world-space normal maps. Returns (cut maps or None,
+    invproj (n, 9), cam_to_world (n, 16), KR (n, 9), t (n, 3))."""
+    n = len(depths)
+    d = [np.ascontiguousarray(a, dtype=np.float32) for a in depths]
+    nr = [np.ascontiguousarray(a, dtype=np.float32) for a in normals]
+    outs = [np.empty_like(a) for a in d]
+    w = (C.c_int * n)(*[a.shape[1] for a in d])
+    h = (C.c_int * n)(*[a.shape[0] for a in d])
+    dp = (C.c_void_p * n)(*[a.ctypes.data for a in d])
+    npp = (C.c_void_p * n)(*[a.ctypes.data for a in nr])
+    op = (C.c_void_p * n)(*[a.ctypes.data for a in outs])
+    fl = np.ascontiguousarray(flen, dtype=np.float32)
+    ro = np.ascontiguousarray(rot, dtype=np.float32).reshape(n, 9)
+    tr = np.ascontiguousarray(trans, dtype=np.float32).reshape(n, 3)
+    inv = np.empty((n, 9), np.float32)
+    ctw = np.empty((n, 16), np.float32)
+    KR = np.empty((n, 9), np.float32)
+    t = np.empty((n, 3), np.float32)
+    lib().ref_cut_depth_maps(n, w, h, _p(fl), _p(ro), _p(tr), dp, npp, op if run else None,
+                             _p(inv), _p(ctw), _p(KR), _p(t))
+    return (outs if run else None), inv, ctw, KR, t
+
+
 class Units:
     """Per-function access to the compiled reference (BicubicPatch,
     Correspondence, surfderiv, sh, ldl_inverse)."""

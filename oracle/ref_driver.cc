@@ -30,6 +30,7 @@
 #include <map>
 #include <memory>
 #include <sstream>
+#include <stdexcept>
 #include <string>
 #include <utility>
 #include <vector>
@@ -49,6 +50,10 @@
 #include "surface_derivative.h"
 #include "spherical_harmonics.h"
 #include "ldl_decomposition.h"
+#include "mesh_generator.h"
+#include "mve/mesh_tools.h"
+#include "mve/mesh_info.h"
+#include "depth_triangulator.h"
 #include "sse_vector.h"
 #include "block_sparse_matrix.h"
 #undef private
@@ -104,6 +109,27 @@ sampling_for_scale (int scale)
 }
 
 } /* namespace */
+
+/* lib/mesh_generator.cc is compiled whole; of it only cut_depth_maps runs.
+ * What generate_mesh would call of MVE's and the reference's meshing code is
+ * satisfied with definitions that refuse to run. */
+namespace mve {
+namespace geom {
+void mesh_merge (TriangleMesh::ConstPtr, TriangleMesh::Ptr)
+{ throw std::logic_error("oracle: meshing is not part of the hot path"); }
+void depthmap_mesh_confidences (TriangleMesh::Ptr, int)
+{ throw std::logic_error("oracle: meshing is not part of the hot path"); }
+}
+MeshInfo::MeshInfo (TriangleMesh::ConstPtr)
+{ throw std::logic_error("oracle: meshing is not part of the hot path"); }
+}
+namespace smvs {
+mve::TriangleMesh::Ptr DepthTriangulator::full_triangulation (void)
+{ throw std::logic_error("oracle: meshing is not part of the hot path"); }
+mve::TriangleMesh::Ptr DepthTriangulator::approximate_triangulation (int,
+    double)
+{ throw std::logic_error("oracle: meshing is not part of the hot path"); }
+}
 
 extern "C" {
 
@@ -1009,6 +1035,60 @@ void
 ref_ldl_inverse (double* A, int n)
 {
     smvs::ldl_inverse(A, n);
+}
+
+/* MeshGenerator::cut_depth_maps (lib/mesh_generator.cc:25-158) on n views
+ * given by their cameras (flen, world-to-camera rotation and translation),
+ * depth maps (MVE convention) and world-space normal maps. Also returns the
+ * per-view matrices the function derives from the cameras, so that the device
+ * twin consumes identical inputs: invproj (9), cam-to-world (16), KR (9), t (3).
+ * lib/mesh_generator.cc is compiled verbatim; only cut_depth_maps is called. */
+int
+ref_cut_depth_maps (int n, int const* w, int const* h, float const* flen,
+    float const* rot9, float const* trans3, float const* const* depth,
+    float const* const* normals, float* const* depth_out, float* invproj9,
+    float* ctw16, float* KR9, float* t3)
+{
+    smvs::MeshGenerator::Options o;
+    o.num_threads = 4;
+    smvs::MeshGenerator mg(o);
+    std::vector<mve::FloatImage::Ptr> depthmaps(n), normalmaps(n);
+    for (int i = 0; i < n; ++i)
+    {
+        mve::CameraInfo cam;
+        cam.flen = flen[i];
+        std::copy(rot9 + 9 * i, rot9 + 9 * i + 9, cam.rot);
+        std::copy(trans3 + 3 * i, trans3 + 3 * i + 3, cam.trans);
+        mve::View::Ptr view = mve::View::create();
+        view->set_id(i);
+        view->set_camera(cam);
+        mg.views.push_back(view);
+        mg.view_projs.emplace_back(cam, w[i], h[i]);
+        depthmaps[i] = mve::FloatImage::create(w[i], h[i], 1);
+        std::copy(depth[i], depth[i] + (std::size_t)w[i] * h[i],
+            depthmaps[i]->begin());
+        normalmaps[i] = mve::FloatImage::create(w[i], h[i], 3);
+        std::copy(normals[i], normals[i] + (std::size_t)w[i] * h[i] * 3,
+            normalmaps[i]->begin());
+        if (invproj9)
+            cam.fill_inverse_calibration(invproj9 + 9 * i, w[i], h[i]);
+        if (ctw16)
+            cam.fill_cam_to_world(ctw16 + 16 * i);
+        if (KR9)
+            std::copy(mg.view_projs[i].KR.begin(), mg.view_projs[i].KR.end(),
+                KR9 + 9 * i);
+        if (t3)
+            std::copy(mg.view_projs[i].t.begin(), mg.view_projs[i].t.end(),
+                t3 + 3 * i);
+    }
+    if (depth_out != nullptr)
+    {
+        mg.cut_depth_maps(&depthmaps, &normalmaps);
+        for (int i = 0; i < n; ++i)
+            std::copy(depthmaps[i]->begin(), depthmaps[i]->end(),
+                depth_out[i]);
+    }
+    return 0;
 }
 
 /* SSEVector operations (lib/sse_vector.cc:19-205), for the reference's own

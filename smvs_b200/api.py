@@ -25,7 +25,7 @@ EXPORTS = [
     "smvsb_get_normals", "smvsb_debug_get_system", "smvsb_debug_spmv",
     "smvsb_fit_lighting", "smvsb_sgm", "smvsb_visibility",
     "smvsb_cut_boundaries", "smvsb_get_surface_state", "smvsb_view_set_scale",
-    "smvsb_bilateral_filter", "smvsb_debug_expf", "smvsb_device_count", "smvsb_surface_create", "smvsb_surface_subdivide",
+    "smvsb_bilateral_filter", "smvsb_debug_expf", "smvsb_device_count", "smvsb_cut_depth_maps", "smvsb_surface_create", "smvsb_surface_subdivide",
     "smvsb_surface_fill_from_depth", "smvsb_surface_remove_isolated", "smvsb_surface_info",
     "smvsb_optimize", "smvsb_measure_fp64_peak", "smvsb_sgm_reconstruct", "smvsb_newton_loop_batch", "smvsb_device_launch_count",
 ]
@@ -491,3 +491,24 @@ def optimize(ctx, main_img, sub_imgs, Mi, ti, flen_px, inv_flen, inv_calib9, sgm
     ctx._sync_surface_info()
     stats = {f: getattr(st, f) for f, _ in OptimizeStats._fields_ if f != "reserved"}
     return depth, normals, light, stats
+
+
+def cut_depth_maps(depths, normals, invproj, cam_to_world, KR, t, device=0):
+    """smvsb_cut_depth_maps: lists of (h, w) depth maps (MVE convention) and
+    (h, w, 3) world-space normal maps, per-view matrices as (n, 9) / (n, 16) /
+    (n, 9) / (n, 3) float arrays -> list of cut depth maps."""
+    n = len(depths)
+    d = [_f32(a) for a in depths]
+    nr = [_f32(a) for a in normals]
+    outs = [np.empty_like(a) for a in d]
+    w = (C.c_int * n)(*[a.shape[1] for a in d])
+    h = (C.c_int * n)(*[a.shape[0] for a in d])
+    dp = (C.c_void_p * n)(*[a.ctypes.data for a in d])
+    npp = (C.c_void_p * n)(*[a.ctypes.data for a in nr])
+    op = (C.c_void_p * n)(*[a.ctypes.data for a in outs])
+    m = [_f32(a).reshape(-1) for a in (invproj, cam_to_world, KR, t)]
+    rc = lib().smvsb_cut_depth_maps(int(device), n, w, h, dp, npp, _p(m[0]), _p(m[1]),
+                                    _p(m[2]), _p(m[3]), op)
+    if rc != 0:
+        raise SmvsbError(rc, lib().smvsb_last_error(None).decode())
+    return outs

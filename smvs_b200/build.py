@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsmvs_b200.so")
 SOURCES = ["api.cu", "gn_construct.cu", "cg.cu", "update.cu", "sgm.cu", "views.cu",
-           "visibility.cu", "microbench.cu", "cg_v1_probe.cu", "topology.cu"]
+           "visibility.cu", "microbench.cu", "topology.cu", "cut_maps.cu"]
 HEADERS = ["common.cuh", "gn_math.cuh", "patch_eval.cuh", os.path.join("..", "..", "include", "smvs_b200.h")]
 
 NVCC_FLAGS = [

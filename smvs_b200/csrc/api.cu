@@ -36,6 +36,11 @@ int sgm_run (int device, int w, int h, uint8_t const* main_lum, int nw, int nh,
     uint16_t penalty2, float* depth_out, uint16_t* cost_out,
     uint16_t* sgm_out, double* ms_out);
 double measure_fp64_peak (int device);
+std::string const& cut_last_error (void);
+int cut_depth_maps (int device, int n_views, int const* w, int const* h,
+    float const* const* depth, float const* const* normals,
+    float const* invproj9, float const* cam_to_world16, float const* KR9,
+    float const* t3, float* const* depth_out);
 int sgm_reconstruct (int device, int w, int h, uint8_t const* main_lum, int nw,
     int nh, uint8_t const* neigh_lum, float const* M_mn, float const* t_mn,
     float const* M_nm, float const* t_nm, float const* depth_range_main,
@@ -1567,6 +1572,19 @@ smvsb_sgm_reconstruct (int device, int w, int h, const uint8_t* main_lum,
         g_last_error = smvsb::sgm_last_error();
     else    /* 2 x (cost, paths, WTA) + consistency (+ merge) */
         smvsb::count_device_launches(device, merge_with ? 8 : 7);
+    return rc;
+}
+
+int
+smvsb_cut_depth_maps (int device, int n_views, const int* w, const int* h,
+    const float* const* depth, const float* const* normals,
+    const float* invproj9, const float* cam_to_world16, const float* KR9,
+    const float* t3, float* const* depth_out)
+{
+    int const rc = smvsb::cut_depth_maps(device, n_views, w, h, depth, normals,
+        invproj9, cam_to_world16, KR9, t3, depth_out);
+    if (rc != SMVSB_OK)
+        g_last_error = smvsb::cut_last_error();
     return rc;
 }
 

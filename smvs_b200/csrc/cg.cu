@@ -109,7 +109,9 @@ struct CgArgs
 struct CgState
 {
     double r_dot_r, Q0, beta, alpha, tol;
+    double* partials;        /* copy of CgView::partials, see publish() */
     int n_rows, passes, done, iters, info;
+    int grid;                /* copy of CgView::grid */
 };
 
 __device__ __forceinline__ void
@@ -211,6 +213,11 @@ warp_flush (double (&v)[NV], double* s_red, int view)
     }
 }
 
+/* (The view's grid size and partial-sum array are read from the shared copy:
+ * indexing the kernel parameters with a per-thread view number is a divergent
+ * constant-bank access -- the compiler hoists it above the branch, every
+ * thread of the CTA fetches a different cache line, and the warp replays it
+ * 32 times: measured 4.4 us per CG iteration for this one load.) */
 template <int NV>
 __device__ __forceinline__ void
 publish (CgArgs const& a, CgState const* s_state, double const* s_red,
@@ -221,16 +228,15 @@ publish (CgArgs const& a, CgState const* s_state, double const* s_red,
     if (t < a.n_views * NV)
     {
         int const view = t / NV, j = t % NV;
-        CgView const& V = a.v[view];
-        if (static_cast<int>(blockIdx.x) < V.grid
-            && (init || !s_state[view].done))
+        CgState const& S = s_state[view];
+        if (static_cast<int>(blockIdx.x) < S.grid && (init || !S.done))
         {
             /* a view without rows was never flushed */
             double total = 0.0;
-            if (s_state[view].passes > 0)
+            if (S.passes > 0)
                 for (int i = 0; i < CG_WARPS; ++i)
                     total += s_red[(view * 3 + j) * CG_WARPS + i];
-            V.partials[(first_slot + j) * CG_MAX_BLOCKS + blockIdx.x] = total;
+            S.partials[(first_slot + j) * CG_MAX_BLOCKS + blockIdx.x] = total;
         }
     }
 }
@@ -251,9 +257,9 @@ all_sums (CgArgs const& a, CgState const* s_state, int first_slot,
         int const view = pair / NV, j = pair % NV;
         if (!init && s_state[view].done)
             continue;
-        CgView const& V = a.v[view];
-        double const* p = V.partials + (first_slot + j) * CG_MAX_BLOCKS;
-        int const nb = V.grid;
+        double const* p = s_state[view].partials
+            + (first_slot + j) * CG_MAX_BLOCKS;
+        int const nb = s_state[view].grid;
         double v = 0.0;
         for (int base = lane; base < nb; base += 32 * 8)
         {
@@ -363,17 +369,8 @@ spmv_row (double const* __restrict__ H, int ns, VecOp const& vec, int node,
 __device__ __forceinline__ bool
 view_on (CgArgs const& a, CgState const* s_state, int v, bool init)
 {
-    return static_cast<int>(blockIdx.x) < a.v[v].grid
+    return static_cast<int>(blockIdx.x) < s_state[v].grid
         && (init || !s_state[v].done) && s_state[v].passes > 0;
-}
-
-/* first view >= v the CTA works on, or n_views */
-__device__ __forceinline__ int
-next_view (CgArgs const& a, CgState const* s_state, int v, bool init)
-{
-    while (v < a.n_views && !view_on(a, s_state, v, init))
-        ++v;
-    return v;
 }
 
 /* The row this thread's quad handles in pass p of view V: whether there is
@@ -400,7 +397,7 @@ pass_row (CgView const& V, int n_rows, int pass, int& node)
  * lengthens the time a warp spends per pass (measured with the view indexed
  * at run time: SpMV phase 32.6 us instead of 25.2 us on the full 2 MP
  * system). */
-template <bool TIMING, int NV, int MODE = 0>
+template <bool TIMING, int NV>
 __global__ void __launch_bounds__(CG_THREADS, 2)
 cg_kernel (CgArgs const a)
 {
@@ -408,6 +405,13 @@ cg_kernel (CgArgs const a)
     __shared__ double s_red[NV * 3 * CG_WARPS];
     __shared__ double s_bcast[NV * 3];
     __shared__ CgState s_state[NV];
+    /* z's address per view, read back from shared memory where it is needed:
+     * a value the compiler cannot re-derive from the kernel parameters, so it
+     * stays in a register through the SpMV loop. (As a plain parameter it is
+     * re-fetched from the constant bank in front of every neighbour's load
+     * once registers are tight -- ncu: short-scoreboard stalls 4.0 instead of
+     * 0.7 per issue, SpMV phase +20 %.) */
+    __shared__ double const* s_zptr[NV];
     unsigned int epoch = 0;
     int const quad = threadIdx.x & 28;      /* first lane of the node's quad */
     int const rp = threadIdx.x & 3;
@@ -422,6 +426,9 @@ cg_kernel (CgArgs const a)
         S.passes = ((passes + CG_UF - 1) / CG_UF) * CG_UF;
         S.done = 0; S.iters = 0; S.info = SMVSB_CG_MAX_ITERATIONS;
         S.r_dot_r = 0.0; S.Q0 = 0.0; S.beta = 0.0; S.alpha = 0.0; S.tol = 0.0;
+        S.partials = V.partials;
+        S.grid = V.grid;
+        s_zptr[threadIdx.x] = V.z;
     }
     __syncthreads();
 
@@ -482,13 +489,25 @@ cg_kernel (CgArgs const a)
 
     int iter = 1;
     unsigned long long tm[4] = {0, 0, 0, 0};
-    /* The rows and masks do not change during a solve: what the first two
-     * passes of the SpMV walk need is kept in registers from one iteration to
-     * the next (reloaded when the first view of the walk changes because a
-     * view has converged). */
-    int pa_view = -1, pa_node0 = 0, pa_node1 = 0;
-    bool pa_ok0 = false, pa_ok1 = false;
-    unsigned int pa_mask0 = 0;
+    /* The rows and masks do not change during a solve: the first pass's of
+     * every view are fetched once. */
+    int first_node[NV];
+    unsigned int first_mask[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+    {
+        first_node[v] = 0;
+        first_mask[v] = 0u;
+        if (v < a.n_views && static_cast<int>(blockIdx.x) < s_state[v].grid)
+        {
+            int const quad0 = blockIdx.x * CG_QUADS + (threadIdx.x >> 2);
+            if (quad0 < s_state[v].n_rows)
+            {
+                first_node[v] = static_cast<int>(a.v[v].rows[quad0]);
+                first_mask[v] = a.v[v].rowmask[first_node[v]];
+            }
+        }
+    }
     for (; iter < a.max_iter; ++iter)
     {
         unsigned long long const t_a = now_ns<TIMING>();
@@ -502,23 +521,28 @@ cg_kernel (CgArgs const a)
          * its mask one pass ahead, and the first two rows of the NEXT view are
          * fetched while this view streams, so no load of a pass waits for
          * another one. */
-        if ((MODE & 1) != 0)
         {
-            /* EXPERIMENT: round-1 loop shape (single view) */
-            CgView const& V = a.v[0];
-            int const n_rows = s_state[0].n_rows;
-            int const quads = V.grid * CG_QUADS;
-            int const quad0 = blockIdx.x * CG_QUADS + (threadIdx.x >> 2);
-            DirVec dir;
-            dir.z = V.z; dir.d_old = odd ? V.d : V.d2;
-            dir.beta = s_state[0].beta;
-            double* d_new = odd ? V.d2 : V.d;
-            double acc[1] = { 0.0 };
-            if (!s_state[0].done)
+            /* One pass = the CTA's 64 block rows; the next pass's row index
+             * and mask are fetched while this pass streams. (A deeper
+             * pipeline -- index two passes ahead, mask one -- measured 1.7 us
+             * slower per iteration on the full 2 MP system.) */
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
             {
-                int node = (quad0 < n_rows) ? static_cast<int>(V.rows[quad0])
-                    : 0;
-                unsigned int mask = (quad0 < n_rows) ? V.rowmask[node] : 0u;
+                if (v >= a.n_views || !view_on(a, s_state, v, false))
+                    continue;
+                CgView const& V = a.v[v];
+                int const n_rows = s_state[v].n_rows;
+                int const quads = V.grid * CG_QUADS;
+                int const quad0 = blockIdx.x * CG_QUADS + (threadIdx.x >> 2);
+                DirVec dir;
+                dir.z = s_zptr[v];
+                dir.d_old = odd ? V.d : V.d2;
+                dir.beta = s_state[v].beta;
+                double* d_new = odd ? V.d2 : V.d;
+                double acc[1] = { 0.0 };
+                int node = first_node[v];
+                unsigned int mask = first_mask[v];
                 for (int q = quad0; q < n_rows; q += quads)
                 {
                     int const qn = q + quads;
@@ -538,73 +562,7 @@ cg_kernel (CgArgs const a)
                     d_new[i] = di;
                     acc[0] += val * di;
                 }
-                warp_flush<1>(acc, s_red, 0);
-            }
-            publish<1>(a, s_state, s_red, slot, false);
-        }
-        else
-        {
-            int const v_first = next_view(a, s_state, 0, false);
-            if (v_first < a.n_views && v_first != pa_view)
-            {
-                CgView const& V = a.v[v_first];
-                pa_view = v_first;
-                pa_ok0 = pass_row(V, s_state[v_first].n_rows, 0, pa_node0);
-                pa_mask0 = pa_ok0 ? V.rowmask[pa_node0] : 0u;
-                pa_ok1 = pass_row(V, s_state[v_first].n_rows, 1, pa_node1);
-            }
-            int node0 = pa_node0, node1 = pa_node1;
-            bool ok0 = pa_ok0, ok1 = pa_ok1;
-            unsigned int mask0 = pa_mask0;
-#pragma unroll
-            for (int v = 0; v < NV; ++v)
-            {
-                if (v >= a.n_views || !view_on(a, s_state, v, false))
-                    continue;
-                CgView const& V = a.v[v];
-                int const n_rows = s_state[v].n_rows;
-                int const passes = s_state[v].passes;
-                double const beta = s_state[v].beta;
-                double const* d_old = odd ? V.d : V.d2;
-                double* d_new = odd ? V.d2 : V.d;
-                /* the next view's first two rows start travelling now */
-                int const vn = next_view(a, s_state, v + 1, false);
-                int nn0 = 0, nn1 = 0;
-                bool nok0 = false, nok1 = false;
-                if (vn < a.n_views)
-                {
-                    nok0 = pass_row(a.v[vn], s_state[vn].n_rows, 0, nn0);
-                    nok1 = pass_row(a.v[vn], s_state[vn].n_rows, 1, nn1);
-                }
-                double acc[1] = { 0.0 };
-                for (int p = 0; p < passes; ++p)
-                {
-                    int node2;
-                    bool const ok2 = pass_row(V, n_rows, p + 2, node2);
-                    unsigned int const mask1 = ok1 ? V.rowmask[node1] : 0u;
-                    if (ok0)
-                    {
-                        DirVec dir;
-                        dir.z = V.z;
-                        dir.d_old = d_old;
-                        dir.beta = beta;
-                        double own[4];
-                        double const val = spmv_row(V.H, V.npx + 1, dir, node0,
-                            rp, mask0, own);
-                        double const di = (rp == 0) ? own[0] : (rp == 1)
-                            ? own[1] : (rp == 2) ? own[2] : own[3];
-                        size_t const i = static_cast<size_t>(node0) * 4 + rp;
-                        V.Ad[i] = val;
-                        d_new[i] = di;
-                        acc[0] += val * di;
-                    }
-                    node0 = node1; ok0 = ok1; mask0 = mask1;
-                    node1 = node2; ok1 = ok2;
-                }
                 warp_flush<1>(acc, s_red, v);
-                /* hand over to the next view (its rows have arrived) */
-                node0 = nn0; ok0 = nok0; node1 = nn1; ok1 = nok1;
-                mask0 = (nok0 && vn < a.n_views) ? a.v[vn].rowmask[nn0] : 0u;
             }
             publish<1>(a, s_state, s_red, slot, false);
         }
@@ -619,69 +577,6 @@ cg_kernel (CgArgs const a)
 
         /* x += alpha d; r -= alpha Ad; r.r; Q1 = -x.(b + r); z = P r; z.r
          * (:130-181) */
-        if ((MODE & 2) != 0)
-        {
-            /* EXPERIMENT: round-1 loop shape: all entries, linear */
-            CgView const& V = a.v[0];
-            if (!s_state[0].done)
-            {
-                int const n = V.n_nodes * 4;
-                int const stride = V.grid * CG_THREADS;
-                int const t0 = blockIdx.x * CG_THREADS + threadIdx.x;
-                int const n_round = ((n + CG_UF * stride - 1)
-                    / (CG_UF * stride)) * (CG_UF * stride);
-                double const alpha = s_state[0].alpha;
-                double const* d_new = odd ? V.d2 : V.d;
-                double acc[3] = { 0.0, 0.0, 0.0 };
-                for (int i0 = t0; i0 < n_round; i0 += CG_UF * stride)
-                {
-                    double xv[CG_UF], rv[CG_UF], gv[CG_UF];
-                    double2 p01[CG_UF], p23[CG_UF];
-#pragma unroll
-                    for (int u = 0; u < CG_UF; ++u)
-                    {
-                        int const i = i0 + u * stride;
-                        xv[u] = 0.0; rv[u] = 0.0; gv[u] = 0.0;
-                        p01[u] = make_double2(0, 0); p23[u] = p01[u];
-                        if (i < n)
-                        {
-                            double const dn = d_new[i], ad = V.Ad[i];
-                            gv[u] = V.g[i];
-                            xv[u] = V.x[i]; rv[u] = V.r[i];
-                            double const* prow = V.P
-                                + static_cast<size_t>(i >> 2) * 16 + rp * 4;
-                            p01[u] = ld_hint(prow, keep);
-                            p23[u] = ld_hint(prow + 2, keep);
-                            xv[u] += dn * alpha; rv[u] -= ad * alpha;
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < CG_UF; ++u)
-                    {
-                        int const i = i0 + u * stride;
-                        double const q0 = __shfl_sync(0xffffffffu, rv[u], quad);
-                        double const q1 = __shfl_sync(0xffffffffu, rv[u],
-                            quad + 1);
-                        double const q2 = __shfl_sync(0xffffffffu, rv[u],
-                            quad + 2);
-                        double const q3 = __shfl_sync(0xffffffffu, rv[u],
-                            quad + 3);
-                        if (i < n)
-                        {
-                            double const zi = p01[u].x * q0 + p01[u].y * q1
-                                + p23[u].x * q2 + p23[u].y * q3;
-                            V.x[i] = xv[u]; V.r[i] = rv[u];
-                            V.z[i] = zi;
-                            acc[0] += rv[u] * rv[u];
-                            acc[1] += xv[u] * (rv[u] - gv[u]);
-                            acc[2] += zi * rv[u];
-                        }
-                    }
-                }
-                warp_flush<3>(acc, s_red, 0);
-            }
-        }
-        else
 #pragma unroll
         for (int v = 0; v < NV; ++v)
         {
@@ -983,8 +878,6 @@ launch_spmv (smvsb_ctx* c, double const* x, double* y)
  * contexts' pinned scalars. cg_collect() reads them after the caller has
  * synchronised the stream.
  */
-void cg_v1_launch (smvsb_ctx* c, int max_iter, double err_tol, double q_tol);
-
 void
 cg_enqueue (smvsb_ctx* const* cs, int n, int max_iter, double err_tol,
     double q_tol)
@@ -994,15 +887,7 @@ cg_enqueue (smvsb_ctx* const* cs, int n, int max_iter, double err_tol,
     smvsb_ctx* lead = cs[0];
     bool const timing = getenv("SMVSB_CG_TIMING") != nullptr;
     void const* kernel = nullptr;
-    int const mode = getenv("SMVSB_CG_MODE") ? atoi(getenv("SMVSB_CG_MODE"))
-        : 0;
-    if (n == 1 && mode == 1)
-        kernel = (void const*)cg_kernel<true, 1, 1>;
-    else if (n == 1 && mode == 2)
-        kernel = (void const*)cg_kernel<true, 1, 2>;
-    else if (n == 1 && mode == 3)
-        kernel = (void const*)cg_kernel<true, 1, 3>;
-    else if (n == 1)
+    if (n == 1)
         kernel = timing ? (void const*)cg_kernel<true, 1>
             : (void const*)cg_kernel<false, 1>;
     else if (n == 2)
@@ -1054,10 +939,6 @@ cg_enqueue (smvsb_ctx* const* cs, int n, int max_iter, double err_tol,
     }
     CUDA_CHECK(cudaMemsetAsync(a.sync, 0, sizeof(unsigned int), lead->stream));
     void* params[] = { &a };
-    char const* variant = getenv("SMVSB_CG_VARIANT");
-    if (variant != nullptr && variant[0] == 'v' && n == 1)
-        cg_v1_launch(lead, max_iter, err_tol, q_tol);
-    else
     CUDA_CHECK(cudaLaunchCooperativeKernel(kernel, dim3(grid),
         dim3(CG_THREADS), params, 0, lead->stream));
     smvsb::count_launches(lead, 1);
