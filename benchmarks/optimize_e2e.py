@@ -33,13 +33,16 @@ def main():
     os.makedirs(CACHE, exist_ok=True)
     sc = synth.make_scene(1920, 1080, 6, seed_index=31, shading=shading)
     path = None if mode == "cpu" else oref.INTEGRATION_LIB_PATH
-    R = oref.RefScene(sc, init_linear=shading, lib_path=path)
-    t0 = time.time()
-    depth, normals, _ = R.optimize(sc.init_depth, regularization=0.01, num_iterations=5,
-                                   min_scale=2, use_shading=shading,
-                                   debug_lvl=int(os.environ.get("SMVS_DEBUG", "0")))
-    secs = time.time() - t0
-    R.close()
+    all_secs = []
+    for _ in range(1 if mode == "cpu" else 3):   # gpu: first call pays CUDA start-up
+        R = oref.RefScene(sc, init_linear=shading, lib_path=path)
+        t0 = time.time()
+        depth, normals, _ = R.optimize(sc.init_depth, regularization=0.01, num_iterations=5,
+                                       min_scale=2, use_shading=shading,
+                                       debug_lvl=int(os.environ.get("SMVS_DEBUG", "0")))
+        all_secs.append(time.time() - t0)
+        R.close()
+    secs = all_secs[-1]
     cache = os.path.join(CACHE, f"optimize_cpu_{tag}.npz")
     if mode == "cpu":
         np.savez_compressed(cache, depth=depth, normals=normals, secs=secs)
@@ -51,6 +54,9 @@ def main():
     rel = np.abs(depth[m] - d_cpu[m]) / d_cpu[m]
     out = {"config": "1920x1080, 6 neighbours, -o2" + (" -S" if shading else ""),
            "cpu_seconds": float(ref["secs"]), "gpu_build_seconds": secs,
+           "gpu_build_seconds_each_call": all_secs,
+           "members": os.environ.get("SMVSB_MEMBERWISE", "0") == "1" and "member-wise drop-ins"
+           or "resident optimize() drop-in",
            "same_valid_mask": bool(np.array_equal(d_cpu > 0, depth > 0)),
            "valid_fraction": float(m.mean()),
            "depth_rel_linf": float(rel.max()),

@@ -356,11 +356,12 @@ class RefScene:
 # unit-level entry points (the reference's own known-answer tests run on them)
 # ---------------------------------------------------------------------------
 
-def cut_depth_maps(flen, rot, trans, depths, normals, run=True):
+def cut_depth_maps(flen, rot, trans, depths, normals, run=True, lib_path=None):
     """MeshGenerator::cut_depth_maps of the compiled reference on n views:
     cameras (flen (n,), world-to-camera rot (n, 9), trans (n, 3)), depth maps in
     MVE convention, world-space normal maps. Returns (cut maps or None,
-    invproj (n, 9), cam_to_world (n, 16), KR (n, 9), t (n, 3))."""
+    invproj (n, 9), cam_to_world (n, 16), KR (n, 9), t (n, 3)). lib_path =
+    INTEGRATION_LIB_PATH runs the drop-in member (integration/b200_mesh_generator.cc)."""
     n = len(depths)
     d = [np.ascontiguousarray(a, dtype=np.float32) for a in depths]
     nr = [np.ascontiguousarray(a, dtype=np.float32) for a in normals]
@@ -377,8 +378,8 @@ def cut_depth_maps(flen, rot, trans, depths, normals, run=True):
     ctw = np.empty((n, 16), np.float32)
     KR = np.empty((n, 9), np.float32)
     t = np.empty((n, 3), np.float32)
-    lib().ref_cut_depth_maps(n, w, h, _p(fl), _p(ro), _p(tr), dp, npp, op if run else None,
-                             _p(inv), _p(ctw), _p(KR), _p(t))
+    load(lib_path).ref_cut_depth_maps(n, w, h, _p(fl), _p(ro), _p(tr), dp, npp, op if run else None,
+                                      _p(inv), _p(ctw), _p(KR), _p(t))
     return (outs if run else None), inv, ctw, KR, t
 
 

@@ -367,7 +367,7 @@ set_scale_tma_kernel (T const* __restrict__ img, int w, int h, int R,
 
 /* Launches the fused kernel if the image qualifies; false = use the three
  * kernels (pitch not a multiple of 16 bytes, very large blur radius, or
- * SMVSB_NO_TMA set -- the A/B switch of benchmarks/members_bench.py). */
+ * SMVSB_NO_TMA set -- the A/B switch of benchmarks/set_scale_bench.py). */
 template <typename T>
 bool
 try_set_scale_tma (smvsb_ctx* c, T const* img_dev, int w, int h,

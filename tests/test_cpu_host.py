@@ -36,6 +36,28 @@ def test_library_exports_every_declared_symbol():
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure path")
+@pytest.mark.skipif(not os.path.exists(oref.INTEGRATION_LIB_PATH),
+                    reason="integration/_build not built")
+def test_drop_in_build_resolves_every_symbol():
+    """integration/_build/libsmvs_ref_b200.so (reference objects + drop-in
+    members + libsmvs_b200.so) loads with immediate binding: no reference member
+    is left without a body, and each drop-in member is the strong definition."""
+    C.CDLL(oref.INTEGRATION_LIB_PATH, mode=os.RTLD_NOW)
+    import subprocess
+    out = subprocess.run(["nm", "-DC", "--defined-only", oref.INTEGRATION_LIB_PATH],
+                         capture_output=True, text=True).stdout
+    for member in ("smvs::DepthOptimizer::optimize()",
+                   "smvs::DepthOptimizer::run_newton_iterations(int)",
+                   "smvs::DepthOptimizer::create_subview_surfaces()",
+                   "smvs::DepthOptimizer::cut_boundaries()",
+                   "smvs::StereoView::set_scale(int, bool)",
+                   "smvs::SGMStereo::run_sgm(float, float)",
+                   "smvs::SGMStereo::reconstruct(",
+                   "smvs::MeshGenerator::cut_depth_maps("):
+        lines = [ln for ln in out.splitlines() if member in ln]
+        assert lines and all(" T " in ln for ln in lines), (member, lines)
+
+
 def test_no_cpu_fallback():
     h = C.c_void_p()
     rc = api.lib().smvsb_create(0, C.byref(h))
