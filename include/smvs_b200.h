@@ -261,11 +261,25 @@ float smvsb_debug_expf (float x);
  * and `sgm_depth` (w*h floats, 0 = no depth), then per (patch, neighbour) the
  * 3 % border test, the 0.95 depth test and the warp-anisotropy test (> 8).
  * Patches no neighbour sees are deleted, nodes without a patch removed, the
- * context's visibility lists replaced. sgm_depth == NULL (the use_sgm = false
- * mode with its NCC filter) -> SMVSB_ERR_INVALID.
+ * context's visibility lists replaced.
+ * sgm_depth == NULL is the use_sgm = false mode: only the surface's own depth
+ * map fills the z-buffers, and a neighbour that passes the three tests must
+ * also pass the NCC occlusion filter DepthOptimizer::ncc_for_patch (:795-912)
+ * on the colour images set by smvsb_set_color_images -- including the
+ * reference's carry-over of the patch's two-pixel rim into the NEXT
+ * neighbour's border and depth tests (:508, :514, :551, :579).
  */
 int smvsb_visibility (smvsb_ctx* ctx, const float* sgm_depth,
     uint64_t* removed_patches);
+
+/*
+ * The colour images ncc_for_patch compares: StereoView::get_image() of the
+ * main view (w*h*3 floats, interleaved) and of every neighbour (sub_w*sub_h*3
+ * each) at the current scale, sizes as given to smvsb_set_views. Needed only
+ * for smvsb_visibility(ctx, NULL, ..); a new smvsb_set_views invalidates them.
+ */
+int smvsb_set_color_images (smvsb_ctx* ctx, const float* main_rgb, int n_sub,
+    const float* const* sub_rgb);
 
 /*
  * One DepthOptimizer::cut_boundaries() (lib/depth_optimizer.cc:360-431):
@@ -306,6 +320,11 @@ int smvsb_surface_fill_from_depth (smvsb_ctx* ctx, const float* init_depth);
  * reference's sequential semantics. */
 int smvsb_surface_remove_isolated (smvsb_ctx* ctx);
 /* scale, npx, npy, start_x, start_y, patchsize of the context's surface */
+/* Surface::expand (lib/surface.cc:482-628): two rounds of extrapolated rim
+ * nodes, fill_holes, remove_nodes_without_patch; *filled_out = its return
+ * value (patches created). The no-SGM mode's growth step
+ * (lib/depth_optimizer.cc:330-337). */
+int smvsb_surface_expand (smvsb_ctx* ctx, int* filled_out);
 int smvsb_surface_info (smvsb_ctx* ctx, int* info6);
 
 /* DepthOptimizer::Options as far as optimize() in the use_sgm mode reads them

@@ -5,8 +5,10 @@
  * GPU through the C ABI of libsmvs_b200.so:
  *   run_newton_iterations    lib/depth_optimizer.cc:164-358 (inner Newton
  *                            loop :204-304 -> smvsb_newton_loop)
- *   create_subview_surfaces  :433-604 -> smvsb_visibility (use_sgm mode; the
- *                            use_sgm = false mode keeps the reference's body)
+ *   create_subview_surfaces  :433-604 -> smvsb_visibility (both modes; the
+ *                            use_sgm = false mode with its NCC filter
+ *                            ncc_for_patch :795-912 needs 3-channel images,
+ *                            otherwise the reference's body runs)
  *   cut_boundaries           :360-431 -> smvsb_cut_boundaries
  *   depthmap_bilateral_filter :957-1004 -> smvsb_bilateral_filter
  * Everything else -- surface expansion / subdivision, isolated-patch removal,
@@ -192,28 +194,74 @@ namespace
 
 /* The reference's own create_subview_surfaces, kept under this name by
  * integration/Makefile (objcopy --redefine-sym on a private copy of the
- * object) for the use_sgm = false mode. */
+ * object): the use_sgm = false mode on images that are not 3-channel (where
+ * the reference's ncc_for_patch indexes channels 1 and 2 of whatever it is
+ * given, lib/depth_optimizer.cc:884-889). */
 extern "C" void smvs_ref_create_subview_surfaces (DepthOptimizer* self);
+
+namespace
+{
+    /* whose colour images the context holds (they do not depend on the
+     * scale: StereoView::get_image() is the unscaled image) */
+    struct ColorKey
+    {
+        void const* owner = nullptr;
+        std::uint64_t generation = 0;
+    };
+
+    bool
+    upload_color_images (smvsb::Context& gpu, void const* owner,
+        StereoView::Ptr main_view, std::vector<StereoView::Ptr> const& subs)
+    {
+        static thread_local ColorKey key;
+        if (main_view->get_image()->channels() != 3)
+            return false;
+        std::vector<float const*> ptrs(subs.size());
+        for (std::size_t k = 0; k < subs.size(); ++k)
+        {
+            if (subs[k]->get_image()->channels() != 3)
+                return false;
+            ptrs[k] = subs[k]->get_image()->begin();
+        }
+        std::uint64_t const gen = smvs_b200_integration::views_generation();
+        if (key.owner == owner && key.generation == gen)
+            return true;
+        gpu.check(smvsb_set_color_images(gpu.get(),
+            main_view->get_image()->begin(), static_cast<int>(subs.size()),
+            ptrs.data()));
+        key.owner = owner;
+        key.generation = gen;
+        return true;
+    }
+}
 
 void
 DepthOptimizer::create_subview_surfaces (void)
 {
-    if (!this->opts.use_sgm)
+    smvsb::Context& gpu = thread_context();
+    int const scale = this->surface->get_scale();
+    if (!this->opts.use_sgm
+        && (this->main_view->get_image()->channels() != 3
+            || this->sub_views.empty()))
     {
         smvs_ref_create_subview_surfaces(this);
         return;
     }
-    smvsb::Context& gpu = thread_context();
-    int const scale = this->surface->get_scale();
     if (!views_current(this, scale, this->main_view))
         upload_views(gpu, this, scale, this->main_view, this->sub_views,
             this->Mi, this->ti);
+    if (!this->opts.use_sgm && !upload_color_images(gpu, this,
+        this->main_view, this->sub_views))
+    {
+        smvs_ref_create_subview_surfaces(this);
+        return;
+    }
 
     PackedSurface packed;
     upload_surface(gpu, this->surface, nullptr, &packed);
     uint64_t removed = 0;
-    gpu.check(smvsb_visibility(gpu.get(), this->sgm_depth->begin(),
-        &removed));
+    gpu.check(smvsb_visibility(gpu.get(), this->opts.use_sgm
+        ? this->sgm_depth->begin() : nullptr, &removed));
 
     std::size_t const np = packed.patch_valid.size();
     std::vector<uint32_t> vis_off(np + 1);

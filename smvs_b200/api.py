@@ -26,7 +26,8 @@ EXPORTS = [
     "smvsb_fit_lighting", "smvsb_sgm", "smvsb_visibility",
     "smvsb_cut_boundaries", "smvsb_get_surface_state", "smvsb_view_set_scale",
     "smvsb_bilateral_filter", "smvsb_debug_expf", "smvsb_device_count", "smvsb_cut_depth_maps", "smvsb_surface_create", "smvsb_surface_subdivide",
-    "smvsb_surface_fill_from_depth", "smvsb_surface_remove_isolated", "smvsb_surface_info",
+    "smvsb_surface_fill_from_depth", "smvsb_surface_remove_isolated", "smvsb_surface_expand", "smvsb_surface_info",
+    "smvsb_set_color_images",
     "smvsb_optimize", "smvsb_measure_fp64_peak", "smvsb_sgm_reconstruct", "smvsb_newton_loop_batch", "smvsb_device_launch_count",
 ]
 
@@ -216,9 +217,19 @@ class Context:
         return out
 
     # -- visibility / boundary cutting --------------------------------------
+    def set_color_images(self, main_rgb, sub_rgbs):
+        """StereoView::get_image() of every view at the current scale
+        ((h, w, 3) floats) for the use_sgm = false visibility."""
+        m = _f32(main_rgb)
+        subs = [_f32(a) for a in sub_rgbs]
+        assert m.shape == (self.h, self.w, 3)
+        ptrs = (C.c_void_p * max(len(subs), 1))(*[a.ctypes.data for a in subs])
+        self._check(lib().smvsb_set_color_images(self._h, _p(m), len(subs), ptrs))
+
     def visibility(self, sgm_depth):
-        """DepthOptimizer::create_subview_surfaces (use_sgm mode) on the
-        context's surface; returns the number of patches it deleted."""
+        """DepthOptimizer::create_subview_surfaces on the context's surface;
+        sgm_depth None = the use_sgm = false mode (needs set_color_images).
+        Returns the number of patches it deleted."""
         d = None if sgm_depth is None else np.ascontiguousarray(sgm_depth, dtype=np.float32)
         removed = C.c_uint64(0)
         self._check(lib().smvsb_visibility(self._h, _p(d), C.byref(removed)))
@@ -270,6 +281,12 @@ class Context:
 
     def surface_remove_isolated(self):
         self._check(lib().smvsb_surface_remove_isolated(self._h))
+
+    def surface_expand(self):
+        """Surface::expand; returns the patches it created."""
+        filled = C.c_int(0)
+        self._check(lib().smvsb_surface_expand(self._h, C.byref(filled)))
+        return filled.value
 
     def set_nodes(self, nodes):
         nodes = _f64(nodes)

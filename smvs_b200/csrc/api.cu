@@ -484,6 +484,14 @@ smvsb_set_views (smvsb_ctx* ctx, int w, int h, double flen_px,
          * image size and neighbour count */
         if (c->w != w || c->h != h || c->n_sub != n_sub)
             c->have_surface = false;
+        /* colour images (smvsb_set_color_images) stay while the geometry of
+         * the views does: the reference's get_image() does not change with
+         * the scale */
+        if (c->w != w || c->h != h || c->n_sub != n_sub)
+            c->have_color = false;
+        for (int k = 0; c->have_color && k < n_sub; ++k)
+            if (c->subs[k].w != sub_w[k] || c->subs[k].h != sub_h[k])
+                c->have_color = false;
         c->w = w; c->h = h; c->flen = flen_px; c->inv_flen = inv_flen;
         size_t const npix = static_cast<size_t>(w) * h;
         upload(c, c->main_grad, main_grad, npix * 2);
@@ -544,6 +552,14 @@ smvsb_set_views_u8 (smvsb_ctx* ctx, int scale, int w, int h, double flen_px,
         smvsb_ctx* c = ctx;
         if (c->w != w || c->h != h || c->n_sub != n_sub)
             c->have_surface = false;
+        /* colour images (smvsb_set_color_images) stay while the geometry of
+         * the views does: the reference's get_image() does not change with
+         * the scale */
+        if (c->w != w || c->h != h || c->n_sub != n_sub)
+            c->have_color = false;
+        for (int k = 0; c->have_color && k < n_sub; ++k)
+            if (c->subs[k].w != sub_w[k] || c->subs[k].h != sub_h[k])
+                c->have_color = false;
         c->w = w; c->h = h; c->flen = flen_px; c->inv_flen = inv_flen;
         size_t max_pix = static_cast<size_t>(w) * h;
         for (int k = 0; k < n_sub; ++k)
@@ -1096,6 +1112,19 @@ smvsb_surface_remove_isolated (smvsb_ctx* ctx)
 }
 
 int
+smvsb_surface_expand (smvsb_ctx* ctx, int* filled_out)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_surface, SMVSB_ERR_STATE, "no surface set");
+        uint64_t const filled = smvsb::topo_expand(ctx);
+        if (filled_out)
+            *filled_out = static_cast<int>(filled);
+        refresh_validity(ctx);
+    });
+}
+
+int
 smvsb_surface_info (smvsb_ctx* ctx, int* info6)
 {
     if (ctx == nullptr) return SMVSB_ERR_INVALID;
@@ -1311,14 +1340,51 @@ smvsb_visibility (smvsb_ctx* ctx, const float* sgm_depth,
     return guarded(ctx, [&]() {
         require(ctx->have_views && ctx->have_surface, SMVSB_ERR_STATE,
             "views / surface not set");
-        require(sgm_depth != nullptr, SMVSB_ERR_INVALID,
-            "sgm_depth missing (the use_sgm = false mode, with its NCC "
-            "occlusion filter, is not offered on the device)");
         require(ctx->n_sub <= 32, SMVSB_ERR_INVALID,
             "more than 32 neighbours");
-        uint64_t const removed = smvsb::run_visibility(ctx, sgm_depth);
+        require(sgm_depth != nullptr || ctx->have_color, SMVSB_ERR_STATE,
+            "sgm_depth is NULL (use_sgm = false) but no colour images are "
+            "set: call smvsb_set_color_images first");
+        uint64_t const removed = (sgm_depth != nullptr)
+            ? smvsb::run_visibility(ctx, sgm_depth)
+            : smvsb::run_visibility_ncc(ctx);
         refresh_validity(ctx);
         if (removed_patches) *removed_patches = removed;
+    });
+}
+
+int
+smvsb_set_color_images (smvsb_ctx* ctx, const float* main_rgb, int n_sub,
+    const float* const* sub_rgb)
+{
+    if (ctx == nullptr) return SMVSB_ERR_INVALID;
+    return guarded(ctx, [&]() {
+        require(ctx->have_views, SMVSB_ERR_STATE, "views not set");
+        require(main_rgb != nullptr && sub_rgb != nullptr
+            && n_sub == ctx->n_sub, SMVSB_ERR_INVALID,
+            "colour images: one per view of the context");
+        size_t const npix = static_cast<size_t>(ctx->w) * ctx->h;
+        ctx->color_main.reserve(npix * 3);
+        CUDA_CHECK(cudaMemcpyAsync(ctx->color_main.p, main_rgb,
+            npix * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        std::vector<float const*> ptrs(n_sub);
+        for (int k = 0; k < n_sub; ++k)
+        {
+            require(sub_rgb[k] != nullptr, SMVSB_ERR_INVALID,
+                "colour image missing");
+            size_t const n = static_cast<size_t>(ctx->subs[k].w)
+                * ctx->subs[k].h * 3;
+            ctx->color_subs[k].reserve(n);
+            CUDA_CHECK(cudaMemcpyAsync(ctx->color_subs[k].p, sub_rgb[k],
+                n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+            ptrs[k] = ctx->color_subs[k].p;
+        }
+        ctx->color_ptrs.reserve(n_sub + 1);
+        CUDA_CHECK(cudaMemcpyAsync(ctx->color_ptrs.p, ptrs.data(),
+            n_sub * sizeof(float const*), cudaMemcpyHostToDevice,
+            ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        ctx->have_color = true;
     });
 }
 

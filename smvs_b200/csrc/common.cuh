@@ -178,6 +178,14 @@ struct smvsb_ctx
     smvsb::DevBuf<unsigned int> zbuf, vis_mask;
     smvsb::DevBuf<unsigned long long> zoff;
     smvsb::DevBuf<float> sgm_depth;
+    /* use_sgm = false: colour images of the current scale, rim lists */
+    bool have_color = false;
+    smvsb::DevBuf<float> color_main;
+    smvsb::DevBuf<float> color_subs[SMVSB_MAX_SUBS];
+    smvsb::DevBuf<float const*> color_ptrs;
+    smvsb::DevBuf<short4> rim_lists;
+    int rim_ps = 0;
+    int rim_off[9] = {};
     smvsb::DevBuf<uint32_t> vis_counts;
 
     /* lighting */
@@ -256,7 +264,8 @@ void launch_render_normals (smvsb_ctx* c, float* out_dev);
 void run_fit_lighting (smvsb_ctx* c, double* A_b_host /*272*/);
 void launch_count_processed (smvsb_ctx* c, unsigned long long* n_proc_host);
 uint64_t run_visibility (smvsb_ctx* c, float const* sgm_depth_host);
-uint64_t run_visibility_device (smvsb_ctx* c);   /* c->sgm_depth already set */
+uint64_t run_visibility_device (smvsb_ctx* c, bool use_sgm = true);   /* c->sgm_depth already set */
+uint64_t run_visibility_ncc (smvsb_ctx* c);      /* use_sgm = false, colour images set */
 void launch_remove_nodes (smvsb_ctx* c);
 void topo_fill_from_depth (smvsb_ctx* c);
 void topo_set_init_depth (smvsb_ctx* c, float const* src_dev);
@@ -264,6 +273,7 @@ void topo_subdivide (smvsb_ctx* c, int* new_npx, int* new_npy, int* new_sx,
     int* new_sy);
 void topo_subdivide_finish (smvsb_ctx* c);
 void topo_remove_isolated (smvsb_ctx* c);
+uint64_t topo_expand (smvsb_ctx* c);
 uint64_t topo_count_patches (smvsb_ctx* c);
 uint64_t run_cut_boundaries (smvsb_ctx* c, float const* inv_calib9);
 

@@ -24,6 +24,13 @@
  *                          over t = 2x + y (a patch depends on (x-1, y-1),
  *                          (x-1, y), (x-1, y+1) and (x, y-1): all earlier
  *                          wavefronts)
+ *   expand_round_kernel    Surface::expand (:482-628): two rounds of new rim
+ *                          nodes. A round reads only the nodes as they were
+ *                          before it (the reference collects the round's nodes
+ *                          in a map and commits them after its loop), so a
+ *                          round is one thread per node; the up to eight
+ *                          offers of a node are taken in the reference's order
+ *                          with check_swap_nodes' 0.9 hysteresis (:472-480)
  *
  * No arithmetic here can differ from the CPU: selections (min, median),
  * copies, divisions by 2 and 4, and BicubicPatch::evaluate_* in the
@@ -191,6 +198,102 @@ fill_holes_kernel (int npx, int npy, uint8_t const* __restrict__ node_valid,
     if (node_valid[n0] && node_valid[n0 + 1] && node_valid[n0 + npx + 1]
         && node_valid[n0 + npx + 2])
         patch_valid[patch] = 1;
+}
+
+/* fill_holes with the count Surface::expand returns */
+__global__ void
+fill_holes_count_kernel (int npx, int npy,
+    uint8_t const* __restrict__ node_valid, uint8_t* __restrict__ patch_valid,
+    unsigned long long* __restrict__ counter)
+{
+    int const patch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (patch >= npx * npy || patch_valid[patch])
+        return;
+    int const idx = patch % npx, idy = patch / npx;
+    int const n0 = idy * (npx + 1) + idx;
+    if (node_valid[n0] && node_valid[n0 + 1] && node_valid[n0 + npx + 1]
+        && node_valid[n0 + npx + 2])
+    {
+        patch_valid[patch] = 1;
+        atomicAdd(counter, 1ull);
+    }
+}
+
+/* One round of Surface::expand step 1 (lib/surface.cc:490-616). has_new /
+ * new_f carry the nodes the earlier round made (the reference's new_nodes
+ * map); nodes / node_valid are read only. */
+__global__ void
+expand_round_kernel (int npx, int npy, double const* __restrict__ nodes,
+    uint8_t const* __restrict__ node_valid, uint8_t* __restrict__ has_new,
+    double* __restrict__ new_f)
+{
+    int const node = blockIdx.x * blockDim.x + threadIdx.x;
+    int const ns = npx + 1;
+    if (node >= ns * (npy + 1))
+        return;
+    bool have = has_new[node] != 0;
+    if (node_valid[node] && !have)
+        return;
+    double best = new_f[node];
+    int const ix = node % ns, iy = node / ns;
+    /* fill_node_neighbors: 0..7 = NW N NE W E SW S SE */
+    bool ok[8];
+    double f[8], dx[8], dy[8];
+    int k = 0;
+    for (int oy = -1; oy < 2; ++oy)
+        for (int ox = -1; ox < 2; ++ox)
+        {
+            if (ox == 0 && oy == 0)
+                continue;
+            int const qx = ix + ox, qy = iy + oy;
+            ok[k] = qx >= 0 && qy >= 0 && qx <= npx && qy <= npy
+                && node_valid[qy * ns + qx];
+            f[k] = dx[k] = dy[k] = 0.0;
+            if (ok[k])
+            {
+                double const* n = nodes + static_cast<size_t>(qy * ns + qx) * 4;
+                f[k] = n[0]; dx[k] = n[1]; dy[k] = n[2];
+            }
+            k += 1;
+        }
+    /* check_swap_nodes */
+    auto offer = [&] (xd value)
+    {
+        if (!have || (value * xd(0.9)).v > best)
+        {
+            have = true;
+            best = value.v;
+        }
+    };
+    xd const two(2.0), three(3.0);
+    auto px = [&] (int i) { return xd(f[i]) + xd(dx[i]) / two; };
+    auto mx = [&] (int i) { return xd(f[i]) - xd(dx[i]) / two; };
+    auto py = [&] (int i) { return xd(f[i]) + xd(dy[i]) / two; };
+    auto my = [&] (int i) { return xd(f[i]) - xd(dy[i]) / two; };
+    if (ok[0] && ok[1] && ok[3]) offer((px(3) + py(1)) / two);
+    if (ok[1] && ok[2] && ok[4]) offer((mx(4) + py(1)) / two);
+    if (ok[3] && ok[5] && ok[6]) offer((px(3) + my(6)) / two);
+    if (ok[4] && ok[6] && ok[7]) offer((mx(4) + my(6)) / two);
+    if (ok[0] && ok[1] && ok[2]) offer((py(0) + py(1) + py(2)) / three);
+    if (ok[0] && ok[3] && ok[5]) offer((px(0) + px(3) + px(5)) / three);
+    if (ok[5] && ok[6] && ok[7]) offer((my(5) + my(6) + my(7)) / three);
+    if (ok[2] && ok[4] && ok[7]) offer((mx(2) + mx(4) + mx(7)) / three);
+    has_new[node] = have ? 1 : 0;
+    new_f[node] = best;
+}
+
+/* the round's nodes become the surface's (:617-619; dx = dy = dxy = 0) */
+__global__ void
+expand_commit_kernel (int n_nodes, uint8_t const* __restrict__ has_new,
+    double const* __restrict__ new_f, double* __restrict__ nodes,
+    uint8_t* __restrict__ node_valid)
+{
+    int const node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= n_nodes || !has_new[node])
+        return;
+    node_valid[node] = 1;
+    double* n = nodes + static_cast<size_t>(node) * 4;
+    n[0] = new_f[node]; n[1] = 0.0; n[2] = 0.0; n[3] = 0.0;
 }
 
 /* BicubicPatch::evaluate_f / _dx / _dy / _dxy (lib/bicubic_patch.cc:121-187)
@@ -487,6 +590,40 @@ topo_remove_isolated (smvsb_ctx* c)
     CUDA_CHECK(cudaGetLastError());
     count_launches(c, 1);
     launch_remove_nodes(c);
+}
+
+/* Surface::expand; returns the patches fill_holes created (synchronises) */
+uint64_t
+topo_expand (smvsb_ctx* c)
+{
+    int const nn = c->n_nodes, np = c->n_patches;
+    c->node_valid_tmp.reserve(nn);
+    c->nodes_tmp.reserve(static_cast<size_t>(nn) * 4);
+    c->counters.reserve(4);
+    CUDA_CHECK(cudaMemsetAsync(c->node_valid_tmp.p, 0, nn, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->nodes_tmp.p, 0, nn * sizeof(double),
+        c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long),
+        c->stream));
+    for (int round = 0; round < 2; ++round)
+    {
+        expand_round_kernel<<<(nn + 127) / 128, 128, 0, c->stream>>>(c->npx,
+            c->npy, c->nodes.p, c->node_valid.p, c->node_valid_tmp.p,
+            c->nodes_tmp.p);
+        expand_commit_kernel<<<(nn + 255) / 256, 256, 0, c->stream>>>(nn,
+            c->node_valid_tmp.p, c->nodes_tmp.p, c->nodes.p,
+            c->node_valid.p);
+    }
+    fill_holes_count_kernel<<<(np + 255) / 256, 256, 0, c->stream>>>(c->npx,
+        c->npy, c->node_valid.p, c->patch_valid.p, c->counters.p);
+    CUDA_CHECK(cudaGetLastError());
+    count_launches(c, 5);
+    launch_remove_nodes(c);
+    unsigned long long n = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n, c->counters.p, sizeof(n),
+        cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return n;
 }
 
 /* number of valid patches (synchronises) */

@@ -1,7 +1,8 @@
 /*
  * visibility.cu -- which neighbours see which patch, and where the surface is
  * cut: DepthOptimizer::create_subview_surfaces (lib/depth_optimizer.cc:433-604,
- * the use_sgm mode) and DepthOptimizer::cut_boundaries (:360-431) with
+ * both modes; use_sgm = false adds ncc_for_patch :795-912 on the colour
+ * images) and DepthOptimizer::cut_boundaries (:360-431) with
  * mse_for_patch (:747-793), Surface::remove_nodes_without_patch
  * (lib/surface.cc:762-867), on the surface resident in the context.
  *
@@ -53,6 +54,11 @@ struct VisArgs
     float const* sgm_depth;         /* w*h */
     unsigned int* vis_mask;         /* n_patches */
     unsigned long long* counters;   /* [0] removed / deleted patches */
+    /* use_sgm = false only */
+    float const* color_main;        /* w*h*3 */
+    float const* const* color_subs; /* n_sub pointers, sub_w*sub_h*3 each */
+    short4 const* rim;              /* the eight rim lists, concatenated */
+    int rim_off[9];
 };
 
 __global__ void
@@ -78,6 +84,8 @@ zbuf_scatter_kernel (VisArgs const a)
     int const x = pix % sf.w, y = pix / sf.w;
     for (int src = 0; src < 2; ++src)
     {
+        if (src == 1 && a.sgm_depth == nullptr)
+            break;                  /* use_sgm = false: surface pixels only */
         float const dep = (src == 0) ? a.surf_depth[pix] : a.sgm_depth[pix];
         if (dep == 0.0f)
             continue;
@@ -102,6 +110,32 @@ zbuf_scatter_kernel (VisArgs const a)
                         + (cx + dx), key);
         }
     }
+}
+
+/* anisotropy of the warp over a patch: largest ratio of the squared singular
+ * values of the 2x2 Jacobian, :555-577 */
+__device__ __forceinline__ double
+warp_anisotropy (double const* cf, double const* __restrict__ Mt, int px0,
+    int py0, int ps)
+{
+    double worst = 0.0;
+    for (int pid = 0; pid < ps * ps; ++pid)
+    {
+        int const i = pid % ps, j = pid / ps;
+        PatchSample const smp = patch_sample<true>(cf, i, j, ps);
+        Warp const c = warp_pixel<true>(Mt, px0 + i + 0.5, py0 + j + 0.5,
+            smp.w, smp.wx, smp.wy);
+        xd const j0(c.jac[0]), j1(c.jac[1]), j2(c.jac[2]), j3(c.jac[3]);
+        xd const e = j0 - j3, f = j1 + j2, g = j0 + j3, h = j1 - j2;
+        xd const q = xsqrt(e * e + f * f);
+        xd const s0 = (q + xsqrt(g * g + h * h)) / xd(2.0);
+        double const s1 = fabs((s0 - q).v);
+        double const big = (s0.v < s1) ? s1 : s0.v;     /* std::max(S0, S1) */
+        double const small = (s1 < s0.v) ? s1 : s0.v;   /* std::min(S0, S1) */
+        double const ratio = (xd(big) * xd(big) / (xd(small) * xd(small))).v;
+        worst = (worst < ratio) ? ratio : worst;        /* std::max */
+    }
+    return worst;
 }
 
 /* second pass, :502-583: one thread per (patch, neighbour) */
@@ -154,28 +188,239 @@ vis_patch_kernel (VisArgs const a)
             }
     }
 
-    /* anisotropy of the warp: ratio of the squared singular values of the
-     * 2x2 Jacobian, :555-577 */
-    double worst = 0.0;
-    for (int pid = 0; pid < ps * ps; ++pid)
-    {
-        int const i = pid % ps, j = pid / ps;
-        PatchSample const smp = patch_sample<true>(cf, i, j, ps);
-        Warp const c = warp_pixel<true>(Mt, px0 + i + 0.5, py0 + j + 0.5,
-            smp.w, smp.wx, smp.wy);
-        xd const j0(c.jac[0]), j1(c.jac[1]), j2(c.jac[2]), j3(c.jac[3]);
-        xd const e = j0 - j3, f = j1 + j2, g = j0 + j3, h = j1 - j2;
-        xd const q = xsqrt(e * e + f * f);
-        xd const s0 = (q + xsqrt(g * g + h * h)) / xd(2.0);
-        double const s1 = fabs((s0 - q).v);
-        double const big = (s0.v < s1) ? s1 : s0.v;     /* std::max(S0, S1) */
-        double const small = (s1 < s0.v) ? s1 : s0.v;   /* std::min(S0, S1) */
-        double const ratio = (xd(big) * xd(big) / (xd(small) * xd(small))).v;
-        worst = (worst < ratio) ? ratio : worst;        /* std::max */
-    }
+    double const worst = warp_anisotropy(cf, Mt, px0, py0, ps);
     if (worst > 8.0)
         return;
     atomicOr(a.vis_mask + patch, 1u << sub);
+}
+
+
+/* ---- use_sgm = false: the NCC occlusion filter ----------------------- */
+
+/* mve::Image<float>::linear_at(x, y, channel) on an interleaved 3-channel
+ * image: clamped fp32 coordinates, fp32 weights, left-to-right fp32 sum, no
+ * contraction (as the reference is built, -ffp-contract=off). */
+__device__ __forceinline__ float
+linear_at_rgb (float const* __restrict__ img, int w, int h, float x, float y,
+    int ch)
+{
+    x = fmaxf(0.0f, fminf(static_cast<float>(w - 1), x));
+    y = fmaxf(0.0f, fminf(static_cast<float>(h - 1), y));
+    int const fx = static_cast<int>(x), fy = static_cast<int>(y);
+    int const fx1 = min(fx + 1, w - 1), fy1 = min(fy + 1, h - 1);
+    float const w1 = __fsub_rn(x, static_cast<float>(fx));
+    float const w0 = __fsub_rn(1.0f, w1);
+    float const w3 = __fsub_rn(y, static_cast<float>(fy));
+    float const w2 = __fsub_rn(1.0f, w3);
+    float const v00 = img[(static_cast<size_t>(fy) * w + fx) * 3 + ch];
+    float const v10 = img[(static_cast<size_t>(fy) * w + fx1) * 3 + ch];
+    float const v01 = img[(static_cast<size_t>(fy1) * w + fx) * 3 + ch];
+    float const v11 = img[(static_cast<size_t>(fy1) * w + fx1) * 3 + ch];
+    float acc = __fmul_rn(v00, __fmul_rn(w0, w2));
+    acc = __fadd_rn(acc, __fmul_rn(v10, __fmul_rn(w1, w2)));
+    acc = __fadd_rn(acc, __fmul_rn(v01, __fmul_rn(w0, w3)));
+    acc = __fadd_rn(acc, __fmul_rn(v11, __fmul_rn(w1, w3)));
+    return acc;
+}
+
+/* Entry i of the pixel list ncc_for_patch builds (:803-859): the patch's own
+ * pixels, then the rim the growing loop appends. The list's SHAPE depends
+ * only on the patch size and on three yes/no conditions of the patch's
+ * position, so the host builds the eight lists once (offsets from the patch
+ * origin and where each entry's depth is copied from: a patch pixel or a
+ * corner node) and the device walks them. */
+struct ListEntry
+{
+    double x, y, depth;
+};
+
+__device__ __forceinline__ ListEntry
+list_entry (short4 const* __restrict__ rim, int i, int ps,
+    double const* cf, double const* theta, int px0, int py0)
+{
+    int ox, oy, src;
+    if (i < ps * ps)
+    {
+        ox = i % ps; oy = i / ps; src = i;
+    }
+    else
+    {
+        short4 const e = rim[i - ps * ps];
+        ox = e.x; oy = e.y; src = e.z;
+    }
+    ListEntry out;
+    out.x = static_cast<double>(px0 + ox);
+    out.y = static_cast<double>(py0 + oy);
+    /* src < 0: corner node -src - 1 (fill_values_at_nodes, :804), else the
+     * depth of patch pixel src (fill_values_at_pixels, :807) */
+    out.depth = (src < 0) ? theta[(-src - 1) * 4]
+        : patch_sample<false>(cf, src % ps, src / ps, ps).w;
+    return out;
+}
+
+/* DepthOptimizer::ncc_for_patch. Only the sign of the result is used
+ * (:579-581). Two passes over the list instead of the reference's two
+ * value vectors: the means first, then the three sums, in the order
+ * SSEVector::dot adds them. */
+__device__ double
+ncc_for_patch_dev (VisArgs const& a, int sub, short4 const* rim, int n_list,
+    int ps, double const* cf, double const* theta, int px0, int py0)
+{
+    SurfaceDev const& sf = a.s;
+    double const* Mt = sf.Mt + sub * 12;
+    int const sw = sf.sub_dims[2 * sub], sh = sf.sub_dims[2 * sub + 1];
+    float const* simg = a.color_subs[sub];
+    xd means0[3], means1[3], counter[3];
+    for (int c = 0; c < 3; ++c)
+        means0[c] = means1[c] = counter[c] = xd(0.0);
+    double const hi_x = static_cast<double>(sw - 2);
+    double const hi_y = static_cast<double>(sh - 2);
+    for (int i = 0; i < n_list; ++i)
+    {
+        ListEntry const e = list_entry(rim, i, ps, cf, theta, px0, py0);
+        Warp const c = warp_pixel<false>(Mt, (xd(e.x) + xd(0.5)).v,
+            (xd(e.y) + xd(0.5)).v, e.depth, 0.0, 0.0);
+        if (c.projx < 1 || c.projx > hi_x || c.projy < 1 || c.projy > hi_y)
+            return -1.0;
+        size_t const mp = (static_cast<size_t>(static_cast<int>(e.y)) * sf.w
+            + static_cast<int>(e.x)) * 3;
+        for (int ch = 0; ch < 3; ++ch)
+        {
+            xd const cm(static_cast<double>(a.color_main[mp + ch]));
+            xd const cs(static_cast<double>(linear_at_rgb(simg, sw, sh,
+                static_cast<float>(c.projx), static_cast<float>(c.projy),
+                ch)));
+            counter[ch] += xd(1.0);
+            means0[ch] += (cm - means0[ch]) / counter[ch];
+            means1[ch] += (cs - means1[ch]) / counter[ch];
+        }
+    }
+    /* SSEVector::dot (lib/sse_vector.cc:19-41, SSE branch): the products of
+     * an element pair are added to each other first (_mm_dp_pd), then to the
+     * running sum; an odd last element is added on its own */
+    xd s00(0.0), s11(0.0), s01(0.0);
+    xd p00(0.0), p11(0.0), p01(0.0);
+    int k = 0;
+    for (int i = 0; i < n_list; ++i)
+    {
+        ListEntry const e = list_entry(rim, i, ps, cf, theta, px0, py0);
+        Warp const c = warp_pixel<false>(Mt, (xd(e.x) + xd(0.5)).v,
+            (xd(e.y) + xd(0.5)).v, e.depth, 0.0, 0.0);
+        size_t const mp = (static_cast<size_t>(static_cast<int>(e.y)) * sf.w
+            + static_cast<int>(e.x)) * 3;
+        for (int ch = 0; ch < 3; ++ch, ++k)
+        {
+            xd const v0 = xd(static_cast<double>(a.color_main[mp + ch]))
+                - means0[ch];
+            xd const v1 = xd(static_cast<double>(linear_at_rgb(simg, sw, sh,
+                static_cast<float>(c.projx), static_cast<float>(c.projy),
+                ch))) - means1[ch];
+            if ((k & 1) == 0)
+            {
+                p00 = v0 * v0; p11 = v1 * v1; p01 = v0 * v1;
+            }
+            else
+            {
+                s00 += p00 + v0 * v0;
+                s11 += p11 + v1 * v1;
+                s01 += p01 + v0 * v1;
+            }
+        }
+    }
+    if (k & 1)
+    {
+        s00 += p00; s11 += p11; s01 += p01;
+    }
+    xd const norm0 = xsqrt(s00), norm1 = xsqrt(s11);
+    if ((norm0 + norm1).v < (xd(0.001) * xd(static_cast<double>(n_list))).v)
+        return 1.0;
+    return (s01 / (norm0 * norm1)).v;
+}
+
+/* second pass in the use_sgm = false mode: one thread per PATCH, neighbours
+ * in order, because the reference's member vectors `pixels` / `depths` carry
+ * state from one neighbour to the next (:508, :514, :551, :579): after
+ * ncc_for_patch ran they hold the patch AND its rim, and the next
+ * neighbour's border and depth tests run over that longer list until a
+ * neighbour passes them (which resets the vectors to the patch's pixels). */
+__global__ void __launch_bounds__(128)
+vis_patch_ncc_kernel (VisArgs const a)
+{
+    SurfaceDev const& sf = a.s;
+    int const patch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (patch >= sf.npx * sf.npy || !sf.patch_valid[patch])
+        return;
+    int const idx = patch % sf.npx, idy = patch / sf.npx;
+    int const ps = sf.ps;
+    double theta[16], cf[16];
+    load_patch_theta(sf.nodes, sf.npx, idx, idy, theta);
+    patch_coefficients(theta, cf);
+    int const px0 = sf.start_x + idx * ps, py0 = sf.start_y + idy * ps;
+
+    /* which of the eight rim lists: corners (:813-824), top (:828), left
+     * (:844); the bottom and right conditions (:836, :852) compare pixel
+     * coordinates with the patch's far corner and never hold */
+    int const min0 = px0, min1 = py0, max0 = px0 + ps, max1 = py0 + ps;
+    int shape = 0;
+    if (min0 > 1 && max0 < sf.w - 2 && min1 > 1 && max1 < sf.h - 2)
+        shape |= 1;
+    if (min1 > 2)
+        shape |= 2;
+    if (min0 > 2)
+        shape |= 4;
+    short4 const* rim = a.rim + a.rim_off[shape];
+    int const n_long = ps * ps + a.rim_off[shape + 1] - a.rim_off[shape];
+
+    unsigned int mask = 0;
+    bool extended = false;
+    for (int sub = 0; sub < sf.n_sub; ++sub)
+    {
+        double const* Mt = sf.Mt + sub * 12;
+        int const sw = sf.sub_dims[2 * sub], sh = sf.sub_dims[2 * sub + 1];
+        unsigned int const* z = a.zbuf + a.zoff[sub];
+        double const cut = (xd(0.03) * xd(static_cast<double>(max(sw, sh)))).v;
+        double const hi_x = (xd(static_cast<double>(sw)) - xd(cut)).v;
+        double const hi_y = (xd(static_cast<double>(sh)) - xd(cut)).v;
+        int const n_list = extended ? n_long : ps * ps;
+        bool success = true;
+        for (int i = 0; i < n_list && success; ++i)
+        {
+            ListEntry const e = list_entry(rim, i, ps, cf, theta, px0, py0);
+            Warp const c = warp_pixel<false>(Mt, (xd(e.x) + xd(0.5)).v,
+                (xd(e.y) + xd(0.5)).v, e.depth, 0.0, 0.0);
+            if (!(c.projx >= cut && c.projx < hi_x
+                && c.projy >= cut && c.projy < hi_y))
+            {
+                success = false;
+                break;
+            }
+            int const cx = static_cast<int>(c.projx);
+            int const cy = static_cast<int>(c.projy);
+            double const near = (xd(c.depth) * xd(0.95)).v;
+            for (int dy = -1; dy < 2; ++dy)
+                for (int dx = -1; dx < 2; ++dx)
+                {
+                    int const zx = cx + dx, zy = cy + dy;
+                    if (zx < 0 || zy < 0 || zx > sw || zy > sh)
+                        continue;
+                    float const zc = key_float(z[static_cast<size_t>(zy)
+                        * (sw + 1) + zx]);
+                    if (near > static_cast<double>(zc))
+                        success = false;
+                }
+        }
+        if (!success)
+            continue;
+        extended = false;           /* :551 refills the vectors */
+        if (warp_anisotropy(cf, Mt, px0, py0, ps) > 8.0)
+            continue;
+        extended = true;            /* ncc_for_patch leaves the rim in them */
+        if (ncc_for_patch_dev(a, sub, rim, n_long, ps, cf, theta, px0, py0)
+            < 0)
+            continue;
+        mask |= 1u << sub;
+    }
+    a.vis_mask[patch] = mask;
 }
 
 /* :585-600: patches no neighbour sees are deleted */
@@ -454,8 +699,76 @@ run_visibility (smvsb_ctx* c, float const* sgm_depth_host)
     return run_visibility_device(c);
 }
 
+/* The pixel lists ncc_for_patch builds (lib/depth_optimizer.cc:803-859),
+ * relative to the patch origin: entries beyond the patch's own ps * ps pixels
+ * for each of the eight combinations of (corners fit, top rim fits, left rim
+ * fits). Run exactly like the reference: the loop walks the list while it
+ * grows. z = where the depth comes from (patch pixel index, or -1 - corner). */
+static void
+build_rim_lists (int ps, std::vector<short4>* out, int* off)
+{
+    out->clear();
+    for (int shape = 0; shape < 8; ++shape)
+    {
+        off[shape] = static_cast<int>(out->size());
+        struct E { int x, y, src; };
+        std::vector<E> list;
+        for (int i = 0; i < ps * ps; ++i)
+            list.push_back(E{ i % ps, i / ps, i });
+        int const min0 = 0, min1 = 0, max0 = ps, max1 = ps;
+        if (shape & 1)
+        {
+            list.push_back(E{ min0 - 1, min1 - 1, -1 });
+            list.push_back(E{ max0 + 1, min1 - 1, -2 });
+            list.push_back(E{ min0 - 1, max1 + 1, -3 });
+            list.push_back(E{ max0 + 1, max1 + 1, -4 });
+        }
+        for (std::size_t i = 0; i < list.size(); ++i)
+        {
+            E const e = list[i];
+            if ((shape & 2) && e.y == min1)
+            {
+                list.push_back(E{ e.x, e.y - 2, e.src });
+                list.push_back(E{ e.x, e.y - 1, e.src });
+            }
+            /* :836 / :852 compare with the far corner (max = origin + ps);
+             * no list entry ever lies on it, whatever the image size */
+            if (e.y == max1 || e.x == max0)
+                throw smvsb::Error(SMVSB_ERR_INVALID,
+                    "rim list: bottom / right rule would fire");
+            if ((shape & 4) && e.x == min0)
+            {
+                list.push_back(E{ e.x - 2, e.y, e.src });
+                list.push_back(E{ e.x - 1, e.y, e.src });
+            }
+        }
+        for (std::size_t i = static_cast<std::size_t>(ps) * ps;
+            i < list.size(); ++i)
+            out->push_back(make_short4(static_cast<short>(list[i].x),
+                static_cast<short>(list[i].y),
+                static_cast<short>(list[i].src), 0));
+    }
+    off[8] = static_cast<int>(out->size());
+}
+
 uint64_t
-run_visibility_device (smvsb_ctx* c)
+run_visibility_ncc (smvsb_ctx* c)
+{
+    if (c->rim_ps != c->ps)
+    {
+        std::vector<short4> lists;
+        build_rim_lists(c->ps, &lists, c->rim_off);
+        c->rim_lists.reserve(lists.size() + 1);
+        CUDA_CHECK(cudaMemcpyAsync(c->rim_lists.p, lists.data(),
+            lists.size() * sizeof(short4), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));   /* `lists` goes away */
+        c->rim_ps = c->ps;
+    }
+    return run_visibility_device(c, false);
+}
+
+uint64_t
+run_visibility_device (smvsb_ctx* c, bool use_sgm)
 {
     size_t const npix = static_cast<size_t>(c->w) * c->h;
     int const np = c->n_patches;
@@ -487,15 +800,24 @@ run_visibility_device (smvsb_ctx* c)
     VisArgs a;
     a.s = surface_args(c);
     a.zbuf = c->zbuf.p; a.zoff = c->zoff.p;
-    a.surf_depth = c->image_out.p; a.sgm_depth = c->sgm_depth.p;
+    a.surf_depth = c->image_out.p;
+    a.sgm_depth = use_sgm ? c->sgm_depth.p : nullptr;
     a.vis_mask = c->vis_mask.p; a.counters = c->counters.p;
+    a.color_main = use_sgm ? nullptr : c->color_main.p;
+    a.color_subs = use_sgm ? nullptr : c->color_ptrs.p;
+    a.rim = use_sgm ? nullptr : c->rim_lists.p;
+    for (int i = 0; i < 9; ++i)
+        a.rim_off[i] = use_sgm ? 0 : c->rim_off[i];
 
     zbuf_fill_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(c->zbuf.p,
         zoff[c->n_sub], float_key(ZBUF_FAR));
     zbuf_scatter_kernel<<<static_cast<unsigned int>((npix + 255) / 256), 256,
         0, c->stream>>>(a);
     int const nt = np * c->n_sub;
-    vis_patch_kernel<<<(nt + 127) / 128, 128, 0, c->stream>>>(a);
+    if (use_sgm)
+        vis_patch_kernel<<<(nt + 127) / 128, 128, 0, c->stream>>>(a);
+    else
+        vis_patch_ncc_kernel<<<(np + 127) / 128, 128, 0, c->stream>>>(a);
     vis_finalize_kernel<<<(np + 255) / 256, 256, 0, c->stream>>>(a,
         c->patch_valid.p, c->vis_counts.p);
     remove_nodes_kernel<<<(c->n_nodes + 255) / 256, 256, 0, c->stream>>>(

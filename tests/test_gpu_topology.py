@@ -114,6 +114,42 @@ def test_remove_isolated_patches(w, h, scale, drop):
         R.close()
 
 
+@pytest.mark.parametrize("w,h,scale", [(640, 480, 3), (333, 207, 2), (1920, 1080, 4),
+                                       (1920, 1080, 2)])
+def test_surface_expand(w, h, scale):
+    """Surface::expand (lib/surface.cc:482-628): two rounds of extrapolated
+    rim nodes (largest of up to eight offers, 0.9 hysteresis), fill_holes,
+    remove_nodes_without_patch -- nodes, flags and the returned patch count
+    EQUAL to the reference's, on a surface with holes and sloped nodes."""
+    sc = synth.make_scene(w, h, 2, seed_index=85 + scale)
+    init = _holes(sc.init_depth, 10 + scale)
+    R = oref.RefScene(sc)
+    ctx = _ctx_with_views(sc, scale)
+    try:
+        R.surface_create(scale, init)
+        ctx.surface_create(scale, init)
+        nodes, nv, pv = _state(ctx)
+        info = ctx.surface_info()
+        rng = np.random.default_rng(scale)
+        nodes = nodes.copy()
+        nodes[:, 1:3] = rng.normal(0.0, 0.05, size=(nodes.shape[0], 2)) * nodes[:, :1]
+        pv2 = pv.copy()
+        pv2[rng.random(pv.shape) < 0.05] = 0
+        ctx.set_surface(info["scale"], info["npx"], info["npy"], info["start_x"],
+                        info["start_y"], nodes, nv, pv2, None, None)
+        R.surface_set(nodes, nv, pv2)
+        before = int(pv2.sum())
+        for round_ in range(2):
+            filled_r = R.surface_expand()
+            filled_g = ctx.surface_expand()
+            assert filled_g == filled_r > 0, (round_, filled_g, filled_r)
+            _assert_same(ctx, R, f"expand {round_}")
+        assert int(ctx.surface_state()[1].sum()) > before
+    finally:
+        ctx.close()
+        R.close()
+
+
 @pytest.mark.parametrize("shading", [False, True])
 def test_resident_optimize_matches_reference(shading):
     """smvsb_optimize (the whole DepthOptimizer::optimize() of a view on the

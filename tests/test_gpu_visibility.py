@@ -87,21 +87,66 @@ def test_visibility_and_cut_parity(width, height, n_sub, scale, seed):
     assert sum(st["cuts"]) > 0
 
 
-def test_visibility_requires_sgm_depth():
-    sc = synth.make_scene(160, 120, 1, seed_index=46)
-    R = oref.RefScene(sc)
-    R.set_scale(3)
-    R.surface_create(3, sc.init_depth)
+def colour_scene(width, height, n_sub, seed_index):
+    """Three different channels per view (the NCC filter works on colour)."""
+    import copy
+    sc = synth.make_scene(width, height, n_sub, seed_index=seed_index)
+    col = copy.copy(sc)
+    rng = np.random.default_rng(seed_index)
+    imgs = []
+    for im in sc.images:
+        f = im.astype(np.float32)
+        chans = [np.clip(f * g + o + rng.normal(0, 2.0, f.shape), 0, 255)
+                 for g, o in ((1.0, 0.0), (0.8, 20.0), (1.1, -10.0))]
+        imgs.append(np.stack(chans, axis=2).astype(np.uint8))
+    col.images = imgs
+    return col
+
+
+@pytest.mark.parametrize("width,height,n_sub,scale,seed", [
+    (256, 192, 3, 3, 63), (320, 240, 4, 2, 64), (333, 207, 3, 4, 65), (640, 480, 5, 2, 66)])
+def test_visibility_without_sgm_parity(width, height, n_sub, scale, seed):
+    """use_sgm = false: z-buffers from the surface's depth map only, and the
+    NCC occlusion filter ncc_for_patch (lib/depth_optimizer.cc:795-912) with
+    the rim carried over to the next neighbour's tests -- deleted patches,
+    nodes and visibility lists EQUAL to the reference's."""
+    col = colour_scene(width, height, n_sub, seed)
+    init = col.init_depth.astype(np.float32).copy()
+    init[height // 3:height // 2, width // 3:width // 2 + 20] *= 0.8
+    init[height // 2 + 10:height // 2 + 50, width // 8:width // 4] *= 1.15
+    R = oref.RefScene(col)
+    R.set_scale(scale)
+    R.surface_create(scale, init)
     info = R.surface_info()
     nodes, nv, pv = R.surface_get()
     Mi, ti = R.Mt()
     with api.Context(0) as ctx:
-        ctx.set_views(R.gradients(0), [R.gradients(1)], [R.hessian(1)], Mi, ti,
+        ctx.set_views(R.gradients(0), [R.gradients(k + 1) for k in range(n_sub)],
+                      [R.hessian(k + 1) for k in range(n_sub)], Mi, ti,
                       R.flen(0), R.inverse_flen(0))
         ctx.set_surface(info["scale"], info["npx"], info["npy"], info["start_x"],
                         info["start_y"], nodes, nv, pv, None, None)
         with pytest.raises(api.SmvsbError):
-            ctx.visibility(None)
+            ctx.visibility(None)                 # no colour images yet
+        ctx.set_color_images(R.image(0), [R.image(k + 1) for k in range(n_sub)])
+        left = R.create_subview_surfaces(False)
+        removed = ctx.visibility(None)
+        _, nv_r, pv_r = R.surface_get()
+        off_r, ids_r = R.get_visibility()
+        nv_g, pv_g, off_g, ids_g = ctx.surface_state()
+        assert np.array_equal(pv_g, pv_r) and np.array_equal(nv_g, nv_r)
+        assert int(pv.sum()) - removed == left == int(pv_g.sum())
+        lr, lg = lists_of(off_r, ids_r, pv_r), lists_of(off_g, ids_g, pv_g)
+        assert lr == lg
+        # the filter must have mattered: with the SGM-mode tests alone (and the
+        # same z-buffer) more neighbours would be listed
+        ctx.set_surface(info["scale"], info["npx"], info["npy"], info["start_x"],
+                        info["start_y"], nodes, nv, pv, None, None)
+        ctx.visibility(np.zeros((height, width), np.float32))
+        _, pv_s, off_s, ids_s = ctx.surface_state()
+        n_ncc = sum(len(l) for l in lg)
+        n_plain = sum(len(l) for l in lists_of(off_s, ids_s, pv_s))
+        assert 0 < n_ncc < n_plain
     R.close()
 
 

@@ -93,22 +93,28 @@ def test_visibility_and_cut_members_on_gpu():
         r.close()
 
 
-def test_visibility_without_sgm_keeps_reference_body():
-    """use_sgm = false (NCC occlusion filter on colour images) is not offered
-    on the device: the patched build must run the reference's own body."""
+def test_visibility_without_sgm_member_on_gpu():
+    """use_sgm = false: the drop-in create_subview_surfaces uploads the colour
+    images and runs the NCC occlusion filter (ncc_for_patch) on the device;
+    lists and deletions equal to the pure-CPU build's."""
     import copy
     sc = synth.make_scene(320, 240, 2, seed_index=48)
     col = copy.copy(sc)
-    col.images = [np.repeat(im[:, :, None], 3, axis=2) if im.ndim == 2 else im
+    rng = np.random.default_rng(5)
+    col.images = [np.stack([np.clip(im.astype(np.float32) * g + rng.normal(0, 2, im.shape),
+                                    0, 255).astype(np.uint8) for g in (1.0, 0.8, 1.1)], axis=2)
                   for im in sc.images]
+    init = sc.init_depth.copy()
+    init[80:120, 100:180] *= 0.8
     out = []
     for path in (None, oref.INTEGRATION_LIB_PATH):
         r = oref.RefScene(col, lib_path=path)
         r.set_scale(3)
-        r.surface_create(3, sc.init_depth)
+        r.surface_create(3, init)
         before = api.lib().smvsb_global_launch_count()
         left = r.create_subview_surfaces(False)
-        assert api.lib().smvsb_global_launch_count() == before
+        launched = api.lib().smvsb_global_launch_count() - before
+        assert (launched > 0) == (path is not None)
         out.append((left,) + _vis_state(r))
         r.close()
     assert out[0][0] == out[1][0] > 0
