@@ -314,15 +314,20 @@ def _system_blocks_full(wl):
 # named below (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on.sum of
 # one launch / its samples). This is the basis-space formulation's work -- the
 # reference's 16-wide rank-1 formulation would be ~20 kFLOP.
-K1_FLOP_PER_PIXEL_ITER = 5600.0
+# Captured launch: 6.195e9 DFMA + 3.090e9 DMUL + 1.646e9 DADD thread instructions
+# for 118 326 processed patches x 16 pixels. 43 % of the fp64 instructions are not
+# fused (the bitwise-parity arithmetic), so the pipe is busier than the flop rate
+# says: `pipe_frac` counts instructions against the DFMA issue rate.
+K1_FLOP_PER_PIXEL_ITER = 17.126e9 / (118326 * 16)           # 9046
+K1_FP64_INSTR_PER_PIXEL_ITER = 10.931e9 / (118326 * 16)     # 5774
 K1_FLOP_SOURCE = "profiles/r2_k1.txt"
 
 # DRAM bytes per 4x4 block and CG iteration of cg_kernel, from the ncu --set
 # full capture named below (dram__bytes_read.sum + dram__bytes_write.sum of a
 # 200-iteration launch on the full system / (200 x its blocks)): H only, the
 # preconditioner and the vectors stay in L2.
-CG_DRAM_BYTES_PER_BLOCK_ITER = 27.15e9 / (200.0 * 1067206)
-CG_TRAFFIC_SOURCE = "profiles/r1g_cg.txt"
+CG_DRAM_BYTES_PER_BLOCK_ITER = (26.800e9 + 0.362e9) / (200.0 * 1067206)   # 127.3
+CG_TRAFFIC_SOURCE = "profiles/r2_cg.txt"
 
 
 def cg_roofline(stats_sum, cg_ms, launches, hbm_peak, peak_source, views_per_launch=1):
@@ -504,7 +509,10 @@ def run_product(args):
                            "achieved": k1_tflops, "peak": fp64_peak,
                            "peak_source": "smvsb_measure_fp64_peak (DFMA micro-benchmark, this run)",
                            "unit": "TFLOP/s", "frac": k1_tflops / fp64_peak,
+                           "pipe_frac": k1_tflops * K1_FP64_INSTR_PER_PIXEL_ITER
+                           / K1_FLOP_PER_PIXEL_ITER / (fp64_peak / 2.0),
                            "flop_per_pixel_iteration": K1_FLOP_PER_PIXEL_ITER,
+                           "fp64_instructions_per_pixel_iteration": K1_FP64_INSTR_PER_PIXEL_ITER,
                            "flop_source": K1_FLOP_SOURCE}
         except Exception as exc:      # noqa: BLE001
             roofline_k1 = {"error": str(exc)}

@@ -104,9 +104,9 @@ floor_pos (float x, float& fl, int& n)
 }
 
 /* warped_neighbors_for_depth (lib/sgm_stereo.cc:150-190) for one pixel and
- * plane: the neighbour's luminance as the byte value the reference stores,
- * returned as a float (0 = no sample). neigh: float copy of the byte image. */
-__device__ __forceinline__ float
+ * plane: the neighbour's luminance as the byte value the reference stores
+ * (0 = no sample). neigh: float copy of the byte image. */
+__device__ __forceinline__ unsigned
 warp_from_tp (SgmParams const& p, float const* __restrict__ neigh,
     float const* tp, float depth, float nw1, float nh1)
 {
@@ -114,13 +114,13 @@ warp_from_tp (SgmParams const& p, float const* __restrict__ neigh,
     float q1 = __fadd_rn(__fmul_rn(tp[1], depth), p.t[1]);
     float const q2 = __fadd_rn(__fmul_rn(tp[2], depth), p.t[2]);
     if (q2 < 0)
-        return 0.0f;
+        return 0u;
     q0 = __fsub_rn(__fdiv_rn(q0, q2), 0.5f);
     q1 = __fsub_rn(__fdiv_rn(q1, q2), 0.5f);
     /* written so that NaN coordinates pass like in the reference's test
      * (all comparisons false) and are then clamped by fmaxf / fminf */
     if (q0 < 0 || q1 < 0 || q0 > nw1 || q1 > nh1)
-        return 0.0f;
+        return 0u;
     /* mve::Image<uint8_t>::linear_at */
     float const xx = fmaxf(0.0f, fminf(nw1, q0));
     float const yy = fmaxf(0.0f, fminf(nh1, q1));
@@ -146,7 +146,7 @@ warp_from_tp (SgmParams const& p, float const* __restrict__ neigh,
     float fl;
     int n;
     floor_pos(s, fl, n);
-    return fl;
+    return static_cast<unsigned>(n);
 }
 
 /* Pair of 16-bit fields at element offset e (0..8) of the five words
@@ -176,39 +176,45 @@ u8_to_float_kernel (size_t n, uint8_t const* __restrict__ in,
         out[i] = static_cast<float>(in[i]);
 }
 
-__global__ void __launch_bounds__(CT_THREADS, 2)
-sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
-    float const* __restrict__ neigh, float const* __restrict__ depths,
-    uint8_t* __restrict__ cost)
-{
-    /* tile of fp16 pixels, HALO_W even; as words: HALO_W / 2 per row */
-    __shared__ unsigned s_tile[PLANES][HALO_H][HALO_W / 2];
-    /* signs of the main comparison bits, [63][CT_THREADS] half2 = 63 KB:
-     * dynamic; then [CT_THREADS] half2 of the bit counts K */
-    extern __shared__ unsigned s_mask_dyn[];
-    unsigned (*s_mask)[CT_THREADS] =
-        reinterpret_cast<unsigned (*)[CT_THREADS]>(s_mask_dyn);
-    __shared__ float s_depths[256];
+/*
+ * Warped neighbour volume: W[plane][row][col] = the byte
+ * warped_neighbors_for_depth (:150-190) gives main pixel (col - 4, row - 3)
+ * at that plane, 0 outside the image -- a margin of the census window's halo
+ * (4 columns, 3 rows, rounded up to the cost kernel's tiles) is part of the
+ * volume, so the cost kernel loads its tiles without bounds tests. One thread
+ * warps four neighbouring pixels through all planes (M * (x, y, 1) stays in
+ * registers) and stores one word per plane; every voxel is warped ONCE (inside
+ * the cost kernel the tiles' halos overlap and every voxel was warped 1.7
+ * times, two thirds of that kernel's instructions).
+ */
+constexpr int WV_BX = 32, WV_BY = 4;
 
-    int const tid = threadIdx.x;
-    int const tx = tid % (CT_W / 2), ty = tid / (CT_W / 2);
-    int const x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
-    int const px = x0 + 2 * tx, py = y0 + ty;        /* left pixel of the pair */
+__global__ void __launch_bounds__(WV_BX * WV_BY)
+sgm_warp_volume_kernel (SgmParams const p, float const* __restrict__ neigh,
+    float const* __restrict__ depths, uint8_t* __restrict__ Wv, int pitch,
+    int rows)
+{
+    __shared__ float s_depths[256];
+    int const tid = threadIdx.y * WV_BX + threadIdx.x;
+    for (int i = tid; i < p.D; i += WV_BX * WV_BY)
+        s_depths[i] = depths[i];
+    __syncthreads();
+    int const col = (blockIdx.x * WV_BX + threadIdx.x) * 4;   /* padded */
+    int const row = blockIdx.y * WV_BY + threadIdx.y;
+    if (col >= pitch || row >= rows)
+        return;
+    int const gy = row - 3;
     float const nw1 = static_cast<float>(p.nw - 1);
     float const nh1 = static_cast<float>(p.nh - 1);
-
-    for (int i = tid; i < p.D; i += CT_THREADS)
-        s_depths[i] = depths[i];
-
-    /* plane-independent part of the warp for this thread's halo pixels */
-    float tp[HALO_PER_THREAD][3];
-    bool in_img[HALO_PER_THREAD];
+    float tp[4][3];
+    bool in_img[4];
+    bool any = false;
 #pragma unroll
-    for (int k = 0; k < HALO_PER_THREAD; ++k)
+    for (int k = 0; k < 4; ++k)
     {
-        int const i = tid + k * CT_THREADS;
-        int const gx = x0 - 4 + i % HALO_W, gy = y0 - 3 + i / HALO_W;
-        in_img[k] = (i < HALO_N && gx >= 0 && gx < p.w && gy >= 0 && gy < p.h);
+        int const gx = col - 4 + k;
+        in_img[k] = (gx >= 0 && gx < p.w && gy >= 0 && gy < p.h);
+        any = any || in_img[k];
         float const fx = 0.5f + static_cast<float>(gx);
         float const fy = 0.5f + static_cast<float>(gy);
 #pragma unroll
@@ -219,6 +225,54 @@ sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
             tp[k][r] = __fadd_rn(s, p.M[3 * r + 2]);      /* * 1.f */
         }
     }
+    size_t const plane_stride = static_cast<size_t>(pitch) * rows;
+    unsigned* dst = reinterpret_cast<unsigned*>(Wv
+        + static_cast<size_t>(row) * pitch + col);
+    if (!any)
+    {
+        for (int d = 0; d < p.D; ++d)
+            dst[d * (plane_stride / 4)] = 0u;
+        return;
+    }
+#pragma unroll 2
+    for (int d = 0; d < p.D; ++d)
+    {
+        float const depth = s_depths[d];
+        unsigned word = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            unsigned v = 0;
+            if (in_img[k])
+                v = warp_from_tp(p, neigh, tp[k], depth, nw1, nh1);
+            word |= v << (8 * k);
+        }
+        dst[d * (plane_stride / 4)] = word;
+    }
+}
+
+/*
+ * Census + Hamming distance from the warped volume. Pixels enter the fp16
+ * comparisons as 1024 + byte (0x6400 | byte: one PRMT turns two bytes into a
+ * half2, no conversion instruction; the order of the values is the bytes').
+ */
+__global__ void __launch_bounds__(CT_THREADS, 2)
+sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
+    uint8_t const* __restrict__ Wv, int pitch, int rows,
+    uint8_t* __restrict__ cost)
+{
+    /* tile of fp16 pixels, HALO_W even; as words: HALO_W / 2 per row */
+    __shared__ unsigned s_tile[PLANES][HALO_H][HALO_W / 2];
+    /* signs of the main comparison bits, [63][CT_THREADS] half2 = 63 KB:
+     * dynamic */
+    extern __shared__ unsigned s_mask_dyn[];
+    unsigned (*s_mask)[CT_THREADS] =
+        reinterpret_cast<unsigned (*)[CT_THREADS]>(s_mask_dyn);
+
+    int const tid = threadIdx.x;
+    int const tx = tid % (CT_W / 2), ty = tid / (CT_W / 2);
+    int const x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+    int const px = x0 + 2 * tx, py = y0 + ty;        /* left pixel of the pair */
 
     /* main image tile -> signs of its comparison bits per offset */
     __half* tile16 = reinterpret_cast<__half*>(&s_tile[0][0][0]);
@@ -229,8 +283,8 @@ sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
         if (i < HALO_N)
         {
             int const gx = x0 - 4 + i % HALO_W, gy = y0 - 3 + i / HALO_W;
-            tile16[i] = __ushort2half_rn(in_img[k]
-                ? main_img[gy * p.w + gx] : 0);
+            bool const in = (gx >= 0 && gx < p.w && gy >= 0 && gy < p.h);
+            tile16[i] = __ushort2half_rn(in ? main_img[gy * p.w + gx] : 0);
         }
     }
     __syncthreads();
@@ -264,26 +318,24 @@ sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
         }
     }
 
+    size_t const plane_stride = static_cast<size_t>(pitch) * rows;
+    constexpr int ROW_WORDS = HALO_W / 4;                    /* 10 */
+    constexpr int TILE_WORDS = PLANES * HALO_H * ROW_WORDS;  /* 880 */
     for (int d0 = 0; d0 < p.D; d0 += PLANES)
     {
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < HALO_PER_THREAD; ++k)
+        /* the four planes' tiles: aligned words of four bytes -> two half2 */
+        for (int i = tid; i < TILE_WORDS; i += CT_THREADS)
         {
-            int const i = tid + k * CT_THREADS;
-            if (i < HALO_N)
-            {
-#pragma unroll
-                for (int pl = 0; pl < PLANES; ++pl)
-                {
-                    float v = 0.0f;
-                    if (in_img[k])
-                        v = warp_from_tp(p, neigh, tp[k], s_depths[d0 + pl],
-                            nw1, nh1);
-                    reinterpret_cast<__half*>(&s_tile[pl][0][0])[i]
-                        = __float2half_rn(v);
-                }
-            }
+            int const pl = i / (HALO_H * ROW_WORDS);
+            int const rem = i % (HALO_H * ROW_WORDS);
+            int const r = rem / ROW_WORDS, q = rem % ROW_WORDS;
+            unsigned const b = __ldg(reinterpret_cast<unsigned const*>(Wv
+                + (d0 + pl) * plane_stride
+                + static_cast<size_t>(y0 + r) * pitch + x0) + q);
+            *reinterpret_cast<uint2*>(&s_tile[pl][r][2 * q]) = make_uint2(
+                __byte_perm(b, 0x64646464u, 0x4140),
+                __byte_perm(b, 0x64646464u, 0x4342));
         }
         __syncthreads();
 
@@ -325,8 +377,9 @@ sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
                 __half2int_rn(__low2half(acc[pl]))) : 0u;
             unsigned c1 = int1 ? static_cast<unsigned>(
                 __half2int_rn(__high2half(acc[pl]))) : 0u;
-            if ((as_word(A[pl]) & 0x7fffu) == 0) c0 = 255u;
-            if ((as_word(A[pl]) & 0x7fff0000u) == 0) c1 = 255u;
+            /* warped pixel 0 (= 1024 here): no sample */
+            if ((as_word(A[pl]) & 0xffffu) == 0x6400u) c0 = 255u;
+            if ((as_word(A[pl]) & 0xffff0000u) == 0x64000000u) c1 = 255u;
             out0 |= c0 << (8 * pl);
             out1 |= c1 << (8 * pl);
         }
@@ -360,6 +413,130 @@ enum PathKind
  * racing, so each writes its own byte volume of L - C, which lies in [0, P2]
  * (P2 <= 255): 1 B/voxel/direction. sgm_sum_wta_kernel adds them up.
  */
+/*
+ * 128 planes, TWO scan lines per warp: a half-warp owns a line, a lane eight
+ * disparities (four registers of 16-bit pairs). The kernel is bound by
+ * instruction issue, and the per-step bookkeeping (position, pointers, the
+ * shuffle tree of min_k, the loop) costs the same for 256 voxels as it does
+ * for 128 in the one-line-per-warp kernel below; the tree is one level
+ * shorter. The two lines of a warp are neighbours of the same direction, so
+ * they take the same number of steps; a diagonal restarts at different steps
+ * on the two, hence no branch around the shuffles: the recurrence is always
+ * evaluated and a restarting line overrides it.
+ */
+__global__ void __launch_bounds__(128)
+sgm_paths128_kernel (int w, int h, unsigned P1, unsigned P2,
+    uint8_t const* __restrict__ cost, uint8_t* __restrict__ Dvol)
+{
+    constexpr int D = 128;
+    int const pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int const lane = threadIdx.x & 31;
+    int const sl = lane & 15;                   /* lane within the line */
+    int const hp = (h + 1) / 2, wp = (w + 1) / 2;
+    int kind, line, count;
+    if (pair < 2 * hp)
+    {
+        kind = pair / hp;                       /* PATH_L2R, PATH_R2L */
+        line = 2 * (pair % hp) + (lane >> 4);
+        count = h;
+    }
+    else
+    {
+        int const q = pair - 2 * hp;
+        if (q >= 6 * wp)
+            return;
+        kind = 2 + q / wp;                      /* PATH_T2B .. PATH_B2T_D2 */
+        line = 2 * (q % wp) + (lane >> 4);
+        count = w;
+    }
+    /* odd line count: the last warp's second half repeats its first line
+     * (it takes part in the shuffles) and stores nothing */
+    bool const live = line < count;
+    if (!live)
+        line = count - 1;
+    bool const horizontal = (kind < 2);
+    int const steps = horizontal ? w : h;
+    size_t const nvox = static_cast<size_t>(w) * h * D;
+    uint8_t* __restrict__ Dr = Dvol + static_cast<size_t>(kind) * nvox;
+
+    int x, y, dx, dy;
+    switch (kind)
+    {
+    case PATH_L2R: x = 0; y = line; dx = 1; dy = 0; break;
+    case PATH_R2L: x = w - 1; y = line; dx = -1; dy = 0; break;
+    case PATH_T2B: x = line; y = 0; dx = 0; dy = 1; break;
+    case PATH_T2B_D1: x = line; y = 0; dx = 1; dy = 1; break;
+    case PATH_T2B_D2: x = line; y = 0; dx = -1; dy = 1; break;
+    case PATH_B2T: x = line; y = h - 1; dx = 0; dy = -1; break;
+    case PATH_B2T_D1: x = line; y = h - 1; dx = 1; dy = -1; break;
+    default: x = line; y = h - 1; dx = -1; dy = -1; break;   /* B2T_D2 */
+    }
+    int const restart_x = (dx > 0) ? 0 : w - 1;   /* diagonals only */
+    bool const diagonal = (!horizontal && dx != 0);
+
+    unsigned const P1x2 = P1 | (P1 << 16), P2x2 = P2 | (P2 << 16);
+    unsigned const BIG = 0x7000u;          /* "no neighbour" sentinel */
+    unsigned Pa = 0, Pb = 0, Pc = 0, Pd = 0;
+    long long const row_bytes = static_cast<long long>(w) * D;
+    long long const step_bytes = dy * row_bytes + dx * D;
+    uint8_t const* pc = cost + (static_cast<size_t>(y) * w + x) * D + sl * 8;
+    uint8_t* pd = Dr + (static_cast<size_t>(y) * w + x) * D + sl * 8;
+    uint2 c8 = *reinterpret_cast<uint2 const*>(pc);
+    bool start = true;
+    for (int s = 0; s < steps; ++s)
+    {
+        int xn = x + dx;
+        long long adv = step_bytes;
+        if (xn < 0) { xn = w - 1; adv += row_bytes; }
+        if (xn >= w) { xn = 0; adv -= row_bytes; }
+        uint2 c8n = make_uint2(0u, 0u);
+        if (s + 1 < steps)
+            c8n = *reinterpret_cast<uint2 const*>(pc + adv);
+
+        unsigned const Ca = __byte_perm(c8.x, 0, 0x4140);
+        unsigned const Cb = __byte_perm(c8.x, 0, 0x4342);
+        unsigned const Cc = __byte_perm(c8.y, 0, 0x4140);
+        unsigned const Cd = __byte_perm(c8.y, 0, 0x4342);
+
+        unsigned const m2 = __vminu2(__vminu2(Pa, Pb), __vminu2(Pc, Pd));
+        unsigned mn = min(m2 & 0xffffu, m2 >> 16);
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1)
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+        unsigned below = __shfl_up_sync(0xffffffffu, Pd, 1) >> 16;
+        unsigned above = __shfl_down_sync(0xffffffffu, Pa, 1) & 0xffffu;
+        if (sl == 0) below = BIG;
+        if (sl == 15) above = BIG;
+        unsigned const lo_a = below | (Pa << 16);               /* -, L0 */
+        unsigned const ab = __funnelshift_r(Pa, Pb, 16);         /* L1, L2 */
+        unsigned const bc = __funnelshift_r(Pb, Pc, 16);         /* L3, L4 */
+        unsigned const cd = __funnelshift_r(Pc, Pd, 16);         /* L5, L6 */
+        unsigned const hi_d = (Pd >> 16) | (above << 16);        /* L7, - */
+        unsigned const mn2 = mn * 0x10001u;
+        unsigned const far2 = mn2 + P2x2;
+        unsigned const ba = __vimin3_u16x2(Pa, far2,
+            __viaddmin_u16x2(ab, P1x2, lo_a + P1x2));
+        unsigned const bb = __vimin3_u16x2(Pb, far2,
+            __viaddmin_u16x2(bc, P1x2, ab + P1x2));
+        unsigned const bcv = __vimin3_u16x2(Pc, far2,
+            __viaddmin_u16x2(cd, P1x2, bc + P1x2));
+        unsigned const bd = __vimin3_u16x2(Pd, far2,
+            __viaddmin_u16x2(hi_d, P1x2, cd + P1x2));
+        /* L - C, in [0, P2] per half; zero where the path (re)starts */
+        unsigned const Da = start ? 0u : ba - mn2;
+        unsigned const Db = start ? 0u : bb - mn2;
+        unsigned const Dc = start ? 0u : bcv - mn2;
+        unsigned const Dd = start ? 0u : bd - mn2;
+        Pa = Ca + Da; Pb = Cb + Db; Pc = Cc + Dc; Pd = Cd + Dd;
+        if (live)
+            *reinterpret_cast<uint2*>(pd) = make_uint2(
+                __byte_perm(Da, Db, 0x6420), __byte_perm(Dc, Dd, 0x6420));
+        c8 = c8n;
+        x = xn; pc += adv; pd += adv;
+        start = diagonal && (xn == restart_x);
+    }
+}
+
 template <int DPL>
 __global__ void __launch_bounds__(128)
 sgm_paths_kernel (int w, int h, unsigned P1, unsigned P2,
@@ -642,6 +819,15 @@ void
 run_paths (int w, int h, unsigned P1, unsigned P2, uint8_t const* cost,
     uint8_t* Dvol, cudaStream_t st)
 {
+    if (DPL == 4 && getenv("SMVSB_SGM_PATHS_1LINE") == nullptr)
+    {
+        /* two lines per warp */
+        int const warps = 2 * ((h + 1) / 2) + 6 * ((w + 1) / 2);
+        sgm_paths128_kernel<<<(warps * 32 + 127) / 128, 128, 0, st>>>(w, h,
+            P1, P2, cost, Dvol);
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     int const warps = 2 * h + 6 * w;
     sgm_paths_kernel<DPL><<<(warps * 32 + 127) / 128, 128, 0, st>>>(w, h, P1,
         P2, cost, Dvol);
@@ -748,7 +934,7 @@ struct SgmWorkspace
     bool ready = false;
     cudaStream_t st = nullptr;
     cudaEvent_t ev[8] = {};
-    DevBuf<uint8_t> d_main, d_neigh, d_cost, d_D;
+    DevBuf<uint8_t> d_main, d_neigh, d_cost, d_D, d_warp;
     DevBuf<uint16_t> d_S;
     DevBuf<float> d_depths, d_out, d_out2, d_prev, d_neigh_f;
 };
@@ -845,14 +1031,24 @@ sgm_pair (SgmWorkspace& ws, int w, int h, uint8_t const* main_dev, int nw,
     u8_to_float_kernel<<<static_cast<unsigned>((nnpix + 255) / 256), 256, 0,
         st>>>(nnpix, neigh_dev, ws.d_neigh_f.p);
     CUDA_CHECK(cudaGetLastError());
+    /* warped volume with the cost tiles' halo as margin (zeros, written by
+     * the kernel itself) */
+    int const pitch = (w + CT_W - 1) / CT_W * CT_W + 16;
+    int const rows = (h + CT_H - 1) / CT_H * CT_H + 6;
+    ws.d_warp.reserve(static_cast<size_t>(pitch) * rows * num_steps);
+    dim3 const wb(WV_BX, WV_BY);
+    dim3 const wg((pitch / 4 + WV_BX - 1) / WV_BX, (rows + WV_BY - 1) / WV_BY);
+    sgm_warp_volume_kernel<<<wg, wb, 0, st>>>(p, ws.d_neigh_f.p, depths_dev,
+        ws.d_warp.p, pitch, rows);
+    CUDA_CHECK(cudaGetLastError());
     dim3 const cb(CT_THREADS);
     dim3 const cg((w + CT_W - 1) / CT_W, (h + CT_H - 1) / CT_H);
     size_t const mask_bytes = 63 * CT_THREADS * sizeof(unsigned);
     CUDA_CHECK(cudaFuncSetAttribute(sgm_cost_kernel,
         cudaFuncAttributeMaxDynamicSharedMemorySize,
         static_cast<int>(mask_bytes)));
-    sgm_cost_kernel<<<cg, cb, mask_bytes, st>>>(p, main_dev, ws.d_neigh_f.p,
-        depths_dev, ws.d_cost.p);
+    sgm_cost_kernel<<<cg, cb, mask_bytes, st>>>(p, main_dev, ws.d_warp.p,
+        pitch, rows, ws.d_cost.p);
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaEventRecord(ws.ev[e0 + 1], st));
 

@@ -115,24 +115,31 @@ zbuf_scatter_kernel (VisArgs const a)
 /* anisotropy of the warp over a patch: largest ratio of the squared singular
  * values of the 2x2 Jacobian, :555-577 */
 __device__ __forceinline__ double
+warp_anisotropy_at (double const* cf, double const* __restrict__ Mt, int px0,
+    int py0, int ps, int pid)
+{
+    int const i = pid % ps, j = pid / ps;
+    PatchSample const smp = patch_sample<true>(cf, i, j, ps);
+    Warp const c = warp_pixel<true>(Mt, px0 + i + 0.5, py0 + j + 0.5,
+        smp.w, smp.wx, smp.wy);
+    xd const j0(c.jac[0]), j1(c.jac[1]), j2(c.jac[2]), j3(c.jac[3]);
+    xd const e = j0 - j3, f = j1 + j2, g = j0 + j3, h = j1 - j2;
+    xd const q = xsqrt(e * e + f * f);
+    xd const s0 = (q + xsqrt(g * g + h * h)) / xd(2.0);
+    double const s1 = fabs((s0 - q).v);
+    double const big = (s0.v < s1) ? s1 : s0.v;     /* std::max(S0, S1) */
+    double const small = (s1 < s0.v) ? s1 : s0.v;   /* std::min(S0, S1) */
+    return (xd(big) * xd(big) / (xd(small) * xd(small))).v;
+}
+
+__device__ __forceinline__ double
 warp_anisotropy (double const* cf, double const* __restrict__ Mt, int px0,
     int py0, int ps)
 {
     double worst = 0.0;
     for (int pid = 0; pid < ps * ps; ++pid)
     {
-        int const i = pid % ps, j = pid / ps;
-        PatchSample const smp = patch_sample<true>(cf, i, j, ps);
-        Warp const c = warp_pixel<true>(Mt, px0 + i + 0.5, py0 + j + 0.5,
-            smp.w, smp.wx, smp.wy);
-        xd const j0(c.jac[0]), j1(c.jac[1]), j2(c.jac[2]), j3(c.jac[3]);
-        xd const e = j0 - j3, f = j1 + j2, g = j0 + j3, h = j1 - j2;
-        xd const q = xsqrt(e * e + f * f);
-        xd const s0 = (q + xsqrt(g * g + h * h)) / xd(2.0);
-        double const s1 = fabs((s0 - q).v);
-        double const big = (s0.v < s1) ? s1 : s0.v;     /* std::max(S0, S1) */
-        double const small = (s1 < s0.v) ? s1 : s0.v;   /* std::min(S0, S1) */
-        double const ratio = (xd(big) * xd(big) / (xd(small) * xd(small))).v;
+        double const ratio = warp_anisotropy_at(cf, Mt, px0, py0, ps, pid);
         worst = (worst < ratio) ? ratio : worst;        /* std::max */
     }
     return worst;
@@ -194,6 +201,81 @@ vis_patch_kernel (VisArgs const a)
     atomicOr(a.vis_mask + patch, 1u << sub);
 }
 
+
+/* The same decisions with one WARP per (patch, neighbour): at the coarse
+ * scales (patch size 8 .. 64 pixels, a few thousand patches) one thread per
+ * pair leaves the GPU to a handful of threads that each walk up to 4096
+ * pixels. All three tests are order-free (every pixel passes / largest
+ * ratio), so the lanes take the pixels in turn. */
+__global__ void __launch_bounds__(128)
+vis_patch_warp_kernel (VisArgs const a)
+{
+    SurfaceDev const& sf = a.s;
+    int const t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int const lane = threadIdx.x & 31;
+    if (t >= sf.npx * sf.npy * sf.n_sub)
+        return;
+    int const patch = t / sf.n_sub, sub = t % sf.n_sub;
+    if (!sf.patch_valid[patch])
+        return;
+    int const idx = patch % sf.npx, idy = patch / sf.npx;
+    int const ps = sf.ps;
+    double theta[16], cf[16];
+    load_patch_theta(sf.nodes, sf.npx, idx, idy, theta);
+    patch_coefficients(theta, cf);
+    double const* Mt = sf.Mt + sub * 12;
+    int const sw = sf.sub_dims[2 * sub], sh = sf.sub_dims[2 * sub + 1];
+    int const px0 = sf.start_x + idx * ps, py0 = sf.start_y + idy * ps;
+    unsigned int const* z = a.zbuf + a.zoff[sub];
+    double const cut = (xd(0.03) * xd(static_cast<double>(max(sw, sh)))).v;
+    double const hi_x = (xd(static_cast<double>(sw)) - xd(cut)).v;
+    double const hi_y = (xd(static_cast<double>(sh)) - xd(cut)).v;
+    bool fail = false;
+    for (int pid = lane; pid < ps * ps && !fail; pid += 32)
+    {
+        int const i = pid % ps, j = pid / ps;
+        PatchSample const smp = patch_sample<false>(cf, i, j, ps);
+        Warp const c = warp_pixel<false>(Mt, px0 + i + 0.5, py0 + j + 0.5,
+            smp.w, 0.0, 0.0);
+        if (!(c.projx >= cut && c.projx < hi_x
+            && c.projy >= cut && c.projy < hi_y))
+        {
+            fail = true;
+            break;
+        }
+        int const cx = static_cast<int>(c.projx);
+        int const cy = static_cast<int>(c.projy);
+        double const near = (xd(c.depth) * xd(0.95)).v;
+        for (int dy = -1; dy < 2; ++dy)
+            for (int dx = -1; dx < 2; ++dx)
+            {
+                int const zx = cx + dx, zy = cy + dy;
+                if (zx < 0 || zy < 0 || zx > sw || zy > sh)
+                    continue;
+                float const zc = key_float(z[static_cast<size_t>(zy)
+                    * (sw + 1) + zx]);
+                if (near > static_cast<double>(zc))
+                    fail = true;
+            }
+    }
+    if (__any_sync(0xffffffffu, fail))
+        return;
+    double worst = 0.0;
+    for (int pid = lane; pid < ps * ps; pid += 32)
+    {
+        double const ratio = warp_anisotropy_at(cf, Mt, px0, py0, ps, pid);
+        worst = (worst < ratio) ? ratio : worst;
+    }
+    for (int off = 16; off > 0; off >>= 1)
+    {
+        double const other = __shfl_xor_sync(0xffffffffu, worst, off);
+        worst = (worst < other) ? other : worst;
+    }
+    if (worst > 8.0)
+        return;
+    if (lane == 0)
+        atomicOr(a.vis_mask + patch, 1u << sub);
+}
 
 /* ---- use_sgm = false: the NCC occlusion filter ----------------------- */
 
@@ -602,20 +684,12 @@ cut_depth_kernel (CutArgs const a)
     }
 }
 
-/* high photometric error at the rim of the surface, :402-428 with
- * mse_for_patch :747-793 */
-__global__ void __launch_bounds__(128)
-cut_border_kernel (CutArgs const a)
+/* a patch at the rim (:402-412): one of its nodes has more than one of its
+ * eight neighbours missing (neighbours outside the grid count as missing) */
+__device__ __forceinline__ bool
+patch_at_rim (SurfaceDev const& sf, int idx, int idy)
 {
-    SurfaceDev const& sf = a.s;
-    int const patch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (patch >= sf.npx * sf.npy || !a.patch_valid[patch])
-        return;
-    int const idx = patch % sf.npx, idy = patch / sf.npx;
     int const ns = sf.npx + 1;
-
-    /* a node at the rim: more than one of its eight neighbours missing
-     * (neighbours outside the grid count as missing) */
     bool rim = false;
     for (int nd = 0; nd < 4 && !rim; ++nd)
     {
@@ -633,7 +707,44 @@ cut_border_kernel (CutArgs const a)
             }
         rim = (8 - present) > 1;
     }
-    if (!rim)
+    return rim;
+}
+
+/* one term of mse_for_patch (:760-788): pixel pid of the patch against
+ * neighbour sub, |grad_main - J grad_sub| */
+__device__ __forceinline__ xd
+mse_term (SurfaceDev const& sf, double const* cf, int px0, int py0, int ps,
+    int pid, int sub)
+{
+    int const i = pid % ps, j = pid / ps;
+    PatchSample const smp = patch_sample<true>(cf, i, j, ps);
+    size_t const pix = static_cast<size_t>(py0 + j) * sf.w + (px0 + i);
+    xd const gmx(static_cast<double>(sf.main_grad[2 * pix]));
+    xd const gmy(static_cast<double>(sf.main_grad[2 * pix + 1]));
+    Warp const c = warp_pixel<true>(sf.Mt + sub * 12, px0 + i + 0.5,
+        py0 + j + 0.5, smp.w, smp.wx, smp.wy);
+    float tap[5];
+    tap_neighbour(sf.sub_texels[sub], sf.sub_dims[2 * sub],
+        sf.sub_dims[2 * sub + 1], c.projx, c.projy, tap);
+    xd const gx(static_cast<double>(tap[0]));
+    xd const gy(static_cast<double>(tap[1]));
+    /* diff = grad_main - jac * grad_sub; error += |diff| */
+    xd const dx = gmx - (xd(0.0) + xd(c.jac[0]) * gx + xd(c.jac[1]) * gy);
+    xd const dy = gmy - (xd(0.0) + xd(c.jac[2]) * gx + xd(c.jac[3]) * gy);
+    return xsqrt(xd(0.0) + dx * dx + dy * dy);
+}
+
+/* high photometric error at the rim of the surface, :402-428 with
+ * mse_for_patch :747-793 */
+__global__ void __launch_bounds__(128)
+cut_border_kernel (CutArgs const a)
+{
+    SurfaceDev const& sf = a.s;
+    int const patch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (patch >= sf.npx * sf.npy || !a.patch_valid[patch])
+        return;
+    int const idx = patch % sf.npx, idy = patch / sf.npx;
+    if (!patch_at_rim(sf, idx, idy))
         return;
 
     double theta[16], cf[16];
@@ -645,31 +756,58 @@ cut_border_kernel (CutArgs const a)
     int const n = static_cast<int>(sf.vis_off[patch + 1] - v0);
     xd error(0.0), counter(0.0);
     for (int pid = 0; pid < ps * ps; ++pid)
-    {
-        int const i = pid % ps, j = pid / ps;
-        PatchSample const smp = patch_sample<true>(cf, i, j, ps);
-        size_t const pix = static_cast<size_t>(py0 + j) * sf.w + (px0 + i);
-        xd const gmx(static_cast<double>(sf.main_grad[2 * pix]));
-        xd const gmy(static_cast<double>(sf.main_grad[2 * pix + 1]));
         for (int k = 0; k < n; ++k)
         {
-            int const sub = sf.vis_ids[v0 + k];
-            Warp const c = warp_pixel<true>(sf.Mt + sub * 12, px0 + i + 0.5,
-                py0 + j + 0.5, smp.w, smp.wx, smp.wy);
-            float tap[5];
-            tap_neighbour(sf.sub_texels[sub], sf.sub_dims[2 * sub],
-                sf.sub_dims[2 * sub + 1], c.projx, c.projy, tap);
-            xd const gx(static_cast<double>(tap[0]));
-            xd const gy(static_cast<double>(tap[1]));
-            /* diff = grad_main - jac * grad_sub; error += |diff| */
-            xd const dx = gmx - (xd(0.0) + xd(c.jac[0]) * gx + xd(c.jac[1]) * gy);
-            xd const dy = gmy - (xd(0.0) + xd(c.jac[2]) * gx + xd(c.jac[3]) * gy);
-            error += xsqrt(xd(0.0) + dx * dx + dy * dy);
+            error += mse_term(sf, cf, px0, py0, ps, pid, sf.vis_ids[v0 + k]);
             counter += xd(1.0);
         }
-    }
     double const mse = (counter.v == 0.0) ? 1.0 : (error / counter).v;
     if (mse > 0.05)
+    {
+        a.patch_valid[patch] = 0;
+        atomicAdd(a.counters, 1ull);
+    }
+}
+
+/* The same with one WARP per patch, for the coarse scales (see
+ * vis_patch_warp_kernel). mse_for_patch is a sequential sum (pixels outer,
+ * neighbours inner); the lanes evaluate 32 terms at a time and the terms are
+ * then added one after the other in that order (every lane keeps the same
+ * running sum), so the sum is bitwise the one-thread sum. */
+__global__ void __launch_bounds__(128)
+cut_border_warp_kernel (CutArgs const a)
+{
+    SurfaceDev const& sf = a.s;
+    int const patch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int const lane = threadIdx.x & 31;
+    if (patch >= sf.npx * sf.npy || !a.patch_valid[patch])
+        return;
+    int const idx = patch % sf.npx, idy = patch / sf.npx;
+    if (!patch_at_rim(sf, idx, idy))
+        return;
+    double theta[16], cf[16];
+    load_patch_theta(sf.nodes, sf.npx, idx, idy, theta);
+    patch_coefficients(theta, cf);
+    int const ps = sf.ps;
+    int const px0 = sf.start_x + idx * ps, py0 = sf.start_y + idy * ps;
+    uint32_t const v0 = sf.vis_off[patch];
+    int const n = static_cast<int>(sf.vis_off[patch + 1] - v0);
+    int const total = ps * ps * n;
+    xd error(0.0);
+    for (int base = 0; base < total; base += 32)
+    {
+        int const t = base + lane;
+        double term = 0.0;
+        if (t < total)
+            term = mse_term(sf, cf, px0, py0, ps, t / n,
+                sf.vis_ids[v0 + t % n]).v;
+        int const m = min(32, total - base);
+        for (int l = 0; l < m; ++l)
+            error += xd(__shfl_sync(0xffffffffu, term, l));
+    }
+    double const counter = static_cast<double>(total);
+    double const mse = (total == 0) ? 1.0 : (error / xd(counter)).v;
+    if (lane == 0 && mse > 0.05)
     {
         a.patch_valid[patch] = 0;
         atomicAdd(a.counters, 1ull);
@@ -814,7 +952,9 @@ run_visibility_device (smvsb_ctx* c, bool use_sgm)
     zbuf_scatter_kernel<<<static_cast<unsigned int>((npix + 255) / 256), 256,
         0, c->stream>>>(a);
     int const nt = np * c->n_sub;
-    if (use_sgm)
+    if (use_sgm && c->ps >= 8)
+        vis_patch_warp_kernel<<<(nt + 3) / 4, 128, 0, c->stream>>>(a);
+    else if (use_sgm)
         vis_patch_kernel<<<(nt + 127) / 128, 128, 0, c->stream>>>(a);
     else
         vis_patch_ncc_kernel<<<(np + 127) / 128, 128, 0, c->stream>>>(a);
@@ -849,7 +989,10 @@ run_cut_boundaries (smvsb_ctx* c, float const* inv_calib)
     a.counters = c->counters.p;
     int const np = c->n_patches;
     cut_depth_kernel<<<(np + 255) / 256, 256, 0, c->stream>>>(a);
-    cut_border_kernel<<<(np + 127) / 128, 128, 0, c->stream>>>(a);
+    if (c->ps >= 8)
+        cut_border_warp_kernel<<<(np + 3) / 4, 128, 0, c->stream>>>(a);
+    else
+        cut_border_kernel<<<(np + 127) / 128, 128, 0, c->stream>>>(a);
     remove_nodes_kernel<<<(c->n_nodes + 255) / 256, 256, 0, c->stream>>>(
         c->npx, c->npy, c->patch_valid.p, c->node_valid.p);
     smvsb::count_launches(c, 3);
