@@ -23,7 +23,7 @@ END{
 }' | sed 's/_GLOBAL__N__[0-9a-f_]*_cu_[0-9a-f]*//' | sort
 echo
 echo "# excerpts"
-for pat in "UBLKCP" "SYNCS.ARRIVE" "LDG.E.NA.EFL2.256" "VIMNMX3" "VIADDMNMX" "HSET2.BF.LT" "CREDUX\|REDUX"; do
+for pat in "UBLKCP" "SYNCS.ARRIVE" "LDG.E.NA.EFL2.256" "VIMNMX3.U16x2" "VIADDMNMX.U16x2" "HSET2.BF.LT" "HFMA2" "CREDUX\|REDUX"; do
   echo "## $pat"
   cuobjdump -sass "$LIB" 2>/dev/null | grep -m 3 "$pat" | sed 's/^ *//' | cut -c1-120
 done

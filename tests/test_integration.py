@@ -26,9 +26,17 @@ def _run(scene, lib_path, shading):
     return depth, normals, light
 
 
+@pytest.mark.parametrize("memberwise", [False, True])
 @pytest.mark.parametrize("shading", [False, True])
-def test_optimize_depth_parity_config0(shading):
-    """configs[0]: 1 ref + 2 neighbours, 640x480, -o2."""
+def test_optimize_depth_parity_config0(shading, memberwise, monkeypatch):
+    """configs[0]: 1 ref + 2 neighbours, 640x480, -o2: the reference's
+    optimize() through the resident drop-in member (one smvsb_optimize call)
+    and, with SMVSB_MEMBERWISE=1, through the reference's own ladder with the
+    per-call drop-in members."""
+    if memberwise:
+        monkeypatch.setenv("SMVSB_MEMBERWISE", "1")
+    else:
+        monkeypatch.delenv("SMVSB_MEMBERWISE", raising=False)
     sc = synth.make_scene(640, 480, 2, seed_index=21, shading=shading)
     d_cpu, n_cpu, _ = _run(sc, None, shading)
     before = api.lib().smvsb_global_launch_count()
