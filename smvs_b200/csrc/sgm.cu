@@ -106,6 +106,7 @@ floor_pos (float x, float& fl, int& n)
 /* warped_neighbors_for_depth (lib/sgm_stereo.cc:150-190) for one pixel and
  * plane: the neighbour's luminance as the byte value the reference stores
  * (0 = no sample). neigh: float copy of the byte image. */
+template <bool F2I>
 __device__ __forceinline__ unsigned
 warp_from_tp (SgmParams const& p, float const* __restrict__ neigh,
     float const* tp, float depth, float nw1, float nh1)
@@ -142,7 +143,11 @@ warp_from_tp (SgmParams const& p, float const* __restrict__ neigh,
     s = __fadd_rn(s, __fmul_rn(v01, __fmul_rn(w0, w3)));
     s = __fadd_rn(s, __fmul_rn(v11, __fmul_rn(w1, w3)));
     s = __fadd_rn(s, 0.5f);
-    /* static_cast<uint8_t>(s): truncation, 0 <= s < 256 */
+    /* static_cast<uint8_t>(s): truncation, 0 <= s < 256. One conversion
+     * instruction on the otherwise idle XU pipe, or six on the ALU / FMA
+     * pipes the kernel is bound by (A/B: SMVSB_SGM_NO_F2I=1) */
+    if (F2I)
+        return __float2uint_rz(s);
     float fl;
     int n;
     floor_pos(s, fl, n);
@@ -189,6 +194,7 @@ u8_to_float_kernel (size_t n, uint8_t const* __restrict__ in,
  */
 constexpr int WV_BX = 32, WV_BY = 4;
 
+template <bool F2I>
 __global__ void __launch_bounds__(WV_BX * WV_BY)
 sgm_warp_volume_kernel (SgmParams const p, float const* __restrict__ neigh,
     float const* __restrict__ depths, uint8_t* __restrict__ Wv, int pitch,
@@ -244,7 +250,7 @@ sgm_warp_volume_kernel (SgmParams const p, float const* __restrict__ neigh,
         {
             unsigned v = 0;
             if (in_img[k])
-                v = warp_from_tp(p, neigh, tp[k], depth, nw1, nh1);
+                v = warp_from_tp<F2I>(p, neigh, tp[k], depth, nw1, nh1);
             word |= v << (8 * k);
         }
         dst[d * (plane_stride / 4)] = word;
@@ -391,6 +397,257 @@ sgm_cost_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
                 + px + 1) * p.D + d0) = out1;
     }
 }
+
+/*
+ * Census + Hamming distance, second formulation (round 2): comparison BITS
+ * instead of signed sums, collected on the FMA pipe. A thread owns four
+ * neighbouring pixels (two half2 pairs); per offset and plane a pair costs
+ * one HSET2 (1.0 where centre < neighbour) and one HFMA2 that adds
+ * 2^e to the accumulator of the window row: an accumulator starts at 1024.0
+ * and the nine offsets of a row add distinct powers of two below 512, so its
+ * fp16 bit pattern is 0x6400 | (the row's nine comparison bits) -- exact, no
+ * conversion. The main image's bits are built the same way once per block
+ * and stay in fourteen REGISTERS; distance = popcount of the XOR (two rows
+ * per POPC after a byte permute).
+ * Why: the signed-sum kernel read 63 sign words per pair and iteration from
+ * shared memory and was bound by the shared-memory queue (ncu: mio throttle
+ * 3.1 of 8.3 stall cycles per issue); collecting the bits with HSET2 mask
+ * output + LOP3 moved everything onto the half-rate ALU pipe (81 % busy,
+ * 1.54 ms). Here the per-offset work is split between the ALU pipe (HSET2)
+ * and the FMA pipe (HFMA2), and the odd-offset windows come from a second
+ * copy of the tile shifted by one pixel (an LDS instead of a funnel shift).
+ * Tiles are 64 x 16 pixels (halo redundancy 1.55 instead of 1.72), loaded as
+ * aligned words one iteration ahead into the other half of a double buffer.
+ */
+constexpr int C2_W = 64, C2_H = 16;
+constexpr int C2_THREADS = (C2_W / 4) * C2_H;            /* 256 */
+constexpr int C2_HALO_W = C2_W + 8, C2_HALO_H = C2_H + 6;  /* 72 x 22 */
+constexpr int C2_ROW_WORDS = C2_HALO_W / 2;              /* 36 half2 words */
+constexpr int C2_LOAD_WORDS = PLANES * C2_HALO_H * (C2_HALO_W / 4);  /* 1584 */
+constexpr int C2_LOADS = (C2_LOAD_WORDS + C2_THREADS - 1) / C2_THREADS; /* 7 */
+
+/* one window row: ev[0..5] = elements (0,1) .. (10,11) of the row counted from
+ * the thread's first pixel's column - 4, od[0..4] = (1,2) .. (9,10) */
+#define SMVSB_ROW_BITS(A0, A1, ev, od, acc0, acc1)                          \
+    do {                                                                    \
+        _Pragma("unroll")                                                   \
+        for (int e_ = 0; e_ < 9; ++e_)                                      \
+        {                                                                   \
+            __half2 const wgt_ = __float2half2_rn(static_cast<float>(       \
+                1 << e_));                                                  \
+            unsigned const n0_ = (e_ & 1) ? (od)[e_ >> 1] : (ev)[e_ >> 1];  \
+            unsigned const n1_ = (e_ & 1) ? (od)[(e_ >> 1) + 1]             \
+                : (ev)[(e_ >> 1) + 1];                                      \
+            acc0 = __hfma2(__hlt2(A0, as_half2(n0_)), wgt_, acc0);          \
+            acc1 = __hfma2(__hlt2(A1, as_half2(n1_)), wgt_, acc1);          \
+        }                                                                   \
+    } while (0)
+
+__global__ void __launch_bounds__(C2_THREADS, 2)
+sgm_cost_bits_kernel (SgmParams const p, uint8_t const* __restrict__ main_img,
+    uint8_t const* __restrict__ Wv, int pitch, int rows,
+    uint8_t* __restrict__ cost)
+{
+    /* [buffer][0 = pairs at even, 1 = at odd columns][plane][row][word],
+     * 50 KB: dynamic */
+    extern __shared__ __align__(16) unsigned s_bits_dyn[];
+    unsigned (*s_tile)[2][PLANES][C2_HALO_H][C2_ROW_WORDS] =
+        reinterpret_cast<unsigned (*)[2][PLANES][C2_HALO_H][C2_ROW_WORDS]>(
+            s_bits_dyn);
+
+    int const tid = threadIdx.x;
+    int const tx = tid % (C2_W / 4), ty = tid / (C2_W / 4);
+    int const x0 = blockIdx.x * C2_W, y0 = blockIdx.y * C2_H;
+    int const px = x0 + 4 * tx, py = y0 + ty;      /* first of four pixels */
+
+    /* main image tile (0x6400 | byte, like the warped tiles), both copies */
+    {
+        unsigned short* t0 = reinterpret_cast<unsigned short*>(
+            &s_tile[0][0][0][0][0]);
+        unsigned short* t1 = reinterpret_cast<unsigned short*>(
+            &s_tile[0][1][0][0][0]);
+        for (int i = tid; i < C2_HALO_W * C2_HALO_H; i += C2_THREADS)
+        {
+            int const c = i % C2_HALO_W, r = i / C2_HALO_W;
+            int const gx = x0 - 4 + c, gy = y0 - 3 + r;
+            bool const in = (gx >= 0 && gx < p.w && gy >= 0 && gy < p.h);
+            unsigned short const v = static_cast<unsigned short>(0x6400u
+                | (in ? main_img[gy * p.w + gx] : 0));
+            t0[i] = v;
+            if (c > 0)
+                t1[i - 1] = v;
+        }
+    }
+    __syncthreads();
+    bool in_px[4], int_px[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        in_px[i] = (px + i < p.w && py < p.h);
+        int_px[i] = in_px[i] && px + i >= 4 && px + i < p.w - 5 && py >= 3
+            && py < p.h - 4;
+    }
+    __half2 const bias = as_half2(0x64006400u);          /* 1024.0 */
+    /* census bits of the main pixels per window row (with the 0x6400 bias);
+     * pixels without a census (border, zero centre) have all bits 0
+     * (lib/sgm_stereo.cc:131-147) */
+    unsigned mb0[7], mb1[7];
+    {
+        __half2 const A0 = as_half2(s_tile[0][0][0][ty + 3][2 * tx + 2]);
+        __half2 const A1 = as_half2(s_tile[0][0][0][ty + 3][2 * tx + 3]);
+        unsigned const a0 = as_word(A0), a1 = as_word(A1);
+        unsigned const keep0 =
+            ((int_px[0] && (a0 & 0xffffu) != 0x6400u) ? 0x01ffu : 0u)
+            | ((int_px[1] && (a0 >> 16) != 0x6400u) ? 0x01ff0000u : 0u);
+        unsigned const keep1 =
+            ((int_px[2] && (a1 & 0xffffu) != 0x6400u) ? 0x01ffu : 0u)
+            | ((int_px[3] && (a1 >> 16) != 0x6400u) ? 0x01ff0000u : 0u);
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+        {
+            unsigned ev[6], od[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q)
+            {
+                ev[q] = s_tile[0][0][0][ty + j][2 * tx + q];
+                od[q] = s_tile[0][1][0][ty + j][2 * tx + q];
+            }
+            __half2 m0 = bias, m1 = bias;
+            SMVSB_ROW_BITS(A0, A1, ev, od, m0, m1);
+            mb0[j] = (as_word(m0) & keep0) | 0x64006400u;
+            mb1[j] = (as_word(m1) & keep1) | 0x64006400u;
+        }
+    }
+    __syncthreads();
+
+    size_t const plane_stride = static_cast<size_t>(pitch) * rows;
+    constexpr int RW = C2_HALO_W / 4;                        /* 18 words */
+    /* a tile word and the word after it (the shifted copy needs its first
+     * byte; the volume's margin keeps the read inside the row) */
+    auto fetch = [&] (int d0, unsigned* nb, unsigned* nx)
+    {
+#pragma unroll
+        for (int k = 0; k < C2_LOADS; ++k)
+        {
+            int const i = tid + k * C2_THREADS;
+            nb[k] = 0u; nx[k] = 0u;
+            if (i < C2_LOAD_WORDS)
+            {
+                int const pl = i / (C2_HALO_H * RW);
+                int const rem = i % (C2_HALO_H * RW);
+                int const r = rem / RW, q = rem % RW;
+                unsigned const* src = reinterpret_cast<unsigned const*>(Wv
+                    + (d0 + pl) * plane_stride
+                    + static_cast<size_t>(y0 + r) * pitch + x0) + q;
+                nb[k] = __ldg(src);
+                nx[k] = __ldg(src + 1);
+            }
+        }
+    };
+    auto stash = [&] (int buf, unsigned const* nb, unsigned const* nx)
+    {
+#pragma unroll
+        for (int k = 0; k < C2_LOADS; ++k)
+        {
+            int const i = tid + k * C2_THREADS;
+            if (i < C2_LOAD_WORDS)
+            {
+                int const pl = i / (C2_HALO_H * RW);
+                int const rem = i % (C2_HALO_H * RW);
+                int const r = rem / RW, q = rem % RW;
+                unsigned const b = nb[k];
+                *reinterpret_cast<uint2*>(&s_tile[buf][0][pl][r][2 * q])
+                    = make_uint2(__byte_perm(b, 0x64646464u, 0x4140),
+                        __byte_perm(b, 0x64646464u, 0x4342));
+                *reinterpret_cast<uint2*>(&s_tile[buf][1][pl][r][2 * q])
+                    = make_uint2(__byte_perm(b, 0x64646464u, 0x4241),
+                        (__byte_perm(b, nx[k], 0x4443) & 0x00ff00ffu)
+                            | 0x64006400u);
+            }
+        }
+    };
+
+    unsigned nb[C2_LOADS], nx[C2_LOADS];
+    fetch(0, nb, nx);
+    stash(0, nb, nx);
+    __syncthreads();
+    int cur = 0;
+    for (int d0 = 0; d0 < p.D; d0 += PLANES)
+    {
+        bool const more = d0 + PLANES < p.D;
+        if (more)
+            fetch(d0 + PLANES, nb, nx);
+
+        unsigned out[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int pl = 0; pl < PLANES; ++pl)
+        {
+            __half2 const A0 = as_half2(s_tile[cur][0][pl][ty + 3][2 * tx + 2]);
+            __half2 const A1 = as_half2(s_tile[cur][0][pl][ty + 3][2 * tx + 3]);
+            unsigned x0w[7], x1w[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j)
+            {
+                unsigned ev[6], od[6];
+#pragma unroll
+                for (int q = 0; q < 6; q += 2)
+                {
+                    uint2 const e2 = *reinterpret_cast<uint2 const*>(
+                        &s_tile[cur][0][pl][ty + j][2 * tx + q]);
+                    uint2 const o2 = *reinterpret_cast<uint2 const*>(
+                        &s_tile[cur][1][pl][ty + j][2 * tx + q]);
+                    ev[q] = e2.x; ev[q + 1] = e2.y;
+                    od[q] = o2.x; od[q + 1] = o2.y;
+                }
+                __half2 b0 = bias, b1 = bias;
+                SMVSB_ROW_BITS(A0, A1, ev, od, b0, b1);
+                x0w[j] = as_word(b0) ^ mb0[j];
+                x1w[j] = as_word(b1) ^ mb1[j];
+            }
+            /* Hamming distances: low halves = even pixel, high = odd */
+            unsigned c[4];
+            c[0] = __popc(__byte_perm(x0w[0], x0w[1], 0x5410))
+                + __popc(__byte_perm(x0w[2], x0w[3], 0x5410))
+                + __popc(__byte_perm(x0w[4], x0w[5], 0x5410))
+                + __popc(x0w[6] & 0xffffu);
+            c[1] = __popc(__byte_perm(x0w[0], x0w[1], 0x7632))
+                + __popc(__byte_perm(x0w[2], x0w[3], 0x7632))
+                + __popc(__byte_perm(x0w[4], x0w[5], 0x7632))
+                + __popc(x0w[6] >> 16);
+            c[2] = __popc(__byte_perm(x1w[0], x1w[1], 0x5410))
+                + __popc(__byte_perm(x1w[2], x1w[3], 0x5410))
+                + __popc(__byte_perm(x1w[4], x1w[5], 0x5410))
+                + __popc(x1w[6] & 0xffffu);
+            c[3] = __popc(__byte_perm(x1w[0], x1w[1], 0x7632))
+                + __popc(__byte_perm(x1w[2], x1w[3], 0x7632))
+                + __popc(__byte_perm(x1w[4], x1w[5], 0x7632))
+                + __popc(x1w[6] >> 16);
+            unsigned const a0 = as_word(A0), a1 = as_word(A1);
+            bool const zero[4] = { (a0 & 0xffffu) == 0x6400u,
+                (a0 >> 16) == 0x6400u, (a1 & 0xffffu) == 0x6400u,
+                (a1 >> 16) == 0x6400u };
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                /* border pixels have no census on either side: distance 0;
+                 * warped pixel 0: no sample, 255 */
+                unsigned v = int_px[i] ? c[i] : 0u;
+                if (zero[i]) v = 255u;
+                out[i] |= v << (8 * pl);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (in_px[i])
+                *reinterpret_cast<unsigned*>(cost + (static_cast<size_t>(py)
+                    * p.w + px + i) * p.D + d0) = out[i];
+        if (more)
+            stash(cur ^ 1, nb, nx);
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+#undef SMVSB_ROW_BITS
 #undef SMVSB_WINDOW
 
 /* ------------------------------------------------------------------ */
@@ -1033,22 +1290,43 @@ sgm_pair (SgmWorkspace& ws, int w, int h, uint8_t const* main_dev, int nw,
     CUDA_CHECK(cudaGetLastError());
     /* warped volume with the cost tiles' halo as margin (zeros, written by
      * the kernel itself) */
-    int const pitch = (w + CT_W - 1) / CT_W * CT_W + 16;
+    bool const bits = getenv("SMVSB_SGM_COST_SUMS") == nullptr;
+    int const tile_w = bits ? C2_W : CT_W;
+    int const pitch = (w + tile_w - 1) / tile_w * tile_w + 16;
     int const rows = (h + CT_H - 1) / CT_H * CT_H + 6;
     ws.d_warp.reserve(static_cast<size_t>(pitch) * rows * num_steps);
     dim3 const wb(WV_BX, WV_BY);
     dim3 const wg((pitch / 4 + WV_BX - 1) / WV_BX, (rows + WV_BY - 1) / WV_BY);
-    sgm_warp_volume_kernel<<<wg, wb, 0, st>>>(p, ws.d_neigh_f.p, depths_dev,
-        ws.d_warp.p, pitch, rows);
+    if (getenv("SMVSB_SGM_NO_F2I") == nullptr)
+        sgm_warp_volume_kernel<true><<<wg, wb, 0, st>>>(p, ws.d_neigh_f.p,
+            depths_dev, ws.d_warp.p, pitch, rows);
+    else
+        sgm_warp_volume_kernel<false><<<wg, wb, 0, st>>>(p, ws.d_neigh_f.p,
+            depths_dev, ws.d_warp.p, pitch, rows);
     CUDA_CHECK(cudaGetLastError());
-    dim3 const cb(CT_THREADS);
-    dim3 const cg((w + CT_W - 1) / CT_W, (h + CT_H - 1) / CT_H);
-    size_t const mask_bytes = 63 * CT_THREADS * sizeof(unsigned);
-    CUDA_CHECK(cudaFuncSetAttribute(sgm_cost_kernel,
-        cudaFuncAttributeMaxDynamicSharedMemorySize,
-        static_cast<int>(mask_bytes)));
-    sgm_cost_kernel<<<cg, cb, mask_bytes, st>>>(p, main_dev, ws.d_warp.p,
-        pitch, rows, ws.d_cost.p);
+    if (bits)
+    {
+        dim3 const cg((w + C2_W - 1) / C2_W, (h + C2_H - 1) / C2_H);
+        size_t const tile_bytes = sizeof(unsigned) * 2 * 2 * PLANES
+            * C2_HALO_H * C2_ROW_WORDS;
+        CUDA_CHECK(cudaFuncSetAttribute(sgm_cost_bits_kernel,
+            cudaFuncAttributeMaxDynamicSharedMemorySize,
+            static_cast<int>(tile_bytes)));
+        sgm_cost_bits_kernel<<<cg, C2_THREADS, tile_bytes, st>>>(p, main_dev,
+            ws.d_warp.p, pitch, rows, ws.d_cost.p);
+    }
+    else
+    {
+        /* the signed-sum formulation (A/B: SMVSB_SGM_COST_SUMS=1) */
+        dim3 const cb(CT_THREADS);
+        dim3 const cg((w + CT_W - 1) / CT_W, (h + CT_H - 1) / CT_H);
+        size_t const mask_bytes = 63 * CT_THREADS * sizeof(unsigned);
+        CUDA_CHECK(cudaFuncSetAttribute(sgm_cost_kernel,
+            cudaFuncAttributeMaxDynamicSharedMemorySize,
+            static_cast<int>(mask_bytes)));
+        sgm_cost_kernel<<<cg, cb, mask_bytes, st>>>(p, main_dev, ws.d_warp.p,
+            pitch, rows, ws.d_cost.p);
+    }
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaEventRecord(ws.ev[e0 + 1], st));
 

@@ -52,7 +52,7 @@ def make_views(n, w, h, seed, normal_sign=-1.0):
         dirs_cam /= np.linalg.norm(dirs_cam, axis=-1, keepdims=True)
         dirs = dirs_cam @ R                       # cam -> world: R^T d
         tt = np.full((h, w), 5.0)
-        for _ in range(25):
+        for _ in range(12):
             px, py = c[0] + tt * dirs[..., 0], c[1] + tt * dirs[..., 1]
             tt = (surface(px, py) - c[2]) / dirs[..., 2]
         px, py = c[0] + tt * dirs[..., 0], c[1] + tt * dirs[..., 1]
@@ -91,17 +91,28 @@ def test_oracle_cut_depth_maps_runs_and_cuts():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,w,h", [(3, 160, 120), (5, 320, 240), (4, 333, 207)])
+@pytest.mark.parametrize("n,w,h", [(3, 160, 120), (5, 320, 240), (4, 333, 207),
+                                   (7, 1920, 1080)])
 def test_cut_depth_maps_equal_to_reference(n, w, h):
+    """The last case is BASELINE.json's view size: 7 views at 1920x1080."""
+    import json
+    import time
     flen, rot, trans, depths, normals = make_views(n, w, h, n)
+    t0 = time.perf_counter()
     outs, inv, ctw, KR, t = oref.cut_depth_maps(flen, rot, trans, depths, normals)
+    t_cpu = time.perf_counter() - t0
+    api.cut_depth_maps(depths, normals, inv, ctw, KR, t)          # warm-up
+    t0 = time.perf_counter()
     got = api.cut_depth_maps(depths, normals, inv, ctw, KR, t)
+    t_gpu = time.perf_counter() - t0
+    print(json.dumps({"cut_depth_maps": f"{n} views {w}x{h}",
+                      "reference_s_4_threads": t_cpu, "abi_call_s": t_gpu}))
     kept, cut = 0, 0
     for g, o, d in zip(got, outs, depths):
         assert np.array_equal(g, o)
         kept += int((o > 0).sum())
         cut += int(((o == 0) & (d > 0)).sum())
-    assert kept > 0.15 * n * w * h and cut > 0.05 * n * w * h
+    assert kept > 0.15 * n * w * h and cut > 0.03 * n * w * h
 
 
 @pytest.mark.gpu
