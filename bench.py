@@ -466,6 +466,35 @@ def run_product(args):
     barrier()
     wall_e2e = time.perf_counter() - t0
 
+    # ---- end-to-end, two host threads per GPU ---------------------------------
+    # The reference's host runs one view per pool thread (app/smvsrecon.cc:
+    # 658-733) and the drop-in build gives thread k the device k mod N, so
+    # with more pool threads than GPUs several views share a device: one
+    # view's uploads and downloads overlap another's kernels. Same steps, same
+    # copies per step; thread t takes the steps s = t (mod 2), which use
+    # disjoint contexts (POOL is even). Reported next to the one-thread figure.
+    import threading
+    parts_1t = e2e_parts.copy()
+    pix_2t = [0.0, 0.0]
+
+    def e2e_worker(t):
+        torch.cuda.set_device(local)
+        for s in range(t, args.steps, 2):
+            st, _ = e2e_step(s)
+            pix_2t[t] += st["pixel_iterations"]
+
+    barrier()
+    t0 = time.perf_counter()
+    workers2 = [threading.Thread(target=e2e_worker, args=(t,)) for t in range(2)]
+    for th in workers2:
+        th.start()
+    for th in workers2:
+        th.join()
+    barrier()
+    wall_e2e_2t = time.perf_counter() - t0
+    pix_e2e_2t = sum(pix_2t)
+    e2e_parts[:] = parts_1t
+
     # ---- reduce over ranks ---------------------------------------------------
     def reduce(vals_max, vals_sum):
         if world == 1:
@@ -476,8 +505,10 @@ def run_product(args):
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         return mx.tolist(), sm.tolist()
 
-    (t_dev_ms_max, wall_e2e_max), (pix_all, pix_e2e_all, launches_all) = reduce(
-        [t_dev_ms, wall_e2e], [pix, pix_e2e, float(launches)])
+    (t_dev_ms_max, wall_e2e_max, wall_e2e_2t_max), \
+        (pix_all, pix_e2e_all, launches_all, pix_e2e_2t_all) = reduce(
+            [t_dev_ms, wall_e2e, wall_e2e_2t],
+            [pix, pix_e2e, float(launches), pix_e2e_2t])
 
     peaks = {}
     try:
@@ -550,7 +581,13 @@ def run_product(args):
                     "d2h_bytes_per_step": int(nodes_out.nbytes),
                     "ms_per_step": 1e3 * wall_e2e_max / max(args.steps, 1),
                     "ms_set_views_set_surface_loop_get_nodes":
-                        [1e3 * float(x) / max(args.steps, 1) for x in e2e_parts]},
+                        [1e3 * float(x) / max(args.steps, 1) for x in e2e_parts],
+                    "two_host_threads_per_gpu": {
+                        "value": pix_e2e_2t_all / wall_e2e_2t_max / 1e6,
+                        "ms_per_step": 1e3 * wall_e2e_2t_max / max(args.steps, 1),
+                        "note": "same steps and copies, two views in flight per GPU "
+                                "(one host thread each, like the reference's thread pool): "
+                                "a view's copies overlap the other's kernels"}},
             "gpu_launches": int(launches_all),
             "roofline": roofline,
             "roofline_construct": roofline_k1,
