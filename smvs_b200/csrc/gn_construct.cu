@@ -120,8 +120,8 @@ struct ConstructArgs
  */
 /* 3 CTAs / SM (168 registers, a few spills) beats 2 CTAs at 248 registers by
  * 13 % on B200: the kernel is fp64-latency bound and wants the warps. */
-template <int S>
-__global__ void __launch_bounds__(K1_THREADS, 4)
+template <int S, int MINB = 4>
+__global__ void __launch_bounds__(K1_THREADS, MINB)
 gn_patch_kernel (ConstructArgs const args)
 {
     /* samples of one patch per chunk, chunks per patch, patches per block,
@@ -234,11 +234,13 @@ gn_patch_kernel (ConstructArgs const args)
             double w, wx, wy, wxy, wxx, wyy;
             {
                 double const* cf = s_coef[pl];
-                xd const size(static_cast<double>(sf.ps));
+                /* the patch size is a power of two: dividing by it and
+                 * multiplying by its reciprocal are the same exact scaling */
+                xd const inv_size(1.0 / static_cast<double>(sf.ps));
                 xd const sx = (xd(static_cast<double>(ix * sf.sampling))
-                    + xd(0.5)) / size;
+                    + xd(0.5)) * inv_size;
                 xd const sy = (xd(static_cast<double>(iy * sf.sampling))
-                    + xd(0.5)) / size;
+                    + xd(0.5)) * inv_size;
                 xd ex[4], ey[4];
                 ex[0] = xd(1.0); ex[1] = sx; ex[2] = sx * sx; ex[3] = ex[2] * sx;
                 ey[0] = xd(1.0); ey[1] = sy; ey[2] = sy * sy; ey[3] = ey[2] * sy;
@@ -278,13 +280,13 @@ gn_patch_kernel (ConstructArgs const args)
                     for (int j = 1; j < 4; ++j)
                         fxy += xd(cf[i * 4 + j]) * xd(double(i)) * ex[i - 1]
                             * xd(double(j)) * ey[j - 1];
-                xd const size2(static_cast<double>(sf.ps * sf.ps));
+                xd const inv_size2(1.0 / static_cast<double>(sf.ps * sf.ps));
                 w = f.v;
-                wx = (fx / size).v;
-                wy = (fy / size).v;
-                wxy = (fxy / size2).v;
-                wxx = (fxx / size2).v;
-                wyy = (fyy / size2).v;
+                wx = (fx * inv_size).v;
+                wy = (fy * inv_size).v;
+                wxy = (fxy * inv_size2).v;
+                wxx = (fxx * inv_size2).v;
+                wyy = (fyy * inv_size2).v;
             }
 
             int const idx = patch % sf.npx, idy = patch / sf.npx;
@@ -668,7 +670,20 @@ launch_construct (smvsb_ctx* c, bool use_light, double reg, double light_reg)
     case 4:
         gn_patch_kernel<4><<<blocks(8), K1_THREADS, 0, c->stream>>>(a); break;
     case 16:
-        gn_patch_kernel<16><<<blocks(8), K1_THREADS, 0, c->stream>>>(a); break;
+    {
+        /* occupancy experiment (benchmarks only): SMVSB_K1_MINB = 3, 5, 6 */
+        static int const minb = getenv("SMVSB_K1_MINB")
+            ? atoi(getenv("SMVSB_K1_MINB")) : 4;
+        if (minb == 3)
+            gn_patch_kernel<16, 3><<<blocks(8), K1_THREADS, 0, c->stream>>>(a);
+        else if (minb == 5)
+            gn_patch_kernel<16, 5><<<blocks(8), K1_THREADS, 0, c->stream>>>(a);
+        else if (minb == 6)
+            gn_patch_kernel<16, 6><<<blocks(8), K1_THREADS, 0, c->stream>>>(a);
+        else
+            gn_patch_kernel<16><<<blocks(8), K1_THREADS, 0, c->stream>>>(a);
+        break;
+    }
     case 64:
         gn_patch_kernel<64><<<blocks(2), K1_THREADS, 0, c->stream>>>(a); break;
     case 256:

@@ -54,6 +54,32 @@ __device__ __forceinline__ xd& operator-= (xd& a, xd b) { a = a - b; return a; }
 __device__ __forceinline__ xd& operator/= (xd& a, xd b) { a = a / b; return a; }
 __device__ __forceinline__ xd xsqrt (xd a) { return xd(__dsqrt_rn(a.v)); }
 
+/* Division by a divisor that is used many times: r = RN(1 / d) once (a true
+ * division), then per quotient q = RN(x r), e = x - d q (exact in an FMA),
+ * RN(q + e r) -- Markstein's correction step, which returns the correctly
+ * rounded x / d whenever q is within one ulp of it. Three instructions
+ * instead of the ~13 of a division; gn_patch_kernel divides 22 times per
+ * sample and neighbour by d, d^2 and d^4. (The decision kernels of
+ * visibility.cu keep true divisions: there every bit counts; here a rare
+ * last-bit difference is far below the 4e-15 of the row sums.) */
+struct xrecip
+{
+    double d, r;
+};
+__device__ __forceinline__ xrecip xrcp (xd d)
+{
+    xrecip out;
+    out.d = d.v;
+    out.r = __ddiv_rn(1.0, d.v);
+    return out;
+}
+__device__ __forceinline__ xd operator/ (xd x, xrecip const& c)
+{
+    double const q = __dmul_rn(x.v, c.r);
+    double const e = __fma_rn(-c.d, q, x.v);
+    return xd(__fma_rn(e, c.r, q));
+}
+
 /*
  * mve::Image<float>::linear_at on a packed neighbour texel image, restated
  * bit-for-bit: coordinates narrowed to fp32 and clamped to the image, fp32
@@ -136,19 +162,20 @@ neighbour_row (double const* __restrict__ Mt, float const* __restrict__ tex,
     xd const b = W * q + T1;
     xd const d = W * r + T2;
     xd const d2 = d * d;
+    xrecip const rd = xrcp(d), rd2 = xrcp(d2);
 
     /* fill (:46-51) and the caller's -0.5 (gauss_newton_step.cc:189-190) */
-    double const projx = (a / d - xd(0.5)).v;
-    double const projy = (b / d - xd(0.5)).v;
+    double const projx = (a / rd - xd(0.5)).v;
+    double const projy = (b / rd - xd(0.5)).v;
     /* fill_jacobian, :88-100 */
-    xd j0 = (WX * p + W * m0) / d;
-    xd j2 = (WY * p + W * m1) / d;
-    j0 -= a * (WX * r + W * m6) / d2;
-    j2 -= a * (WY * r + W * m7) / d2;
-    xd j1 = (WX * q + W * m3) / d;
-    xd j3 = (WY * q + W * m4) / d;
-    j1 -= b * (WX * r + W * m6) / d2;
-    j3 -= b * (WY * r + W * m7) / d2;
+    xd j0 = (WX * p + W * m0) / rd;
+    xd j2 = (WY * p + W * m1) / rd;
+    j0 -= a * (WX * r + W * m6) / rd2;
+    j2 -= a * (WY * r + W * m7) / rd2;
+    xd j1 = (WX * q + W * m3) / rd;
+    xd j3 = (WY * q + W * m4) / rd;
+    j1 -= b * (WX * r + W * m6) / rd2;
+    j3 -= b * (WY * r + W * m7) / rd2;
 
     float tap[5];
     tap_neighbour(tex, sw, sh, projx, projy, tap);
@@ -164,11 +191,12 @@ neighbour_row (double const* __restrict__ Mt, float const* __restrict__ tex,
     double const jh10 = (j2 * H0 + j3 * H1).v;
     double const jh11 = (j2 * H1 + j3 * H3).v;
     /* fill_derivative, :74-86 */
-    double const du_w = ((p * d - r * a) / d2).v;
-    double const dv_w = ((q * d - r * b) / d2).v;
+    double const du_w = ((p * d - r * a) / rd2).v;
+    double const dv_w = ((q * d - r * b) / rd2).v;
 
     /* fill_jacobian_derivative_grad, :102-187 */
     xd const d4 = d2 * d2;
+    xrecip const rd4 = xrcp(d4);
     xd const d_prime = xd(2.0) * d * r;
     xd const du_c_prime = p * T2 - r * T0;
     xd const dv_c_prime = q * T2 - r * T1;
@@ -176,16 +204,16 @@ neighbour_row (double const* __restrict__ Mt, float const* __restrict__ tex,
     xd const du_b0 = m0 * T2 - m6 * T0, du_b1 = m1 * T2 - m7 * T0;
     xd const dv_a_t0 = W * (m3 * r - q * m6), dv_a_t1 = W * (m4 * r - q * m7);
     xd const dv_b0 = m3 * T2 - m6 * T1, dv_b1 = m4 * T2 - m7 * T1;
-    double const A0 = ((xd(2.0) * du_a_t0 + du_b0) / d2
-        - (W * (du_a_t0 + du_b0) + WX * du_c_prime) * d_prime / d4).v;
-    double const A1 = ((xd(2.0) * du_a_t1 + du_b1) / d2
-        - (W * (du_a_t1 + du_b1) + WY * du_c_prime) * d_prime / d4).v;
-    double const B0 = ((xd(2.0) * dv_a_t0 + dv_b0) / d2
-        - (W * (dv_a_t0 + dv_b0) + WX * dv_c_prime) * d_prime / d4).v;
-    double const B1 = ((xd(2.0) * dv_a_t1 + dv_b1) / d2
-        - (W * (dv_a_t1 + dv_b1) + WY * dv_c_prime) * d_prime / d4).v;
-    double const cu = (du_c_prime / d2).v;
-    double const cv = (dv_c_prime / d2).v;
+    double const A0 = ((xd(2.0) * du_a_t0 + du_b0) / rd2
+        - (W * (du_a_t0 + du_b0) + WX * du_c_prime) * d_prime / rd4).v;
+    double const A1 = ((xd(2.0) * du_a_t1 + du_b1) / rd2
+        - (W * (du_a_t1 + du_b1) + WY * du_c_prime) * d_prime / rd4).v;
+    double const B0 = ((xd(2.0) * dv_a_t0 + dv_b0) / rd2
+        - (W * (dv_a_t0 + dv_b0) + WX * dv_c_prime) * d_prime / rd4).v;
+    double const B1 = ((xd(2.0) * dv_a_t1 + dv_b1) / rd2
+        - (W * (dv_a_t1 + dv_b1) + WY * dv_c_prime) * d_prime / rd4).v;
+    double const cu = (du_c_prime / rd2).v;
+    double const cv = (dv_c_prime / rd2).v;
 
     out.ax = A0 * gx + B0 * gy + jh00 * du_w + jh01 * dv_w;
     out.ay = A1 * gx + B1 * gy + jh10 * du_w + jh11 * dv_w;
@@ -289,6 +317,7 @@ surface_geometry (double x_, double y_, double f_, double w_, double dx_,
     double const X = x_, Y = y_, F = f_, A = a.v, AX = ax.v, AY = ay.v;
     double const DX = dx_, DY = dy_, DXY = dxy_, DXX = dxx_, DYY = dyy_;
     double const inv_t = 1.0 / t;
+    double const inv_n = 1.0 / n;
     double const inv_tt = inv_t * inv_t;
     double const inv_ttf = inv_tt / F;
     double const inv_tf = inv_t / F;
@@ -303,7 +332,7 @@ surface_geometry (double x_, double y_, double f_, double w_, double dx_,
         double const ax_p = 2.0 * dx_p + X * dxx_p + Y * dxy_p;
         double const ay_p = 2.0 * dy_p + Y * dyy_p + X * dxy_p;
         double const t_p2 = DX * dx_p + DY * dy_p + f_sqr_inv * A * a_p;
-        double const n_p = t_p2 / n;
+        double const n_p = t_p2 * inv_n;
         double const b_p = (dx_p * DXX + DX * dxx_p)
             + (dy_p * DXY + DY * dxy_p) + f_sqr_inv * (a_p * AX + A * ax_p);
         double const c_p = (dx_p * DXY + DX * dxy_p)
