@@ -395,6 +395,13 @@ def run_product(args):
     for wl in pool:
         wl.scene.images = [pin(a) for a in wl.scene.images]
         wl.nodes = pin(wl.nodes)
+        wl.node_valid = pin(wl.node_valid)
+        wl.patch_valid = pin(wl.patch_valid)
+        wl.vis_off = pin(wl.vis_off)
+        wl.vis_ids = pin(wl.vis_ids)
+    # page-locked result buffers, one per context (the two-thread arm below
+    # has two steps in flight)
+    nodes_host = [pin(np.empty_like(wl.nodes)) for wl in pool]
     ctxs = [api.Context(local) for _ in pool]
     nodes_out = None
     e2e_parts = np.zeros(4)
@@ -412,7 +419,7 @@ def run_product(args):
         t.append(time.perf_counter())
         st = ctx.newton_loop(None, REGULARIZATION, 0.0)
         t.append(time.perf_counter())
-        nodes = ctx.get_nodes()
+        nodes = ctx.get_nodes(out=nodes_host[j])
         t.append(time.perf_counter())
         e2e_parts[:] += np.diff(t)
         return st, nodes

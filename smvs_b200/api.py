@@ -340,8 +340,16 @@ class Context:
                     cg_row_iterations=st.cg_row_iterations)
 
     # -- outputs ---------------------------------------------------------
-    def get_nodes(self):
-        out = np.empty((self.n_nodes, 4), dtype=np.float64)
+    def get_nodes(self, out=None):
+        """Node parameters (n_nodes, 4). `out`: a caller-owned C-contiguous
+        float64 array to read into (e.g. page-locked memory, so that the
+        device-to-host copy is one DMA transfer)."""
+        if out is None:
+            out = np.empty((self.n_nodes, 4), dtype=np.float64)
+        else:
+            if (out.dtype != np.float64 or not out.flags.c_contiguous
+                    or out.size != self.n_nodes * 4):
+                raise ValueError("out must be C-contiguous float64 with n_nodes * 4 entries")
         self._check(lib().smvsb_get_nodes(self._h, _p(out)))
         return out
 

@@ -58,6 +58,17 @@ namespace {
 
 thread_local std::string g_last_error = "";
 
+/* A call that fails may have asynchronous copies from the caller's buffers
+ * queued: they are finished before the error is returned. */
+void
+quiesce (smvsb_ctx* ctx)
+{
+    if (ctx == nullptr)
+        return;
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+}
+
 template <typename F>
 int
 guarded (smvsb_ctx* ctx, F&& fn)
@@ -76,11 +87,13 @@ guarded (smvsb_ctx* ctx, F&& fn)
     }
     catch (smvsb::Error const& e)
     {
+        quiesce(ctx);
         if (ctx) ctx->last_error = e.msg; else g_last_error = e.msg;
         return e.code;
     }
     catch (std::exception const& e)
     {
+        quiesce(ctx);
         if (ctx) ctx->last_error = e.what(); else g_last_error = e.what();
         return SMVSB_ERR_INVALID;
     }
@@ -91,6 +104,43 @@ require (bool cond, int code, char const* msg)
 {
     if (!cond)
         throw smvsb::Error(code, msg);
+}
+
+/* smvsb_set_surface: the visibility lists as the kernels will read them --
+ * bit 0: offsets not monotone (or beyond the id array), 1: a list longer than
+ * the number of neighbours, 2: an id out of range, 3: a neighbour twice. */
+__global__ void __launch_bounds__(256)
+vis_validate_kernel (int n_patches, int n_sub, uint32_t total,
+    uint32_t const* __restrict__ vis_off, uint8_t const* __restrict__ vis_ids,
+    unsigned long long* __restrict__ flags)
+{
+    int const p = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int bad = 0;
+    if (p < n_patches)
+    {
+        uint32_t const b = vis_off[p], e = vis_off[p + 1];
+        if (b > e || e > total)
+            bad |= 1u;
+        else if (e - b > static_cast<uint32_t>(n_sub))
+            bad |= 2u;
+        else
+        {
+            uint32_t seen = 0;
+            for (uint32_t i = b; i < e; ++i)
+            {
+                uint32_t const id = vis_ids[i];
+                if (id >= static_cast<uint32_t>(n_sub))
+                    bad |= 4u;
+                uint32_t const bit = 1u << (id & 31u);
+                if (seen & bit)
+                    bad |= 8u;
+                seen |= bit;
+            }
+        }
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && bad != 0)
+        atomicOr(flags, static_cast<unsigned long long>(bad));
 }
 
 template <typename T>
@@ -434,6 +484,15 @@ smvsb_create (int device, smvsb_ctx** out)
                 cudaStreamNonBlocking));
             for (int i = 0; i < SMVSB_NUM_EVENTS; ++i)
                 CUDA_CHECK(cudaEventCreate(&c->ev[i]));
+            CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream,
+                cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i)
+            {
+                CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_copied[i],
+                    cudaEventDisableTiming));
+                CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_consumed[i],
+                    cudaEventDisableTiming));
+            }
             CUDA_CHECK(cudaDeviceGetAttribute(&c->num_sms,
                 cudaDevAttrMultiProcessorCount, device));
             CUDA_CHECK(cudaMallocHost(&c->h_scalars, 32 * sizeof(double)));
@@ -441,6 +500,15 @@ smvsb_create (int device, smvsb_ctx** out)
         catch (...)
         {
             if (c->h_scalars) cudaFreeHost(c->h_scalars);
+            for (int i = 0; i < 2; ++i)
+            {
+                if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+                if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
+            }
+            for (int i = 0; i < SMVSB_NUM_EVENTS; ++i)
+                if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+            if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+            if (c->stream) cudaStreamDestroy(c->stream);
             delete c;
             throw;
         }
@@ -457,6 +525,13 @@ smvsb_destroy (smvsb_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < SMVSB_NUM_EVENTS; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    for (int i = 0; i < 2; ++i)
+    {
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     delete ctx;
@@ -570,20 +645,51 @@ smvsb_set_views_u8 (smvsb_ctx* ctx, int scale, int w, int h, double flen_px,
                 * sub_h[k]);
         }
         c->stage_u8.reserve(max_pix);
+        c->stage_u8b.reserve(max_pix);
         c->stage_a.reserve(max_pix);
         c->stage_b.reserve(max_pix);
         size_t const npix = static_cast<size_t>(w) * h;
         c->main_grad.reserve(npix * 2);
-        upload(c, c->stage_u8, main_img, npix);
-        smvsb::device_set_scale(c, c->stage_u8.p, w, h, scale, c->stage_a.p,
-            c->stage_b.p, 0, c->main_grad.p);
-        c->have_shading = (with_shading != 0);
-        if (c->have_shading)
+        /* Image k travels on the copy stream into staging buffer k mod 2
+         * while set_scale of image k - 1 runs on the context's stream; from
+         * page-locked host memory the copies are asynchronous, so the PCIe
+         * transfers and the kernels overlap (from pageable memory the same
+         * calls simply serialise). Whatever the context's stream still has
+         * queued may read the staging buffers: the first copies wait for it. */
+        uint8_t* const stage[2] = { c->stage_u8.p, c->stage_u8b.p };
+        CUDA_CHECK(cudaEventRecord(c->ev_consumed[0], c->stream));
+        CUDA_CHECK(cudaEventRecord(c->ev_consumed[1], c->stream));
+        auto stage_image = [&](int k, uint8_t const* img, size_t n) {
+            int const slot = k & 1;
+            CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream,
+                c->ev_consumed[slot], 0));
+            CUDA_CHECK(cudaMemcpyAsync(stage[slot], img, n,
+                cudaMemcpyHostToDevice, c->copy_stream));
+            CUDA_CHECK(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+        };
+        auto acquire = [&](int k) -> uint8_t const* {
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_copied[k & 1], 0));
+            return stage[k & 1];
+        };
+        auto release = [&](int k) {
+            CUDA_CHECK(cudaEventRecord(c->ev_consumed[k & 1], c->stream));
+        };
+        stage_image(0, main_img, npix);
+        if (n_sub > 0)
+            stage_image(1, sub_img[0], static_cast<size_t>(sub_w[0]) * sub_h[0]);
         {
-            c->main_shading.reserve(npix);
-            c->main_shading_grad.reserve(npix * 2);
-            smvsb::device_shading_inputs(c, c->stage_u8.p, w, h,
-                c->main_shading.p, c->main_shading_grad.p);
+            uint8_t const* src = acquire(0);
+            smvsb::device_set_scale(c, src, w, h, scale, c->stage_a.p,
+                c->stage_b.p, 0, c->main_grad.p);
+            c->have_shading = (with_shading != 0);
+            if (c->have_shading)
+            {
+                c->main_shading.reserve(npix);
+                c->main_shading_grad.reserve(npix * 2);
+                smvsb::device_shading_inputs(c, src, w, h,
+                    c->main_shading.p, c->main_shading_grad.p);
+            }
+            release(0);
         }
         c->n_sub = n_sub;
         std::vector<float const*> ptrs(std::max(n_sub, 1), nullptr);
@@ -591,13 +697,17 @@ smvsb_set_views_u8 (smvsb_ctx* ctx, int scale, int w, int h, double flen_px,
         std::vector<double> mt(std::max(12 * n_sub, 12), 0.0);
         for (int k = 0; k < n_sub; ++k)
         {
-            size_t const n = static_cast<size_t>(sub_w[k]) * sub_h[k];
             smvsb::SubViewDev& sv = c->subs[k];
             sv.w = sub_w[k]; sv.h = sub_h[k];
-            sv.texels.reserve(n * SMVSB_NB_STRIDE);
-            upload(c, c->stage_u8, sub_img[k], n);
-            smvsb::device_set_scale(c, c->stage_u8.p, sv.w, sv.h, scale,
+            sv.texels.reserve(static_cast<size_t>(sv.w) * sv.h
+                * SMVSB_NB_STRIDE);
+            if (k + 1 < n_sub)
+                stage_image(k + 2, sub_img[k + 1],
+                    static_cast<size_t>(sub_w[k + 1]) * sub_h[k + 1]);
+            uint8_t const* src = acquire(k + 1);
+            smvsb::device_set_scale(c, src, sv.w, sv.h, scale,
                 c->stage_a.p, c->stage_b.p, 1, sv.texels.p);
+            release(k + 1);
             ptrs[k] = sv.texels.p;
             dims[2 * k] = sv.w; dims[2 * k + 1] = sv.h;
             std::copy(Mi + 9 * k, Mi + 9 * k + 9, mt.begin() + 12 * k);
@@ -728,7 +838,14 @@ smvsb_set_surface (smvsb_ctx* ctx, int scale, int npx, int npy, int start_x,
         require((vis_off == nullptr) == (vis_ids == nullptr),
             SMVSB_ERR_INVALID, "vis_off and vis_ids go together");
         smvsb_ctx* c = ctx;
+        /* a call that fails leaves the context without a surface */
+        c->have_surface = false;
         configure_grid(c, scale, npx, npy, start_x, start_y);
+        /* the node and validity arrays travel while the host checks the
+         * lists (asynchronous from page-locked buffers) */
+        upload(c, c->nodes, nodes, static_cast<size_t>(c->n_nodes) * 4);
+        upload(c, c->node_valid, node_valid, c->n_nodes);
+        upload(c, c->patch_valid, patch_valid, c->n_patches);
         /* no lists: nothing visible yet (smvsb_visibility fills them) */
         std::vector<uint32_t> no_off;
         uint8_t const no_id = 0;
@@ -740,35 +857,47 @@ smvsb_set_surface (smvsb_ctx* ctx, int scale, int npx, int npy, int start_x,
         }
         /* the kernels fill a fixed array of SMVSB_MAX_SUBS rows per patch
          * from these lists: offsets must start at 0 and be monotone, a list
-         * holds each neighbour at most once */
+         * holds each neighbour at most once. The lists are checked where
+         * they land (one thread per patch; 0.5 ms on a host core at 2 MP). */
         require(vis_off[0] == 0, SMVSB_ERR_INVALID, "vis_off[0] must be 0");
-        for (int p = 0; p < npx * npy; ++p)
         {
-            require(vis_off[p] <= vis_off[p + 1], SMVSB_ERR_INVALID,
-                "vis_off must be monotone");
-            require(vis_off[p + 1] - vis_off[p] <= static_cast<uint32_t>(
-                c->n_sub), SMVSB_ERR_INVALID,
-                "visibility list longer than the number of neighbours");
-            uint32_t seen = 0;
-            for (uint32_t i = vis_off[p]; i < vis_off[p + 1]; ++i)
+            /* the offsets on the host (they bound what is read of vis_ids) */
+            uint32_t const n_sub = static_cast<uint32_t>(c->n_sub);
+            unsigned int bad_order = 0, bad_len = 0;
+            for (int p = 0; p < c->n_patches; ++p)
             {
-                require(vis_ids[i] < c->n_sub, SMVSB_ERR_INVALID,
-                    "visibility id out of range");
-                require(!((seen >> vis_ids[i]) & 1u), SMVSB_ERR_INVALID,
-                    "duplicate neighbour in a visibility list");
-                seen |= 1u << vis_ids[i];
+                bad_order |= vis_off[p] > vis_off[p + 1];
+                bad_len |= (vis_off[p + 1] - vis_off[p]) > n_sub;
             }
+            require(!bad_order, SMVSB_ERR_INVALID, "vis_off must be monotone");
+            require(!bad_len, SMVSB_ERR_INVALID,
+                "visibility list longer than the number of neighbours");
         }
         size_t const total_vis = vis_off[c->n_patches];
-        upload(c, c->nodes, nodes, static_cast<size_t>(c->n_nodes) * 4);
-        upload(c, c->node_valid, node_valid, c->n_nodes);
-        upload(c, c->patch_valid, patch_valid, c->n_patches);
         upload(c, c->vis_off, vis_off, static_cast<size_t>(c->n_patches) + 1);
         upload(c, c->vis_ids, vis_ids, std::max<size_t>(total_vis, 1));
+        c->counters.reserve(8);
+        CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, sizeof(unsigned long long),
+            c->stream));
+        vis_validate_kernel<<<(c->n_patches + 255) / 256, 256, 0, c->stream>>>(
+            c->n_patches, c->n_sub, static_cast<uint32_t>(total_vis),
+            c->vis_off.p, c->vis_ids.p, c->counters.p);
+        smvsb::count_launches(c, 1);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(c->h_scalars + 16, c->counters.p,
+            sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         c->h_node_valid.assign(node_valid, node_valid + c->n_nodes);
         c->h_patch_valid.assign(patch_valid, patch_valid + c->n_patches);
-        CUDA_CHECK(cudaStreamSynchronize(c->stream));
         set_active(c, nullptr);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        unsigned long long bad = 0;
+        std::memcpy(&bad, c->h_scalars + 16, sizeof(bad));
+        require(!(bad & 1u), SMVSB_ERR_INVALID, "vis_off must be monotone");
+        require(!(bad & 2u), SMVSB_ERR_INVALID,
+            "visibility list longer than the number of neighbours");
+        require(!(bad & 4u), SMVSB_ERR_INVALID, "visibility id out of range");
+        require(!(bad & 8u), SMVSB_ERR_INVALID,
+            "duplicate neighbour in a visibility list");
         c->have_surface = true;
         c->have_system = false;
         c->x_count = 0;

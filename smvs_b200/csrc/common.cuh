@@ -106,6 +106,10 @@ struct smvsb_ctx
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[SMVSB_NUM_EVENTS] = {};
+    /* smvsb_set_views_u8: the upload of image k + 1 (copy stream) runs under
+     * set_scale of image k (two staging buffers) */
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
     std::string last_error;
     uint64_t launches = 0;
     int num_sms = 0;
@@ -121,6 +125,7 @@ struct smvsb_ctx
     smvsb::DevBuf<int> sub_dims;
     smvsb::DevBuf<double> Mt;
     smvsb::DevBuf<uint8_t> stage_u8;       /* upload staging (reused) */
+    smvsb::DevBuf<uint8_t> stage_u8b;
     smvsb::DevBuf<float> stage_a, stage_b;
     smvsb::DevBuf<float> view_in, view_texels, view_out;   /* smvsb_view_set_scale */
 
