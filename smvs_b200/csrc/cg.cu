@@ -60,6 +60,16 @@
  * not limited by what comes out of DRAM but by what the SMs can keep in flight
  * through L2 (H at 5.5 TB/s plus the gathered vector entries), so an L2 hit is
  * worth no more than an HBM access here (profiles/r2_cg_keep_probe.txt).
+ * Fetching across the grid barriers -- the Hessian row of the first SpMV
+ * pass and the thread's own operands of the first vector-update rows loaded
+ * BEFORE the barrier in front of the phase, used after it: on a system of one
+ * pass per CTA the SpMV phase drops from 3.3 to 1.9 us, but on the full system
+ * it rises from 24.8 to 40.2 us (72 registers live across the barrier change
+ * the streaming loop's schedule: fewer loads in flight), and the update-side
+ * variant gains 0.7 us in its phase and loses 2.9 in the SpMV
+ * (profiles/r2_cg_ahead_probe.txt). What a barrier costs CTA 0 between its
+ * last store of a phase and the first instruction of the next is 2.3 - 2.8 us
+ * whatever the system size.
  */
 #include <algorithm>
 #include <cstdlib>
