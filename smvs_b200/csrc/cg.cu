@@ -383,70 +383,6 @@ spmv_row (double const* __restrict__ H, int ns, VecOp const& vec, int node,
     return acc;
 }
 
-/* The Hessian entries of one block row, fetched ahead of their use (across a
- * grid barrier, see cg_kernel). */
-struct RowAhead
-{
-    double2 h01[9], h23[9];
-};
-
-__device__ __forceinline__ void
-fetch_row (double const* __restrict__ H, int node, int rp, unsigned int mask,
-    RowAhead& ra)
-{
-    double const* hrow = H + static_cast<size_t>(node) * 144 + rp * 4;
-#pragma unroll
-    for (int k = 0; k < 9; ++k)
-    {
-        ra.h01[k] = make_double2(0.0, 0.0);
-        ra.h23[k] = make_double2(0.0, 0.0);
-        if ((mask >> k) & 1u)
-            ld_stream(hrow + k * 16, ra.h01[k], ra.h23[k]);
-    }
-}
-
-/* spmv_row() on a row fetched by fetch_row(): same blocks, same order. */
-template <typename VecOp>
-__device__ __forceinline__ double
-spmv_row_ahead (RowAhead const& ra, int ns, VecOp const& vec, int node,
-    unsigned int mask, double* own)
-{
-    int const ix = node % ns, iy = node / ns;
-    double acc = 0.0;
-    own[0] = 0.0; own[1] = 0.0; own[2] = 0.0; own[3] = 0.0;
-    if (mask == 0)
-        return 0.0;
-#pragma unroll
-    for (int k = 0; k < 9; ++k)
-    {
-        if (!((mask >> k) & 1u))
-            continue;
-        int const jx = ix + (k % 3) - 1, jy = iy + (k / 3) - 1;
-        int const nj = jy * ns + jx;
-        double v[4];
-        vec.load(nj, v);
-        if (k == 4)
-        {
-            own[0] = v[0]; own[1] = v[1]; own[2] = v[2]; own[3] = v[3];
-        }
-        acc += ra.h01[k].x * v[0];
-        acc += ra.h01[k].y * v[1];
-        acc += ra.h23[k].x * v[2];
-        acc += ra.h23[k].y * v[3];
-    }
-    return acc;
-}
-
-/* The operands of the vector update of CG_UF rows, fetched ahead likewise:
- * all of them belong to rows this thread alone reads and writes. */
-struct UpdateAhead
-{
-    int nodes[CG_UF];
-    bool oks[CG_UF];
-    double dn[CG_UF], ad[CG_UF], g[CG_UF], x[CG_UF], r[CG_UF];
-    double2 p01[CG_UF], p23[CG_UF];
-};
-
 /* Does CTA b work on view v between the next two barriers? */
 __device__ __forceinline__ bool
 view_on (CgArgs const& a, CgState const* s_state, int v, bool init)
@@ -590,25 +526,6 @@ cg_kernel (CgArgs const a)
             }
         }
     }
-    /* Single-view launches fetch across the grid barriers: what the first pass
-     * of a phase reads and no other CTA writes -- the Hessian row of the SpMV,
-     * the thread's own vector entries and preconditioner rows of the update --
-     * is loaded BEFORE the barrier in front of the phase and used after it, so
-     * the wait for the grid hides one memory latency per phase (a system of
-     * one pass per CTA, the late Newton steps, is all first pass). The
-     * arithmetic and its order are unchanged. */
-#ifndef SMVSB_CG_AHEAD_H
-#define SMVSB_CG_AHEAD_H 1
-#endif
-#ifndef SMVSB_CG_AHEAD_U
-#define SMVSB_CG_AHEAD_U 1
-#endif
-    constexpr bool AHEAD_H = (NV == 1) && SMVSB_CG_AHEAD_H;
-    constexpr bool AHEAD_U = (NV == 1) && SMVSB_CG_AHEAD_U;
-    RowAhead row_ahead;
-    UpdateAhead upd_ahead;
-    if (AHEAD_H)
-        fetch_row(a.v[0].H, first_node[0], rp, first_mask[0], row_ahead);
     for (; iter < a.max_iter; ++iter)
     {
         unsigned long long const t_a = now_ns<TIMING>();
@@ -644,29 +561,7 @@ cg_kernel (CgArgs const a)
                 double acc[1] = { 0.0 };
                 int node = first_node[v];
                 unsigned int mask = first_mask[v];
-                int q = quad0;
-                if (AHEAD_H && q < n_rows)
-                {
-                    /* first pass: the Hessian row came in under the barrier */
-                    int const qn = q + quads;
-                    int const node_next = (qn < n_rows)
-                        ? static_cast<int>(V.rows[qn]) : 0;
-                    unsigned int const mask_next = (qn < n_rows)
-                        ? V.rowmask[node_next] : 0u;
-                    double own[4];
-                    size_t const i = static_cast<size_t>(node) * 4 + rp;
-                    double const val = spmv_row_ahead(row_ahead, V.npx + 1,
-                        dir, node, mask, own);
-                    node = node_next;
-                    mask = mask_next;
-                    double const di = (rp == 0) ? own[0] : (rp == 1) ? own[1]
-                        : (rp == 2) ? own[2] : own[3];
-                    V.Ad[i] = val;
-                    d_new[i] = di;
-                    acc[0] += val * di;
-                    q = qn;
-                }
-                for (; q < n_rows; q += quads)
+                for (int q = quad0; q < n_rows; q += quads)
                 {
                     int const qn = q + quads;
                     int const node_next = (qn < n_rows)
@@ -684,40 +579,6 @@ cg_kernel (CgArgs const a)
                     V.Ad[i] = val;
                     d_new[i] = di;
                     acc[0] += val * di;
-                }
-                if (AHEAD_U)
-                {
-                    /* operands of the first CG_UF rows of the vector update:
-                     * they do not depend on alpha, so their loads travel
-                     * while the CTA waits for the grid */
-                    double const* dn_p = d_new;
-#pragma unroll
-                    for (int u = 0; u < CG_UF; ++u)
-                    {
-                        upd_ahead.oks[u] = pass_row(V, n_rows, u,
-                            upd_ahead.nodes[u]);
-                        upd_ahead.dn[u] = 0.0; upd_ahead.ad[u] = 0.0;
-                        upd_ahead.g[u] = 0.0; upd_ahead.x[u] = 0.0;
-                        upd_ahead.r[u] = 0.0;
-                        upd_ahead.p01[u] = make_double2(0, 0);
-                        upd_ahead.p23[u] = upd_ahead.p01[u];
-                    }
-#pragma unroll
-                    for (int u = 0; u < CG_UF; ++u)
-                        if (upd_ahead.oks[u])
-                        {
-                            size_t const i = static_cast<size_t>(
-                                upd_ahead.nodes[u]) * 4 + rp;
-                            upd_ahead.dn[u] = dn_p[i];
-                            upd_ahead.ad[u] = V.Ad[i];
-                            upd_ahead.g[u] = V.g[i];
-                            upd_ahead.x[u] = V.x[i];
-                            upd_ahead.r[u] = V.r[i];
-                            double const* prow = V.P + static_cast<size_t>(
-                                upd_ahead.nodes[u]) * 16 + rp * 4;
-                            upd_ahead.p01[u] = ld_hint(prow, keep);
-                            upd_ahead.p23[u] = ld_hint(prow + 2, keep);
-                        }
                 }
                 warp_flush<1>(acc, s_red, v);
             }
@@ -749,15 +610,7 @@ cg_kernel (CgArgs const a)
             bool oks[CG_UF];
 #pragma unroll
             for (int u = 0; u < CG_UF; ++u)
-            {
-                if (AHEAD_U)
-                {
-                    nodes[u] = upd_ahead.nodes[u];
-                    oks[u] = upd_ahead.oks[u];
-                }
-                else
-                    oks[u] = pass_row(V, n_rows, u, nodes[u]);
-            }
+                oks[u] = pass_row(V, n_rows, u, nodes[u]);
             /* CG_UF rows per thread in flight: the pass is latency bound */
             for (int p = 0; p < passes; p += CG_UF)
             {
@@ -770,41 +623,22 @@ cg_kernel (CgArgs const a)
 
                 double xv[CG_UF], rv[CG_UF], gv[CG_UF];
                 double2 p01[CG_UF], p23[CG_UF];
-                if (AHEAD_U && p == 0)
-                {
 #pragma unroll
-                    for (int u = 0; u < CG_UF; ++u)
-                    {
-                        gv[u] = upd_ahead.g[u];
-                        p01[u] = upd_ahead.p01[u]; p23[u] = upd_ahead.p23[u];
-                        xv[u] = upd_ahead.x[u]; rv[u] = upd_ahead.r[u];
-                        if (oks[u])
-                        {
-                            xv[u] += upd_ahead.dn[u] * alpha;
-                            rv[u] -= upd_ahead.ad[u] * alpha;
-                        }
-                    }
-                }
-                else
+                for (int u = 0; u < CG_UF; ++u)
                 {
-#pragma unroll
-                    for (int u = 0; u < CG_UF; ++u)
+                    xv[u] = 0.0; rv[u] = 0.0; gv[u] = 0.0;
+                    p01[u] = make_double2(0, 0); p23[u] = p01[u];
+                    if (oks[u])
                     {
-                        xv[u] = 0.0; rv[u] = 0.0; gv[u] = 0.0;
-                        p01[u] = make_double2(0, 0); p23[u] = p01[u];
-                        if (oks[u])
-                        {
-                            size_t const i = static_cast<size_t>(nodes[u]) * 4
-                                + rp;
-                            double const dn = d_new[i], ad = V.Ad[i];
-                            gv[u] = V.g[i];
-                            xv[u] = V.x[i]; rv[u] = V.r[i];
-                            double const* prow = V.P
-                                + static_cast<size_t>(nodes[u]) * 16 + rp * 4;
-                            p01[u] = ld_hint(prow, keep);
-                            p23[u] = ld_hint(prow + 2, keep);
-                            xv[u] += dn * alpha; rv[u] -= ad * alpha;
-                        }
+                        size_t const i = static_cast<size_t>(nodes[u]) * 4 + rp;
+                        double const dn = d_new[i], ad = V.Ad[i];
+                        gv[u] = V.g[i];
+                        xv[u] = V.x[i]; rv[u] = V.r[i];
+                        double const* prow = V.P
+                            + static_cast<size_t>(nodes[u]) * 16 + rp * 4;
+                        p01[u] = ld_hint(prow, keep);
+                        p23[u] = ld_hint(prow + 2, keep);
+                        xv[u] += dn * alpha; rv[u] -= ad * alpha;
                     }
                 }
 #pragma unroll
@@ -833,9 +667,6 @@ cg_kernel (CgArgs const a)
                     oks[u] = oks_next[u];
                 }
             }
-            /* the Hessian row of the next iteration's first pass */
-            if (AHEAD_H)
-                fetch_row(V.H, first_node[v], rp, first_mask[v], row_ahead);
             warp_flush<3>(acc, s_red, v);
         }
         publish<3>(a, s_state, s_red, slot + 1, false);
