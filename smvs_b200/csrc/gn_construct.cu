@@ -118,9 +118,13 @@ struct ConstructArgs
  * S >= 16: groups of 16 samples; a 256-sample patch takes two chunks of 128.
  * S < 16: 8 patches per block, 8 * S threads busy in phase 1.
  */
-/* 3 CTAs / SM (168 registers, a few spills) beats 2 CTAs at 248 registers by
- * 13 % on B200: the kernel is fp64-latency bound and wants the warps. */
-template <int S, int MINB = 4, int PAIR = 0>
+/* 4 CTAs / SM at 128 registers: measured best of 3 / 4 / 5 / 6 (168 / 128 / 96 /
+ * 80 registers). The kernel is fp64-latency bound (4 warps per scheduler,
+ * one instruction issued per warp every ~10 cycles). Giving the in-order
+ * scheduler two independent streams -- two neighbours' rows computed side by
+ * side, the divisions of two pair terms hoisted -- does not help at this
+ * register budget: construct 2.93 -> 3.16 / 2.97 ms per loop (job r2z). */
+template <int S, int MINB = 4>
 __global__ void __launch_bounds__(K1_THREADS, MINB)
 gn_patch_kernel (ConstructArgs const args)
 {
@@ -301,24 +305,7 @@ gn_patch_kernel (ConstructArgs const args)
             uint32_t const v0 = sf.vis_off[patch];
             int const n = static_cast<int>(sf.vis_off[patch + 1] - v0);
             NbRow rows[SMVSB_MAX_SUBS];
-            int j = 0;
-            /* two neighbours at a time: two independent instruction streams
-             * for the scheduler of an in-order core */
-            if (PAIR & 1)
-            for (; j + 1 < n; j += 2)
-            {
-                int const sub0 = sf.vis_ids[v0 + j];
-                int const sub1 = sf.vis_ids[v0 + j + 1];
-                NbRow const r0 = neighbour_row(sf.Mt + sub0 * 12,
-                    sf.sub_texels[sub0], sf.sub_dims[2 * sub0],
-                    sf.sub_dims[2 * sub0 + 1], px + 0.5, py + 0.5, w, wx, wy);
-                NbRow const r1 = neighbour_row(sf.Mt + sub1 * 12,
-                    sf.sub_texels[sub1], sf.sub_dims[2 * sub1],
-                    sf.sub_dims[2 * sub1 + 1], px + 0.5, py + 0.5, w, wx, wy);
-                rows[j] = r0;
-                rows[j + 1] = r1;
-            }
-            for (; j < n; ++j)
+            for (int j = 0; j < n; ++j)
             {
                 int const sub = sf.vis_ids[v0 + j];
                 rows[j] = neighbour_row(sf.Mt + sub * 12, sf.sub_texels[sub],
@@ -335,27 +322,7 @@ gn_patch_kernel (ConstructArgs const args)
                     1.0 / (fabs(dx_) + SMVSB_R_FACTOR));
                 add_photo_row<2>(A, b, rj.ay, rj.be, dy_,
                     1.0 / (fabs(dy_) + SMVSB_R_FACTOR));
-                int j2 = j + 1;
-                if (PAIR & 2)
-                for (; j2 + 1 < n; j2 += 2)
-                {
-                    /* two pairs at a time: the four weights (a division
-                     * each) are independent; the rows are added in the same
-                     * order as one by one */
-                    NbRow const ra = rows[j2], rb = rows[j2 + 1];
-                    double const sxa = rj.jgx - ra.jgx, sya = rj.jgy - ra.jgy;
-                    double const sxb = rj.jgx - rb.jgx, syb = rj.jgy - rb.jgy;
-                    double const wxa = 1.0 / (fabs(sxa) + SMVSB_R_FACTOR);
-                    double const wya = 1.0 / (fabs(sya) + SMVSB_R_FACTOR);
-                    double const wxb = 1.0 / (fabs(sxb) + SMVSB_R_FACTOR);
-                    double const wyb = 1.0 / (fabs(syb) + SMVSB_R_FACTOR);
-                    double const bea = rj.be - ra.be, beb = rj.be - rb.be;
-                    add_photo_row<1>(A, b, rj.ax - ra.ax, bea, sxa, wxa);
-                    add_photo_row<2>(A, b, rj.ay - ra.ay, bea, sya, wya);
-                    add_photo_row<1>(A, b, rj.ax - rb.ax, beb, sxb, wxb);
-                    add_photo_row<2>(A, b, rj.ay - rb.ay, beb, syb, wyb);
-                }
-                for (; j2 < n; ++j2)
+                for (int j2 = j + 1; j2 < n; ++j2)
                 {
                     NbRow const r2 = rows[j2];
                     double const sx_ = rj.jgx - r2.jgx;
@@ -708,23 +675,7 @@ launch_construct (smvsb_ctx* c, bool use_light, double reg, double light_reg)
         gn_patch_kernel<4><<<blocks(8), K1_THREADS, 0, c->stream>>>(a); break;
     case 16:
     {
-        /* experiments (benchmarks only): SMVSB_K1_MINB = 3 (168 registers),
-         * SMVSB_K1_PAIR bit 0 = neighbours two at a time, bit 1 = pair terms
-         * two at a time */
-        static int const minb = getenv("SMVSB_K1_MINB")
-            ? atoi(getenv("SMVSB_K1_MINB")) : 4;
-        static int const pair = getenv("SMVSB_K1_PAIR")
-            ? atoi(getenv("SMVSB_K1_PAIR")) & 3 : 0;
-        dim3 const g(blocks(8)), t(K1_THREADS);
-        if (minb == 3)
-        {
-            if (pair == 3) gn_patch_kernel<16, 3, 3><<<g, t, 0, c->stream>>>(a);
-            else gn_patch_kernel<16, 3, 0><<<g, t, 0, c->stream>>>(a);
-        }
-        else if (pair == 1) gn_patch_kernel<16, 4, 1><<<g, t, 0, c->stream>>>(a);
-        else if (pair == 2) gn_patch_kernel<16, 4, 2><<<g, t, 0, c->stream>>>(a);
-        else if (pair == 3) gn_patch_kernel<16, 4, 3><<<g, t, 0, c->stream>>>(a);
-        else gn_patch_kernel<16, 4, 0><<<g, t, 0, c->stream>>>(a);
+        gn_patch_kernel<16><<<blocks(8), K1_THREADS, 0, c->stream>>>(a);
         break;
     }
     case 64:
