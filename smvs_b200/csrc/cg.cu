@@ -140,18 +140,23 @@ grid_barrier (unsigned int* counter, unsigned int& epoch)
     {
         epoch += 1;
         unsigned int const target = epoch * gridDim.x;
-        __threadfence();
-        atomicAdd(counter, 1u);
-        /* spin with relaxed loads (served by L2), one fence at the end: an
-         * acquire load in the loop invalidates the SM's L1 on every poll
-         * (CCTL.IVALL, ~40 polls per barrier) -- under the other CTA of the
-         * SM, which may still be gathering vector entries through L1 */
+        /* arrive: one release reduction (the CTA's stores, ordered before it
+         * by the bar.sync above, are visible to whoever observes the count);
+         * 0.3 us per barrier less than fence + atomicAdd
+         * (benchmarks/micro/barrier_probe.cu) */
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;"
+            :: "l"(counter) : "memory");
+        /* spin with relaxed loads (served by L2) and acquire once at the
+         * end: an acquire load in the loop invalidates the SM's L1 on every
+         * poll (CCTL.IVALL, ~40 polls per barrier) -- under the other CTA of
+         * the SM, which may still be gathering vector entries through L1 */
         unsigned int v;
         do {
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];"
                 : "=r"(v) : "l"(counter) : "memory");
         } while (v < target);
-        __threadfence();
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
+            : "=r"(v) : "l"(counter) : "memory");
     }
     __syncthreads();
 }
@@ -279,14 +284,16 @@ all_sums (CgArgs const& a, CgState const* s_state, int first_slot,
             + (first_slot + j) * CG_MAX_BLOCKS;
         int const nb = s_state[view].grid;
         double v = 0.0;
-        for (int base = lane; base < nb; base += 32 * 8)
+        /* 12 loads per lane in flight: one L2 round trip for up to 384 CTAs
+         * (2 x 148 on B200) */
+        for (int base = lane; base < nb; base += 32 * 12)
         {
-            double t[8];
+            double t[12];
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
+            for (int u = 0; u < 12; ++u)
                 t[u] = (base + 32 * u < nb) ? __ldcg(p + base + 32 * u) : 0.0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
+            for (int u = 0; u < 12; ++u)
                 if (base + 32 * u < nb)
                     v += t[u];
         }
@@ -300,10 +307,10 @@ all_sums (CgArgs const& a, CgState const* s_state, int first_slot,
 
 /*
  * Plain (weak, L1-cached) loads are correct for the vectors other CTAs wrote
- * in the previous phase: the grid barrier is a release (fence + atomic) /
- * acquire (relaxed polls + fence) pair extended to the CTA by bar.sync, so
- * causality order covers them, and the gpu-scope fence after the spin drops
- * the SM's L1 lines. Each vector entry is used by up to nine rows, most of
+ * in the previous phase: the grid barrier is a release (red.release.gpu) /
+ * acquire (relaxed polls + one ld.acquire.gpu) pair extended to the CTA by
+ * bar.sync, so causality order covers them, and the gpu-scope acquire after
+ * the spin drops the SM's L1 lines. Each vector entry is used by up to nine rows, most of
  * them in the same CTA pass: L1 serves the re-use instead of L2.
  *
  * VecOp: the vector the matrix is applied to. For CG it is the NEW search
