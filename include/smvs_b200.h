@@ -239,6 +239,18 @@ int smvsb_view_set_scale (smvsb_ctx* ctx, int w, int h, const float* image,
     int scale, float* scaleimage, float* grad, float* hess);
 
 /*
+ * The same for an image of `channels` = 1 or 3 interleaved channels
+ * (StereoView::image of a colour view): mve::image::blur_gaussian blurs
+ * channel by channel, initialize_image_gradients (lib/stereo_view.cc:48-62)
+ * desaturates the blurred image (luminance, 0.21 / 0.72 / 0.07) before the
+ * stencil. scaleimage receives the blurred image with all its channels
+ * (w*h*channels); grad and hess as above.
+ */
+int smvsb_view_set_scale_c (smvsb_ctx* ctx, int w, int h, int channels,
+    const float* image, int scale, float* scaleimage, float* grad,
+    float* hess);
+
+/*
  * DepthOptimizer::depthmap_bilateral_filter (lib/depth_optimizer.cc:957-1004):
  * joint bilateral filter of a depth map (dm_w*dm_h, 0 = no depth) guided by
  * the w*h*channels float image; spatial Gaussian `sigma` over a
@@ -374,6 +386,23 @@ int smvsb_optimize (smvsb_ctx* ctx, int w, int h, double flen_px,
     double inv_flen, const float* inv_calib9, const uint8_t* main_img,
     int n_sub, const int* sub_w, const int* sub_h,
     const uint8_t* const* sub_img, const double* Mi, const double* ti,
+    const float* shading, const float* shading_grad, int sgm_w, int sgm_h,
+    const float* sgm_depth, const smvsb_optimize_options* opts,
+    float* depth_out, float* normals_out, double* light16_out,
+    smvsb_optimize_stats* stats);
+
+/*
+ * The same for colour views: the images are what StereoView::get_image()
+ * holds of a three-channel view (interleaved float RGB in [0, 1], w*h*3 and
+ * sub_w*sub_h*3). set_scale blurs the three channels and desaturates
+ * (smvsb_view_set_scale_c), the bilateral filter of the SGM depth is guided
+ * by the colour image (lib/depth_optimizer.cc:42, 957-1004); everything else
+ * is smvsb_optimize.
+ */
+int smvsb_optimize_rgb_f32 (smvsb_ctx* ctx, int w, int h, double flen_px,
+    double inv_flen, const float* inv_calib9, const float* main_rgb,
+    int n_sub, const int* sub_w, const int* sub_h,
+    const float* const* sub_rgb, const double* Mi, const double* ti,
     const float* shading, const float* shading_grad, int sgm_w, int sgm_h,
     const float* sgm_depth, const smvsb_optimize_options* opts,
     float* depth_out, float* normals_out, double* light16_out,

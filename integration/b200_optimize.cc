@@ -2,16 +2,18 @@
  * integration/b200_optimize.cc
  *
  * Drop-in body for smvs::DepthOptimizer::optimize (reference:
- * lib/depth_optimizer.cc:54-162). In the use_sgm mode with single-channel
- * images and no debug output the whole coarse-to-fine ladder of the view runs
- * on the GPU through ONE call, smvsb_optimize: the view goes up as byte
- * images, the depth and normal maps come back, and what optimize() has to
- * leave behind -- the two view embeddings (:158-161), the final surface for
- * get_depth() / get_normals(), the fitted lighting -- is put in place. Every
- * other configuration (use_sgm = false with its expansion and NCC filter,
- * colour images, debug levels that write intermediate images) runs the
- * reference's own optimize(), whose members are the per-call drop-ins of
- * b200_depth_optimizer.cc. lib/depth_optimizer.h is untouched.
+ * lib/depth_optimizer.cc:54-162). In the use_sgm mode without debug output the
+ * whole coarse-to-fine ladder of the view runs on the GPU through ONE call:
+ * smvsb_optimize for single-channel views (uploaded as byte images),
+ * smvsb_optimize_rgb_f32 for three-channel views (uploaded as the float
+ * images StereoView::get_image() holds -- what real MVE scenes contain). The
+ * depth and normal maps come back, and what optimize() has to leave behind --
+ * the two view embeddings (:158-161), the final surface for get_depth() /
+ * get_normals(), the fitted lighting -- is put in place. Every other
+ * configuration (use_sgm = false with its expansion and NCC filter, views of
+ * mixed or other channel counts, debug levels that write intermediate
+ * images) runs the reference's own optimize(), whose members are the per-call
+ * drop-ins of b200_depth_optimizer.cc. lib/depth_optimizer.h is untouched.
  *
  *   SMVSB_MEMBERWISE=1   forces the reference's optimize() (per-member path)
  */
@@ -31,21 +33,24 @@ extern "C" void smvs_ref_optimize (DepthOptimizer* self);
 namespace
 {
     bool
-    single_channel (StereoView::Ptr const& v)
+    has_channels (StereoView::Ptr const& v, int channels)
     {
-        return v->get_image() != nullptr && v->get_image()->channels() == 1;
+        return v->get_image() != nullptr
+            && v->get_image()->channels() == channels;
     }
 }
 
 void
 DepthOptimizer::optimize (void)
 {
+    bool const colour = has_channels(this->main_view, 3);
+    int const channels = colour ? 3 : 1;
     bool resident = this->opts.use_sgm && this->opts.debug_lvl == 0
         && std::getenv("SMVSB_MEMBERWISE") == nullptr
-        && single_channel(this->main_view) && !this->sub_views.empty()
+        && has_channels(this->main_view, channels) && !this->sub_views.empty()
         && this->sub_views.size() <= 32;
     for (auto const& v : this->sub_views)
-        resident = resident && single_channel(v);
+        resident = resident && has_channels(v, channels);
     if (this->opts.use_shading)
         resident = resident && this->main_view->get_shading_image() != nullptr;
     if (!resident)
@@ -60,17 +65,30 @@ DepthOptimizer::optimize (void)
 
     /* the view as the reference's StereoViews hold it */
     std::size_t const n = this->sub_views.size();
-    mve::ByteImage::ConstPtr main_img = this->main_view->get_byte_image();
+    mve::ByteImage::ConstPtr main_img;
     std::vector<mve::ByteImage::ConstPtr> sub_keep(n);
     std::vector<int> sw(n), sh(n);
     std::vector<uint8_t const*> simg(n);
+    std::vector<float const*> simg_rgb(n);
     std::vector<double> M(9 * n), t(3 * n);
+    if (!colour)
+        main_img = this->main_view->get_byte_image();
     for (std::size_t k = 0; k < n; ++k)
     {
-        sub_keep[k] = this->sub_views[k]->get_byte_image();
-        sw[k] = sub_keep[k]->width();
-        sh[k] = sub_keep[k]->height();
-        simg[k] = sub_keep[k]->begin();
+        if (colour)
+        {
+            mve::FloatImage::ConstPtr img = this->sub_views[k]->get_image();
+            sw[k] = img->width();
+            sh[k] = img->height();
+            simg_rgb[k] = img->begin();
+        }
+        else
+        {
+            sub_keep[k] = this->sub_views[k]->get_byte_image();
+            sw[k] = sub_keep[k]->width();
+            sh[k] = sub_keep[k]->height();
+            simg[k] = sub_keep[k]->begin();
+        }
         for (int j = 0; j < 9; ++j) M[9 * k + j] = this->Mi[k][j];
         for (int j = 0; j < 3; ++j) t[3 * k + j] = this->ti[k][j];
     }
@@ -91,14 +109,24 @@ DepthOptimizer::optimize (void)
     mve::FloatImage::Ptr normals = mve::FloatImage::create(w, h, 3);
     double light[16];
     smvsb_optimize_stats st;
-    gpu.check(smvsb_optimize(gpu.get(), w, h, this->main_view->get_flen(),
-        this->main_view->get_inverse_flen(), *invproj, main_img->begin(),
-        static_cast<int>(n), sw.data(), sh.data(), simg.data(), M.data(),
-        t.data(),
-        lit ? this->main_view->get_shading_image()->begin() : nullptr,
-        lit ? this->main_view->get_shading_gradients()->begin() : nullptr,
-        sgm->width(), sgm->height(), sgm->begin(), &o, depth->begin(),
-        normals->begin(), light, &st));
+    float const* shading = lit
+        ? this->main_view->get_shading_image()->begin() : nullptr;
+    float const* shading_grad = lit
+        ? this->main_view->get_shading_gradients()->begin() : nullptr;
+    if (colour)
+        gpu.check(smvsb_optimize_rgb_f32(gpu.get(), w, h,
+            this->main_view->get_flen(), this->main_view->get_inverse_flen(),
+            *invproj, this->main_view->get_image()->begin(),
+            static_cast<int>(n), sw.data(), sh.data(), simg_rgb.data(),
+            M.data(), t.data(), shading, shading_grad, sgm->width(),
+            sgm->height(), sgm->begin(), &o, depth->begin(), normals->begin(),
+            light, &st));
+    else
+        gpu.check(smvsb_optimize(gpu.get(), w, h, this->main_view->get_flen(),
+            this->main_view->get_inverse_flen(), *invproj, main_img->begin(),
+            static_cast<int>(n), sw.data(), sh.data(), simg.data(), M.data(),
+            t.data(), shading, shading_grad, sgm->width(), sgm->height(),
+            sgm->begin(), &o, depth->begin(), normals->begin(), light, &st));
 
     /* ---- what optimize() leaves behind -------------------------------- */
     /* the final surface, for get_depth() / get_normals(): the grid geometry

@@ -3,11 +3,12 @@
  *
  * Drop-in body for smvs::StereoView::set_scale (reference:
  * lib/stereo_view.cc:24-46, with initialize_image_gradients :48-62 and
- * compute_gradients_and_hessian :97-188): Gaussian blur + gradient / Hessian
- * images of a single-channel view on the GPU through smvsb_view_set_scale,
- * results written into the members every other reference function reads
- * (scaleimage, image_grad, image_hessian). Colour images and the debug
- * variant keep the reference's own body. lib/stereo_view.h untouched.
+ * compute_gradients_and_hessian :97-188): Gaussian blur (+ luminance of a
+ * colour view) + gradient / Hessian images on the GPU through
+ * smvsb_view_set_scale_c, results written into the members every other
+ * reference function reads (scaleimage, image_grad, image_hessian). Images
+ * with 2 or 4 channels and the debug variant keep the reference's own body.
+ * lib/stereo_view.h untouched.
  */
 #include "stereo_view.h"
 
@@ -25,19 +26,20 @@ StereoView::set_scale (int scale, bool debug)
 {
     /* whatever a context of this thread holds of older images is stale now */
     smvs_b200_integration::views_generation() += 1;
-    if (debug || this->image->channels() != 1)
+    int const ch = this->image->channels();
+    if (debug || (ch != 1 && ch != 3))
     {
         smvs_ref_stereo_view_set_scale(this, scale, debug);
         return;
     }
     smvsb::Context& gpu = smvs_b200_integration::thread_context();
     int const w = this->image->width(), h = this->image->height();
-    this->scaleimage = mve::FloatImage::create(w, h, 1);
+    this->scaleimage = mve::FloatImage::create(w, h, ch);
     this->image_grad = mve::FloatImage::create(w, h, 2);
     this->image_hessian = mve::FloatImage::create(w, h, 3);
-    gpu.check(smvsb_view_set_scale(gpu.get(), w, h, this->image->begin(),
-        scale, this->scaleimage->begin(), this->image_grad->begin(),
-        this->image_hessian->begin()));
+    gpu.check(smvsb_view_set_scale_c(gpu.get(), w, h, ch,
+        this->image->begin(), scale, this->scaleimage->begin(),
+        this->image_grad->begin(), this->image_hessian->begin()));
     this->view->cache_cleanup();
 }
 

@@ -98,9 +98,12 @@ class RefScene:
         return out
 
     def scaleimage(self, v):
-        out = np.empty((self.h, self.w), dtype=np.float32)
+        """StereoView::get_scaleimage(): the blurred image with all its channels."""
+        im = self.scene.images[v]
+        ch = 1 if im.ndim == 2 else im.shape[2]
+        out = np.empty((self.h, self.w, ch), dtype=np.float32)
         self.L.ref_view_get_scaleimage(self.h_, v, _p(out))
-        return out
+        return out[:, :, 0] if ch == 1 else out
 
     def shading(self):
         img = np.empty((self.h, self.w), dtype=np.float32)

@@ -28,7 +28,7 @@ EXPORTS = [
     "smvsb_bilateral_filter", "smvsb_debug_expf", "smvsb_device_count", "smvsb_cut_depth_maps", "smvsb_surface_create", "smvsb_surface_subdivide",
     "smvsb_surface_fill_from_depth", "smvsb_surface_remove_isolated", "smvsb_surface_expand", "smvsb_surface_info",
     "smvsb_set_color_images",
-    "smvsb_optimize", "smvsb_measure_fp64_peak", "smvsb_sgm_reconstruct", "smvsb_newton_loop_batch", "smvsb_device_launch_count",
+    "smvsb_optimize", "smvsb_optimize_rgb_f32", "smvsb_view_set_scale_c", "smvsb_measure_fp64_peak", "smvsb_sgm_reconstruct", "smvsb_newton_loop_batch", "smvsb_device_launch_count",
 ]
 
 
@@ -192,15 +192,16 @@ class Context:
         self.n_patches = npx * npy
 
     def view_set_scale(self, image, scale):
-        """StereoView::set_scale of one single-channel float image:
-        (scaleimage, gradients, hessian) as host arrays."""
+        """StereoView::set_scale of one float image, (h, w) single channel or
+        (h, w, 3) colour: (scaleimage, gradients, hessian) as host arrays."""
         img = np.ascontiguousarray(image, dtype=np.float32)
-        h, w = img.shape
-        blur = np.empty((h, w), dtype=np.float32)
+        h, w = img.shape[:2]
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        blur = np.empty(img.shape, dtype=np.float32)
         grad = np.empty((h, w, 2), dtype=np.float32)
         hess = np.empty((h, w, 3), dtype=np.float32)
-        self._check(lib().smvsb_view_set_scale(self._h, w, h, _p(img), int(scale),
-                                               _p(blur), _p(grad), _p(hess)))
+        self._check(lib().smvsb_view_set_scale_c(self._h, w, h, ch, _p(img), int(scale),
+                                                 _p(blur), _p(grad), _p(hess)))
         return blur, grad, hess
 
     def bilateral_filter(self, guide, depth, sigma=5.0, kernel_size=5):
@@ -489,12 +490,16 @@ class OptimizeStats(C.Structure):
 def optimize(ctx, main_img, sub_imgs, Mi, ti, flen_px, inv_flen, inv_calib9, sgm_depth,
              regularization=0.01, num_iterations=5, min_scale=2, shading=None,
              shading_grad=None, light_surf_regularization=0.0, full_optimization=False):
-    """smvsb_optimize: DepthOptimizer::optimize() of one view, resident on the
-    device. Returns (depth, normals, light16, stats dict)."""
-    main_img = _u8(main_img)
-    h, w = main_img.shape
+    """smvsb_optimize / smvsb_optimize_rgb_f32: DepthOptimizer::optimize() of
+    one view, resident on the device. Images: (h, w) bytes, or (h, w, 3) float
+    RGB in [0, 1] for colour views. Returns (depth, normals, light16, stats
+    dict)."""
+    colour = np.asarray(main_img).ndim == 3
+    conv = _f32 if colour else _u8          # colour: float RGB as get_image() holds it
+    main_img = conv(main_img)
+    h, w = main_img.shape[:2]
     n = len(sub_imgs)
-    si = [_u8(a) for a in sub_imgs]
+    si = [conv(a) for a in sub_imgs]
     sw = (C.c_int * n)(*[a.shape[1] for a in si])
     shh = (C.c_int * n)(*[a.shape[0] for a in si])
     ip = (C.c_void_p * n)(*[a.ctypes.data for a in si])
@@ -508,7 +513,8 @@ def optimize(ctx, main_img, sub_imgs, Mi, ti, flen_px, inv_flen, inv_calib9, sgm
     normals = np.empty((h, w, 3), dtype=np.float32)
     light = np.zeros(16, dtype=np.float64)
     st = OptimizeStats()
-    ctx._check(lib().smvsb_optimize(
+    fn = lib().smvsb_optimize_rgb_f32 if colour else lib().smvsb_optimize
+    ctx._check(fn(
         ctx._h, w, h, C.c_double(flen_px), C.c_double(inv_flen), _p(k), _p(main_img), n,
         sw, shh, ip, _p(Mi), _p(ti), _p(sh), _p(shg), sgm.shape[1], sgm.shape[0], _p(sgm),
         C.byref(opts), _p(depth), _p(normals), _p(light), C.byref(st)))

@@ -21,6 +21,9 @@ void device_shading_inputs (smvsb_ctx* c, uint8_t const* img_dev, int w, int h,
     float* shading_dev, float* shading_grad_dev);
 void device_set_scale_float (smvsb_ctx* c, float const* img_dev, int w, int h,
     int scale, float* tmp_a, float* tmp_b, float* out_dev);
+void device_set_scale_rgb (smvsb_ctx* c, float const* img_dev, int w, int h,
+    int scale, float* tmp_a, float* tmp_b, int mode, float* out_dev,
+    float* blur_out);
 void device_bilateral_filter (smvsb_ctx* c, float const* ci_dev, int w, int h,
     int channels, float const* dm_dev, int dm_w, int dm_h, float sigma,
     int kernel_size, float* out_dev);
@@ -377,26 +380,35 @@ surface_subdivide_device (smvsb_ctx* c)
     refresh_validity(c);
 }
 
-/* StereoView::set_scale of all views from the byte images kept on the
- * device (smvsb_optimize). */
+/* StereoView::set_scale of all views from the images kept on the device
+ * (smvsb_optimize): single-channel byte images, or three-channel float
+ * images (StereoView::get_image() of a colour view) in the colour buffers. */
 void
-views_from_resident_u8 (smvsb_ctx* c, int scale)
+views_from_resident (smvsb_ctx* c, int scale, bool colour)
 {
     size_t max_pix = static_cast<size_t>(c->w) * c->h;
     for (int k = 0; k < c->n_sub; ++k)
         max_pix = std::max(max_pix, static_cast<size_t>(c->subs[k].w)
             * c->subs[k].h);
-    c->stage_a.reserve(max_pix);
+    c->stage_a.reserve(max_pix * (colour ? 3 : 1));
     c->stage_b.reserve(max_pix);
     c->main_grad.reserve(static_cast<size_t>(c->w) * c->h * 2);
-    smvsb::device_set_scale(c, c->u8_main.p, c->w, c->h, scale, c->stage_a.p,
-        c->stage_b.p, 0, c->main_grad.p);
+    if (colour)
+        smvsb::device_set_scale_rgb(c, c->color_main.p, c->w, c->h, scale,
+            c->stage_a.p, c->stage_b.p, 0, c->main_grad.p, nullptr);
+    else
+        smvsb::device_set_scale(c, c->u8_main.p, c->w, c->h, scale,
+            c->stage_a.p, c->stage_b.p, 0, c->main_grad.p);
     for (int k = 0; k < c->n_sub; ++k)
     {
         smvsb::SubViewDev& sv = c->subs[k];
         sv.texels.reserve(static_cast<size_t>(sv.w) * sv.h * SMVSB_NB_STRIDE);
-        smvsb::device_set_scale(c, c->u8_subs[k].p, sv.w, sv.h, scale,
-            c->stage_a.p, c->stage_b.p, 1, sv.texels.p);
+        if (colour)
+            smvsb::device_set_scale_rgb(c, c->color_subs[k].p, sv.w, sv.h,
+                scale, c->stage_a.p, c->stage_b.p, 1, sv.texels.p, nullptr);
+        else
+            smvsb::device_set_scale(c, c->u8_subs[k].p, sv.w, sv.h, scale,
+                c->stage_a.p, c->stage_b.p, 1, sv.texels.p);
     }
     c->have_system = false;
 }
@@ -751,29 +763,43 @@ smvsb_debug_get_view (smvsb_ctx* ctx, int view, float* grad, float* hess)
 }
 
 int
-smvsb_view_set_scale (smvsb_ctx* ctx, int w, int h, const float* image,
-    int scale, float* scaleimage, float* grad, float* hess)
+smvsb_view_set_scale_c (smvsb_ctx* ctx, int w, int h, int channels,
+    const float* image, int scale, float* scaleimage, float* grad,
+    float* hess)
 {
     if (ctx == nullptr) return SMVSB_ERR_INVALID;
     return guarded(ctx, [&]() {
         smvsb_ctx* c = ctx;
         require(w >= 3 && h >= 3 && image != nullptr, SMVSB_ERR_INVALID,
             "image missing or smaller than 3x3");
+        require(channels == 1 || channels == 3, SMVSB_ERR_INVALID,
+            "1 or 3 channels");
         require(scale >= 0 && scale <= 8, SMVSB_ERR_INVALID,
             "scale out of range");
         size_t const n = static_cast<size_t>(w) * h;
-        c->stage_a.reserve(n);
+        size_t const nc = n * channels;
+        c->stage_a.reserve(nc);
         c->stage_b.reserve(n);
-        c->view_in.reserve(n);
+        c->view_in.reserve(nc);
         c->view_texels.reserve(n * SMVSB_NB_STRIDE);
         c->view_out.reserve(n * 5);
-        CUDA_CHECK(cudaMemcpyAsync(c->view_in.p, image, n * sizeof(float),
+        CUDA_CHECK(cudaMemcpyAsync(c->view_in.p, image, nc * sizeof(float),
             cudaMemcpyHostToDevice, c->stream));
-        smvsb::device_set_scale_float(c, c->view_in.p, w, h, scale,
-            c->stage_a.p, c->stage_b.p, c->view_texels.p);
+        float const* blurred = c->stage_b.p;
+        if (channels == 1)
+            smvsb::device_set_scale_float(c, c->view_in.p, w, h, scale,
+                c->stage_a.p, c->stage_b.p, c->view_texels.p);
+        else
+        {
+            /* the blurred colour image overwrites the input copy */
+            smvsb::device_set_scale_rgb(c, c->view_in.p, w, h, scale,
+                c->stage_a.p, c->stage_b.p, 1, c->view_texels.p,
+                (scaleimage != nullptr) ? c->view_in.p : nullptr);
+            blurred = c->view_in.p;
+        }
         if (scaleimage != nullptr)
-            CUDA_CHECK(cudaMemcpyAsync(scaleimage, c->stage_b.p,
-                n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaMemcpyAsync(scaleimage, blurred,
+                nc * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
         if (grad != nullptr || hess != nullptr)
         {
             smvsb::device_unpack_texels(c, c->view_texels.p,
@@ -787,6 +813,14 @@ smvsb_view_set_scale (smvsb_ctx* ctx, int w, int h, const float* image,
         }
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
     });
+}
+
+int
+smvsb_view_set_scale (smvsb_ctx* ctx, int w, int h, const float* image,
+    int scale, float* scaleimage, float* grad, float* hess)
+{
+    return smvsb_view_set_scale_c(ctx, w, h, 1, image, scale, scaleimage,
+        grad, hess);
 }
 
 int
@@ -1270,14 +1304,18 @@ smvsb_surface_info (smvsb_ctx* ctx, int* info6)
  * resident on the device from the SGM initialisation to the depth and normal
  * maps.
  */
-int
-smvsb_optimize (smvsb_ctx* ctx, int w, int h, double flen_px, double inv_flen,
-    const float* inv_calib9, const uint8_t* main_img, int n_sub,
-    const int* sub_w, const int* sub_h, const uint8_t* const* sub_img,
-    const double* Mi, const double* ti, const float* shading,
-    const float* shading_grad, int sgm_w, int sgm_h, const float* sgm_depth,
-    const smvsb_optimize_options* opts, float* depth_out, float* normals_out,
-    double* light16_out, smvsb_optimize_stats* stats_out)
+/* The body of smvsb_optimize / smvsb_optimize_f32. colour: the images are
+ * three-channel float images (StereoView::get_image() of a colour view),
+ * otherwise single-channel bytes. */
+static int
+optimize_resident (smvsb_ctx* ctx, int w, int h, double flen_px,
+    double inv_flen, const float* inv_calib9, bool colour,
+    const void* main_img, int n_sub, const int* sub_w, const int* sub_h,
+    const void* const* sub_img, const double* Mi, const double* ti,
+    const float* shading, const float* shading_grad, int sgm_w, int sgm_h,
+    const float* sgm_depth, const smvsb_optimize_options* opts,
+    float* depth_out, float* normals_out, double* light16_out,
+    smvsb_optimize_stats* stats_out)
 {
     if (ctx == nullptr) return SMVSB_ERR_INVALID;
     return guarded(ctx, [&]() {
@@ -1302,7 +1340,14 @@ smvsb_optimize (smvsb_ctx* ctx, int w, int h, double flen_px, double inv_flen,
         c->n_sub = n_sub;
         c->have_surface = false;
         size_t const npix = static_cast<size_t>(w) * h;
-        upload(c, c->u8_main, main_img, npix);
+        c->have_color = false;
+        if (colour)
+            upload(c, c->color_main, static_cast<float const*>(main_img),
+                npix * 3);
+        else
+            upload(c, c->u8_main, static_cast<uint8_t const*>(main_img), npix);
+        std::vector<float const*> colour_ptrs(n_sub + 1, nullptr);
+        colour_ptrs[0] = c->color_main.p;
         std::vector<float const*> ptrs(n_sub, nullptr);
         std::vector<int> dims(2 * n_sub, 0);
         std::vector<double> mt(12 * n_sub, 0.0);
@@ -1311,7 +1356,15 @@ smvsb_optimize (smvsb_ctx* ctx, int w, int h, double flen_px, double inv_flen,
             require(sub_w[k] > 2 && sub_h[k] > 2 && sub_img[k],
                 SMVSB_ERR_INVALID, "neighbour image missing");
             size_t const n = static_cast<size_t>(sub_w[k]) * sub_h[k];
-            upload(c, c->u8_subs[k], sub_img[k], n);
+            if (colour)
+            {
+                upload(c, c->color_subs[k],
+                    static_cast<float const*>(sub_img[k]), n * 3);
+                colour_ptrs[k + 1] = c->color_subs[k].p;
+            }
+            else
+                upload(c, c->u8_subs[k],
+                    static_cast<uint8_t const*>(sub_img[k]), n);
             smvsb::SubViewDev& sv = c->subs[k];
             sv.w = sub_w[k]; sv.h = sub_h[k];
             sv.texels.reserve(n * SMVSB_NB_STRIDE);
@@ -1323,6 +1376,11 @@ smvsb_optimize (smvsb_ctx* ctx, int w, int h, double flen_px, double inv_flen,
         upload(c, c->sub_ptrs, ptrs.data(), ptrs.size());
         upload(c, c->sub_dims, dims.data(), dims.size());
         upload(c, c->Mt, mt.data(), mt.size());
+        if (colour)
+        {
+            upload(c, c->color_ptrs, colour_ptrs.data(), colour_ptrs.size());
+            c->have_color = true;
+        }
         c->have_shading = (shading != nullptr);
         if (c->have_shading)
         {
@@ -1340,17 +1398,22 @@ smvsb_optimize (smvsb_ctx* ctx, int w, int h, double flen_px, double inv_flen,
         {
             /* depthmap_bilateral_filter(sgm depth, main image), :42 */
             size_t const nd = static_cast<size_t>(sgm_w) * sgm_h;
-            c->guide.reserve(npix);
-            smvsb::device_byte_to_float(c, c->u8_main.p, npix, c->guide.p);
+            float const* guide = c->color_main.p;
+            if (!colour)
+            {
+                c->guide.reserve(npix);
+                smvsb::device_byte_to_float(c, c->u8_main.p, npix, c->guide.p);
+                guide = c->guide.p;
+            }
             c->view_in.reserve(nd);
             CUDA_CHECK(cudaMemcpyAsync(c->view_in.p, sgm_depth,
                 nd * sizeof(float), cudaMemcpyHostToDevice, c->stream));
             c->sgm_depth.reserve(npix);
-            smvsb::device_bilateral_filter(c, c->guide.p, w, h, 1,
+            smvsb::device_bilateral_filter(c, guide, w, h, colour ? 3 : 1,
                 c->view_in.p, sgm_w, sgm_h, 5.0f, 5, c->sgm_depth.p);
         }
         surface_create_device(c, init_scale, c->sgm_depth.p);
-        views_from_resident_u8(c, c->scale);
+        views_from_resident(c, c->scale, colour);
 
         bool have_light = false;
         double light[16];
@@ -1407,7 +1470,7 @@ smvsb_optimize (smvsb_ctx* ctx, int w, int h, double flen_px, double inv_flen,
         while (c->scale > opts->min_scale && c->scale > 0)
         {
             surface_subdivide_device(c);                     /* :90 */
-            views_from_resident_u8(c, c->scale);             /* :91-95 */
+            views_from_resident(c, c->scale, colour);             /* :91-95 */
             smvsb::topo_fill_from_depth(c);                  /* :99 */
             refresh_validity(c);
             if (opts->use_shading && c->scale < 4)           /* :102-109 */
@@ -1447,6 +1510,39 @@ smvsb_optimize (smvsb_ctx* ctx, int w, int h, double flen_px, double inv_flen,
         st.patches = smvsb::topo_count_patches(c);
         if (stats_out) *stats_out = st;
     });
+}
+
+int
+smvsb_optimize (smvsb_ctx* ctx, int w, int h, double flen_px, double inv_flen,
+    const float* inv_calib9, const uint8_t* main_img, int n_sub,
+    const int* sub_w, const int* sub_h, const uint8_t* const* sub_img,
+    const double* Mi, const double* ti, const float* shading,
+    const float* shading_grad, int sgm_w, int sgm_h, const float* sgm_depth,
+    const smvsb_optimize_options* opts, float* depth_out, float* normals_out,
+    double* light16_out, smvsb_optimize_stats* stats_out)
+{
+    return optimize_resident(ctx, w, h, flen_px, inv_flen, inv_calib9, false,
+        main_img, n_sub, sub_w, sub_h,
+        reinterpret_cast<const void* const*>(sub_img), Mi, ti, shading,
+        shading_grad, sgm_w, sgm_h, sgm_depth, opts, depth_out, normals_out,
+        light16_out, stats_out);
+}
+
+int
+smvsb_optimize_rgb_f32 (smvsb_ctx* ctx, int w, int h, double flen_px,
+    double inv_flen, const float* inv_calib9, const float* main_rgb,
+    int n_sub, const int* sub_w, const int* sub_h,
+    const float* const* sub_rgb, const double* Mi, const double* ti,
+    const float* shading, const float* shading_grad, int sgm_w, int sgm_h,
+    const float* sgm_depth, const smvsb_optimize_options* opts,
+    float* depth_out, float* normals_out, double* light16_out,
+    smvsb_optimize_stats* stats_out)
+{
+    return optimize_resident(ctx, w, h, flen_px, inv_flen, inv_calib9, true,
+        main_rgb, n_sub, sub_w, sub_h,
+        reinterpret_cast<const void* const*>(sub_rgb), Mi, ti, shading,
+        shading_grad, sgm_w, sgm_h, sgm_depth, opts, depth_out, normals_out,
+        light16_out, stats_out);
 }
 
 int

@@ -84,6 +84,70 @@ blur_y_kernel (float const* __restrict__ in, int w, int h,
     out[static_cast<size_t>(y) * w + x] = __fdiv_rn(acc, k.wsum);
 }
 
+/* Colour views (mve::image::blur_gaussian works channel by channel on the
+ * interleaved image, StereoView::initialize_image_gradients desaturates the
+ * blurred image, lib/stereo_view.cc:24-62): x pass over the three interleaved
+ * channels ... */
+__global__ void
+blur_x_rgb_kernel (float const* __restrict__ img, int w, int h,
+    BlurKernel const k, float* __restrict__ out)
+{
+    int const x = blockIdx.x * blockDim.x + threadIdx.x;
+    int const y = blockIdx.y;
+    if (x >= w)
+        return;
+    float const* row = img + static_cast<size_t>(y) * w * 3;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+    for (int i = -k.ks; i <= k.ks; ++i)
+    {
+        int const xi = min(max(x + i, 0), w - 1);
+        float const wgt = k.w[abs(i)];
+        a0 = __fadd_rn(a0, __fmul_rn(row[3 * xi + 0], wgt));
+        a1 = __fadd_rn(a1, __fmul_rn(row[3 * xi + 1], wgt));
+        a2 = __fadd_rn(a2, __fmul_rn(row[3 * xi + 2], wgt));
+    }
+    float* o = out + (static_cast<size_t>(y) * w + x) * 3;
+    o[0] = __fdiv_rn(a0, k.wsum);
+    o[1] = __fdiv_rn(a1, k.wsum);
+    o[2] = __fdiv_rn(a2, k.wsum);
+}
+
+/* ... y pass, then mve::image::desaturate<float>(DESATURATE_LUMINANCE):
+ * v0 * 0.21f + v1 * 0.72f + v2 * 0.07f, evaluated left to right. The blurred
+ * colour image (StereoView::scaleimage) is written when asked for. */
+__global__ void
+blur_y_rgb_desaturate_kernel (float const* __restrict__ in, int w, int h,
+    BlurKernel const k, float* __restrict__ gray,
+    float* __restrict__ blur_out)
+{
+    int const x = blockIdx.x * blockDim.x + threadIdx.x;
+    int const y = blockIdx.y;
+    if (x >= w)
+        return;
+    float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+    for (int i = -k.ks; i <= k.ks; ++i)
+    {
+        int const yi = min(max(y + i, 0), h - 1);
+        float const* p = in + (static_cast<size_t>(yi) * w + x) * 3;
+        float const wgt = k.w[abs(i)];
+        a0 = __fadd_rn(a0, __fmul_rn(p[0], wgt));
+        a1 = __fadd_rn(a1, __fmul_rn(p[1], wgt));
+        a2 = __fadd_rn(a2, __fmul_rn(p[2], wgt));
+    }
+    float const v0 = __fdiv_rn(a0, k.wsum);
+    float const v1 = __fdiv_rn(a1, k.wsum);
+    float const v2 = __fdiv_rn(a2, k.wsum);
+    size_t const pix = static_cast<size_t>(y) * w + x;
+    if (blur_out != nullptr)
+    {
+        blur_out[3 * pix + 0] = v0;
+        blur_out[3 * pix + 1] = v1;
+        blur_out[3 * pix + 2] = v2;
+    }
+    gray[pix] = __fadd_rn(__fadd_rn(__fmul_rn(v0, 0.21f),
+        __fmul_rn(v1, 0.72f)), __fmul_rn(v2, 0.07f));
+}
+
 __global__ void
 byte_to_float_kernel (uint8_t const* __restrict__ img, int n,
     float* __restrict__ out)
@@ -464,6 +528,28 @@ device_set_scale_float (smvsb_ctx* c, float const* img_dev, int w, int h,
     blur_y_kernel<<<grid, block, 0, c->stream>>>(tmp_a, w, h, k, tmp_b);
     CUDA_CHECK(cudaGetLastError());
     grad_hess_kernel<<<grid, block, 0, c->stream>>>(tmp_b, w, h, 1, out_dev);
+    CUDA_CHECK(cudaGetLastError());
+    count_launches(c, 3);
+}
+
+/* StereoView::set_scale of a three-channel float image on the device
+ * (w*h*3, interleaved). tmp_a: w*h*3 floats, tmp_b: w*h floats (receives the
+ * desaturated blurred image); mode as in grad_hess_kernel; blur_out: the
+ * blurred colour image (w*h*3) or null. */
+void
+device_set_scale_rgb (smvsb_ctx* c, float const* img_dev, int w, int h,
+    int scale, float* tmp_a, float* tmp_b, int mode, float* out_dev,
+    float* blur_out)
+{
+    BlurKernel const k = make_blur_kernel(scale);
+    dim3 const block(128, 1), grid((w + 127) / 128, h);
+    blur_x_rgb_kernel<<<grid, block, 0, c->stream>>>(img_dev, w, h, k, tmp_a);
+    CUDA_CHECK(cudaGetLastError());
+    blur_y_rgb_desaturate_kernel<<<grid, block, 0, c->stream>>>(tmp_a, w, h,
+        k, tmp_b, blur_out);
+    CUDA_CHECK(cudaGetLastError());
+    grad_hess_kernel<<<grid, block, 0, c->stream>>>(tmp_b, w, h, mode,
+        out_dev);
     CUDA_CHECK(cudaGetLastError());
     count_launches(c, 3);
 }

@@ -155,6 +155,30 @@ def test_device_set_scale_bitwise(w, h):
             assert np.array_equal(a["g"], b["g"]) and np.array_equal(a["Hvals"], b["Hvals"])
 
 
+@pytest.mark.gpu
+def test_view_set_scale_colour_bitwise():
+    """smvsb_view_set_scale_c on three-channel views: channel-wise Gaussian
+    blur, luminance of the blurred image, gradient / Hessian stencil
+    (lib/stereo_view.cc:24-62) -- scaleimage, gradients and Hessian bitwise
+    the compiled reference's."""
+    from util_scene import colour_scene
+    sc = colour_scene(333, 207, 2, 71)
+    R = oref.RefScene(sc)
+    try:
+        with api.Context(0) as ctx:
+            for scale in (0, 2, 3, 5):
+                R.set_scale(scale)
+                for v in range(3):
+                    img = R.image(v)
+                    assert img.shape == (207, 333, 3)
+                    blur, grad, hess = ctx.view_set_scale(img, scale)
+                    assert np.array_equal(blur, R.scaleimage(v)), (scale, v)
+                    assert np.array_equal(grad, R.gradients(v)), (scale, v)
+                    assert np.array_equal(hess, R.hessian(v)), (scale, v)
+    finally:
+        R.close()
+
+
 def test_view_set_scale_bitwise():
     """smvsb_view_set_scale (one StereoView::set_scale, host image in, host
     images out -- what the drop-in member calls) against the numpy mirror."""

@@ -187,3 +187,30 @@ def test_resident_optimize_matches_reference(shading):
         assert rel.max() < 1e-4, rel.max()
         assert np.abs(n - n_cpu)[m].max() < 1e-3
         assert np.max(np.abs(light - l_cpu)) / np.max(np.abs(l_cpu)) < 1e-4
+
+
+def test_resident_optimize_colour_views():
+    """smvsb_optimize_rgb_f32: three-channel views (what real MVE scenes hold)
+    through the resident optimize() -- set_scale blurs the channels and
+    desaturates, the SGM depth is filtered with the colour image as guide --
+    against the compiled reference on the same colour scene."""
+    from util_scene import colour_scene
+    sc = colour_scene(640, 480, 3, 91)
+    R = oref.RefScene(sc)
+    d_cpu, n_cpu, _ = R.optimize(sc.init_depth, regularization=0.01, num_iterations=5,
+                                 min_scale=2, use_shading=False)
+    Mi, ti = R.Mt()
+    sgm = R.sgm_roundtrip(sc.init_depth)
+    imgs = [R.image(v) for v in range(4)]            # StereoView::get_image()
+    assert imgs[0].shape == (480, 640, 3)
+    with api.Context(0) as ctx:
+        d, n, _, st = api.optimize(ctx, imgs[0], imgs[1:], Mi, ti, R.flen(0),
+                                   R.inverse_flen(0), R.inverse_calibration(), sgm)
+    R.close()
+    assert st["final_scale"] == 2 and st["scales"] >= 3 and st["newton_steps"] > 5
+    assert np.array_equal(d_cpu > 0, d > 0)
+    m = d_cpu > 0
+    assert m.mean() > 0.5
+    rel = np.abs(d[m] - d_cpu[m]) / d_cpu[m]
+    assert rel.max() < 1e-4, rel.max()
+    assert np.abs(n - n_cpu)[m].max() < 1e-3

@@ -7,6 +7,8 @@ import pytest
 from smvs_b200 import api, synth
 from oracle import ref as oref
 
+from util_scene import colour_scene
+
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")]
 
@@ -85,22 +87,6 @@ def test_visibility_and_cut_parity(width, height, n_sub, scale, seed):
     # the scene must actually exercise the rules
     assert st["removed"] > 0 or st["partial"] > 0
     assert sum(st["cuts"]) > 0
-
-
-def colour_scene(width, height, n_sub, seed_index):
-    """Three different channels per view (the NCC filter works on colour)."""
-    import copy
-    sc = synth.make_scene(width, height, n_sub, seed_index=seed_index)
-    col = copy.copy(sc)
-    rng = np.random.default_rng(seed_index)
-    imgs = []
-    for im in sc.images:
-        f = im.astype(np.float32)
-        chans = [np.clip(f * g + o + rng.normal(0, 2.0, f.shape), 0, 255)
-                 for g, o in ((1.0, 0.0), (0.8, 20.0), (1.1, -10.0))]
-        imgs.append(np.stack(chans, axis=2).astype(np.uint8))
-    col.images = imgs
-    return col
 
 
 @pytest.mark.parametrize("width,height,n_sub,scale,seed", [

@@ -10,6 +10,22 @@ from smvs_b200 import api, synth
 from oracle import ref as oref
 
 
+def colour_scene(width, height, n_sub, seed_index, shading=False):
+    """Three different channels per view (the NCC filter works on colour)."""
+    import copy
+    sc = synth.make_scene(width, height, n_sub, seed_index=seed_index, shading=shading)
+    col = copy.copy(sc)
+    rng = np.random.default_rng(seed_index)
+    imgs = []
+    for im in sc.images:
+        f = im.astype(np.float32)
+        chans = [np.clip(f * g + o + rng.normal(0, 2.0, f.shape), 0, 255)
+                 for g, o in ((1.0, 0.0), (0.8, 20.0), (1.1, -10.0))]
+        imgs.append(np.stack(chans, axis=2).astype(np.uint8))
+    col.images = imgs
+    return col
+
+
 class Pair:
     """Reference scene + (optionally) a GPU context fed with the reference's
     own prepared arrays at one scale."""
