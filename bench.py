@@ -314,12 +314,13 @@ def _system_blocks_full(wl):
 # named below (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on.sum of
 # one launch / its samples). This is the basis-space formulation's work -- the
 # reference's 16-wide rank-1 formulation would be ~20 kFLOP.
-# Captured launch: 6.195e9 DFMA + 3.090e9 DMUL + 1.646e9 DADD thread instructions
-# for 118 326 processed patches x 16 pixels. 43 % of the fp64 instructions are not
+# Captured launch (final kernel of round 2, divisions by d, d^2, d^4 through one
+# reciprocal): 5.074e9 DFMA + 3.088e9 DMUL + 1.563e9 DADD thread instructions for
+# 118 326 processed patches x 16 pixels. 48 % of the fp64 instructions are not
 # fused (the bitwise-parity arithmetic), so the pipe is busier than the flop rate
 # says: `pipe_frac` counts instructions against the DFMA issue rate.
-K1_FLOP_PER_PIXEL_ITER = 17.126e9 / (118326 * 16)           # 9046
-K1_FP64_INSTR_PER_PIXEL_ITER = 10.931e9 / (118326 * 16)     # 5774
+K1_FLOP_PER_PIXEL_ITER = 14.798e9 / (118326 * 16)           # 7816
+K1_FP64_INSTR_PER_PIXEL_ITER = 9.725e9 / (118326 * 16)      # 5137
 K1_FLOP_SOURCE = "profiles/r2_k1.txt"
 
 # DRAM bytes per 4x4 block and CG iteration of cg_kernel, from the ncu --set
