@@ -327,7 +327,7 @@ K1_FLOP_SOURCE = "profiles/r2_k1.txt"
 # full capture named below (dram__bytes_read.sum + dram__bytes_write.sum of a
 # 200-iteration launch on the full system / (200 x its blocks)): H only, the
 # preconditioner and the vectors stay in L2.
-CG_DRAM_BYTES_PER_BLOCK_ITER = (26.800e9 + 0.362e9) / (200.0 * 1067206)   # 127.3
+CG_DRAM_BYTES_PER_BLOCK_ITER = (26.721e9 + 0.250e9) / (200.0 * 1067206)   # 126.4
 CG_TRAFFIC_SOURCE = "profiles/r2_cg.txt"
 
 

@@ -6,11 +6,11 @@ LIB=${1:-smvs_b200/libsmvs_b200.so}
 echo "# cuobjdump -sass $LIB | per-kernel counts of the instructions the design relies on"
 echo "# UBLKCP = cp.async.bulk (TMA engine, 1-D bulk copy), SYNCS = mbarrier, LDG.E.NA.EFL2.256 = 256-bit"
 echo "# no-L1-allocate evict-first load, VIMNMX3 / VIADDMNMX = DPX 16x2 min, HSET2 / HFMA2 = fp16x2 census,"
-echo "# DFMA = fp64 FMA, REDUX / CREDUX = warp reduction to a uniform register, MEMBAR.SC.GPU = grid barrier fence"
+echo "# DFMA = fp64 FMA, REDUX / CREDUX = warp reduction to a uniform register; grid barrier of cg_kernel: MEMBAR.ALL.GPU + REDG.E.ADD.STRONG.GPU (red.release.gpu), LDG.E.STRONG.GPU + CCTL.IVALL (ld.acquire.gpu)"
 cuobjdump -sass "$LIB" 2>/dev/null | awk '
 /Function : /{name=$3; sub(/^_ZN5smvsb/,"",name); next}
 {
-  n=split("UBLKCP UTMALDG SYNCS LDG.E.NA.EFL2.256 LDG.E.128 VIMNMX3 VIADDMNMX HSET2 HFMA2 DFMA DADD DMUL REDUX MEMBAR.SC.GPU ATOMG RED.E", pats, " ")
+  n=split("UBLKCP UTMALDG SYNCS LDG.E.NA.EFL2.256 LDG.E.128 VIMNMX3 VIADDMNMX HSET2 HFMA2 DFMA DADD DMUL REDUX MEMBAR.ALL.GPU REDG.E.ADD.STRONG.GPU LDG.E.STRONG.GPU CCTL.IVALL ATOMG", pats, " ")
   for (i=1;i<=n;i++) if (index($0, pats[i])>0) cnt[name,pats[i]]++
   names[name]=1
 }
@@ -23,7 +23,7 @@ END{
 }' | sed 's/_GLOBAL__N__[0-9a-f_]*_cu_[0-9a-f]*//' | sort
 echo
 echo "# excerpts"
-for pat in "UBLKCP" "SYNCS.ARRIVE" "LDG.E.NA.EFL2.256" "VIMNMX3.U16x2" "VIADDMNMX.U16x2" "HSET2.BF.LT" "HFMA2" "CREDUX\|REDUX"; do
+for pat in "UBLKCP" "SYNCS.ARRIVE" "REDG.E.ADD.STRONG.GPU" "LDG.E.STRONG.GPU R" "CCTL.IVALL" "LDG.E.NA.EFL2.256" "VIMNMX3.U16x2" "VIADDMNMX.U16x2" "HSET2.BF.LT" "HFMA2" "CREDUX\|REDUX"; do
   echo "## $pat"
   cuobjdump -sass "$LIB" 2>/dev/null | grep -m 3 "$pat" | sed 's/^ *//' | cut -c1-120
 done
