@@ -349,6 +349,8 @@ typedef struct smvsb_optimize_options
     int32_t min_scale;
     int32_t use_shading;
     int32_t full_optimization;
+    int32_t no_sgm;              /* 1: Options::use_sgm = false (--no-sgm) */
+    int32_t reserved;            /* 0 */
 } smvsb_optimize_options;
 
 typedef struct smvsb_optimize_stats
@@ -398,6 +400,13 @@ int smvsb_optimize (smvsb_ctx* ctx, int w, int h, double flen_px,
  * (smvsb_view_set_scale_c), the bilateral filter of the SGM depth is guided
  * by the colour image (lib/depth_optimizer.cc:42, 957-1004); everything else
  * is smvsb_optimize.
+ * With opts->no_sgm the call is optimize() in the use_sgm = false mode:
+ * sgm_depth (then w * h) is the sparse initial depth Surface::create makes of
+ * the bundle's features (lib/surface.cc:43-46, 91-128; 0 = no feature), taken
+ * without the bilateral filter; the ladder starts one scale coarser (:51);
+ * visibility runs the NCC occlusion filter on the colour images (:433-604 with
+ * :795-912), and every outer iteration expands the surface by a ring of
+ * patches before the next visibility / cutting round (:331-339).
  */
 int smvsb_optimize_rgb_f32 (smvsb_ctx* ctx, int w, int h, double flen_px,
     double inv_flen, const float* inv_calib9, const float* main_rgb,

@@ -9,14 +9,17 @@
  * images StereoView::get_image() holds -- what real MVE scenes contain). The
  * depth and normal maps come back, and what optimize() has to leave behind --
  * the two view embeddings (:158-161), the final surface for get_depth() /
- * get_normals(), the fitted lighting -- is put in place. Every other
- * configuration (use_sgm = false with its expansion and NCC filter, views of
- * mixed or other channel counts, debug levels that write intermediate
- * images) runs the reference's own optimize(), whose members are the per-call
+ * get_normals(), the fitted lighting -- is put in place. use_sgm = false
+ * (--no-sgm; colour views and a bundle) takes the same call with the sparse
+ * depth of the bundle's features as initial depth. Every other configuration
+ * (views of mixed or other channel counts, debug levels that write
+ * intermediate images) runs the reference's own optimize(), whose members are the per-call
  * drop-ins of b200_depth_optimizer.cc. lib/depth_optimizer.h is untouched.
  *
  *   SMVSB_MEMBERWISE=1   forces the reference's optimize() (per-member path)
  */
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -45,7 +48,11 @@ DepthOptimizer::optimize (void)
 {
     bool const colour = has_channels(this->main_view, 3);
     int const channels = colour ? 3 : 1;
-    bool resident = this->opts.use_sgm && this->opts.debug_lvl == 0
+    /* use_sgm = false: the NCC filter needs colour views, the initial
+     * surface the bundle's features */
+    bool const no_sgm = !this->opts.use_sgm;
+    bool resident = (!no_sgm || (colour && this->bundle != nullptr))
+        && this->opts.debug_lvl == 0
         && std::getenv("SMVSB_MEMBERWISE") == nullptr
         && has_channels(this->main_view, channels) && !this->sub_views.empty()
         && this->sub_views.size() <= 32;
@@ -94,7 +101,45 @@ DepthOptimizer::optimize (void)
     }
     math::Matrix3f invproj;
     this->main_view->get_camera().fill_inverse_calibration(*invproj, w, h);
-    mve::FloatImage::Ptr sgm = this->main_view->get_sgm_depth();   /* :41 */
+    mve::FloatImage::Ptr sgm;
+    if (no_sgm)
+    {
+        /* the depth image Surface::create makes of the bundle
+         * (lib/surface.cc:43-46 with initialize_depth_from_bundle, :91-128):
+         * every feature the main view observes, projected with the view's
+         * camera in the reference's types and order of operations; its depth
+         * in the pixel it falls into, later features overwrite earlier ones */
+        sgm = mve::FloatImage::create(w, h, 1);
+        sgm->fill(0.0f);
+        mve::CameraInfo const& cam = this->main_view->get_camera();
+        int const view_id = this->main_view->get_view_id();
+        math::Matrix3f const rot(cam.rot);
+        math::Vec3f const trans(cam.trans);
+        float const flen = cam.flen;
+        double const half_w = static_cast<double>(w) / 2.0;
+        double const half_h = static_cast<double>(h) / 2.0;
+        double const norm = static_cast<double>(std::max(w, h));
+        for (mve::Bundle::Feature3D const& feat
+            : this->bundle->get_features())
+            for (mve::Bundle::Feature2D const& ref : feat.refs)
+            {
+                if (ref.view_id != view_id)
+                    continue;
+                math::Vec3f const fpos(feat.pos);
+                math::Vec3f proj = rot * fpos + trans;
+                float const depth = proj[2];
+                proj[0] = proj[0] * flen / proj[2];
+                proj[1] = proj[1] * flen / proj[2];
+                float const ix = proj[0] * norm + half_w;
+                float const iy = proj[1] * norm + half_h;
+                int const x = std::floor(ix), y = std::floor(iy);
+                if (x >= 0 && x < w && y >= 0 && y < h)
+                    sgm->at(x, y, 0) = depth;
+                break;
+            }
+    }
+    else
+        sgm = this->main_view->get_sgm_depth();                     /* :41 */
     bool const lit = this->opts.use_shading;
 
     smvsb_optimize_options o;
@@ -104,6 +149,8 @@ DepthOptimizer::optimize (void)
     o.min_scale = this->opts.min_scale;
     o.use_shading = lit ? 1 : 0;
     o.full_optimization = this->opts.full_optimization ? 1 : 0;
+    o.no_sgm = no_sgm ? 1 : 0;
+    o.reserved = 0;
 
     mve::FloatImage::Ptr depth = mve::FloatImage::create(w, h, 1);
     mve::FloatImage::Ptr normals = mve::FloatImage::create(w, h, 3);

@@ -316,6 +316,19 @@ class RefScene:
                            int(debug_lvl), _p(depth), _p(normals), _p(light))
         return depth, normals, light
 
+    def optimize_nosgm(self, features, regularization=0.01, num_iterations=5, min_scale=2):
+        """DepthOptimizer::optimize() with use_sgm = false: `features` (n, 3)
+        world points the main view observes (the bundle). Returns (sparse
+        initial depth as Surface::create makes it, depth, normals)."""
+        f = np.ascontiguousarray(features, dtype=np.float32)
+        sparse = np.empty((self.h, self.w), dtype=np.float32)
+        depth = np.empty((self.h, self.w), dtype=np.float32)
+        normals = np.empty((self.h, self.w, 3), dtype=np.float32)
+        self.L.ref_optimize_nosgm(self.h_, int(f.shape[0]), _p(f), C.c_double(regularization),
+                                  int(num_iterations), int(min_scale), _p(sparse), _p(depth),
+                                  _p(normals))
+        return sparse, depth, normals
+
     def sgm_roundtrip(self, depth):
         """StereoView::get_sgm_depth() of a depth stored as "smvs-sgm"."""
         d = np.ascontiguousarray(depth, dtype=np.float32)

@@ -875,6 +875,69 @@ ref_optimize (void* scene, float const* sgm_depth, double regularization,
     return 0;
 }
 
+/* DepthOptimizer::optimize() with use_sgm = false (app/smvsrecon.cc's
+ * --no-sgm): the initial surface comes from the bundle's features
+ * (lib/surface.cc:43-46, 91-128). n_feat points `pos3` (world coordinates),
+ * each observed by the main view. sparse_out (w*h, may be NULL) receives the
+ * depth image Surface::create makes of them -- what the resident GPU path is
+ * given as its initial depth. */
+int
+ref_optimize_nosgm (void* scene, int n_feat, float const* pos3,
+    double regularization, int num_iterations, int min_scale,
+    float* sparse_out, float* depth_out, float* normals_out)
+{
+    RefScene* s = static_cast<RefScene*>(scene);
+    mve::Bundle::Ptr bundle = mve::Bundle::create();
+    for (int i = 0; i < n_feat; ++i)
+    {
+        mve::Bundle::Feature3D f;
+        for (int k = 0; k < 3; ++k)
+        {
+            f.pos[k] = pos3[3 * i + k];
+            f.color[k] = 0.5f;
+        }
+        mve::Bundle::Feature2D r;
+        r.view_id = s->main_view->get_view_id();
+        r.feature_id = i;
+        r.pos[0] = r.pos[1] = 0.0f;
+        f.refs.push_back(r);
+        bundle->get_features().push_back(f);
+    }
+    if (sparse_out)
+    {
+        int const w = s->main_view->get_width(), h = s->main_view->get_height();
+        int const init_scale = (int)std::max(std::ceil(std::log2(w * h / 1.7e6)
+            / 2) + 4, 4.0);
+        smvs::Surface::Ptr tmp = smvs::Surface::create(bundle, s->main_view,
+            init_scale + 1);
+        std::copy(tmp->depth->begin(), tmp->depth->end(), sparse_out);
+    }
+    s->opts.regularization = regularization;
+    s->opts.num_iterations = num_iterations;
+    s->opts.min_scale = min_scale;
+    s->opts.use_shading = false;
+    s->opts.use_sgm = false;
+    s->opts.debug_lvl = 0;
+    s->opts.output_name = "smvs-out";
+    s->optimizer.reset(new smvs::DepthOptimizer(s->main_view, s->sub_views,
+        bundle, s->opts));
+    silence_cout(true);
+    s->optimizer->optimize();
+    silence_cout(false);
+    s->opts.use_sgm = true;
+    if (depth_out)
+    {
+        mve::FloatImage::Ptr d = s->optimizer->surface->get_depth_map();
+        std::copy(d->begin(), d->end(), depth_out);
+    }
+    if (normals_out)
+    {
+        mve::FloatImage::Ptr n = s->optimizer->get_normals();
+        std::copy(n->begin(), n->end(), normals_out);
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ */
 /* SGM                                                                */
 /* ------------------------------------------------------------------ */

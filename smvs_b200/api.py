@@ -476,7 +476,8 @@ def measure_fp64_peak(device=0):
 class OptimizeOptions(C.Structure):
     _fields_ = [("regularization", C.c_double), ("light_surf_regularization", C.c_double),
                 ("num_iterations", C.c_int32), ("min_scale", C.c_int32),
-                ("use_shading", C.c_int32), ("full_optimization", C.c_int32)]
+                ("use_shading", C.c_int32), ("full_optimization", C.c_int32),
+                ("no_sgm", C.c_int32), ("reserved", C.c_int32)]
 
 
 class OptimizeStats(C.Structure):
@@ -489,11 +490,13 @@ class OptimizeStats(C.Structure):
 
 def optimize(ctx, main_img, sub_imgs, Mi, ti, flen_px, inv_flen, inv_calib9, sgm_depth,
              regularization=0.01, num_iterations=5, min_scale=2, shading=None,
-             shading_grad=None, light_surf_regularization=0.0, full_optimization=False):
+             shading_grad=None, light_surf_regularization=0.0, full_optimization=False,
+             use_sgm=True):
     """smvsb_optimize / smvsb_optimize_rgb_f32: DepthOptimizer::optimize() of
     one view, resident on the device. Images: (h, w) bytes, or (h, w, 3) float
-    RGB in [0, 1] for colour views. Returns (depth, normals, light16, stats
-    dict)."""
+    RGB in [0, 1] for colour views. use_sgm=False (colour views only): sgm_depth
+    is the sparse initial depth of the bundle's features, (h, w). Returns (depth,
+    normals, light16, stats dict)."""
     colour = np.asarray(main_img).ndim == 3
     conv = _f32 if colour else _u8          # colour: float RGB as get_image() holds it
     main_img = conv(main_img)
@@ -508,7 +511,8 @@ def optimize(ctx, main_img, sub_imgs, Mi, ti, flen_px, inv_flen, inv_calib9, sgm
     sgm = _f32(sgm_depth)
     sh, shg = _f32(shading), _f32(shading_grad)
     opts = OptimizeOptions(regularization, light_surf_regularization, num_iterations,
-                           min_scale, int(shading is not None), int(full_optimization))
+                           min_scale, int(shading is not None), int(full_optimization),
+                           int(not use_sgm), 0)
     depth = np.empty((h, w), dtype=np.float32)
     normals = np.empty((h, w, 3), dtype=np.float32)
     light = np.zeros(16, dtype=np.float64)

@@ -1346,8 +1346,7 @@ optimize_resident (smvsb_ctx* ctx, int w, int h, double flen_px,
                 npix * 3);
         else
             upload(c, c->u8_main, static_cast<uint8_t const*>(main_img), npix);
-        std::vector<float const*> colour_ptrs(n_sub + 1, nullptr);
-        colour_ptrs[0] = c->color_main.p;
+        std::vector<float const*> colour_ptrs(n_sub, nullptr);
         std::vector<float const*> ptrs(n_sub, nullptr);
         std::vector<int> dims(2 * n_sub, 0);
         std::vector<double> mt(12 * n_sub, 0.0);
@@ -1360,7 +1359,7 @@ optimize_resident (smvsb_ctx* ctx, int w, int h, double flen_px,
             {
                 upload(c, c->color_subs[k],
                     static_cast<float const*>(sub_img[k]), n * 3);
-                colour_ptrs[k + 1] = c->color_subs[k].p;
+                colour_ptrs[k] = c->color_subs[k].p;
             }
             else
                 upload(c, c->u8_subs[k],
@@ -1391,10 +1390,25 @@ optimize_resident (smvsb_ctx* ctx, int w, int h, double flen_px,
         c->have_views = true;
 
         /* ---- create_initial_surface, :35-52 --------------------------- */
+        bool const no_sgm = (opts->no_sgm != 0);
+        require(!no_sgm || colour, SMVSB_ERR_INVALID,
+            "no_sgm needs three-channel views (the NCC filter, "
+            "lib/depth_optimizer.cc:795-912, reads channels 0..2)");
+        require(!no_sgm || (sgm_w == w && sgm_h == h), SMVSB_ERR_INVALID,
+            "no_sgm: the initial depth must have the size of the main view");
         int const init_scale = static_cast<int>(std::max(std::ceil(std::log2(
-            w * h / 1.7e6) / 2) + 4, 4.0));
+            w * h / 1.7e6) / 2) + 4, 4.0)) + (no_sgm ? 1 : 0);   /* :37-38, :51 */
         require(init_scale <= 6, SMVSB_ERR_INVALID,
             "image too large: initial scale above 6");
+        if (no_sgm)
+        {
+            /* the sparse depth of the bundle's features (lib/surface.cc:91-128)
+             * as the host projected it */
+            c->sgm_depth.reserve(npix);
+            CUDA_CHECK(cudaMemcpyAsync(c->sgm_depth.p, sgm_depth,
+                npix * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        }
+        else
         {
             /* depthmap_bilateral_filter(sgm depth, main image), :42 */
             size_t const nd = static_cast<size_t>(sgm_w) * sgm_h;
@@ -1426,7 +1440,10 @@ optimize_resident (smvsb_ctx* ctx, int w, int h, double flen_px,
                 if (iter == 0)
                 {
                     /* :189-195 */
-                    smvsb::run_visibility_device(c);
+                    if (no_sgm)
+                        smvsb::run_visibility_ncc(c);
+                    else
+                        smvsb::run_visibility_device(c);
                     refresh_validity(c);
                     for (uint64_t del = ~0ull; del > 10;)
                     {
@@ -1452,6 +1469,20 @@ optimize_resident (smvsb_ctx* ctx, int w, int h, double flen_px,
                 {
                     del = smvsb::run_cut_boundaries(c, inv_calib9);
                     refresh_validity(c);
+                }
+                if (no_sgm)
+                {
+                    /* :331-339: grow the surface by a ring of patches, see
+                     * which neighbours see them, cut again */
+                    smvsb::topo_expand(c);
+                    refresh_validity(c);
+                    smvsb::run_visibility_ncc(c);
+                    refresh_validity(c);
+                    for (uint64_t del = ~0ull; del > 10;)
+                    {
+                        del = smvsb::run_cut_boundaries(c, inv_calib9);
+                        refresh_validity(c);
+                    }
                 }
                 smvsb::topo_remove_isolated(c);
                 refresh_validity(c);

@@ -214,3 +214,65 @@ def test_resident_optimize_colour_views():
     rel = np.abs(d[m] - d_cpu[m]) / d_cpu[m]
     assert rel.max() < 1e-4, rel.max()
     assert np.abs(n - n_cpu)[m].max() < 1e-3
+
+
+def _features_on_surface(sc, n, seed):
+    """World points on the scene's true surface that the main view (identity
+    pose, focal length flen * max(w, h) pixels) sees at random pixels: what a
+    bundle's SfM features are to Surface::create."""
+    rng = np.random.default_rng(seed)
+    w, h = sc.width, sc.height
+    x = rng.integers(8, w - 8, n)
+    y = rng.integers(8, h - 8, n)
+    d = sc.true_depth[y, x].astype(np.float64)
+    f = float(sc.flen[0]) * max(w, h)
+    X = (x + 0.5 - w / 2.0) / f * d
+    Y = (y + 0.5 - h / 2.0) / f * d
+    return np.stack([X, Y, d], axis=1).astype(np.float32)
+
+
+def test_resident_optimize_without_sgm():
+    """smvsb_optimize_rgb_f32 with no_sgm: DepthOptimizer::optimize() in the
+    use_sgm = false mode -- initial surface from the bundle's features, one scale
+    coarser, NCC visibility, expansion by a ring of patches every outer
+    iteration -- against the compiled reference given the same features."""
+    from util_scene import colour_scene
+    sc = colour_scene(640, 480, 3, 92)
+    feats = _features_on_surface(sc, 400, 92)
+    R = oref.RefScene(sc)
+    sparse, d_cpu, n_cpu = R.optimize_nosgm(feats, regularization=0.01, num_iterations=5,
+                                            min_scale=2)
+    assert 300 < (sparse > 0).sum() <= 400
+    Mi, ti = R.Mt()
+    imgs = [R.image(v) for v in range(4)]
+    with api.Context(0) as ctx:
+        d, n, _, st = api.optimize(ctx, imgs[0], imgs[1:], Mi, ti, R.flen(0),
+                                   R.inverse_flen(0), R.inverse_calibration(), sparse,
+                                   use_sgm=False)
+    R.close()
+    # the ladder starts one scale coarser than with SGM (5 at 640x480) and the
+    # surface has grown from the features' patches over most of the image
+    assert st["final_scale"] == 2 and st["scales"] == 4
+    assert np.array_equal(d_cpu > 0, d > 0)
+    m = d_cpu > 0
+    assert m.mean() > 0.15, m.mean()
+    rel = np.abs(d[m] - d_cpu[m]) / d_cpu[m]
+    print({"rel_median": float(np.median(rel)), "rel_p999": float(np.quantile(rel, 0.999)),
+           "rel_max": float(rel.max()), "frac_above_1e-4": float((rel > 1e-4).mean())})
+    # The ring of patches `expand` adds around the surface is seen by few
+    # neighbours and barely textured at first: its systems are the worst
+    # conditioned of the ladder, a node of it can sit within rounding of the
+    # 0.15 px activity threshold (see test_gpu_fullsize), and one Newton step
+    # more or less on such a node is up to 1e-3 of its depth. Every topological
+    # decision is the reference's (the masks are EQUAL); the bulk of the depths
+    # agrees to 1e-6, a fraction below 1e-3 of the pixels leaves the 1e-4 band,
+    # nothing leaves 1e-3.
+    assert float(np.median(rel)) < 1e-6
+    assert float((rel > 1e-4).mean()) < 1e-3
+    assert rel.max() < 1e-3, rel.max()
+    # normals are slopes: a depth difference of 2e-4 across a 4-pixel patch is a
+    # slope difference of 2e-4 * depth * focal length / 4 ~ 0.1 at those pixels
+    dn = np.abs(n - n_cpu)[m].max(axis=1)
+    print({"normal_median": float(np.median(dn)), "normal_frac_above_1e-3": float((dn > 1e-3).mean())})
+    assert float(np.median(dn)) < 1e-5
+    assert float((dn > 1e-3).mean()) < 5e-2
