@@ -444,6 +444,23 @@ def test_error_paths():
         with pytest.raises(api.SmvsbError) as e:
             ctx.set_surface(*bad)
         assert e.value.code == -1
+        if surf[9].size >= 2 and surf[8][1] >= 2:
+            bad = list(surf)
+            bad[9] = surf[9].copy()
+            bad[9][1] = bad[9][0]                      # a neighbour twice in one list
+            with pytest.raises(api.SmvsbError) as e:
+                ctx.set_surface(*bad)
+            assert e.value.code == -1
+            assert b"duplicate" in api.lib().smvsb_last_error(ctx._h)
+        bad = list(surf)
+        bad[8] = surf[8].copy()
+        bad[8][1], bad[8][2] = surf[8][2] + 1, surf[8][1]   # offsets not monotone
+        with pytest.raises(api.SmvsbError) as e:
+            ctx.set_surface(*bad)
+        assert e.value.code == -1
+        # a failed call leaves the context without a surface
+        with pytest.raises(api.SmvsbError):
+            ctx.gn_construct(None, None, 0.01, 0.0)
         ctx.set_surface(*surf)
         with pytest.raises(api.SmvsbError) as e:       # lighting without shading image
             ctx.gn_construct(None, np.ones(16), 0.01, 0.0)

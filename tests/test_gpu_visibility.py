@@ -206,6 +206,21 @@ def test_error_paths_of_the_new_entry_points():
             ctx.bilateral_filter(np.zeros((8, 8), dtype=np.float32),
                                  np.ones((8, 8), dtype=np.float32), kernel_size=9)
         assert b"kernel_size" in L.smvsb_last_error(ctx._h)
+        # colour entry points: 2 channels, no_sgm without colour / with a
+        # depth image of the wrong size
+        with pytest.raises(api.SmvsbError):
+            ctx.view_set_scale(np.zeros((8, 8, 2), dtype=np.float32), 2)
+        grey = [np.zeros((64, 96), dtype=np.uint8)] * 2
+        rgb = [np.zeros((64, 96, 3), dtype=np.float32)] * 2
+        args = (np.eye(3).reshape(1, 9), np.zeros((1, 3)), 96.0, 1.0 / 96.0,
+                np.eye(3, dtype=np.float32))
+        with pytest.raises(api.SmvsbError):
+            api.optimize(ctx, grey[0], grey[1:], *args, np.ones((64, 96), np.float32),
+                         use_sgm=False)
+        assert b"three-channel" in L.smvsb_last_error(ctx._h)
+        with pytest.raises(api.SmvsbError):
+            api.optimize(ctx, rgb[0], rgb[1:], *args, np.ones((32, 48), np.float32),
+                         use_sgm=False)
         # a filter over an empty depth map gives an empty depth map
         out = ctx.bilateral_filter(np.full((8, 8), 0.5, dtype=np.float32),
                                    np.zeros((8, 8), dtype=np.float32))
