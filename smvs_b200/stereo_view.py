@@ -85,11 +85,30 @@ def gradients_and_hessian(img):
     return grad, hess
 
 
+def desaturate_luminance(img):
+    """mve::image::desaturate<float>(img, DESATURATE_LUMINANCE) of an
+    (H, W, 3) image: v0 * 0.21f + v1 * 0.72f + v2 * 0.07f, left to right."""
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    a = (img[:, :, 0] * np.float32(0.21)).astype(np.float32)
+    b = (img[:, :, 1] * np.float32(0.72)).astype(np.float32)
+    c = (img[:, :, 2] * np.float32(0.07)).astype(np.float32)
+    return ((a + b).astype(np.float32) + c).astype(np.float32)
+
+
 def set_scale(img_u8, scale):
     """Blurred image, gradient and Hessian of one view at `scale`
-    (sigma = 0.12 * 2^scale + 0.2, lib/stereo_view.cc:28)."""
+    (sigma = 0.12 * 2^scale + 0.2, lib/stereo_view.cc:28). A three-channel
+    image is blurred channel by channel (mve::image::blur_gaussian) and the
+    blurred image desaturated before the stencil (:48-62); the blurred image
+    returned keeps its channels."""
     sigma = 0.12 * math.pow(2.0, scale) + 0.2
-    blurred = blur_gaussian(byte_to_float(img_u8), sigma)
+    f = byte_to_float(img_u8)
+    if f.ndim == 3:
+        blurred = np.stack([blur_gaussian(f[:, :, c], sigma) for c in range(f.shape[2])],
+                           axis=2)
+        grad, hess = gradients_and_hessian(desaturate_luminance(blurred))
+        return blurred, grad, hess
+    blurred = blur_gaussian(f, sigma)
     grad, hess = gradients_and_hessian(blurred)
     return blurred, grad, hess
 

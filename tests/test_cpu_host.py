@@ -107,6 +107,48 @@ def test_set_scale_mirror_matches_reference_bitwise():
 
 
 @pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")
+def test_set_scale_mirror_colour_views_bitwise():
+    """Three-channel views: channel-wise blur, luminance of the blurred image
+    (lib/stereo_view.cc:48-62) -- the numpy restatement against the compiled
+    reference, all three outputs bitwise."""
+    from util_scene import colour_scene
+    sc = colour_scene(160, 120, 1, 3)
+    R = oref.RefScene(sc)
+    for scale in (1, 3):
+        R.set_scale(scale)
+        for v in (0, 1):
+            b, g, h = stereo_view.set_scale(sc.images[v], scale)
+            assert b.shape == (120, 160, 3)
+            assert np.array_equal(b, R.scaleimage(v))
+            assert np.array_equal(g, R.gradients(v))
+            assert np.array_equal(h, R.hessian(v))
+    R.close()
+
+
+@pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")
+def test_reference_optimize_without_sgm_grows_from_the_features():
+    """The oracle's use_sgm = false entry (ref_optimize_nosgm): the sparse depth
+    Surface::create makes of the bundle holds the features, and optimize()
+    grows a surface from them that lies on the scene's true surface."""
+    from util_scene import colour_scene
+    sc = colour_scene(320, 240, 2, 4)
+    rng = np.random.default_rng(4)
+    x, y = rng.integers(8, 312, 150), rng.integers(8, 232, 150)
+    d = sc.true_depth[y, x].astype(np.float64)
+    f = float(sc.flen[0]) * 320
+    feats = np.stack([(x + 0.5 - 160) / f * d, (y + 0.5 - 120) / f * d, d], axis=1)
+    R = oref.RefScene(sc)
+    sparse, depth, normals = R.optimize_nosgm(feats, num_iterations=3, min_scale=3)
+    R.close()
+    hit = sparse[y, x]
+    assert (hit > 0).all() and np.abs(hit - d).max() < 1e-3 * d.max()
+    assert (sparse > 0).sum() <= 150
+    m = depth > 0
+    assert m.mean() > 0.05
+    assert np.median(np.abs(depth[m] - sc.true_depth[m]) / sc.true_depth[m]) < 5e-3
+
+
+@pytest.mark.skipif(not oref.available(), reason="oracle/_ref not built")
 def test_surface_grid_matches_reference():
     for (w, h, scale) in ((640, 480, 2), (640, 480, 4), (417, 311, 3), (1920, 1080, 5)):
         sc = synth.make_scene(w, h, 1, seed_index=1) if w < 1000 else None
