@@ -1061,6 +1061,94 @@ sgm_sum_wta_kernel (int w, int h, uint8_t const* __restrict__ cost,
     }
 }
 
+/*
+ * The same for D = 128 with eight lanes per pixel: a lane owns 16 consecutive
+ * disparities and reads them as ONE 16-byte word per volume (nine 128-bit
+ * loads per lane instead of 36 byte loads), adds them as pairs of 16-bit
+ * fields (S < 9 * 255 + 8 * 255: no carry between the fields), and the
+ * argmin -- lowest value, then lowest index, like the reference's first
+ * minimum -- runs over the lane's 16 values and then over the pixel's eight
+ * lanes. The byte-load version spent its time in the load/store unit
+ * (lg_throttle 4.5, mio_throttle 6.4 cycles per issue, 2.4 GB in 0.77 ms).
+ */
+__device__ __forceinline__ void
+wta_add16 (uint4 const v, unsigned mult, unsigned (&even)[4], unsigned (&odd)[4])
+{
+    unsigned const x[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        even[k] += (x[k] & 0x00ff00ffu) * mult;          /* bytes 0, 2 */
+        odd[k] += ((x[k] >> 8) & 0x00ff00ffu) * mult;    /* bytes 1, 3 */
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sgm_sum_wta128_kernel (int w, int h, uint8_t const* __restrict__ cost,
+    uint8_t const* __restrict__ Dvol, uint8_t const* __restrict__ main_img,
+    float const* __restrict__ depths, uint16_t* __restrict__ S_out,
+    float* __restrict__ out)
+{
+    int const npix = w * h;
+    int const t = blockIdx.x * blockDim.x + threadIdx.x;
+    int const p = t >> 3, sub = threadIdx.x & 7;
+    bool const on = p < npix;
+    size_t const nvox = static_cast<size_t>(npix) * 128;
+    size_t const base = static_cast<size_t>(on ? p : 0) * 128 + sub * 16;
+    int const px = p % w, py = p / w;
+    unsigned const mult = 8u + (((px == 0 || px == w - 1)
+        && (py == 0 || py == h - 1)) ? 1u : 0u);
+    unsigned even[4] = { 0u, 0u, 0u, 0u }, odd[4] = { 0u, 0u, 0u, 0u };
+    uint4 v[9];
+    v[0] = __ldg(reinterpret_cast<uint4 const*>(cost + base));
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        v[r + 1] = __ldg(reinterpret_cast<uint4 const*>(Dvol + r * nvox + base));
+    wta_add16(v[0], mult, even, odd);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        wta_add16(v[r + 1], 1u, even, odd);
+    if (S_out != nullptr && on)
+    {
+        /* disparities 4k .. 4k+3 of word k: even = (d0, d2), odd = (d1, d3) */
+        uint4 lo, hi;
+        lo.x = __byte_perm(even[0], odd[0], 0x5410);
+        lo.y = __byte_perm(even[0], odd[0], 0x7632);
+        lo.z = __byte_perm(even[1], odd[1], 0x5410);
+        lo.w = __byte_perm(even[1], odd[1], 0x7632);
+        hi.x = __byte_perm(even[2], odd[2], 0x5410);
+        hi.y = __byte_perm(even[2], odd[2], 0x7632);
+        hi.z = __byte_perm(even[3], odd[3], 0x5410);
+        hi.w = __byte_perm(even[3], odd[3], 0x7632);
+        uint4* dst = reinterpret_cast<uint4*>(S_out + base);
+        dst[0] = lo;
+        dst[1] = hi;
+    }
+    /* key = value << 16 | index; 0xffff is "no minimum found" (the reference
+     * starts from numeric_limits<uint16_t>::max() and compares with <) */
+    unsigned key = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        unsigned const val[4] = { even[k] & 0xffffu, odd[k] & 0xffffu,
+            even[k] >> 16, odd[k] >> 16 };
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (val[i] != 0xffffu)
+                key = min(key, (val[i] << 16)
+                    | static_cast<unsigned>(sub * 16 + k * 4 + i));
+    }
+    key = min(key, __shfl_xor_sync(0xffffffffu, key, 4));
+    key = min(key, __shfl_xor_sync(0xffffffffu, key, 2));
+    key = min(key, __shfl_xor_sync(0xffffffffu, key, 1));
+    if (sub == 0 && on)
+    {
+        int const idx = (key == 0xffffffffu) ? 0 : static_cast<int>(
+            key & 0xffffu);
+        out[p] = (idx < 2 || main_img[p] < 25) ? 0.0f : depths[idx];
+    }
+}
+
 __global__ void
 u8_to_u16_kernel (size_t n, uint8_t const* __restrict__ in,
     uint16_t* __restrict__ out)
@@ -1097,6 +1185,14 @@ run_wta (int w, int h, uint8_t const* cost, uint8_t const* Dvol,
     uint8_t const* main_img, float const* depths, uint16_t* S_out, float* out,
     cudaStream_t st)
 {
+    if (DPL == 4 && getenv("SMVSB_SGM_WTA_BYTES") == nullptr)
+    {
+        int const blocks8 = (w * h * 8 + 255) / 256;
+        sgm_sum_wta128_kernel<<<blocks8, 256, 0, st>>>(w, h, cost, Dvol,
+            main_img, depths, S_out, out);
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     int const blocks = (w * h * 32 + 255) / 256;
     sgm_sum_wta_kernel<DPL><<<blocks, 256, 0, st>>>(w, h, cost, Dvol, main_img,
         depths, S_out, out);
