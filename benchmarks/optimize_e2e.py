@@ -8,6 +8,11 @@ contract.
                                               ~2.5 min) -> benchmarks/_cache/
   python benchmarks/optimize_e2e.py gpu [S]   on the GPU box; compares with the
                                               cached CPU result, prints JSON
+  python benchmarks/optimize_e2e.py time [S]  on the GPU box: wall time of the
+                                              drop-in optimize() only (no
+                                              CPU result needed); with
+                                              SMVSB_REBUILD_SURFACE=1 the host
+                                              Surface is rebuilt as well
 (S = with shading.) SMVSB_TIMING=1 adds the per-scale split of the patched
 run_newton_iterations.
 """
@@ -43,6 +48,12 @@ def main():
         all_secs.append(time.time() - t0)
         R.close()
     secs = all_secs[-1]
+    if mode == "time":
+        print(json.dumps({"config": "1920x1080, 6 neighbours, -o2" + (" -S" if shading else ""),
+                          "rebuild_surface": os.environ.get("SMVSB_REBUILD_SURFACE", "0") == "1",
+                          "seconds_each_call": all_secs,
+                          "valid_fraction": float((depth > 0).mean())}))
+        return
     cache = os.path.join(CACHE, f"optimize_cpu_{tag}.npz")
     if mode == "cpu":
         np.savez_compressed(cache, depth=depth, normals=normals, secs=secs)

@@ -16,7 +16,11 @@
  * intermediate images) runs the reference's own optimize(), whose members are the per-call
  * drop-ins of b200_depth_optimizer.cc. lib/depth_optimizer.h is untouched.
  *
- *   SMVSB_MEMBERWISE=1   forces the reference's optimize() (per-member path)
+ *   SMVSB_MEMBERWISE=1        forces the reference's optimize() (per-member path)
+ *   SMVSB_REBUILD_SURFACE=1   rebuilds the final surface as a host object
+ *                             (default: a stand-in whose get_depth_map /
+ *                             get_normal_map return the device's maps,
+ *                             b200_surface.cc)
  */
 #include <algorithm>
 #include <cmath>
@@ -26,6 +30,12 @@
 #include "depth_optimizer.h"
 
 #include "b200_context.h"
+
+namespace smvs_b200_integration {
+/* b200_surface.cc */
+void hold_maps (smvs::Surface::Ptr const& surface, mve::FloatImage::Ptr depth,
+    mve::FloatImage::Ptr normals, float inv_flen);
+}
 
 SMVS_NAMESPACE_BEGIN
 
@@ -176,11 +186,26 @@ DepthOptimizer::optimize (void)
             sgm->begin(), &o, depth->begin(), normals->begin(), light, &st));
 
     /* ---- what optimize() leaves behind -------------------------------- */
-    /* the final surface, for get_depth() / get_normals(): the grid geometry
+    int const init_scale = st.final_scale + (st.scales - 1);
+    if (std::getenv("SMVSB_REBUILD_SURFACE") == nullptr)
+    {
+        /* get_depth() / get_normals() (the only public doors to the private
+         * surface) are served from the maps the device rendered, see
+         * b200_surface.cc; the member itself is a small stand-in */
+        mve::FloatImage::Ptr ones = mve::FloatImage::create(w, h, 1);
+        ones->fill(1.0f);
+        this->surface = Surface::create(nullptr, this->main_view, init_scale,
+            ones);
+        smvs_b200_integration::hold_maps(this->surface, depth->duplicate(),
+            normals->duplicate(), this->main_view->get_inverse_flen());
+    }
+    else
+    {
+    /* SMVSB_REBUILD_SURFACE=1: the final surface as a host object, for a
+     * host that reaches the surface some other way: the grid geometry
      * of the ladder from a stand-in created and subdivided by the reference's
      * own code (a constant depth image makes every node and patch exist),
      * then the device's nodes and validity */
-    int const init_scale = st.final_scale + (st.scales - 1);
     {
         mve::FloatImage::Ptr ones = mve::FloatImage::create(w, h, 1);
         ones->fill(1.0f);
@@ -217,6 +242,7 @@ DepthOptimizer::optimize (void)
             nodes[i]->dy = values[4 * i + 2];
             nodes[i]->dxy = values[4 * i + 3];
         }
+    }
     }
     if (lit && st.final_scale < 4)
     {

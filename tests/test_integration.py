@@ -120,6 +120,23 @@ def test_optimize_without_sgm_through_the_drop_in():
     assert float((dn > 1e-3).mean()) < 5e-2
 
 
+def test_held_maps_equal_the_rebuilt_surface(monkeypatch):
+    """After the resident optimize() the drop-in leaves a stand-in Surface whose
+    get_depth_map / get_normal_map return the maps the device rendered
+    (integration/b200_surface.cc); with SMVSB_REBUILD_SURFACE=1 it rebuilds the
+    final surface as a host object and the reference's own renderer makes the
+    maps. Both must be the same images, bit for bit."""
+    monkeypatch.delenv("SMVSB_MEMBERWISE", raising=False)
+    sc = synth.make_scene(640, 480, 2, seed_index=25)
+    monkeypatch.delenv("SMVSB_REBUILD_SURFACE", raising=False)
+    d_held, n_held, _ = _run(sc, oref.INTEGRATION_LIB_PATH, False)
+    monkeypatch.setenv("SMVSB_REBUILD_SURFACE", "1")
+    d_host, n_host, _ = _run(sc, oref.INTEGRATION_LIB_PATH, False)
+    assert (d_held > 0).mean() > 0.5
+    assert np.array_equal(d_held, d_host)
+    assert np.array_equal(n_held, n_host)
+
+
 def test_sgm_reconstruct_parity():
     """SGMStereo::reconstruct (both directions + consistency check) with
     run_sgm on the GPU: bit-exact."""
