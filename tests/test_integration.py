@@ -52,21 +52,22 @@ def test_optimize_depth_parity_config0(shading, memberwise, monkeypatch):
     assert np.abs(n_gpu - n_cpu).max() < 1e-3
 
 
-@pytest.mark.parametrize("memberwise", [False, True])
-def test_optimize_colour_views_through_the_drop_in(memberwise, monkeypatch):
+@pytest.mark.parametrize("memberwise,shading", [(False, False), (True, False), (False, True)])
+def test_optimize_colour_views_through_the_drop_in(memberwise, shading, monkeypatch):
     """Three-channel views (what real MVE scenes hold): the reference's
     optimize() through the drop-in build -- resident (smvsb_optimize_rgb_f32)
     and member-wise (StereoView::set_scale through smvsb_view_set_scale_c) --
-    against the pure-CPU build on the same colour scene."""
+    against the pure-CPU build on the same colour scene; with -S the shading
+    image is the luminance of the linear colour image (lib/stereo_view.cc:74-78)."""
     from util_scene import colour_scene
     if memberwise:
         monkeypatch.setenv("SMVSB_MEMBERWISE", "1")
     else:
         monkeypatch.delenv("SMVSB_MEMBERWISE", raising=False)
-    sc = colour_scene(640, 480, 2, 23)
-    d_cpu, n_cpu, _ = _run(sc, None, False)
+    sc = colour_scene(640, 480, 2, 23, shading=shading)
+    d_cpu, n_cpu, _ = _run(sc, None, shading)
     before = api.lib().smvsb_global_launch_count()
-    d_gpu, n_gpu, _ = _run(sc, oref.INTEGRATION_LIB_PATH, False)
+    d_gpu, n_gpu, _ = _run(sc, oref.INTEGRATION_LIB_PATH, shading)
     assert api.lib().smvsb_global_launch_count() - before > 20
     assert np.array_equal(d_cpu > 0, d_gpu > 0)
     m = d_cpu > 0
